@@ -1,0 +1,182 @@
+/*
+ * yabpe.h -- C ABI of libyabpe.so: the B200 (sm_100a) implementation of the BPE hot path of
+ * DreamOneX/yet-another-bpe.
+ *
+ * The reference has no FFI of its own (pure Python); the boundary it exposes for this path is
+ * tests/adapters.py:37-99 (run_train_bpe / get_tokenizer).  Every entry point below names the
+ * reference code it replaces; the Python host layer (yet-another-bpe_b200/yabpe/) mirrors the
+ * reference's classes on top of these calls, and INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative YABPE_ERR_* otherwise;
+ *     yabpe_last_error() returns a static, thread-local description of the last failure
+ *   - all data pointers are CALLER-OWNED DEVICE pointers unless the comment says "host"
+ *   - `stream` is a cudaStream_t passed as void*; all launches are stream-ordered and
+ *     non-blocking; nothing synchronises with the host
+ *   - buffers whose size is data dependent follow count -> allocate -> fill: the counting
+ *     call leaves sizes in a device `stats` / `counters` array the host reads once
+ *   - one host thread per device; no global state besides the per-device Unicode tables and
+ *     the special-token set in constant memory (set per call, stream-ordered)
+ */
+#ifndef YABPE_H
+#define YABPE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YABPE_ABI_VERSION 1
+
+#define YABPE_OK 0
+#define YABPE_ERR_CUDA (-1)
+#define YABPE_ERR_ARG (-2)
+
+/* indices into the int64[16] pre-token statistics array */
+#define YABPE_ST_NTOK 0        /* pre-token occurrences counted                           */
+#define YABPE_ST_UNIQ_SHORT 1  /* unique pre-tokens of <= 14 bytes                        */
+#define YABPE_ST_UNIQ_LONG 2   /* unique pre-tokens of  > 14 bytes                        */
+#define YABPE_ST_UNIQ_BYTES 3  /* sum of the byte lengths of all unique pre-tokens        */
+#define YABPE_ST_ERR_POS 4     /* first invalid UTF-8 offset (INT64_MAX = valid)          */
+#define YABPE_ST_TABLE_FULL 5  /* != 0: a hash table overflowed, retry with larger tables */
+#define YABPE_ST_OVF_N 6       /* pre-tokens longer than the tile window                  */
+#define YABPE_ST_NSPECIAL 8    /* recognised special-token occurrences                    */
+
+/* indices into the int64[32] merge-loop state array */
+#define YABPE_MS_NMERGES 0
+#define YABPE_MS_NTOK 1
+#define YABPE_MS_ERROR 2       /* bit 0: pair table full, bit 1: token pool full, bit 2: internal */
+#define YABPE_MS_NPAIRS 6
+#define YABPE_MS_POOL_USED 8
+#define YABPE_MS_REBUILDS 9
+#define YABPE_MS_TREBUILDS 10
+
+const char* yabpe_last_error(void);
+int yabpe_abi_version(void);
+
+/* Upload the Unicode class tables (regex-module \p{L} \p{N} \s, see tools/gen_unicode_tables.py)
+ * to the current device.  Idempotent.  Replaces the tables compiled into the `regex` C
+ * extension the reference calls at trainer.py:169 / tokenizer.py:95. */
+int yabpe_device_init(void);
+
+/* Class code of one code point from the built-in table (host-side, for tests):
+ * 0 = other, 1 = \p{L}, 2 = \p{N}, 3 = \s. */
+int yabpe_class_of(uint32_t cp);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pre-tokenise + count.   Replaces trainer.py:146-170 (process_chunk: strict UTF-8 decode,
+ * regex.findall of "sp1|..|GPT2_PAT") + trainer.py:221-225 (word_freq), and for mode 1 the
+ * special split + findall of tokenizer.py:169-186.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t* text;        /* device; readable capacity >= round_up(n, 16) + 16             */
+    int64_t n;                  /* bytes of text                                                  */
+    const int64_t* cuts;        /* device, sorted, strictly inside (0, n): hard text boundaries   */
+    int32_t n_cuts;             /*   = reference chunk ends (trainer.py:172-198), file / doc ends */
+    int32_t mode;               /* 0 = trainer (specials are leading alternatives), 1 = encode    */
+    const uint8_t* sp_blob;     /* HOST: special tokens, priority order, concatenated             */
+    const int32_t* sp_offs;     /* HOST: n_sp + 1 offsets into sp_blob                            */
+    int32_t n_sp;
+    int32_t _pad;
+    int64_t own_lo, own_hi;     /* only pre-tokens starting in [own_lo, own_hi) are counted       */
+    uint32_t* cand_bits;        /* device, (n + 63) / 32 words, zeroed; may be NULL when n_sp = 0 */
+    uint32_t* rec_bits;         /* device, same size, zeroed: recognised special starts (output)  */
+    void* short_keys;           /* device, short_cap * 16 bytes, zeroed                           */
+    int64_t* short_counts;      /* device, short_cap, zeroed                                      */
+    int64_t short_cap;          /* power of two                                                   */
+    void* long_entries;         /* device, long_cap * 32 bytes, zeroed                            */
+    int64_t long_cap;           /* power of two                                                   */
+    int64_t* ovf_pos;           /* device scratch for over-long pre-token starts                  */
+    int64_t ovf_cap;
+    int64_t* stats;             /* device int64[16]; caller zeroes it and sets [ERR_POS]=INT64_MAX */
+} yabpe_pretok_args;
+
+/* Stage 1: special-token candidates + resolution (skipped when n_sp == 0).
+ * Stage 2: tile kernel: classes, token starts, keys, hash-table counts.
+ * Stage 3 (yabpe_pretok_finish): pre-tokens longer than the tile window; needs stats[OVF_N],
+ *          which it reads on the device -- no host round trip. */
+int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Word table.  Replaces the dict[tuple[bytes,...], int] built at trainer.py:221-225 by flat
+ * arrays: one int32 symbol slot per byte of every unique pre-token.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t* wsym;              /* device, n_syms slots: current symbols of every word            */
+    int32_t* sym_word;          /* device, n_syms slots: owning word of each slot                 */
+    int64_t* woff;              /* device, n_words: first slot of each word                       */
+    int32_t* wlen;              /* device, n_words: current length                                */
+    int64_t* wcnt;              /* device, n_words: occurrences                                   */
+    int32_t* sword;             /* device, short_cap: slot -> word id (may be NULL)               */
+    int32_t* lword;             /* device, long_cap : slot -> word id (may be NULL)               */
+    int64_t* counters;          /* device int64[2], zeroed: [0] n_words, [1] n_syms (outputs)     */
+} yabpe_word_table;
+
+int yabpe_compact_words(const yabpe_pretok_args* a, const yabpe_word_table* w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Merge loop.  Replaces trainer.py:216-302 (_merge_loop): pair histogram, best-pair selection
+ * max(count, (left_bytes, right_bytes)), left-to-right rewrite, incremental deltas.  One
+ * cooperative launch runs all merges; the host reads `state`, `merges` and the token pool after.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    yabpe_word_table words; int64_t n_words, n_syms;
+    int32_t* wstamp;            /* device, n_words, zeroed                                        */
+    uint8_t* tok_bytes; int64_t tok_bytes_cap;   /* token byte pool; base tokens filled by host   */
+    int64_t* tok_off;           /* device, max_tokens + 1; [0..n_base] filled by the host         */
+    uint64_t* tok_hash;         /* device, max_tokens; polynomial hash (base 0x100000001b3, +1)   */
+    uint64_t* tok_pow;          /* device, max_tokens; base^len                                   */
+    uint64_t* tset; int64_t tset_cap;            /* device hash set of token hashes, pow2         */
+    int64_t max_tokens;
+    uint64_t* pkey; int64_t* pcnt; int64_t pcap; /* pair table, pow2, zeroed                      */
+    uint32_t* ioff;             /* device, pcap + 1                                               */
+    uint32_t* icnt;             /* device, pcap                                                   */
+    int32_t* ipost;             /* device, n_syms                                                 */
+    uint32_t* inact;            /* device, (pcap + 31) / 32                                       */
+    int32_t* act;               /* device, pcap                                                   */
+    int32_t* dlog_slot; int32_t* dlog_word; int64_t dlog_cap;
+    void* partial;              /* device, 24 bytes per CTA (>= 1024 entries)                     */
+    int64_t* bsum;              /* device, one per CTA (>= 1024 entries)                          */
+    int32_t* merges;            /* device, 2 * num_merges: (left id, right id) per merge          */
+    int32_t* merge_new;         /* device, num_merges: resulting id                               */
+    int64_t* state;             /* device int64[32], zeroed except [MS_NTOK] = n_base             */
+    int64_t num_merges; int64_t min_frequency;
+} yabpe_merge_args;
+
+int yabpe_merge_loop(const yabpe_merge_args* m, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Encode.  Replaces tokenizer.py:152-308.  `yabpe_encode_words` applies the merges by rank to
+ * every unique pre-token of the batch (in place in wsym); `yabpe_encode_ids` makes the two
+ * passes over the text that count and then write the ids in text order.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint64_t* mkey; const uint64_t* mval; int64_t mcap;  /* (sym,sym) -> rank<<32 | result  */
+    const int32_t* byte_sym;    /* device, 256                                                    */
+    const int32_t* sym_out;     /* device, n_symbols: vocab id (unk substituted)                  */
+    const int32_t* sp_ids;      /* device, n_sp: vocab id of each special or -1                   */
+    int32_t consistent; int32_t _pad;
+} yabpe_encode_model;
+
+int yabpe_encode_words(const yabpe_encode_model* e, const yabpe_word_table* w, int64_t n_words, void* stream);
+
+typedef struct {
+    int64_t* tile_count;        /* device, n_tiles + 1                                            */
+    int32_t* out_ids; int64_t out_cap;
+    int64_t* doc_off;           /* device, n_cuts + 2 (or NULL)                                   */
+} yabpe_encode_out;
+
+/* pass 0: per-tile id counts + exclusive scan (total in tile_count[n_tiles]);
+ * pass 1: write ids (out_ids must hold tile_count[n_tiles] entries). */
+int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
+                     const yabpe_encode_out* o, int32_t pass, void* stream);
+int64_t yabpe_num_tiles(int64_t own_lo, int64_t own_hi);
+
+/* kernels launched by this library since load (the bench's `gpu_launches`) */
+int64_t yabpe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

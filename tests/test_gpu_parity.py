@@ -1,0 +1,236 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the reference's
+golden vectors and the reference-generated vectors in tests/golden/.  Bit-exact everywhere."""
+from __future__ import annotations
+
+import random
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+ALPHABET = list("ab Z'sdmtlvre19!<|>\n\t \r") + [
+    "é", "中", "１", " ", " ", "​", "\U0001f643", "", "　", "",
+    "́", "\U00016ea0", "'ll", "'ve", " '", "<|endoftext|>", "<|e|>", "don't", " we've",
+]
+
+
+@pytest.fixture(scope="module")
+def yabpe():
+    import yabpe as y
+    from yabpe import _ffi
+    _ffi.require_cuda()          # fails loudly when the library or the device is missing
+    return y
+
+
+def _oracle_counts(data: bytes, specials, mode="train", chunk_size=1 << 30):
+    toks = oracle.pretokenize(data, specials, mode, chunk_size)
+    if mode == "encode":
+        _, kinds = oracle.pretokenize_spans(data, specials, mode, chunk_size)
+        toks = [t for t, k in zip(toks, kinds) if k < 0]
+    return dict(Counter(toks))
+
+
+def _device_counts(data, specials, mode="train", chunk_size=1 << 30):
+    from yabpe.trainer import pretoken_counts
+    d = pretoken_counts(data, specials, mode=mode, chunk_size_bytes=chunk_size)
+    n = d.pop("__n_pretokens__", 0)
+    assert n == sum(d.values())
+    return d
+
+
+# ------------------------------------------------------------------------------- pre-tokeniser
+def test_pretok_counts_fixtures(yabpe):
+    for name in ["corpus.en", "tinystories_sample.txt", "address.txt", "german.txt",
+                 "special_token_trailing_newlines.txt", "special_token_double_newlines_non_whitespace.txt"]:
+        data = (common.FIXTURES / name).read_bytes()
+        for sp in ([], ["<|endoftext|>"]):
+            assert _device_counts(data, sp) == _oracle_counts(data, sp), (name, sp)
+    data = (common.DATA / "unicode.txt").read_bytes()
+    assert _device_counts(data, []) == _oracle_counts(data, [])
+
+
+def test_pretok_counts_golden_cases_concatenated(yabpe):
+    """All reference-generated pre-tokenisation vectors, batched as independent texts via cuts."""
+    from yabpe.trainer import pretoken_counts
+    by_key = {}
+    for c in common.load_pretok_cases():
+        by_key.setdefault((c["mode"], tuple(c["specials"])), []).append(c)
+    for (mode, sp), cases in by_key.items():
+        blobs = [c["text"].encode("utf-8") for c in cases if c["text"]]
+        want = Counter()
+        for c in cases:
+            toks = [t.encode("utf-8") for t in c["tokens"]]
+            if mode == "encode":
+                toks = [t for t in toks if t.decode() not in sp]
+            want.update(toks)
+        data = b"".join(blobs)
+        cuts = np.cumsum([len(b) for b in blobs])[:-1].tolist()
+        got = pretoken_counts(data, list(sp), mode=mode, cuts=cuts)
+        got.pop("__n_pretokens__")
+        assert got == dict(want), (mode, sp)
+
+
+def test_pretok_counts_fuzz_and_adversarial(yabpe):
+    rng = random.Random(123)
+    for sp in ([], ["<|endoftext|>"], ["<|e|>", "<|endoftext|>"], [" <", "<|e|>"], ["\nb", "ab", "a"]):
+        text = "".join(rng.choice(ALPHABET) for _ in range(60000)).encode("utf-8")
+        assert _device_counts(text, sp) == _oracle_counts(text, sp), sp
+        for cs in (97, 4096):
+            assert _device_counts(text[:30000], sp, chunk_size=cs) == _oracle_counts(text[:30000], sp, chunk_size=cs), (sp, cs)
+    adv = common.synth_adversarial(300_000)
+    for sp in ([], ["<|endoftext|>"]):
+        assert _device_counts(adv, sp) == _oracle_counts(adv, sp)
+    for sp in (["<|endoftext|>"], ["<|e|>", "<|endoftext|>", "<|endoftext|><|endoftext|>"], ["a", "ab", " "]):
+        text = "".join(rng.choice(ALPHABET) for _ in range(40000)).encode("utf-8")
+        assert _device_counts(text, sp, mode="encode") == _oracle_counts(text, sp, mode="encode"), sp
+
+
+def test_pretok_long_tokens_and_tile_edges(yabpe):
+    """Tokens straddling tile boundaries, longer than the tile window, and MB-long runs."""
+    parts = [b"x" * 8191, b" ", b"y" * 9000, b"\n", "中".encode() * 5000, b" 1234567890" * 3, b"!" * 20000, b" ",
+             b"z" * 300, b" ", b"z" * 300, b" ", b"q" * 1_200_000, b" tail", b" ", b"q" * 1_200_000]
+    data = b"".join(parts)
+    assert _device_counts(data, ["<|endoftext|>"]) == _oracle_counts(data, ["<|endoftext|>"])
+
+
+def test_invalid_utf8_position(yabpe, tmp_path):
+    p = tmp_path / "bad.txt"
+    for blob, pos in [(b"hello \xff world", 6), (b"a" * 9000 + b"\xe4\xb8" + b"b" * 100, 9000), (b"ok \xc3", 3),
+                      (b"\x80abc", 0), (b"x" * 8190 + b"\xf0\x9f\x99" + b"y", 8190)]:
+        p.write_bytes(blob)
+        with pytest.raises(ValueError, match=f"invalid UTF-8 at position {pos}\\."):
+            yabpe.train_bpe(p, 300, [])
+    with pytest.raises(FileNotFoundError):
+        yabpe.train_bpe(tmp_path / "missing.txt", 300, [])
+    with pytest.raises(ValueError):
+        yabpe.BBPETrainer().train([])
+
+
+# ------------------------------------------------------------------------------- trainer
+def test_train_corpus_en_matches_reference_fixture(yabpe):
+    """The reference's own golden test (tests/test_train_bpe_gpt2.py:27-62)."""
+    vocab, merges = yabpe.train_bpe(common.FIXTURES / "corpus.en", 500, ["<|endoftext|>"])
+    ref = common.reference_merges_corpus_en()
+    assert merges == ref
+    assert set(vocab.keys()) == set(range(500))
+    assert set(vocab.values()) == {bytes([i]) for i in range(256)} | {b"<|endoftext|>"} | {a + b for a, b in ref}
+
+
+def test_train_golden_cases(yabpe, tmp_path):
+    for c in common.load_train_cases():
+        paths = []
+        for i, blob in enumerate(c["inputs"]):
+            p = tmp_path / f"in_{i}.txt"
+            p.write_bytes(blob)
+            paths.append(p)
+        cfg = yabpe.BBPETrainerConfig(vocab_size=c["vocab_size"], min_frequency=c["min_frequency"], max_workers=1,
+                                      chunk_size_bytes=c["chunk_size"], special_tokens=c["specials"])
+        model = yabpe.BBPETrainer(cfg).train(paths)
+        assert model.merges == c["merges_b"], c["name"]
+        assert {v: k for k, v in model.vocab.items()} == c["vocab_b"], c["name"]
+
+
+@pytest.mark.parametrize("kind,size,vocab", [("tinystories", 3_000_000, 2000), ("owt", 3_000_000, 3000),
+                                             ("adversarial", 400_000, 1500)])
+def test_train_synthetic_vs_oracle(yabpe, tmp_path, kind, size, vocab):
+    gen = {"tinystories": common.synth_tinystories, "owt": common.synth_owt, "adversarial": common.synth_adversarial}[kind]
+    data = gen(size)
+    p = tmp_path / "c.txt"
+    p.write_bytes(data)
+    want_vocab, want_merges = oracle.train_bpe(p, vocab, ["<|endoftext|>"], fast=True)
+    got_vocab, got_merges = yabpe.train_bpe(p, vocab, ["<|endoftext|>"])
+    assert got_merges == want_merges
+    assert got_vocab == want_vocab
+
+
+def test_train_edge_cases(yabpe, tmp_path):
+    p = tmp_path / "e.txt"
+    p.write_bytes(b"")
+    vocab, merges = yabpe.train_bpe(p, 300, ["<|endoftext|>"])
+    assert merges == [] and len(vocab) == 257
+    p.write_bytes(b"a")
+    assert yabpe.train_bpe(p, 300, ["<|endoftext|>"]) == oracle.train_bpe(p, 300, ["<|endoftext|>"])
+    p.write_bytes(b"a" * 63)
+    assert yabpe.train_bpe(p, 300, []) == oracle.train_bpe(p, 300, [])
+    assert yabpe.train_bpe(common.FIXTURES / "corpus.en", 100, ["<|endoftext|>"])[1] == []
+    # the special's own bytes are merged like a word and re-created without a new id
+    got = yabpe.train_bpe(common.FIXTURES / "tinystories_sample.txt", 1000, ["<|endoftext|>"])
+    want = oracle.train_bpe(common.FIXTURES / "tinystories_sample.txt", 1000, ["<|endoftext|>"], fast=True)
+    assert got == want
+    assert any(a + b == b"<|endoftext|>" for a, b in got[1])
+
+
+# ------------------------------------------------------------------------------- tokenizer
+def test_encode_golden_cases(yabpe):
+    models, cases = common.load_encode_cases()
+    toks = {}
+    for c in cases:
+        key = (c["model"], tuple(c["specials"]))
+        if key not in toks:
+            v, m = models[c["model"]]
+            toks[key] = yabpe.Tokenizer(v, m, c["specials"])
+        t = toks[key]
+        assert t.encode(c["text"]) == c["ids"], c["text"][:60]
+        assert t.decode(c["ids"]) == c["decoded"]
+
+
+def test_encode_fixtures_vs_oracle_and_tiktoken(yabpe):
+    v, m = common.gpt2_vocab_and_merges()
+    t = yabpe.Tokenizer(v, m, ["<|endoftext|>"])
+    o = oracle.Tokenizer(v, m, ["<|endoftext|>"])
+    texts = {}
+    for name in ["address.txt", "german.txt", "tinystories_sample.txt", "corpus.en"]:
+        with open(common.FIXTURES / name) as f:
+            texts[name] = f.read()
+    for name, text in texts.items():
+        ids = t.encode(text)
+        assert ids == o.encode(text), name
+        assert t.decode(ids) == text
+    try:
+        import tiktoken
+    except ImportError:
+        return
+    enc = tiktoken.Encoding("gpt2-local", pat_str=r"""'(?:[sdmt]|ll|ve|re)| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+""",
+                            mergeable_ranks={b: i for i, b in v.items() if i < 50256},
+                            special_tokens={"<|endoftext|>": 50256})
+    for name, text in texts.items():
+        assert t.encode(text) == enc.encode(text, allowed_special={"<|endoftext|>"}), name
+
+
+def test_encode_iterable_and_batch(yabpe):
+    v, m = common.gpt2_vocab_and_merges()
+    t = yabpe.Tokenizer(v, m, ["<|endoftext|>"])
+    o = oracle.Tokenizer(v, m, ["<|endoftext|>"])
+    with open(common.FIXTURES / "tinystories_sample.txt") as f:
+        lines = f.readlines()
+    lines += ["", "\n", "<|endoftext|>", " ", "a" * 500, "x<|endoftext|>"]
+    assert list(t.encode_iterable(lines)) == list(o.encode_iterable(lines))
+    assert t.encode_batch(lines) == [o.encode(x) for x in lines]
+    assert t.encode("") == [] and t.decode([]) == ""
+
+
+def test_encode_synthetic_and_long_words(yabpe):
+    v, m = common.gpt2_vocab_and_merges()
+    t = yabpe.Tokenizer(v, m, ["<|endoftext|>"])
+    o = oracle.Tokenizer(v, m, ["<|endoftext|>"])
+    text = common.synth_owt(1_500_000).decode("utf-8")
+    assert t.encode(text) == o.encode(text)
+    adv = common.synth_adversarial(120_000).decode("utf-8")
+    assert t.encode(adv) == o.encode(adv)
+    long_text = "a" * 3000 + " " + "ab" * 2500 + " " + "the" * 1000 + "中文" * 700
+    assert t.encode(long_text) == o.encode(long_text)
+
+
+def test_encode_roundtrip_property_large(yabpe):
+    """Size-independent property at a larger size: decode(encode(x)) == x, ids are valid."""
+    v, m = common.gpt2_vocab_and_merges()
+    t = yabpe.Tokenizer(v, m, ["<|endoftext|>"])
+    text = common.synth_owt(8_000_000, seed=7).decode("utf-8")
+    ids = t.encode(text)
+    assert t.decode(ids) == text
+    assert min(ids) >= 0 and max(ids) < 50257

@@ -1,0 +1,39 @@
+"""Ahead-of-time build of libyabpe.so (nvcc, sm_100a only) next to the Python host layer.
+
+The shared object is built IN-TREE (yet-another-bpe_b200/yabpe/libyabpe.so) so that it travels
+with the repository snapshot to the GPU box; it is git-ignored.
+"""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "csrc" / "yabpe.cu"
+OUT = HERE / "yabpe" / "libyabpe.so"
+DEPS = [HERE / "csrc" / n for n in ("yabpe.cu", "common.cuh", "pretok.cuh", "merge.cuh", "encode.cuh",
+                                    "unicode_tables.inc")] + [HERE.parent / "include" / "yabpe.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
+        return OUT
+    cmd = ["nvcc", *NVCC_FLAGS] + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(OUT), str(SRC)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libyabpe.so")
+    if verbose:
+        print(res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,668 @@
+// pretok.cuh -- GPU pre-tokeniser (K1) + pre-token counting (K2).
+//
+// Replaces /root/reference/src/yet_another_bpe/trainer.py:146-170 (process_chunk: strict
+// UTF-8 + regex.findall) and trainer.py:221-225 (word_freq), and the pre-tokenisation
+// half of tokenizer.py:152-193.  Exact semantics: SURVEY.md section 8(a) rows P1-P5, T2.
+//
+// Data flow per 8 KiB tile (one CTA, 256 threads, tiles handed out round-robin):
+//   TMA bulk copy (cp.async.bulk, double buffered)  HBM -> smem text window
+//   pass A  per-byte info (class, continuation, fences), strict UTF-8 validation
+//   pass B  live contractions ('s 'd 'm 't 'll 've 're)
+//   pass C  token-start bit per byte (warp ballot -> 32-bit masks)
+//   pass D  compaction of starts -> one thread per token -> key packing -> hash-table insert
+#pragma once
+
+#include "common.cuh"
+
+#define PT_TILE 8192
+#define PT_HL 32
+#define PT_HR 256
+#define PT_SLACK 16
+#define PT_WIN (PT_HL + PT_TILE + PT_HR + PT_SLACK)       // 8496 bytes, multiple of 16
+#define PT_THREADS 256
+#define PT_NBITS (PT_TILE + PT_HR + 1)                    // start bits for window offsets [HL, HL+TILE+HR]
+#define PT_NMASK ((PT_NBITS + 31) / 32)                   // 265 words
+#define PT_SHORT_MAX 14
+
+// stats slots (device int64[16])
+#define ST_NTOK 0
+#define ST_UNIQ_SHORT 1
+#define ST_UNIQ_LONG 2
+#define ST_UNIQ_BYTES 3
+#define ST_ERR_POS 4
+#define ST_TABLE_FULL 5
+#define ST_OVF_N 6
+#define ST_CHAIN_FAIL 7
+#define ST_NSPECIAL 8
+
+struct LongEntry { u64 h; i64 pos; i64 len; i64 count; };
+
+struct PretokParams {
+    const uint8_t* text; i64 n;
+    const i64* cuts; int n_cuts;
+    int mode; int n_sp;
+    i64 own_lo, own_hi;
+    uint32_t* cand; uint32_t* rec;
+    ulonglong2* skeys; i64* scounts; i64 scap;
+    LongEntry* lent; i64 lcap;
+    i64* ovf_pos; i64 ovf_cap;
+    i64* stats;
+    i64 tile_base; i64 n_tiles;
+};
+
+// ---------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// K1a: special-token candidates -> bitmap
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ i64 logical_end_after(const PretokParams& P, i64 i) {
+    // first hard boundary > i (chunk cut or n): specials never straddle a cut
+    int lo = 0, hi = P.n_cuts;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] <= i) lo = mid + 1; else hi = mid; }
+    return lo < P.n_cuts ? P.cuts[lo] : P.n;
+}
+
+__global__ void __launch_bounds__(256) k_special_candidates(PretokParams P, i64 lo, i64 hi) {
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+        uint8_t b = P.text[i];
+        if (!((c_sp.first_byte_mask[b >> 3] >> (b & 7)) & 1)) continue;
+        i64 lim = logical_end_after(P, i);
+        if (special_match(P.text, i, lim) >= 0) atomicOr(&P.cand[i >> 5], 1u << (i & 31));
+    }
+}
+
+__device__ __forceinline__ bool bit_at(const uint32_t* bm, i64 i) { return (bm[i >> 5] >> (i & 31)) & 1; }
+// next set bit in (from, to], or -1
+__device__ i64 next_bit(const uint32_t* bm, i64 from, i64 to) {
+    for (i64 i = from + 1; i <= to;) {
+        uint32_t w = bm[i >> 5] >> (i & 31);
+        if (w) { i64 r = i + __ffs(w) - 1; return r <= to ? r : -1; }
+        i = ((i >> 5) + 1) << 5;
+    }
+    return -1;
+}
+__device__ bool any_bit(const uint32_t* bm, i64 lo, i64 hi) {   // any set bit in [lo, hi]
+    if (lo < 0) lo = 0;
+    if (hi < lo) return false;
+    return next_bit(bm, lo - 1, hi) >= 0;
+}
+
+// K1b: walk chains of close candidates and decide which are recognised.
+//   trainer: candidate q is recognised iff q is a token start given the previous recognised
+//            special end as a fresh-text fence
+//   encode : leftmost, priority order, non-overlapping (tokenizer.py:97-102,171)
+__global__ void __launch_bounds__(256) k_resolve_specials(PretokParams P, i64 lo, i64 hi, i64 ctx_lo) {
+    const int D = P.mode == 0 ? c_sp.max_len + 16 : c_sp.max_len - 1;
+    i64 nwords_lo = lo >> 5, nwords_hi = (hi + 31) >> 5;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    GlobalText G{P.text, P.n, P.cuts, P.n_cuts, nullptr, -1, P.mode};
+    for (i64 wi = nwords_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; wi < nwords_hi; wi += stride) {
+        uint32_t w = P.cand[wi];
+        while (w) {
+            int bit = __ffs(w) - 1; w &= w - 1;
+            i64 q = (wi << 5) + bit;
+            if (q < lo || q >= hi) continue;
+            // chain head?  no candidate in [q-D, q)
+            if (D > 0 && any_bit(P.cand, q - D, q - 1)) {
+                // a chain that started before the available left context cannot be resolved here
+                if (q - D < ctx_lo && ctx_lo > 0 && !any_bit(P.cand, ctx_lo, q - 1)) { /* head is before ctx */ }
+                continue;
+            }
+            i64 e = -1, cur = q;
+            for (;;) {
+                i64 lim = logical_end_after(P, cur);
+                int s = special_match(P.text, cur, lim);
+                int m = c_sp.offs[s + 1] - c_sp.offs[s];
+                bool ok = false;
+                if (cur >= e) {
+                    if (P.mode == 1) ok = true;
+                    else { G.fence_fl = e; ok = is_token_start(G, cur); }
+                }
+                if (ok) { atomicOr(&P.rec[cur >> 5], 1u << (cur & 31)); e = cur + m; atomicAdd((u64*)&P.stats[ST_NSPECIAL], 1ULL); }
+                i64 nx = D > 0 ? next_bit(P.cand, cur, cur + D < P.n - 1 ? cur + D : P.n - 1) : -1;
+                if (nx < 0) break;
+                cur = nx;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// hash-table inserts
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) { return mix64(k0 * 0x9e3779b97f4a7c15ULL ^ mix64(k1)); }
+
+// returns slot (>=0) and adds `add` to its count; *created = 1 when this call created the entry
+__device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 cap, u64 k0, u64 k1, i64 add, int* created) {
+    u64 mask = (u64)cap - 1;
+    u64 slot = short_hash(k0, k1) & mask;
+    *created = 0;
+    for (int probe = 0; probe < 8192; probe++) {
+        u64* kp = (u64*)&keys[slot];
+        u64 c0 = *(volatile u64*)kp;
+        if (c0 == 0) { c0 = atomicCAS(kp, 0ULL, k0); if (c0 == 0) c0 = k0; }
+        if (c0 == k0) {
+            u64 c1 = *(volatile u64*)(kp + 1);
+            if (c1 == 0) { c1 = atomicCAS(kp + 1, 0ULL, k1); if (c1 == 0) { c1 = k1; *created = 1; } }
+            if (c1 == k1) { atomicAdd((u64*)&counts[slot], (u64)add); return (i64)slot; }
+        }
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
+
+// read-only lookup (encode passes); -1 when absent
+__device__ __forceinline__ i64 short_find(const ulonglong2* keys, i64 cap, u64 k0, u64 k1) {
+    u64 mask = (u64)cap - 1;
+    u64 slot = short_hash(k0, k1) & mask;
+    for (int probe = 0; probe < 8192; probe++) {
+        ulonglong2 kv = keys[slot];
+        if (kv.x == k0 && kv.y == k1) return (i64)slot;
+        if (kv.x == 0) return -1;
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ u64 long_hash_fix(u64 h) { return h < 2 ? h + 2 : h; }
+
+__device__ bool text_equal(const uint8_t* text, i64 a, i64 b, i64 len) {
+    for (i64 k = 0; k < len; k++) if (text[a + k] != text[b + k]) return false;
+    return true;
+}
+
+// thread-level insert of a long pre-token text[pos, pos+len) with hash h (exact: bytes compared)
+__device__ i64 long_insert(LongEntry* ent, i64 cap, const uint8_t* text, u64 h, i64 pos, i64 len, i64 add, int* created) {
+    u64 mask = (u64)cap - 1;
+    u64 slot = h & mask;
+    *created = 0;
+    int probes = 0;
+    for (;;) {
+        u64* hp = &ent[slot].h;
+        u64 cur = *(volatile u64*)hp;
+        if (cur == 0) {
+            cur = atomicCAS(hp, 0ULL, 1ULL);
+            if (cur == 0) {
+                ent[slot].pos = pos; ent[slot].len = len; ent[slot].count = 0;
+                __threadfence();
+                atomicExch(hp, h);
+                atomicAdd((u64*)&ent[slot].count, (u64)add);
+                *created = 1;
+                return (i64)slot;
+            }
+        }
+        if (cur == 1) continue;                       // being published by another thread: retry this slot
+        if (cur == h) {
+            __threadfence();
+            i64 elen = *(volatile i64*)&ent[slot].len, epos = *(volatile i64*)&ent[slot].pos;
+            if (elen == len && (epos == pos || text_equal(text, epos, pos, len))) {
+                atomicAdd((u64*)&ent[slot].count, (u64)add);
+                return (i64)slot;
+            }
+        }
+        slot = (slot + 1) & mask;
+        if (++probes > 8192) return -1;
+    }
+}
+
+__device__ i64 long_find(const LongEntry* ent, i64 cap, const uint8_t* text, u64 h, i64 pos, i64 len) {
+    u64 mask = (u64)cap - 1;
+    u64 slot = h & mask;
+    for (int probes = 0; probes < 8192; probes++) {
+        u64 cur = ent[slot].h;
+        if (cur == 0) return -1;
+        if (cur == h && ent[slot].len == len && (ent[slot].pos == pos || text_equal(text, ent[slot].pos, pos, len))) return (i64)slot;
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------
+// tile machinery
+// ---------------------------------------------------------------------------------
+struct TileSmem {
+    alignas(128) uint8_t txt[2][PT_WIN];
+    alignas(16) uint8_t info[PT_WIN];
+    uint32_t smask[PT_NMASK + 7];
+    uint16_t tokpos[PT_NBITS + 3];
+    uint8_t lut[256];
+    alignas(8) uint64_t bar[2];
+    int scan_tmp[PT_THREADS / 32];
+    int scan_carry;
+    int ntok_total, ntok_own;
+};
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* tmp, int* total) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) tmp[wid] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int k = 0; k < PT_THREADS / 32; k++) { int t = tmp[k]; if (k < wid) base += t; tot += t; }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+// issue the TMA load of tile `t` into buffer `buf`; bytes outside [0, n16) are zero-filled by the caller
+__device__ __forceinline__ void tile_issue_load(const PretokParams& P, TileSmem& S, i64 tile, int buf) {
+    i64 t0 = (P.tile_base + tile) * PT_TILE;
+    i64 g0 = t0 - PT_HL, g1 = g0 + PT_WIN;
+    i64 n16 = (P.n + 15) & ~(i64)15;
+    i64 lo = g0 < 0 ? 0 : g0, hi = g1 > n16 ? n16 : g1;
+    if (hi > lo) {
+        uint32_t bytes = (uint32_t)(hi - lo);
+        mbar_expect_tx(&S.bar[buf], bytes);
+        tma_load_1d(&S.txt[buf][lo - g0], P.text + lo, bytes, &S.bar[buf]);
+    } else {
+        mbar_expect_tx(&S.bar[buf], 0);
+    }
+}
+
+__device__ __forceinline__ void info_or(uint8_t* info, int x, uint32_t bits) {
+    atomicOr((uint32_t*)(info + (x & ~3)), bits << ((x & 3) * 8));
+}
+
+// Passes A-D1 for one tile.  On return S.smask / S.tokpos / S.ntok_* describe the tile's tokens.
+__device__ void tile_scan(const PretokParams& P, TileSmem& S, i64 tile, int buf) {
+    const int tid = threadIdx.x;
+    const i64 t0 = (P.tile_base + tile) * PT_TILE;
+    const i64 g0 = t0 - PT_HL;
+    uint8_t* txt = S.txt[buf];
+    uint8_t* info = S.info;
+    const i64 n16 = (P.n + 15) & ~(i64)15;
+
+    // zero the parts of the window that TMA did not fill, and bytes in [n, n16)
+    {
+        i64 lo = g0 < 0 ? 0 : g0, hi = g0 + PT_WIN > n16 ? n16 : g0 + PT_WIN;
+        for (int x = tid; x < PT_WIN; x += PT_THREADS) {
+            i64 g = g0 + x;
+            if (g < lo || g >= hi || g >= P.n) txt[x] = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- pass A1: base info from the byte LUT
+    for (int k = tid; k < PT_WIN / 4; k += PT_THREADS) {
+        uint32_t w = ((const uint32_t*)txt)[k];
+        uint32_t v = (uint32_t)S.lut[w & 0xff] | ((uint32_t)S.lut[(w >> 8) & 0xff] << 8) |
+                     ((uint32_t)S.lut[(w >> 16) & 0xff] << 16) | ((uint32_t)S.lut[w >> 24] << 24);
+        i64 g = g0 + 4 * (i64)k;
+        if (g + 3 >= P.n || g <= 0) {     // logical ends of the buffer
+            for (int j = 0; j < 4; j++) {
+                i64 gj = g + j;
+                if (gj >= P.n || gj < 0) v = (v & ~(0xffu << (8 * j))) | ((uint32_t)(IB_FL | IB_FR) << (8 * j));
+                else if (gj == 0) v |= (uint32_t)IB_FL << (8 * j);
+            }
+        }
+        ((uint32_t*)info)[k] = v;
+    }
+    __syncthreads();
+
+    // ---- pass A3: fences from chunk cuts and recognised specials
+    if (P.n_cuts > 0) {
+        int lo = 0, hi = P.n_cuts;
+        i64 first = g0 < 1 ? 1 : g0;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] < first) lo = mid + 1; else hi = mid; }
+        for (int c = lo + tid; c < P.n_cuts; c += PT_THREADS) {
+            i64 cp = P.cuts[c];
+            if (cp >= g0 + PT_WIN) break;
+            if (cp < P.n) info_or(info, (int)(cp - g0), IB_FL | IB_FR);
+        }
+    }
+    if (P.n_sp > 0) {
+        i64 lo = g0 - c_sp.max_len; if (lo < 0) lo = 0;
+        i64 hi = g0 + PT_WIN; if (hi > P.n) hi = P.n;
+        for (i64 wi = (lo >> 5) + tid; wi <= ((hi - 1) >> 5) && hi > 0; wi += PT_THREADS) {
+            uint32_t w = P.rec[wi];
+            while (w) {
+                int bit = __ffs(w) - 1; w &= w - 1;
+                i64 q = (wi << 5) + bit;
+                if (q < lo || q >= hi) continue;
+                int s = special_match(P.text, q, P.n);
+                if (s < 0) continue;
+                int m = c_sp.offs[s + 1] - c_sp.offs[s];
+                for (int k = 0; k <= m; k++) {
+                    i64 x = q + k - g0;
+                    if (x < 0 || x >= PT_WIN) continue;
+                    uint32_t bits = k < m ? IB_IN : 0;
+                    if (k == 0) bits |= IB_FL | (P.mode == 1 ? IB_FR : 0);
+                    if (k == m) bits |= IB_FL;
+                    info_or(info, (int)x, bits);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass A2: multi-byte code points (class propagated to continuation bytes) + strict UTF-8
+    for (int k = tid; k < PT_WIN / 4; k += PT_THREADS) {
+        uint32_t w = ((const uint32_t*)txt)[k];
+        if (!(w & 0x80808080u)) continue;
+        for (int j = 0; j < 4; j++) {
+            int x = 4 * k + j;
+            uint8_t b = txt[x];
+            if (b < 0x80) continue;
+            i64 g = g0 + x;
+            if (g >= P.n) continue;
+            bool own = g >= t0 && g < t0 + PT_TILE;
+            if ((b & 0xC0) == 0x80) {
+                if (!own) continue;
+                // stray continuation byte?  must be covered by a lead within 3 bytes
+                bool covered = false;
+                for (int d = 1; d <= 3 && x - d >= 0; d++) {
+                    uint8_t pb = txt[x - d];
+                    if (info[x - d + 1] & IB_FL) break;        // a fence between lead and this byte
+                    if ((pb & 0xC0) == 0x80) continue;
+                    covered = pb >= 0xC0 && utf8_len_from_lead(pb) > d;
+                    break;
+                }
+                if (!covered) atomicMin((i64*)&P.stats[ST_ERR_POS], g);
+                continue;
+            }
+            int len; bool ok = x + 4 <= PT_WIN ? utf8_seq_ok(txt + x, P.n - g, &len) : false;
+            if (x + 4 > PT_WIN) continue;       // slack region: never needed as a class
+            if (ok) for (int d = 1; d < len; d++) if (info[x + d] & IB_FR) ok = false;
+            if (!ok) { if (own) atomicMin((i64*)&P.stats[ST_ERR_POS], g); continue; }
+            int kc = kclass_of_cp(utf8_decode(txt + x, len));
+            if (kc) for (int d = 0; d < len; d++) info_or(info, x + d, (uint32_t)kc);
+        }
+    }
+    __syncthreads();
+
+    // ---- pass B: live contractions
+    for (int k = tid; k < PT_WIN / 4; k += PT_THREADS) {
+        uint32_t w = ((const uint32_t*)txt)[k] ^ 0x27272727u;
+        if (!((w - 0x01010101u) & ~w & 0x80808080u)) continue;
+        for (int j = 0; j < 4; j++) {
+            int a = 4 * k + j;
+            if (txt[a] != '\'' || a + 3 >= PT_WIN || a < 1) continue;
+            uint8_t ia = info[a];
+            if (ia & IB_IN) continue;
+            if (info[a + 1] & IB_FR) continue;
+            uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
+            int clen = 0;
+            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
+            else if (!(info[a + 2] & IB_FR) && ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e'))) clen = 3;
+            if (!clen) continue;
+            bool live = ia & IB_FL;
+            if (!live) { int p = info[a - 1] & IB_CLS; live = (p == KC_L || p == KC_N || p == KC_S); }
+            if (!live) continue;
+            for (int d = 1; d < clen; d++) info_or(info, a + d, IB_INC);
+            info_or(info, a + clen, IB_FL);      // the position after a contraction behaves like a text start
+        }
+    }
+    __syncthreads();
+
+    // ---- pass C: start bit per byte, one ballot per 32 bytes
+    for (int base = 0; base < PT_NMASK * 32; base += PT_THREADS) {
+        int b = base + tid;              // bit index; window offset x = HL + b
+        int x = PT_HL + b;
+        bool start = false;
+        if (b < PT_NBITS) {
+            uint8_t v = info[x];
+            if (v & IB_CONT) start = false;
+            else if (v & IB_FL) start = true;
+            else if (v & (IB_IN | IB_INC)) start = false;
+            else {
+                int c = v & IB_CLS, p = info[x - 1] & IB_CLS;
+                if (c < KC_S) start = (p == KC_SP) ? false : (p >= KC_S ? true : p != c);
+                else if (p < KC_S) start = true;
+                else {
+                    uint8_t nv = info[x + utf8_len_from_lead(txt[x])];
+                    start = !(nv & IB_FR) && (nv & IB_CLS) < KC_S;
+                }
+            }
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, start);
+        if ((tid & 31) == 0 && (b >> 5) < PT_NMASK) S.smask[b >> 5] = m;
+    }
+    __syncthreads();
+
+    // ---- pass D1: compact start positions
+    if (tid == 0) S.scan_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < PT_NMASK; base += PT_THREADS) {
+        int wi = base + tid;
+        uint32_t m = wi < PT_NMASK ? S.smask[wi] : 0;
+        int cnt = __popc(m), total;
+        int off = block_exclusive_scan(cnt, S.scan_tmp, &total) + S.scan_carry;
+        if (wi == PT_TILE / 32) S.ntok_own = off;        // starts with bit index < TILE
+        while (m) { int bit = __ffs(m) - 1; m &= m - 1; S.tokpos[off++] = (uint16_t)(PT_HL + wi * 32 + bit); }
+        __syncthreads();
+        if (tid == 0) S.scan_carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) S.ntok_total = S.scan_carry;
+    __syncthreads();
+}
+
+// 16 bytes of the window starting at offset s (unaligned) as two u64
+__device__ __forceinline__ void load16(const uint8_t* txt, int s, u64* lo, u64* hi) {
+    const uint32_t* tw = (const uint32_t*)txt;
+    int wi = s >> 2, sh = (s & 3) * 8;
+    uint32_t a0 = tw[wi], a1 = tw[wi + 1], a2 = tw[wi + 2], a3 = tw[wi + 3], a4 = tw[wi + 4];
+    uint32_t b0 = __funnelshift_r(a0, a1, sh), b1 = __funnelshift_r(a1, a2, sh);
+    uint32_t b2 = __funnelshift_r(a2, a3, sh), b3 = __funnelshift_r(a3, a4, sh);
+    *lo = (u64)b0 | ((u64)b1 << 32);
+    *hi = (u64)b2 | ((u64)b3 << 32);
+}
+
+// pack a pre-token of len <= 14 into the two key words (len tag in the top byte of k0)
+__device__ __forceinline__ void pack_short_key(const uint8_t* txt, int s, int len, u64* k0, u64* k1) {
+    u64 lo, hi;
+    load16(txt, s, &lo, &hi);
+    if (len < 8) { lo &= (1ULL << (8 * len)) - 1; hi = 0; }
+    else if (len < 16) hi &= (1ULL << (8 * (len - 8))) - 1;
+    *k0 = (lo & 0x00FFFFFFFFFFFFFFULL) | ((u64)len << 56);
+    *k1 = (lo >> 56) | (hi << 8) | (1ULL << 56);
+}
+
+__device__ __forceinline__ void init_tile_smem(TileSmem& S) {
+    // byte LUT: ASCII classes, continuation flag; leads >= 0xC0 get class in pass A2
+    for (int b = threadIdx.x; b < 256; b += PT_THREADS) {
+        uint8_t v = 0;
+        if (b < 0x80) v = (uint8_t)kclass_of_cp((uint32_t)b);
+        else if (b < 0xC0) v = IB_CONT;
+        S.lut[b] = v;
+    }
+    if (threadIdx.x == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// K1+K2: count pre-tokens into the hash tables
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
+    __shared__ TileSmem S;
+    init_tile_smem(S);
+    const int tid = threadIdx.x;
+    u64 my_tok = 0, my_us = 0, my_ul = 0, my_ub = 0;
+    uint32_t phase[2] = {0, 0};
+    i64 tile = blockIdx.x;
+    if (tile < P.n_tiles && tid == 0) tile_issue_load(P, S, tile, 0);
+    int buf = 0;
+    for (; tile < P.n_tiles; tile += gridDim.x, buf ^= 1) {
+        i64 next = tile + gridDim.x;
+        if (next < P.n_tiles && tid == 0) tile_issue_load(P, S, next, buf ^ 1);
+        mbar_wait(&S.bar[buf], phase[buf]); phase[buf] ^= 1;
+        tile_scan(P, S, tile, buf);
+
+        const uint8_t* txt = S.txt[buf];
+        const i64 g0 = (P.tile_base + tile) * PT_TILE - PT_HL;
+        const int ntok = S.ntok_own, ntot = S.ntok_total;
+        for (int k = tid; k < ntok; k += PT_THREADS) {
+            int s = S.tokpos[k];
+            i64 gpos = g0 + s;
+            if (gpos < P.own_lo || gpos >= P.own_hi) continue;
+            if (P.mode == 1 && (S.info[s] & IB_IN)) continue;        // encode: specials are not words
+            my_tok++;
+            if (k + 1 >= ntot) {                                      // end not inside the window
+                u64 idx = atomicAdd((u64*)&P.stats[ST_OVF_N], 1ULL);
+                if ((i64)idx < P.ovf_cap) P.ovf_pos[idx] = gpos;
+                continue;
+            }
+            int len = (int)S.tokpos[k + 1] - s;
+            int created;
+            if (len <= PT_SHORT_MAX) {
+                u64 k0, k1;
+                pack_short_key(txt, s, len, &k0, &k1);
+                if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                if (created) { my_us++; my_ub += len; }
+            } else {
+                u64 h = 0;
+                for (int j = 0; j < len; j++) h += long_hash_term(txt[s + j], j);
+                if (long_insert(P.lent, P.lcap, P.text, long_hash_fix(h), gpos, len, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                if (created) { my_ul++; my_ub += len; }
+            }
+        }
+        __syncthreads();     // everyone is done with txt[buf] and S before the next iteration reuses them
+    }
+    // block-level reduction of the statistics
+    for (int o = 16; o > 0; o >>= 1) {
+        my_tok += __shfl_xor_sync(0xffffffffu, my_tok, o); my_us += __shfl_xor_sync(0xffffffffu, my_us, o);
+        my_ul += __shfl_xor_sync(0xffffffffu, my_ul, o); my_ub += __shfl_xor_sync(0xffffffffu, my_ub, o);
+    }
+    if ((tid & 31) == 0) {
+        if (my_tok) atomicAdd((u64*)&P.stats[ST_NTOK], my_tok);
+        if (my_us) atomicAdd((u64*)&P.stats[ST_UNIQ_SHORT], my_us);
+        if (my_ul) atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], my_ul);
+        if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// very long pre-tokens (end beyond the tile window): one CTA per token
+// ---------------------------------------------------------------------------------
+// find the end of the token starting at s: the first token start > s (or the logical end)
+__device__ i64 block_find_token_end(const PretokParams& P, i64 s, i64* sh_min) {
+    GlobalText G{P.text, P.n, P.cuts, P.n_cuts, P.n_sp > 0 ? P.rec : nullptr, -1, P.mode};
+    i64 base = s + 1;
+    for (;;) {
+        if (threadIdx.x == 0) *sh_min = INT64_MAX;
+        __syncthreads();
+        i64 p = base + threadIdx.x;
+        bool st = p >= P.n ? true : is_token_start(G, p);
+        if (st) atomicMin((i64*)sh_min, p < P.n ? p : P.n);
+        __syncthreads();
+        i64 m = *sh_min;
+        __syncthreads();
+        if (m != INT64_MAX) return m;
+        base += blockDim.x;
+    }
+}
+
+__device__ u64 block_long_hash(const uint8_t* text, i64 s, i64 len, u64* sh_acc) {
+    u64 h = 0;
+    for (i64 j = threadIdx.x; j < len; j += blockDim.x) h += long_hash_term(text[s + j], j);
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (threadIdx.x == 0) *sh_acc = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(sh_acc, h);
+    __syncthreads();
+    u64 r = *sh_acc;
+    __syncthreads();
+    return long_hash_fix(r);
+}
+
+// block-cooperative version of long_insert / long_find (find_only: no insertion, returns slot or -1)
+__device__ i64 block_long_upsert(LongEntry* ent, i64 cap, const uint8_t* text, u64 h, i64 pos, i64 len, i64 add,
+                                 bool find_only, int* created, i64* sh) {
+    // sh[0] = state (0 advance, 1 retry, 2 compare, 3 done, 4 fail), sh[1] = slot, sh[2] = epos
+    u64 mask = (u64)cap - 1;
+    if (threadIdx.x == 0) { sh[1] = (i64)(h & mask); sh[3] = 0; }
+    *created = 0;
+    for (int probes = 0; probes < 1 << 20; probes++) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 slot = (u64)sh[1];
+            u64* hp = &ent[slot].h;
+            u64 cur = *(volatile u64*)hp;
+            int state = 0;
+            if (cur == 0) {
+                if (find_only) state = 4;
+                else {
+                    cur = atomicCAS(hp, 0ULL, 1ULL);
+                    if (cur == 0) {
+                        ent[slot].pos = pos; ent[slot].len = len; ent[slot].count = 0;
+                        __threadfence();
+                        atomicExch(hp, h);
+                        atomicAdd((u64*)&ent[slot].count, (u64)add);
+                        sh[3] = 1; state = 3;
+                    }
+                }
+            }
+            if (state == 0) {
+                if (cur == 1) state = 1;
+                else if (cur == h) {
+                    __threadfence();
+                    i64 elen = *(volatile i64*)&ent[slot].len, epos = *(volatile i64*)&ent[slot].pos;
+                    if (elen == len) { sh[2] = epos; state = epos == pos ? 5 : 2; }
+                }
+            }
+            sh[0] = state;
+        }
+        __syncthreads();
+        int state = (int)sh[0];
+        i64 slot = sh[1];
+        if (state == 3) { *created = (int)sh[3]; return slot; }
+        if (state == 4) return -1;
+        if (state == 1) continue;
+        bool match = state == 5;
+        if (state == 2) {
+            i64 epos = sh[2];
+            int diff = 0;
+            for (i64 j = threadIdx.x; j < len && !diff; j += blockDim.x) if (text[epos + j] != text[pos + j]) diff = 1;
+            match = !__syncthreads_or(diff);
+        }
+        if (match) {
+            if (threadIdx.x == 0 && !find_only) atomicAdd((u64*)&ent[slot].count, (u64)add);
+            return slot;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sh[1] = (i64)(((u64)slot + 1) & mask);
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) k_long_tokens(PretokParams P, i64 n_ovf) {
+    __shared__ i64 sh_min; __shared__ u64 sh_acc; __shared__ i64 sh[4];
+    for (i64 t = blockIdx.x; t < n_ovf; t += gridDim.x) {
+        i64 s = P.ovf_pos[t];
+        i64 e = block_find_token_end(P, s, &sh_min);
+        i64 len = e - s;
+        u64 h = block_long_hash(P.text, s, len, &sh_acc);
+        int created;
+        i64 slot = block_long_upsert(P.lent, P.lcap, P.text, h, s, len, 1, false, &created, sh);
+        if (threadIdx.x == 0) {
+            if (slot < 0) P.stats[ST_TABLE_FULL] = 1;
+            if (created) { atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], 1ULL); atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], (u64)len); }
+        }
+        __syncthreads();
+    }
+}

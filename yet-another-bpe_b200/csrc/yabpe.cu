@@ -1,0 +1,266 @@
+// yabpe.cu -- extern "C" entry points of libyabpe.so (see include/yabpe.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/yabpe.h"
+#include "encode.cuh"
+
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return YABPE_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+#define ARG_CHECK(cond)                                                                          \
+    do {                                                                                        \
+        if (!(cond)) { snprintf(g_err, sizeof g_err, "bad argument: %s (%s:%d)", #cond, __FILE__, __LINE__); return YABPE_ERR_ARG; } \
+    } while (0)
+
+#define LAUNCHED() (g_launches++)
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+extern "C" const char* yabpe_last_error(void) { return g_err; }
+extern "C" int yabpe_abi_version(void) { return YABPE_ABI_VERSION; }
+extern "C" int64_t yabpe_launch_count(void) { return g_launches; }
+
+extern "C" int yabpe_class_of(uint32_t cp) {
+    if (cp >= 0x110000) return 0;
+    unsigned blk = yabpe_ucd_stage1[cp >> 8];
+    unsigned byte = yabpe_ucd_stage2[blk * 64 + ((cp & 255) >> 2)];
+    return (byte >> ((cp & 3) * 2)) & 3;
+}
+
+extern "C" int yabpe_device_init(void) {
+    CUDA_TRY(cudaMemcpyToSymbol(g_ucd_stage1, yabpe_ucd_stage1, sizeof(yabpe_ucd_stage1)));
+    CUDA_TRY(cudaMemcpyToSymbol(g_ucd_stage2, yabpe_ucd_stage2, sizeof(yabpe_ucd_stage2)));
+    return YABPE_OK;
+}
+
+static int upload_specials(const uint8_t* blob, const int32_t* offs, int32_t n, cudaStream_t st) {
+    static thread_local SpecialSet h;
+    ARG_CHECK(n >= 0 && n <= YABPE_MAX_SPECIALS);
+    memset(&h, 0, sizeof h);
+    h.n = n;
+    for (int i = 0; i <= n; i++) h.offs[i] = n ? offs[i] : 0;
+    int total = n ? offs[n] : 0;
+    ARG_CHECK(total <= YABPE_MAX_SPECIAL_BYTES);
+    if (total) memcpy(h.blob, blob, (size_t)total);
+    for (int i = 0; i < n; i++) {
+        int len = offs[i + 1] - offs[i];
+        ARG_CHECK(len > 0);                    /* empty specials are not supported */
+        ARG_CHECK(len <= PT_HR / 2);
+        if (len > h.max_len) h.max_len = len;
+        unsigned char b = blob[offs[i]];
+        h.first_byte_mask[b >> 3] |= (unsigned char)(1u << (b & 7));
+    }
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_sp, &h, sizeof h, 0, cudaMemcpyHostToDevice, st));
+    return YABPE_OK;
+}
+
+static int make_params(const yabpe_pretok_args* a, PretokParams* P) {
+    ARG_CHECK(a && a->text && a->n > 0);
+    ARG_CHECK(a->own_lo >= 0 && a->own_hi <= a->n && a->own_lo <= a->own_hi);
+    ARG_CHECK(a->short_cap > 0 && (a->short_cap & (a->short_cap - 1)) == 0);
+    ARG_CHECK(a->long_cap > 0 && (a->long_cap & (a->long_cap - 1)) == 0);
+    ARG_CHECK(a->n_sp == 0 || (a->cand_bits && a->rec_bits));
+    ARG_CHECK(((uintptr_t)a->text & 15) == 0);
+    P->text = a->text; P->n = a->n; P->cuts = (const i64*)a->cuts; P->n_cuts = a->n_cuts;
+    P->mode = a->mode; P->n_sp = a->n_sp;
+    P->own_lo = a->own_lo; P->own_hi = a->own_hi;
+    P->cand = a->cand_bits; P->rec = a->rec_bits;
+    P->skeys = (ulonglong2*)a->short_keys; P->scounts = (i64*)a->short_counts; P->scap = a->short_cap;
+    P->lent = (LongEntry*)a->long_entries; P->lcap = a->long_cap;
+    P->ovf_pos = (i64*)a->ovf_pos; P->ovf_cap = a->ovf_cap;
+    P->stats = (i64*)a->stats;
+    P->tile_base = a->own_lo / PT_TILE;
+    P->n_tiles = a->own_hi > a->own_lo ? (a->own_hi - 1) / PT_TILE - P->tile_base + 1 : 0;
+    return YABPE_OK;
+}
+
+extern "C" int64_t yabpe_num_tiles(int64_t own_lo, int64_t own_hi) {
+    return own_hi > own_lo ? (own_hi - 1) / PT_TILE - own_lo / PT_TILE + 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_long_tokens_dyn(PretokParams P) {
+    // grid-stride over the device-side overflow count
+    __shared__ i64 sh_min; __shared__ u64 sh_acc; __shared__ i64 sh[4];
+    i64 n_ovf = P.stats[ST_OVF_N];
+    if (n_ovf > P.ovf_cap) { if (threadIdx.x == 0 && blockIdx.x == 0) P.stats[ST_TABLE_FULL] = 3; n_ovf = P.ovf_cap; }
+    for (i64 t = blockIdx.x; t < n_ovf; t += gridDim.x) {
+        i64 s = P.ovf_pos[t];
+        i64 e = block_find_token_end(P, s, &sh_min);
+        i64 len = e - s;
+        u64 h = block_long_hash(P.text, s, len, &sh_acc);
+        int created;
+        i64 slot = block_long_upsert(P.lent, P.lcap, P.text, h, s, len, 1, false, &created, sh);
+        if (threadIdx.x == 0) {
+            if (slot < 0) P.stats[ST_TABLE_FULL] = 1;
+            if (created) { atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], 1ULL); atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], (u64)len); }
+        }
+        __syncthreads();
+    }
+}
+
+static int run_specials(const yabpe_pretok_args* a, const PretokParams& P, cudaStream_t st) {
+    int rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
+    if (rc) return rc;
+    if (a->n_sp == 0) return YABPE_OK;
+    int grid = num_sms() * 8;
+    // candidates / resolution need left context for chains that reach into the owned range
+    i64 lo = 0, hi = P.n;
+    k_special_candidates<<<grid, 256, 0, st>>>(P, lo, hi); LAUNCHED();
+    k_resolve_specials<<<grid, 256, 0, st>>>(P, lo, hi, 0); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
+extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokParams P;
+    int rc = make_params(a, &P);
+    if (rc) return rc;
+    ARG_CHECK(a->ovf_pos && a->ovf_cap > 0 && a->stats);
+    rc = run_specials(a, P, st);
+    if (rc) return rc;
+    if (P.n_tiles > 0) {
+        int grid = num_sms() * 4;
+        if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
+        k_pretok_count<<<grid, PT_THREADS, 0, st>>>(P); LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        k_long_tokens_dyn<<<num_sms(), 256, 0, st>>>(P); LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+    }
+    return YABPE_OK;
+}
+
+static WordTable make_words(const yabpe_word_table* w) {
+    WordTable W;
+    W.wsym = w->wsym; W.sym_word = w->sym_word; W.woff = (i64*)w->woff; W.wlen = w->wlen; W.wcnt = (i64*)w->wcnt;
+    W.sword = w->sword; W.lword = w->lword; W.counters = (i64*)w->counters;
+    return W;
+}
+
+extern "C" int yabpe_compact_words(const yabpe_pretok_args* a, const yabpe_word_table* w, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(a && w && w->wsym && w->sym_word && w->woff && w->wlen && w->wcnt && w->counters);
+    WordTable W = make_words(w);
+    int grid = num_sms() * 8;
+    k_compact_short<<<grid, 256, 0, st>>>((const ulonglong2*)a->short_keys, (const i64*)a->short_counts, a->short_cap, W); LAUNCHED();
+    k_compact_long<<<grid, 256, 0, st>>>((const LongEntry*)a->long_entries, a->long_cap, a->text, W); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
+extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(m && m->pcap > 0 && (m->pcap & (m->pcap - 1)) == 0);
+    ARG_CHECK(m->tset_cap > 0 && (m->tset_cap & (m->tset_cap - 1)) == 0);
+    ARG_CHECK(m->n_syms < 0xffffffffLL && m->pcap < 0x7fffffffLL);
+    static_assert(sizeof(Best) == 24, "Best layout");
+    MergeParams M;
+    M.wsym = m->words.wsym; M.sym_word = m->words.sym_word; M.n_syms = m->n_syms;
+    M.woff = (const i64*)m->words.woff; M.wlen = m->words.wlen; M.wcnt = (const i64*)m->words.wcnt; M.n_words = m->n_words; M.wstamp = m->wstamp;
+    M.tok_bytes = m->tok_bytes; M.tok_bytes_cap = m->tok_bytes_cap; M.tok_off = (i64*)m->tok_off;
+    M.tok_hash = (u64*)m->tok_hash; M.tok_pow = (u64*)m->tok_pow; M.tset = (u64*)m->tset; M.tset_cap = m->tset_cap;
+    M.max_tokens = m->max_tokens;
+    M.pkey = (u64*)m->pkey; M.pcnt = (i64*)m->pcnt; M.pcap = m->pcap;
+    M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = m->ipost; M.inact = m->inact; M.act = m->act;
+    M.dlog_slot = m->dlog_slot; M.dlog_word = m->dlog_word; M.dlog_cap = m->dlog_cap;
+    M.partial = (Best*)m->partial; M.bsum = (i64*)m->bsum;
+    M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
+    M.num_merges = m->num_merges; M.min_freq = m->min_frequency;
+
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, 0));
+    ARG_CHECK(per_sm >= 1);
+    if (per_sm > 2) per_sm = 2;
+    int grid = num_sms() * per_sm;
+    if (grid > 1024) grid = 1024;
+    void* args[] = {&M};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(grid), dim3(ML_THREADS), args, 0, st)); LAUNCHED();
+    return YABPE_OK;
+}
+
+static EncodeModel make_model(const yabpe_encode_model* e) {
+    EncodeModel E;
+    E.mkey = (const u64*)e->mkey; E.mval = (const u64*)e->mval; E.mcap = e->mcap;
+    E.byte_sym = e->byte_sym; E.sym_out = e->sym_out; E.sp_ids = e->sp_ids; E.consistent = e->consistent;
+    return E;
+}
+
+__global__ void __launch_bounds__(256) k_encode_words_short(EncodeModel E, int32_t* wsym, const i64* woff, int32_t* wlen, i64 n_words) {
+    i64 gstride = (i64)gridDim.x * blockDim.x;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gstride) {
+        int n = wlen[w];
+        if (n > ENC_LONG_WORD) continue;
+        wlen[w] = encode_word_thread(E, wsym + woff[w], n);
+    }
+}
+__global__ void __launch_bounds__(256) k_encode_words_long(EncodeModel E, int32_t* wsym, int32_t* scratch, const i64* woff,
+                                                            const int32_t* wlen_in, int32_t* wlen_out, i64 n_words) {
+    __shared__ int sh_i[2 + 8]; __shared__ u64 sh_u;
+    for (i64 w = blockIdx.x; w < n_words; w += gridDim.x) {
+        int n = wlen_in[w];
+        if (n <= ENC_LONG_WORD) continue;
+        int r = encode_word_block(E, wsym + woff[w], scratch + woff[w], n, sh_i, &sh_u);
+        __syncthreads();
+        if (threadIdx.x == 0) wlen_out[w] = r;
+        __syncthreads();
+    }
+}
+
+extern "C" int yabpe_encode_words(const yabpe_encode_model* e, const yabpe_word_table* w, int64_t n_words, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(e && w && n_words >= 0);
+    if (n_words == 0) return YABPE_OK;
+    EncodeModel E = make_model(e);
+    // short words first: they only shrink, so the long kernel (original length > ENC_LONG_WORD)
+    // afterwards still sees exactly the words the short kernel skipped
+    k_encode_words_short<<<num_sms() * 8, 256, 0, st>>>(E, w->wsym, (const i64*)w->woff, w->wlen, n_words); LAUNCHED();
+    k_encode_words_long<<<num_sms() * 2, 256, 0, st>>>(E, w->wsym, w->sym_word, (const i64*)w->woff, w->wlen, w->wlen, n_words); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
+extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
+                                const yabpe_encode_out* o, int32_t pass, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokParams P;
+    int rc = make_params(a, &P);
+    if (rc) return rc;
+    ARG_CHECK(e && w && o && o->tile_count);
+    EncodeModel E = make_model(e);
+    EncodeOut O;
+    O.wsym = w->wsym; O.woff = (const i64*)w->woff; O.wlen = w->wlen; O.sword = w->sword; O.lword = w->lword;
+    O.tile_count = (i64*)o->tile_count; O.out_ids = o->out_ids; O.out_cap = o->out_cap; O.doc_off = (i64*)o->doc_off;
+    if (P.n_tiles == 0) return YABPE_OK;
+    rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
+    if (rc) return rc;
+    int grid = num_sms() * 4;
+    if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
+    if (pass == 0) {
+        k_encode_tiles<false><<<grid, PT_THREADS, 0, st>>>(P, E, O); LAUNCHED();
+        k_scan_tiles<<<1, 1024, 0, st>>>((i64*)o->tile_count, P.n_tiles); LAUNCHED();
+    } else {
+        ARG_CHECK(o->out_ids || o->out_cap == 0);
+        k_encode_tiles<true><<<grid, PT_THREADS, 0, st>>>(P, E, O); LAUNCHED();
+    }
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}

@@ -1,0 +1,265 @@
+"""Host-side orchestration of the CUDA stages (allocation, sizing, retries).
+
+PyTorch is used for device memory, streams and host<->device copies only; every byte of
+compute runs in libyabpe.so.  Shared by the trainer (trainer.py) and the tokenizer
+(tokenizer.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _ffi
+
+TOK_HASH_B = 0x100000001B3
+MASK64 = (1 << 64) - 1
+PT_TILE = 8192
+
+
+def _pow2_at_least(x: int) -> int:
+    return 1 << max(0, int(x - 1).bit_length())
+
+
+def mix64(x: int) -> int:
+    x &= MASK64
+    x ^= x >> 33
+    x = (x * 0xFF51AFD7ED558CCD) & MASK64
+    x ^= x >> 33
+    x = (x * 0xC4CEB9FE1A85EC53) & MASK64
+    x ^= x >> 33
+    return x
+
+
+def pack_specials(specials: list[bytes]) -> tuple[np.ndarray, np.ndarray]:
+    for s in specials:
+        if len(s) == 0:
+            raise ValueError("empty special tokens are not supported")
+    blob = np.frombuffer(b"".join(specials) + b"\0", dtype=np.uint8).copy()
+    offs = np.zeros(len(specials) + 1, dtype=np.int32)
+    if specials:
+        np.cumsum([len(s) for s in specials], out=offs[1:])
+    return blob, offs
+
+
+def to_device_text(torch, host: np.ndarray | "torch.Tensor", non_blocking: bool = False):
+    """Copy `host` bytes into a padded device buffer (capacity round_up(n,16)+64, tail zeroed)."""
+    if isinstance(host, np.ndarray):
+        host = torch.from_numpy(host)
+    n = int(host.numel())
+    cap = ((n + 15) // 16) * 16 + 64
+    dev = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    dev[n:].zero_()
+    if n:
+        dev[:n].copy_(host, non_blocking=non_blocking)
+    return dev, n
+
+
+@dataclass
+class PretokResult:
+    args: _ffi.PretokArgs
+    keep: list = field(default_factory=list)     # tensors / arrays that must outlive the async calls
+    stats: "object" = None
+    short_cap: int = 0
+    long_cap: int = 0
+    text: "object" = None
+    n: int = 0
+
+    def stats_host(self) -> np.ndarray:
+        return self.stats.cpu().numpy()
+
+
+def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: list[bytes], mode: int,
+                 own: tuple[int, int] | None = None, short_cap: int | None = None,
+                 long_cap: int | None = None) -> PretokResult:
+    """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
+    L = _ffi.load()
+    dev = text_dev.device
+    if short_cap is None:
+        short_cap = _pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26))
+    if long_cap is None:
+        long_cap = _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24))
+    n_cuts = 0 if cuts is None else int(len(cuts))
+    cuts_t = torch.from_numpy(np.ascontiguousarray(cuts, dtype=np.int64)).to(dev) if n_cuts else None
+    blob, offs = pack_specials(specials)
+    words32 = (n + 63) // 32 + 1
+    cand = torch.zeros(words32, dtype=torch.int32, device=dev) if specials else None
+    rec = torch.zeros(words32, dtype=torch.int32, device=dev) if specials else None
+    skeys = torch.zeros(short_cap * 2, dtype=torch.int64, device=dev)
+    scounts = torch.zeros(short_cap, dtype=torch.int64, device=dev)
+    lent = torch.zeros(long_cap * 4, dtype=torch.int64, device=dev)
+    ovf_cap = n // PT_TILE + 16
+    ovf = torch.empty(ovf_cap, dtype=torch.int64, device=dev)
+    stats_np = np.zeros(16, dtype=np.int64)
+    stats_np[_ffi.ST_ERR_POS] = _ffi.INT64_MAX
+    stats = torch.from_numpy(stats_np).to(dev)
+    a = _ffi.PretokArgs()
+    a.text = text_dev.data_ptr(); a.n = n
+    a.cuts = cuts_t.data_ptr() if n_cuts else None; a.n_cuts = n_cuts; a.mode = mode
+    a.sp_blob = blob.ctypes.data; a.sp_offs = offs.ctypes.data; a.n_sp = len(specials)
+    a.own_lo, a.own_hi = own if own is not None else (0, n)
+    a.cand_bits = cand.data_ptr() if specials else None
+    a.rec_bits = rec.data_ptr() if specials else None
+    a.short_keys = skeys.data_ptr(); a.short_counts = scounts.data_ptr(); a.short_cap = short_cap
+    a.long_entries = lent.data_ptr(); a.long_cap = long_cap
+    a.ovf_pos = ovf.data_ptr(); a.ovf_cap = ovf_cap
+    a.stats = stats.data_ptr()
+    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf], stats=stats,
+                       short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n)
+    if n > 0:
+        _ffi.check(L.yabpe_pretok_count(C.byref(a), _ffi.stream_ptr(torch)))
+    return res
+
+
+def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None) -> tuple[PretokResult, np.ndarray]:
+    """pretok_count + one host sync; grows the tables and retries when they overflow."""
+    short_cap = long_cap = None
+    for _ in range(8):
+        res = pretok_count(torch, text_dev, n, cuts, specials, mode, own, short_cap, long_cap)
+        st = res.stats_host()
+        if st[_ffi.ST_TABLE_FULL] == 0:
+            return res, st
+        short_cap, long_cap = res.short_cap * 4, res.long_cap * 4
+        del res
+    raise _ffi.YabpeError("pre-token hash tables kept overflowing")
+
+
+@dataclass
+class WordArrays:
+    table: _ffi.WordTable
+    n_words: int
+    n_syms: int
+    keep: list = field(default_factory=list)
+    wsym: "object" = None
+    woff: "object" = None
+    wlen: "object" = None
+    wcnt: "object" = None
+
+
+def compact_words(torch, res: PretokResult, st: np.ndarray, with_maps: bool) -> WordArrays:
+    L = _ffi.load()
+    dev = res.text.device
+    n_words = int(st[_ffi.ST_UNIQ_SHORT] + st[_ffi.ST_UNIQ_LONG])
+    n_syms = int(st[_ffi.ST_UNIQ_BYTES])
+    wsym = torch.empty(n_syms + 8, dtype=torch.int32, device=dev)
+    sym_word = torch.empty(n_syms + 8, dtype=torch.int32, device=dev)
+    woff = torch.empty(n_words + 1, dtype=torch.int64, device=dev)
+    wlen = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
+    wcnt = torch.empty(n_words + 1, dtype=torch.int64, device=dev)
+    sword = torch.empty(res.short_cap, dtype=torch.int32, device=dev) if with_maps else None
+    lword = torch.empty(res.long_cap, dtype=torch.int32, device=dev) if with_maps else None
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    w = _ffi.WordTable()
+    w.wsym = wsym.data_ptr(); w.sym_word = sym_word.data_ptr(); w.woff = woff.data_ptr()
+    w.wlen = wlen.data_ptr(); w.wcnt = wcnt.data_ptr()
+    w.sword = sword.data_ptr() if with_maps else None
+    w.lword = lword.data_ptr() if with_maps else None
+    w.counters = counters.data_ptr()
+    if n_words > 0:
+        _ffi.check(L.yabpe_compact_words(C.byref(res.args), C.byref(w), _ffi.stream_ptr(torch)))
+    return WordArrays(table=w, n_words=n_words, n_syms=n_syms,
+                      keep=[wsym, sym_word, woff, wlen, wcnt, sword, lword, counters],
+                      wsym=wsym, woff=woff, wlen=wlen, wcnt=wcnt)
+
+
+def tok_hash(b: bytes) -> tuple[int, int]:
+    """Polynomial hash of a token's bytes and base^len (must match merge.cuh phase 2)."""
+    h, p = 0, 1
+    for x in b:
+        h = (h * TOK_HASH_B + x + 1) & MASK64
+        p = (p * TOK_HASH_B) & MASK64
+    return h, p
+
+
+@dataclass
+class MergeResult:
+    merges: np.ndarray          # (n_merges, 2) int32 token ids
+    merge_new: np.ndarray       # (n_merges,) int32 resulting id
+    tokens: list[bytes]         # id -> bytes, all tokens
+    state: np.ndarray
+
+
+def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: int, min_frequency: int,
+               pcap: int | None = None, pool_cap: int | None = None, dlog_cap: int | None = None,
+               restore=None) -> MergeResult:
+    """Run the persistent merge kernel.  `restore()` must rebuild `words` in place for a retry."""
+    L = _ffi.load()
+    dev = words.wsym.device
+    n_base = len(base_tokens)
+    max_tokens = n_base + num_merges + 2
+    for attempt in range(6):
+        if pcap is None:
+            pcap = _pow2_at_least(min(max(4 * words.n_syms, 1 << 16), 1 << 26))
+        if pool_cap is None:
+            pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
+        if dlog_cap is None:
+            dlog_cap = min(max(words.n_syms, 1 << 16), 1 << 24)
+        tset_cap = _pow2_at_least(4 * max_tokens)
+        # base tokens on the host
+        tok_bytes = np.zeros(pool_cap, dtype=np.uint8)
+        tok_off = np.zeros(max_tokens + 1, dtype=np.int64)
+        th = np.zeros(max_tokens, dtype=np.uint64)
+        tp = np.zeros(max_tokens, dtype=np.uint64)
+        tset = np.zeros(tset_cap, dtype=np.uint64)
+        pos = 0
+        for i, b in enumerate(base_tokens):
+            tok_bytes[pos:pos + len(b)] = np.frombuffer(b, dtype=np.uint8)
+            pos += len(b)
+            tok_off[i + 1] = pos
+            h, p = tok_hash(b)
+            th[i], tp[i] = h, p
+            slot = mix64(h) & (tset_cap - 1)
+            while tset[slot] != 0:
+                slot = (slot + 1) & (tset_cap - 1)
+            tset[slot] = (h & 0xFFFFFFFF00000000) | (i + 1)
+        t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+        d_tok_bytes, d_tok_off, d_th, d_tp, d_tset = t(tok_bytes), t(tok_off), t(th.view(np.int64)), t(tp.view(np.int64)), t(tset.view(np.int64))
+        z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
+        wstamp = z(words.n_words + 1, torch.int32)
+        pkey, pcnt = z(pcap, torch.int64), z(pcap, torch.int64)
+        ioff, icnt = z(pcap + 1, torch.int32), z(pcap, torch.int32)
+        ipost = z(words.n_syms + 8, torch.int32)
+        inact, act = z((pcap + 31) // 32 + 1, torch.int32), z(pcap, torch.int32)
+        dlog_slot, dlog_word = z(dlog_cap, torch.int32), z(dlog_cap, torch.int32)
+        partial, bsum = z(1024 * 3, torch.int64), z(1024, torch.int64)
+        merges, merge_new = z(2 * max(num_merges, 1), torch.int32), z(max(num_merges, 1), torch.int32)
+        state_np = np.zeros(32, dtype=np.int64)
+        state_np[_ffi.MS_NTOK] = n_base
+        state = t(state_np)
+        m = _ffi.MergeArgs()
+        m.words = words.table; m.n_words = words.n_words; m.n_syms = words.n_syms
+        m.wstamp = wstamp.data_ptr()
+        m.tok_bytes = d_tok_bytes.data_ptr(); m.tok_bytes_cap = pool_cap
+        m.tok_off = d_tok_off.data_ptr(); m.tok_hash = d_th.data_ptr(); m.tok_pow = d_tp.data_ptr()
+        m.tset = d_tset.data_ptr(); m.tset_cap = tset_cap; m.max_tokens = max_tokens
+        m.pkey = pkey.data_ptr(); m.pcnt = pcnt.data_ptr(); m.pcap = pcap
+        m.ioff = ioff.data_ptr(); m.icnt = icnt.data_ptr(); m.ipost = ipost.data_ptr()
+        m.inact = inact.data_ptr(); m.act = act.data_ptr()
+        m.dlog_slot = dlog_slot.data_ptr(); m.dlog_word = dlog_word.data_ptr(); m.dlog_cap = dlog_cap
+        m.partial = partial.data_ptr(); m.bsum = bsum.data_ptr()
+        m.merges = merges.data_ptr(); m.merge_new = merge_new.data_ptr(); m.state = state.data_ptr()
+        m.num_merges = num_merges; m.min_frequency = min_frequency
+        _ffi.check(L.yabpe_merge_loop(C.byref(m), _ffi.stream_ptr(torch)))
+        st = state.cpu().numpy()
+        err = int(st[_ffi.MS_ERROR])
+        if err == 0:
+            nm = int(st[_ffi.MS_NMERGES])
+            ntok = int(st[_ffi.MS_NTOK])
+            mg = merges[:2 * nm].cpu().numpy().reshape(-1, 2)
+            mn = merge_new[:nm].cpu().numpy()
+            used = int(st[_ffi.MS_POOL_USED]) if ntok > n_base else int(tok_off[n_base])
+            pool = d_tok_bytes[:max(used, 1)].cpu().numpy().tobytes()
+            offs = d_tok_off[:ntok + 1].cpu().numpy()
+            tokens = [pool[offs[i]:offs[i + 1]] for i in range(ntok)]
+            return MergeResult(merges=mg, merge_new=mn, tokens=tokens, state=st)
+        if err & _ffi.ME_INTERNAL:
+            raise _ffi.YabpeError(f"merge loop internal error (state={st.tolist()})")
+        if restore is None:
+            raise _ffi.YabpeError(f"merge loop capacity error {err} and no restore callback")
+        if err & _ffi.ME_PAIR_TABLE_FULL:
+            pcap *= 4
+        if err & _ffi.ME_TOK_POOL_FULL:
+            pool_cap *= 4
+        restore()
+    raise _ffi.YabpeError("merge loop kept running out of capacity")

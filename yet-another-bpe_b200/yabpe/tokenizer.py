@@ -1,0 +1,252 @@
+"""B200 tokenizer: the reference's `BBPETokenizer` interface over the CUDA encode pipeline.
+
+Mirrors /root/reference/src/yet_another_bpe/tokenizer.py (encode / decode / encode_batch /
+decode_batch / from_file / vocab_size / special_tokens / get_vocab) and the adapter's
+`encode_iterable` (tests/adapters.py:30-34).  Pre-tokenisation, per-word BPE by rank and the
+id scatter all run in libyabpe.so; `decode` is a host-side byte gather.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from collections.abc import Iterable, Iterator, Sequence
+from pathlib import Path
+
+import numpy as np
+
+from . import _ffi, engine
+
+_ITER_BATCH_BYTES = 4 << 20
+_ITER_BATCH_ITEMS = 1 << 16
+
+
+class BBPETokenizer:
+    """Byte-level BPE tokenizer on one B200."""
+
+    def __init__(self, vocab: dict[bytes, int] | None = None, merges: list[tuple[bytes, bytes]] | None = None,
+                 special_tokens: list[str] | None = None) -> None:
+        self._vocab: dict[bytes, int] = vocab or {}
+        self._vocab_inv: dict[int, bytes] = {v: k for k, v in self._vocab.items()}    # tokenizer.py:63
+        self._merges: list[tuple[bytes, bytes]] = merges or []
+        self._special_tokens: list[str] = special_tokens or []
+        # tokenizer.py:74-76: rank = index, the LAST duplicate wins
+        ranks: dict[tuple[bytes, bytes], int] = {p: i for i, p in enumerate(self._merges)}
+        # symbols = distinct byte strings among single bytes, merge operands and results
+        sym: dict[bytes, int] = {bytes([b]): b for b in range(256)}
+
+        def sid(b: bytes) -> int:
+            s = sym.get(b)
+            if s is None:
+                s = sym[b] = len(sym)
+            return s
+
+        m = np.zeros((len(ranks), 4), dtype=np.int64)     # a, b, rank, result
+        for k, ((a, b), r) in enumerate(ranks.items()):
+            m[k] = (sid(a), sid(b), r, sid(a + b))
+        unk = self._vocab.get(b"[UNK]", 0)                                            # tokenizer.py:299
+        self._sym_out = np.fromiter((self._vocab.get(b, unk) for b in sym), dtype=np.int32, count=len(sym))
+        # batch rule is exact iff every merge that uses a produced symbol ranks after all merges producing it
+        maxprod = np.full(len(sym), -1, dtype=np.int64)
+        if len(m):
+            np.maximum.at(maxprod, m[:, 3], m[:, 2])
+            self._consistent = bool(np.all(m[:, 2] > maxprod[m[:, 0]]) and np.all(m[:, 2] > maxprod[m[:, 1]]))
+        else:
+            self._consistent = True
+        # device merge table: open addressing, key = 1<<63 | a<<32 | b, value = rank<<32 | result
+        mcap = engine._pow2_at_least(max(16, 2 * len(m) + 2))
+        mkey = np.zeros(mcap, dtype=np.uint64)
+        mval = np.zeros(mcap, dtype=np.uint64)
+        for a, b, r, c in m.tolist():
+            key = (1 << 63) | (a << 32) | b
+            slot = engine.mix64(key) & (mcap - 1)
+            while mkey[slot] != 0:
+                slot = (slot + 1) & (mcap - 1)
+            mkey[slot] = key
+            mval[slot] = (r << 32) | c
+        self._mkey, self._mval, self._mcap = mkey, mval, mcap
+        # tokenizer.py:99: longest first (len of the str), stable
+        sp_sorted = sorted(self._special_tokens, key=len, reverse=True)
+        self._sp_bytes = [s.encode("utf-8") for s in sp_sorted]
+        self._sp_ids = np.asarray([self._vocab.get(s, -1) for s in self._sp_bytes] + [-1], dtype=np.int32)
+        self._dev = None
+        self.last_launches = 0
+
+    # -- persistence (tokenizer.py:106-150, literal format) -------------------------------------
+    @classmethod
+    def from_file(cls, model_dir: str | Path) -> "BBPETokenizer":
+        model_path = Path(model_dir)
+        with open(model_path / "vocab.json", encoding="utf-8") as f:
+            vocab = {k.encode("latin-1"): v for k, v in json.load(f).items()}
+        merges: list[tuple[bytes, bytes]] = []
+        with open(model_path / "merges.txt", encoding="utf-8") as f:
+            for line in f:
+                line = line.rstrip("\n")
+                if not line:
+                    continue
+                parts = line.split(" ", 1)
+                if len(parts) == 2:
+                    merges.append((parts[0].encode("latin-1"), parts[1].encode("latin-1")))
+        special_tokens: list[str] = []
+        sp_file = model_path / "special_tokens.json"
+        if sp_file.exists():
+            with open(sp_file, encoding="utf-8") as f:
+                special_tokens = json.load(f)
+        return cls(vocab=vocab, merges=merges, special_tokens=special_tokens)
+
+    # -- device model ---------------------------------------------------------------------------
+    def _device_model(self, torch):
+        dev = torch.cuda.current_device()
+        if self._dev is None or self._dev[0] != dev:
+            t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+            tensors = [t(self._mkey.view(np.int64)), t(self._mval.view(np.int64)), t(np.arange(256, dtype=np.int32)),
+                       t(self._sym_out), t(self._sp_ids)]
+            e = _ffi.EncodeModel()
+            e.mkey, e.mval, e.mcap = tensors[0].data_ptr(), tensors[1].data_ptr(), self._mcap
+            e.byte_sym, e.sym_out, e.sp_ids = tensors[2].data_ptr(), tensors[3].data_ptr(), tensors[4].data_ptr()
+            e.consistent = 1 if self._consistent else 0
+            self._dev = (dev, e, tensors)
+        return self._dev[1]
+
+    def encode_device(self, text_dev, n: int, cuts: np.ndarray | None = None, own: tuple[int, int] | None = None):
+        """Encode `n` bytes resident on the device; `cuts` = interior document boundaries.
+        Returns (ids tensor int32 on device, doc_off tensor int64 or None).  One host sync
+        (table sizes) + one (id count)."""
+        torch = _ffi.require_cuda()
+        L = _ffi.load()
+        if n == 0:
+            return torch.empty(0, dtype=torch.int32, device="cuda"), None
+        e = self._device_model(torch)
+        launches0 = _ffi.launch_count()
+        res, st = engine.pretok_count_checked(torch, text_dev, n, cuts, self._sp_bytes, mode=1, own=own)
+        words = engine.compact_words(torch, res, st, with_maps=True)
+        stream = _ffi.stream_ptr(torch)
+        _ffi.check(L.yabpe_encode_words(C.byref(e), C.byref(words.table), words.n_words, stream))
+        lo, hi = own if own is not None else (0, n)
+        n_tiles = int(L.yabpe_num_tiles(lo, hi))
+        tile_count = torch.zeros(n_tiles + 1, dtype=torch.int64, device="cuda")
+        n_cuts = 0 if cuts is None else len(cuts)
+        doc_off = torch.full((n_cuts + 2,), -1, dtype=torch.int64, device="cuda") if n_cuts else None
+        o = _ffi.EncodeOut()
+        o.tile_count = tile_count.data_ptr(); o.out_ids = None; o.out_cap = 0
+        o.doc_off = doc_off.data_ptr() if n_cuts else None
+        _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 0, stream))
+        total = int(tile_count[n_tiles].item())
+        ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+        o.out_ids = ids.data_ptr(); o.out_cap = total
+        _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
+        self.last_launches = _ffi.launch_count() - launches0
+        self._keep = (res, words, tile_count)
+        return ids[:total], doc_off
+
+    # -- reference API --------------------------------------------------------------------------
+    def encode(self, text: str) -> list[int]:
+        if not text:
+            return []
+        torch = _ffi.require_cuda()
+        raw = np.frombuffer(text.encode("utf-8"), dtype=np.uint8)
+        text_dev, n = engine.to_device_text(torch, raw)
+        ids, _ = self.encode_device(text_dev, n)
+        return ids.cpu().tolist()
+
+    def encode_batch(self, texts: Sequence[str]) -> list[list[int]]:
+        """== [encode(t) for t in texts] (tokenizer.py:351-360), one device pass for the batch."""
+        torch = _ffi.require_cuda()
+        raws = [t.encode("utf-8") for t in texts]
+        lens = np.asarray([len(r) for r in raws], dtype=np.int64)
+        total = int(lens.sum())
+        if total == 0:
+            return [[] for _ in texts]
+        ends = np.cumsum(lens)
+        cuts = np.unique(ends[:-1][(ends[:-1] > 0) & (ends[:-1] < total)])
+        text_dev, n = engine.to_device_text(torch, np.frombuffer(b"".join(raws), dtype=np.uint8))
+        ids, doc_off = self.encode_device(text_dev, n, cuts if len(cuts) else None)
+        ids_h = ids.cpu().numpy()
+        # id offset of every byte boundary that is a document start
+        starts = np.concatenate([[0], ends[:-1]])
+        if len(cuts):
+            off = doc_off.cpu().numpy()
+            off[0] = 0
+            off[len(cuts) + 1] = len(ids_h)
+            for k in range(len(cuts), 0, -1):          # a cut whose first token produced no write keeps -1
+                if off[k] < 0:
+                    off[k] = off[k + 1]
+            cut_off = dict(zip(cuts.tolist(), off[1:len(cuts) + 1].tolist()))
+        else:
+            cut_off = {}
+        cut_off[0] = 0
+        cut_off[total] = len(ids_h)
+        out = []
+        for s, ln in zip(starts.tolist(), lens.tolist()):
+            out.append(ids_h[cut_off[s]:cut_off[s + ln]].tolist() if ln else [])
+        return out
+
+    def encode_iterable(self, iterable: Iterable[str]) -> Iterator[int]:
+        """Lazy, bounded-memory flattening of encode(item) for every item (adapters.py:30-34)."""
+        batch: list[str] = []
+        size = 0
+        for item in iterable:
+            batch.append(item)
+            size += len(item)
+            if size >= _ITER_BATCH_BYTES or len(batch) >= _ITER_BATCH_ITEMS:
+                for ids in self.encode_batch(batch):
+                    yield from ids
+                batch, size = [], 0
+        if batch:
+            for ids in self.encode_batch(batch):
+                yield from ids
+
+    def decode(self, ids: Sequence[int]) -> str:
+        """tokenizer.py:323-349: unknown ids skipped; strict UTF-8, else errors='replace'."""
+        if not len(ids):
+            return ""
+        inv = self._vocab_inv
+        buf = b"".join(inv[i] for i in ids if i in inv)
+        try:
+            return buf.decode("utf-8")
+        except UnicodeDecodeError:
+            return buf.decode("utf-8", errors="replace")
+
+    def decode_batch(self, ids_batch: Sequence[Sequence[int]]) -> list[str]:
+        return [self.decode(ids) for ids in ids_batch]
+
+    @property
+    def vocab_size(self) -> int:
+        return len(self._vocab)
+
+    @property
+    def special_tokens(self) -> list[str]:
+        return self._special_tokens.copy()
+
+    def get_vocab(self) -> dict[str, int]:
+        return {k.decode("latin-1"): v for k, v in self._vocab.items()}
+
+    def clear_cache(self) -> None:
+        """The reference clears its LRU word cache here; the GPU path keeps no cache between calls."""
+
+    def cache_info(self) -> str:
+        return "hits=0, misses=0, size=0/0"
+
+
+class Tokenizer:
+    """`Tokenizer(vocab, merges, special_tokens)` with the adapter's id->bytes vocab (adapters.py:37-63)."""
+
+    def __init__(self, vocab: dict[int, bytes], merges: list[tuple[bytes, bytes]],
+                 special_tokens: list[str] | None = None) -> None:
+        self._tokenizer = BBPETokenizer(vocab={v: k for k, v in vocab.items()}, merges=merges,
+                                        special_tokens=special_tokens or [])
+
+    def encode(self, text: str) -> list[int]:
+        return self._tokenizer.encode(text)
+
+    def decode(self, ids: list[int]) -> str:
+        return self._tokenizer.decode(ids)
+
+    def encode_iterable(self, iterable: Iterable[str]) -> Iterator[int]:
+        return self._tokenizer.encode_iterable(iterable)
+
+    def encode_batch(self, texts: Sequence[str]) -> list[list[int]]:
+        return self._tokenizer.encode_batch(texts)
+
+    @property
+    def inner(self) -> BBPETokenizer:
+        return self._tokenizer

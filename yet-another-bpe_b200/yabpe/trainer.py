@@ -1,0 +1,233 @@
+"""B200 trainer: the reference's `BBPETrainer` interface over the CUDA pipeline.
+
+Mirrors /root/reference/src/yet_another_bpe/trainer.py (same class / field / method names,
+same exceptions) and the adapter entry point tests/adapters.py:66-99 (`train_bpe`).
+All compute happens in libyabpe.so; this module only reads files, sizes buffers and turns
+device arrays back into `dict[bytes, int]` / `list[tuple[bytes, bytes]]`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from collections.abc import Mapping, Sequence
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from . import _ffi, engine
+
+
+@dataclass
+class BBPETrainerConfig:
+    """Same fields and defaults as trainer.py:17-38.  `max_workers` and `seed` are accepted and
+    ignored (the GPU pipeline has no thread pool); `chunk_size_bytes` keeps its SEMANTIC meaning:
+    files larger than it are cut into independent texts."""
+
+    vocab_size: int = 32000
+    min_frequency: int = 2
+    max_workers: int = 8
+    chunk_size_bytes: int = 8 * 1024 * 1024
+    seed: int = 42
+    special_tokens: Sequence[str] = field(default_factory=lambda: ["[PAD]", "[UNK]", "[BOS]", "[EOS]"])
+
+
+class BBPEModel:
+    """Container for a trained model (trainer.py:41-52)."""
+
+    def __init__(self, vocab: Mapping[bytes, int], merges: Sequence[tuple[bytes, bytes]],
+                 special_tokens: Sequence[str]) -> None:
+        self.vocab: dict[bytes, int] = dict(vocab)
+        self.merges: list[tuple[bytes, bytes]] = list(merges)
+        self.special_tokens: list[str] = list(special_tokens)
+
+
+def chunk_cuts(data: np.ndarray, chunk_size: int) -> list[int]:
+    """Reference chunk END offsets for one file (trainer.py:139-144,172-198): cuts every
+    `chunk_size` bytes, moved back (<= 4 bytes) to a byte that is not a UTF-8 continuation."""
+    n = int(data.size)
+    if n == 0:
+        return []
+    if n <= chunk_size:
+        return [n]
+    cuts: list[int] = []
+    start = 0
+    while start < n:
+        tentative = min(start + chunk_size, n)
+        if tentative < n:
+            bstart = max(0, tentative - 4)
+            pos = tentative - bstart
+            while pos > 0 and (int(data[bstart + pos]) & 0xC0) == 0x80:
+                pos -= 1
+            actual = bstart + pos
+        else:
+            actual = n
+        if actual > start:
+            cuts.append(actual)
+            start = actual
+        else:
+            start += 1
+    return cuts
+
+
+@dataclass
+class TrainStats:
+    n_bytes: int = 0
+    n_pretokens: int = 0
+    n_words: int = 0
+    n_syms: int = 0
+    n_merges: int = 0
+    index_rebuilds: int = 0
+    threshold_rebuilds: int = 0
+    n_pairs: int = 0
+    n_specials: int = 0
+
+
+class BBPETrainer:
+    """Byte-level BPE trainer on one B200 (trainer.py:55-302)."""
+
+    def __init__(self, config: BBPETrainerConfig | None = None) -> None:
+        self.config: BBPETrainerConfig = config or BBPETrainerConfig()
+        self._vocab: dict[bytes, int] = {}
+        self._merges: list[tuple[bytes, bytes]] = []
+        self.last_stats = TrainStats()
+
+    # -- reference API ---------------------------------------------------------------------
+    def train(self, files: Sequence[str | Path]) -> BBPEModel:
+        if not files:
+            raise ValueError("At least one file must be provided")       # trainer.py:72-73
+        paths = [Path(f) if isinstance(f, str) else f for f in files]
+        blobs: list[np.ndarray] = []
+        for p in paths:
+            if not p.exists():
+                raise FileNotFoundError(f"File not found: {p}")           # trainer.py:204-205
+            blobs.append(np.fromfile(p, dtype=np.uint8))
+        return self.train_from_buffers(blobs, [str(p) for p in paths])
+
+    def train_from_buffers(self, blobs: Sequence[np.ndarray], names: Sequence[str] | None = None,
+                           device_text=None) -> BBPEModel:
+        """Train from host byte buffers (one per file).  `device_text` may carry an already
+        resident (tensor, n) pair for the concatenation of `blobs` (bench: inputs in HBM)."""
+        torch = _ffi.require_cuda()
+        cfg = self.config
+        specials = [s.encode("utf-8") for s in cfg.special_tokens]
+        names = list(names) if names is not None else [f"<buffer {i}>" for i in range(len(blobs))]
+        # P1: chunk cuts per file; file ends are hard boundaries too
+        file_starts, cuts, total = [], [], 0
+        for b in blobs:
+            file_starts.append(total)
+            cuts += [total + c for c in chunk_cuts(b, cfg.chunk_size_bytes)]
+            total += int(b.size)
+        cuts = [c for c in cuts if 0 < c < total]
+        base_vocab = self._init_base_vocab()
+        if total == 0:
+            return self._finish(base_vocab, [])                           # trainer.py:81-85
+        if device_text is None:
+            host = blobs[0] if len(blobs) == 1 else np.concatenate([b for b in blobs if b.size])
+            text_dev, n = engine.to_device_text(torch, host)
+        else:
+            text_dev, n = device_text
+        assert n == total
+        cuts_np = np.asarray(cuts, dtype=np.int64) if cuts else None
+        res, st = engine.pretok_count_checked(torch, text_dev, n, cuts_np, specials, mode=0)
+        err = int(st[_ffi.ST_ERR_POS])
+        if err != _ffi.INT64_MAX:                                         # trainer.py:157-160
+            fi = int(np.searchsorted(np.asarray(file_starts), err, side="right")) - 1
+            raise ValueError(f"File {names[fi]} contains invalid UTF-8 at position {err - file_starts[fi]}.")
+        words = engine.compact_words(torch, res, st, with_maps=False)
+        stats = TrainStats(n_bytes=n, n_pretokens=int(st[_ffi.ST_NTOK]), n_words=words.n_words, n_syms=words.n_syms,
+                           n_specials=int(st[_ffi.ST_NSPECIAL]))
+        base_tokens = list(base_vocab.keys())
+        num_merges = max(0, cfg.vocab_size - len(base_vocab))            # trainer.py:238
+        if words.n_words == 0 or num_merges == 0:
+            self.last_stats = stats
+            return self._finish(base_vocab, [])
+
+        def restore() -> None:
+            words.keep[-1].zero_()
+            _ffi.check(_ffi.load().yabpe_compact_words(C.byref(res.args), C.byref(words.table), _ffi.stream_ptr(torch)))
+
+        mr = engine.merge_loop(torch, words, base_tokens, num_merges, int(cfg.min_frequency), restore=restore)
+        stats.n_merges = len(mr.merge_new)
+        stats.index_rebuilds = int(mr.state[_ffi.MS_REBUILDS])
+        stats.threshold_rebuilds = int(mr.state[_ffi.MS_TREBUILDS])
+        stats.n_pairs = int(mr.state[_ffi.MS_NPAIRS])
+        self.last_stats = stats
+        vocab = {b: i for i, b in enumerate(mr.tokens)}
+        merges = [(mr.tokens[int(a)], mr.tokens[int(b)]) for a, b in mr.merges]
+        return self._finish(vocab, merges)
+
+    def save(self, output_dir: str | Path) -> None:
+        """Same on-disk format as trainer.py:94-117 (latin-1 keys, "a b" merge lines)."""
+        if not self._vocab:
+            raise ValueError("Model has not been trained yet. Call train() first.")
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        with open(out / "vocab.json", "w", encoding="utf-8") as f:
+            json.dump({k.decode("latin-1"): v for k, v in self._vocab.items()}, f, ensure_ascii=False, indent=2)
+        with open(out / "merges.txt", "w", encoding="utf-8") as f:
+            for a, b in self._merges:
+                f.write(f"{a.decode('latin-1')} {b.decode('latin-1')}\n")
+        with open(out / "special_tokens.json", "w", encoding="utf-8") as f:
+            json.dump(list(self.config.special_tokens), f, ensure_ascii=False, indent=2)
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _init_base_vocab(self) -> dict[bytes, int]:
+        """256 bytes, then each special unless its bytes are already a key (trainer.py:119-134)."""
+        vocab: dict[bytes, int] = {bytes([i]): i for i in range(256)}
+        for s in self.config.special_tokens:
+            b = s.encode("utf-8")
+            if b not in vocab:
+                vocab[b] = len(vocab)
+        return vocab
+
+    def _finish(self, vocab: dict[bytes, int], merges: list[tuple[bytes, bytes]]) -> BBPEModel:
+        self._vocab, self._merges = vocab, merges
+        return BBPEModel(vocab=vocab, merges=merges, special_tokens=list(self.config.special_tokens))
+
+
+def train_bpe(input_path: str | os.PathLike, vocab_size: int, special_tokens: list[str]
+              ) -> tuple[dict[int, bytes], list[tuple[bytes, bytes]]]:
+    """Drop-in for tests/adapters.py:66-99 `run_train_bpe` (min_frequency=1, 1 GiB chunks)."""
+    config = BBPETrainerConfig(vocab_size=vocab_size, min_frequency=1, max_workers=1,
+                               chunk_size_bytes=1024 * 1024 * 1024, seed=42, special_tokens=special_tokens)
+    trainer = BBPETrainer(config)
+    path = Path(input_path) if not isinstance(input_path, Path) else input_path
+    model = trainer.train([path])
+    return {v: k for k, v in model.vocab.items()}, model.merges
+
+
+def pretoken_counts(data: bytes | np.ndarray, special_tokens: Sequence[str] = (), *, mode: str = "train",
+                    chunk_size_bytes: int = 1 << 30, cuts: Sequence[int] | None = None) -> dict[bytes, int]:
+    """Device word-count table of `data` as a dict (the multiset trainer.py:221-225 builds).
+    mode="encode" applies the tokenizer's special handling (specials split first and not counted)."""
+    torch = _ffi.require_cuda()
+    raw = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    if raw.size == 0:
+        return {}
+    if mode == "train":
+        sp = [s.encode("utf-8") for s in special_tokens]
+        cut_list = chunk_cuts(raw, chunk_size_bytes) if cuts is None else list(cuts)
+    else:
+        sp = [s.encode("utf-8") for s in sorted(special_tokens, key=len, reverse=True)]
+        cut_list = [] if cuts is None else list(cuts)
+    cut_list = [c for c in cut_list if 0 < c < raw.size]
+    text_dev, n = engine.to_device_text(torch, raw)
+    res, st = engine.pretok_count_checked(torch, text_dev, n, np.asarray(cut_list, dtype=np.int64) if cut_list else None,
+                                          sp, 0 if mode == "train" else 1)
+    if int(st[_ffi.ST_ERR_POS]) != _ffi.INT64_MAX:
+        raise ValueError(f"invalid UTF-8 at position {int(st[_ffi.ST_ERR_POS])}")
+    words = engine.compact_words(torch, res, st, with_maps=False)
+    out: dict[bytes, int] = {}
+    if words.n_words:
+        wsym = words.wsym.cpu().numpy()
+        woff = words.woff.cpu().numpy()
+        wlen = words.wlen.cpu().numpy()
+        wcnt = words.wcnt.cpu().numpy()
+        for w in range(words.n_words):
+            b = wsym[woff[w]:woff[w] + wlen[w]].astype(np.uint8).tobytes()
+            assert b not in out, "duplicate word in device table"
+            out[b] = int(wcnt[w])
+    out["__n_pretokens__"] = int(st[_ffi.ST_NTOK])  # type: ignore[index]
+    return out
