@@ -1,0 +1,300 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the BPE training hot path on B200 (contract: see the task statement).
+
+A "step" is one full `train_bpe` (pre-tokenise + count + word table + merge loop) over one batch
+of synthetic text.  Default workload (N=1): BASELINE.json configs[1] -- TinyStories-shaped
+synthetic corpus, 2e9 bytes, vocab 10 000, special token <|endoftext|>.
+
+  value        corpus MB / s, inputs already resident in HBM when the timed region starts
+  e2e          the same through the host-buffer API (pinned host bytes -> H2D -> train -> D2H of
+               merges / vocab), copies inside the timed region
+  roofline     dominant kernel (k_pretok_count): corpus bytes / its CUDA-event duration vs the
+               measured HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle port (oracle/bpe_oracle.c, reference algorithm) on a bounded sample
+  --impl reference   the same oracle port on the host cores (the reference is pure Python and is
+               not present on the GPU box; the port follows trainer.py line by line)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "yet-another-bpe_b200", ROOT / "tools"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+WORKLOADS = {
+    # name: (kind, bytes, vocab, seed)
+    "tinystories-2g-v10k": ("tinystories", 2_000_000_000, 10_000, 20260101),
+    "owt-11g-v32k": ("owt", 11_000_000_000, 32_000, 20260102),
+    "tinystories-256m-v10k": ("tinystories", 256_000_000, 10_000, 20260101),
+    "owt-1g-v32k": ("owt", 1_000_000_000, 32_000, 20260102),
+}
+SPECIALS = ["<|endoftext|>"]
+METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
+UNIT = "MB/s"
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index: int = 0):
+        self.rows: list[list[str]] = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self.index = index
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self) -> dict:
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_port_run(sample: bytes, vocab: int) -> tuple[float, int]:
+    """One timed run of the oracle port on `sample`; returns (seconds, merges)."""
+    from oracle import oracle
+    t0 = time.perf_counter()
+    _, merges = oracle.train_bpe_bytes(sample, vocab, SPECIALS, fast=False)
+    return time.perf_counter() - t0, len(merges)
+
+
+def run_reference(args) -> None:
+    """--impl reference: the CPU port of the reference algorithm on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, nbytes, vocab, seed = WORKLOADS[args.workload]
+    sys.path.insert(0, str(ROOT / "tests"))
+    import common
+    sample_bytes = args.cpu_sample_mb << 20
+    gen = common.synth_tinystories if kind == "tinystories" else common.synth_owt
+    sample = gen(sample_bytes, seed=seed)
+    for _ in range(args.warmup):
+        cpu_port_run(sample[: 1 << 20], vocab)
+    t = 0.0
+    nm = 0
+    for _ in range(args.steps):
+        dt, nm = cpu_port_run(sample, vocab)
+        t += dt
+    mbps = len(sample) * args.steps / t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(mbps, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * t / args.steps, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+        "config": {"workload": args.workload, "vocab_size": vocab, "special_tokens": SPECIALS,
+                   "note": "reference is pure Python (not on the GPU box); timed: C port of trainer.py, linear max() scan"},
+        "cpu_baseline": {"value": round(mbps, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{len(sample)} bytes of the {kind}-shaped generator (numpy, seed {seed}), "
+                                   f"vocab {vocab}, {nm} merges; reference uses max_workers=1 (threads are GIL-bound)"},
+        "e2e": {"value": round(mbps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tinystories-2g-v10k", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-mb", type=int, default=48)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--encode-mb", type=int, default=256)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import yabpe
+    from synth_gpu import synth_corpus_device
+    from yabpe import _ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kind, nbytes, vocab, seed = WORKLOADS[args.workload]
+    text_dev, n = synth_corpus_device(torch, nbytes, kind, seed + rank)
+    torch.cuda.synchronize()
+
+    cfg = yabpe.BBPETrainerConfig(vocab_size=vocab, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
+                                  special_tokens=SPECIALS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(profile=False):
+        tr = yabpe.BBPETrainer(cfg)
+        tr.profile = profile
+        if world > 1:
+            from yabpe.distributed import train_device_sharded
+            model = train_device_sharded(tr, text_dev, n)
+        else:
+            model = tr.train_device(text_dev, n)
+        return tr, model
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = _ffi.launch_count()
+    timings = []
+    with ClockSampler(local) as clocks:
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            tr, model = step(profile=True)
+            timings.append(dict(tr.timing))
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+    launches = _ffi.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    total_bytes = n * world
+    value = total_bytes / (ms_step / 1e3) / 1e6
+    stats = tr.last_stats
+
+    # roofline of the dominant kernel: algorithmic bytes = corpus bytes read once per launch
+    peak, peak_kind = measured_peak_gbs()
+    tile_ms = float(np.mean([t["pretok_tiles_ms"] for t in timings if "pretok_tiles_ms" in t])) if timings and "pretok_tiles_ms" in timings[0] else None
+    merge_ms = float(np.mean([t["merge_loop_ms"] for t in timings if "merge_loop_ms" in t])) if timings and "merge_loop_ms" in timings[0] else None
+    roofline = None
+    if tile_ms:
+        achieved = n / (tile_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_pretok_count", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_launch": n, "ms_per_launch": round(tile_ms, 3)}
+
+    # e2e: pinned host bytes -> H2D -> train -> D2H results
+    e2e = None
+    if not args.skip_e2e and world == 1:
+        host = torch.empty(n, dtype=torch.uint8).pin_memory()
+        host.copy_(text_dev[:n])
+        host_np = host.numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 2))
+        for _ in range(reps):
+            tr2 = yabpe.BBPETrainer(cfg)
+            m2 = tr2.train_from_buffers([host_np])
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        d2h = sum(len(a) + len(b) for a, b in m2.merges) + sum(len(k) for k in m2.vocab)
+        e2e = {"value": round(n / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": round(dt * 1e3, 2)}
+        assert m2.merges == model.merges
+        del host, host_np
+
+    # secondary: encode MB/s with the trained model on a slice of the corpus (device-resident in, ids out)
+    encode = None
+    if args.encode_mb > 0 and rank == 0:
+        tok = yabpe.BBPETokenizer(vocab=model.vocab, merges=model.merges, special_tokens=SPECIALS)
+        en = min(n, args.encode_mb << 20)
+        while en > 0 and (int(text_dev[en].item()) & 0xC0) == 0x80:
+            en -= 1
+        sl = text_dev[:((en + 15) // 16) * 16 + 64].clone()
+        sl[en:].zero_()
+        tok.encode_device(sl, en)
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        ids, _ = tok.encode_device(sl, en)
+        b.record(); torch.cuda.synchronize()
+        encode = {"MBps": round(en / (a.elapsed_time(b) / 1e3) / 1e6, 2), "bytes": en, "ids": int(ids.numel())}
+
+    cpu = None
+    if not args.skip_cpu and rank == 0 and world == 1:
+        sample = text_dev[: args.cpu_sample_mb << 20].cpu().numpy().tobytes()
+        while sample and (sample[-1] & 0xC0) == 0x80:
+            sample = sample[:-1]
+        if sample and sample[-1] >= 0xC0:
+            sample = sample[:-1]
+        dt, nm = cpu_port_run(sample, vocab)
+        cpu = {"value": round(len(sample) / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {len(sample)} bytes of the same corpus, vocab {vocab}, {nm} merges, {dt:.1f} s; "
+                         f"C port of trainer.py (linear max() scan); host has {os.cpu_count()} cores, the reference uses 1"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int64", "data": f"synthetic ({kind}-shaped, torch generator, seed {seed})",
+            "config": {"workload": args.workload, "corpus_bytes_per_gpu": n, "vocab_size": vocab, "special_tokens": SPECIALS,
+                       "l2": "inputs (>= 256 MB) larger than the 126 MB L2", "n_pretokens": stats.n_pretokens,
+                       "unique_words": stats.n_words, "merges": stats.n_merges},
+            "train_wall_s": round(ms_step / 1e3, 4),
+            "merges_per_s": round(stats.n_merges / (merge_ms / 1e3), 1) if merge_ms else None,
+            "us_per_merge": round(1e3 * merge_ms / max(stats.n_merges, 1), 2) if merge_ms else None,
+            "pretokenize_GBps": round(n / (tile_ms / 1e3) / 1e9, 2) if tile_ms else None,
+            "stage_ms": {k: round(float(np.mean([t[k] for t in timings])), 3) for k in (timings[0] if timings else {})},
+            "merge_loop": {"index_rebuilds": stats.index_rebuilds, "threshold_rebuilds": stats.threshold_rebuilds,
+                           "pairs_created": stats.n_pairs},
+            "encode": encode,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -78,7 +78,8 @@ typedef struct {
     const uint8_t* sp_blob;     /* HOST: special tokens, priority order, concatenated             */
     const int32_t* sp_offs;     /* HOST: n_sp + 1 offsets into sp_blob                            */
     int32_t n_sp;
-    int32_t _pad;
+    int32_t stages;             /* 0 = all; else bit 0: special resolution, bit 1: tile kernel,   */
+                                /*   bit 2: over-long pre-tokens (lets a caller time each stage)  */
     int64_t own_lo, own_hi;     /* only pre-tokens starting in [own_lo, own_hi) are counted       */
     uint32_t* cand_bits;        /* device, (n + 63) / 32 words, zeroed; may be NULL when n_sp = 0 */
     uint32_t* rec_bits;         /* device, same size, zeroed: recognised special starts (output)  */

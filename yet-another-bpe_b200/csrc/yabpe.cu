@@ -136,13 +136,21 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
     int rc = make_params(a, &P);
     if (rc) return rc;
     ARG_CHECK(a->ovf_pos && a->ovf_cap > 0 && a->stats);
-    rc = run_specials(a, P, st);
-    if (rc) return rc;
-    if (P.n_tiles > 0) {
+    const int stages = a->stages ? a->stages : 7;
+    if (stages & 1) {
+        rc = run_specials(a, P, st);
+        if (rc) return rc;
+    } else {
+        rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
+        if (rc) return rc;
+    }
+    if (P.n_tiles > 0 && (stages & 2)) {
         int grid = num_sms() * 4;
         if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
         k_pretok_count<<<grid, PT_THREADS, 0, st>>>(P); LAUNCHED();
         CUDA_TRY(cudaGetLastError());
+    }
+    if (P.n_tiles > 0 && (stages & 4)) {
         k_long_tokens_dyn<<<num_sms(), 256, 0, st>>>(P); LAUNCHED();
         CUDA_TRY(cudaGetLastError());
     }

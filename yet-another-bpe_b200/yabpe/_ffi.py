@@ -39,7 +39,7 @@ class PretokArgs(C.Structure):
     _fields_ = [
         ("text", C.c_void_p), ("n", C.c_int64),
         ("cuts", C.c_void_p), ("n_cuts", C.c_int32), ("mode", C.c_int32),
-        ("sp_blob", C.c_void_p), ("sp_offs", C.c_void_p), ("n_sp", C.c_int32), ("_pad", C.c_int32),
+        ("sp_blob", C.c_void_p), ("sp_offs", C.c_void_p), ("n_sp", C.c_int32), ("stages", C.c_int32),
         ("own_lo", C.c_int64), ("own_hi", C.c_int64),
         ("cand_bits", C.c_void_p), ("rec_bits", C.c_void_p),
         ("short_keys", C.c_void_p), ("short_counts", C.c_void_p), ("short_cap", C.c_int64),

@@ -72,7 +72,7 @@ class PretokResult:
 
 def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: list[bytes], mode: int,
                  own: tuple[int, int] | None = None, short_cap: int | None = None,
-                 long_cap: int | None = None) -> PretokResult:
+                 long_cap: int | None = None, stage_events: list | None = None) -> PretokResult:
     """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
     L = _ffi.load()
     dev = text_dev.device
@@ -108,7 +108,16 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf], stats=stats,
                        short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n)
     if n > 0:
-        _ffi.check(L.yabpe_pretok_count(C.byref(a), _ffi.stream_ptr(torch)))
+        if stage_events is None:
+            _ffi.check(L.yabpe_pretok_count(C.byref(a), _ffi.stream_ptr(torch)))
+        else:
+            # one call per stage with a CUDA event after each (bench: per-kernel durations)
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); stage_events.append(ev)
+            for bit in (1, 2, 4):
+                a.stages = bit
+                _ffi.check(L.yabpe_pretok_count(C.byref(a), _ffi.stream_ptr(torch)))
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); stage_events.append(ev)
+            a.stages = 0
     return res
 
 
@@ -182,7 +191,7 @@ class MergeResult:
 
 def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: int, min_frequency: int,
                pcap: int | None = None, pool_cap: int | None = None, dlog_cap: int | None = None,
-               restore=None) -> MergeResult:
+               restore=None, timing: dict | None = None) -> MergeResult:
     """Run the persistent merge kernel.  `restore()` must rebuild `words` in place for a retry."""
     L = _ffi.load()
     dev = words.wsym.device
@@ -240,8 +249,14 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.partial = partial.data_ptr(); m.bsum = bsum.data_ptr()
         m.merges = merges.data_ptr(); m.merge_new = merge_new.data_ptr(); m.state = state.data_ptr()
         m.num_merges = num_merges; m.min_frequency = min_frequency
+        if timing is not None:
+            t0 = torch.cuda.Event(enable_timing=True); t0.record()
         _ffi.check(L.yabpe_merge_loop(C.byref(m), _ffi.stream_ptr(torch)))
+        if timing is not None:
+            t1 = torch.cuda.Event(enable_timing=True); t1.record()
         st = state.cpu().numpy()
+        if timing is not None:
+            timing["merge_loop_ms"] = t0.elapsed_time(t1)
         err = int(st[_ffi.MS_ERROR])
         if err == 0:
             nm = int(st[_ffi.MS_NMERGES])

@@ -82,6 +82,7 @@ class TrainStats:
     threshold_rebuilds: int = 0
     n_pairs: int = 0
     n_specials: int = 0
+    launches: int = 0
 
 
 class BBPETrainer:
@@ -92,6 +93,8 @@ class BBPETrainer:
         self._vocab: dict[bytes, int] = {}
         self._merges: list[tuple[bytes, bytes]] = []
         self.last_stats = TrainStats()
+        self.profile = False            # True: record CUDA-event stage durations into self.timing
+        self.timing: dict[str, float] = {}
 
     # -- reference API ---------------------------------------------------------------------
     def train(self, files: Sequence[str | Path]) -> BBPEModel:
@@ -105,13 +108,10 @@ class BBPETrainer:
             blobs.append(np.fromfile(p, dtype=np.uint8))
         return self.train_from_buffers(blobs, [str(p) for p in paths])
 
-    def train_from_buffers(self, blobs: Sequence[np.ndarray], names: Sequence[str] | None = None,
-                           device_text=None) -> BBPEModel:
-        """Train from host byte buffers (one per file).  `device_text` may carry an already
-        resident (tensor, n) pair for the concatenation of `blobs` (bench: inputs in HBM)."""
+    def train_from_buffers(self, blobs: Sequence[np.ndarray], names: Sequence[str] | None = None) -> BBPEModel:
+        """Train from host byte buffers, one per file (pinned memory makes the H2D copy fastest)."""
         torch = _ffi.require_cuda()
         cfg = self.config
-        specials = [s.encode("utf-8") for s in cfg.special_tokens]
         names = list(names) if names is not None else [f"<buffer {i}>" for i in range(len(blobs))]
         # P1: chunk cuts per file; file ends are hard boundaries too
         file_starts, cuts, total = [], [], 0
@@ -119,23 +119,63 @@ class BBPETrainer:
             file_starts.append(total)
             cuts += [total + c for c in chunk_cuts(b, cfg.chunk_size_bytes)]
             total += int(b.size)
-        cuts = [c for c in cuts if 0 < c < total]
-        base_vocab = self._init_base_vocab()
         if total == 0:
-            return self._finish(base_vocab, [])                           # trainer.py:81-85
-        if device_text is None:
-            host = blobs[0] if len(blobs) == 1 else np.concatenate([b for b in blobs if b.size])
-            text_dev, n = engine.to_device_text(torch, host)
-        else:
-            text_dev, n = device_text
-        assert n == total
+            return self._finish(self._init_base_vocab(), [])              # trainer.py:81-85
+        host = blobs[0] if len(blobs) == 1 else np.concatenate([b for b in blobs if b.size])
+        text_dev, n = engine.to_device_text(torch, host)
+        return self._train_on_device(torch, text_dev, n, cuts, file_starts, names)
+
+    def train_device(self, text_dev, n: int, name: str = "<device buffer>") -> BBPEModel:
+        """Train on `n` bytes already resident in HBM (capacity >= round_up(n,16)+16, 16-byte aligned),
+        treated as ONE file: reference chunk cuts are derived from the bytes around each cut."""
+        torch = _ffi.require_cuda()
+        if n == 0:
+            return self._finish(self._init_base_vocab(), [])
+        cs = int(self.config.chunk_size_bytes)
+        cuts: list[int] = []
+        if n > cs:                                                        # trainer.py:172-198 on device bytes
+            start = 0
+            while start < n:
+                tentative = min(start + cs, n)
+                if tentative < n:
+                    bstart = max(0, tentative - 4)
+                    window = text_dev[bstart:tentative + 1].cpu().numpy()
+                    pos = tentative - bstart
+                    while pos > 0 and (int(window[pos]) & 0xC0) == 0x80:
+                        pos -= 1
+                    actual = bstart + pos
+                else:
+                    actual = n
+                if actual > start:
+                    cuts.append(actual)
+                    start = actual
+                else:
+                    start += 1
+        return self._train_on_device(torch, text_dev, n, cuts, [0], [name])
+
+    def _train_on_device(self, torch, text_dev, n: int, cuts: list[int], file_starts: list[int],
+                         names: list[str]) -> BBPEModel:
+        cfg = self.config
+        specials = [s.encode("utf-8") for s in cfg.special_tokens]
+        base_vocab = self._init_base_vocab()
+        cuts = sorted({c for c in cuts if 0 < c < n})
         cuts_np = np.asarray(cuts, dtype=np.int64) if cuts else None
-        res, st = engine.pretok_count_checked(torch, text_dev, n, cuts_np, specials, mode=0)
+        ev: list = [] if self.profile else None                           # type: ignore[assignment]
+        launches0 = _ffi.launch_count()
+        res = engine.pretok_count(torch, text_dev, n, cuts_np, specials, 0, stage_events=ev)
+        st = res.stats_host()
+        if st[_ffi.ST_TABLE_FULL] != 0:
+            del res
+            res, st = engine.pretok_count_checked(torch, text_dev, n, cuts_np, specials, mode=0)
         err = int(st[_ffi.ST_ERR_POS])
         if err != _ffi.INT64_MAX:                                         # trainer.py:157-160
             fi = int(np.searchsorted(np.asarray(file_starts), err, side="right")) - 1
             raise ValueError(f"File {names[fi]} contains invalid UTF-8 at position {err - file_starts[fi]}.")
+        if self.profile:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
         words = engine.compact_words(torch, res, st, with_maps=False)
+        if self.profile:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record()
         stats = TrainStats(n_bytes=n, n_pretokens=int(st[_ffi.ST_NTOK]), n_words=words.n_words, n_syms=words.n_syms,
                            n_specials=int(st[_ffi.ST_NSPECIAL]))
         base_tokens = list(base_vocab.keys())
@@ -148,12 +188,18 @@ class BBPETrainer:
             words.keep[-1].zero_()
             _ffi.check(_ffi.load().yabpe_compact_words(C.byref(res.args), C.byref(words.table), _ffi.stream_ptr(torch)))
 
-        mr = engine.merge_loop(torch, words, base_tokens, num_merges, int(cfg.min_frequency), restore=restore)
+        mr = engine.merge_loop(torch, words, base_tokens, num_merges, int(cfg.min_frequency), restore=restore,
+                               timing=self.timing if self.profile else None)
         stats.n_merges = len(mr.merge_new)
         stats.index_rebuilds = int(mr.state[_ffi.MS_REBUILDS])
         stats.threshold_rebuilds = int(mr.state[_ffi.MS_TREBUILDS])
         stats.n_pairs = int(mr.state[_ffi.MS_NPAIRS])
+        stats.launches = _ffi.launch_count() - launches0
         self.last_stats = stats
+        if self.profile and ev and len(ev) == 4:
+            torch.cuda.synchronize()
+            self.timing.update(specials_ms=ev[0].elapsed_time(ev[1]), pretok_tiles_ms=ev[1].elapsed_time(ev[2]),
+                               long_tokens_ms=ev[2].elapsed_time(ev[3]), compact_ms=e0.elapsed_time(e1))
         vocab = {b: i for i, b in enumerate(mr.tokens)}
         merges = [(mr.tokens[int(a)], mr.tokens[int(b)]) for a, b in mr.merges]
         return self._finish(vocab, merges)
