@@ -284,9 +284,11 @@ def main() -> None:
             "merges_per_s": round(stats.n_merges / (merge_ms / 1e3), 1) if merge_ms else None,
             "us_per_merge": round(1e3 * merge_ms / max(stats.n_merges, 1), 2) if merge_ms else None,
             "pretokenize_GBps": round(n / (tile_ms / 1e3) / 1e9, 2) if tile_ms else None,
-            "stage_ms": {k: round(float(np.mean([t[k] for t in timings])), 3) for k in (timings[0] if timings else {})},
+            "stage_ms": {k: round(float(np.mean([t[k] for t in timings])), 3) for k in (timings[0] if timings else {}) if k.endswith("_ms")},
+            "leader_cycles[argmax,ranges,claim+commit,rewrite,close,sum_act,sum_items,sum_words]": timings[-1].get("leader_cycles") if timings else None,
             "merge_loop": {"index_rebuilds": stats.index_rebuilds, "threshold_rebuilds": stats.threshold_rebuilds,
-                           "pairs_created": stats.n_pairs},
+                           "pairs_created": stats.n_pairs, "leader_mode_merges": stats.leader_merges,
+                           "grid_mode_merges": stats.grid_merges},
             "encode": encode,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks.summary(),

@@ -51,6 +51,8 @@ extern "C" {
 #define YABPE_MS_POOL_USED 8
 #define YABPE_MS_REBUILDS 9
 #define YABPE_MS_TREBUILDS 10
+#define YABPE_MS_LEADER_MERGES 15 /* merges run by the single-CTA fast path */
+#define YABPE_MS_GRID_MERGES 16
 
 const char* yabpe_last_error(void);
 int yabpe_abi_version(void);
@@ -135,8 +137,12 @@ typedef struct {
     uint32_t* icnt;             /* device, pcap                                                   */
     int32_t* ipost;             /* device, n_syms                                                 */
     uint32_t* inact;            /* device, (pcap + 31) / 32                                       */
+    uint32_t* intop;            /* device, (pcap + 31) / 32, zeroed                               */
     int32_t* act;               /* device, pcap                                                   */
-    int32_t* dlog_slot; int32_t* dlog_word; int64_t dlog_cap;
+    int32_t* alog_word; int64_t alog_cap;        /* affected-word log, >= 2 * n_words + 4096      */
+    int32_t* seg_start; int32_t* seg_end;        /* device, num_merges each                       */
+    int32_t* merge_next;        /* device, num_merges                                             */
+    int32_t* tok_first;         /* device, max_tokens                                             */
     void* partial;              /* device, 24 bytes per CTA (>= 1024 entries)                     */
     int64_t* bsum;              /* device, one per CTA (>= 1024 entries)                          */
     int32_t* merges;            /* device, 2 * num_merges: (left id, right id) per merge          */

@@ -8,8 +8,8 @@
 // Tokens are identified by their BYTES: two derivations of the same byte string share one id.
 //
 // One cooperative launch runs the whole loop; per merge: argmax over the active set
-// (pairs with count >= T) -> grid sync -> rewrite of the words listed in the pair's postings
-// (CSR index + delta log) with incremental pair-count deltas -> grid sync.
+// (pairs with count >= T) -> rewrite of the candidate words (CSR postings + affected-word log)
+// with incremental pair-count deltas.  See "merge loop" below for the two execution modes.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -18,7 +18,7 @@
 
 namespace cg = cooperative_groups;
 
-#define ML_THREADS 512
+#define ML_THREADS 1024
 #define PAIR_KEY(a, b) (0x8000000000000000ULL | ((u64)(uint32_t)(a) << 32) | (u64)(uint32_t)(b))
 #define TOK_HASH_B 0x100000001b3ULL
 
@@ -26,16 +26,21 @@ namespace cg = cooperative_groups;
 #define MS_NMERGES 0
 #define MS_NTOK 1
 #define MS_ERROR 2
-#define MS_DLOG_N 3
+#define MS_ALOG_N 3
 #define MS_ACT_N 4
 #define MS_T 5
 #define MS_NPAIRS 6
-#define MS_DLOG_OVF 7
+#define MS_DONE 7
 #define MS_POOL_USED 8
 #define MS_REBUILDS 9
 #define MS_TREBUILDS 10
 #define MS_MAXCNT 11
 #define MS_SCRATCH 12
+#define MS_ACT_BASE 13
+#define MS_LAST_REBUILD_M 14
+#define MS_LEADER_MERGES 15
+#define MS_GRID_MERGES 16
+#define MS_LEADER_GEN 17
 
 #define ME_PAIR_TABLE_FULL 1
 #define ME_TOK_POOL_FULL 2
@@ -96,7 +101,26 @@ __global__ void __launch_bounds__(256) k_compact_long(const LongEntry* ent, i64 
 // ---------------------------------------------------------------------------------
 // merge loop
 // ---------------------------------------------------------------------------------
+// Index of "which words contain pair (p, q)":
+//   * CSR postings built from the current words (rebuild_index), valid for every adjacency that
+//     existed at rebuild time;
+//   * every adjacency created later involves the token produced by the merge that created it,
+//     so the words rewritten by merge m (the "affected log" segment of m) are a superset of the
+//     words that contain any pair created by m.  Candidates for (p, q) = CSR postings of its slot
+//     + the segments of the merges that produced p or q since the last rebuild.
+// Stale and duplicate candidates are filtered by a per-word stamp and by re-scanning the word.
+//
+// Two execution modes, chosen uniformly by all CTAs after a grid barrier:
+//   grid mode   every CTA takes part (argmax -> grid sync -> rewrite -> grid sync)
+//   leader mode CTA 0 alone runs merges back to back with block barriers only, while the
+//               other CTAs wait at one grid barrier; used while the active set and the
+//               affected word lists are small (the common case after the first few hundred merges)
 struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
+
+#define ML_MAX_RANGES 12
+#define ML_LEADER_ACT_MAX 32768
+#define ML_LEADER_ITEMS_MAX 1024
+#define ML_LEADER_BATCH 4096
 
 struct MergeParams {
     // words
@@ -107,8 +131,12 @@ struct MergeParams {
     u64* tset; i64 tset_cap; i64 max_tokens;
     // pairs
     u64* pkey; i64* pcnt; i64 pcap;
-    uint32_t* ioff; uint32_t* icnt; int32_t* ipost; uint32_t* inact; int32_t* act;
-    int32_t* dlog_slot; int32_t* dlog_word; i64 dlog_cap;
+    uint32_t* ioff; uint32_t* icnt; int32_t* ipost; uint32_t* inact; uint32_t* intop; int32_t* act;
+    // affected-word log: alog_word[seg_start[m] .. seg_end[m]) = words rewritten by merge m
+    int32_t* alog_word; i64 alog_cap;
+    int32_t* seg_start; int32_t* seg_end;      // per merge
+    int32_t* merge_next;                        // per merge: previous merge (since rebuild) with the same product token
+    int32_t* tok_first;                         // per token: latest merge since the last rebuild producing it, or -1
     Best* partial; i64* bsum;
     // outputs
     int32_t* merges; int32_t* merge_new; i64* state;
@@ -119,7 +147,7 @@ __device__ __forceinline__ i64 pair_find(const MergeParams& M, u64 key) {
     u64 mask = (u64)M.pcap - 1;
     u64 slot = mix64(key) & mask;
     for (i64 probes = 0; probes < M.pcap; probes++) {
-        u64 k = M.pkey[slot];
+        u64 k = __ldcg(&M.pkey[slot]);
         if (k == key) return (i64)slot;
         if (k == 0) return -1;
         slot = (slot + 1) & mask;
@@ -133,7 +161,11 @@ __device__ __forceinline__ i64 pair_upsert(const MergeParams& M, u64 key) {
         u64 k = *(volatile u64*)&M.pkey[slot];
         if (k == 0) {
             k = atomicCAS(&M.pkey[slot], 0ULL, key);
-            if (k == 0) { atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL); return (i64)slot; }
+            if (k == 0) {
+                u64 np = atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL);
+                if ((i64)np * 4 > M.pcap * 3) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL);
+                return (i64)slot;
+            }
         }
         if (k == key) return (i64)slot;
         slot = (slot + 1) & mask;
@@ -186,18 +218,52 @@ __device__ Best block_best(const MergeParams& M, Best v, Best* sh) {
     return r;
 }
 
+// best over act[lo, hi) strided by this thread's position among `nthreads` cooperating threads
+__device__ __forceinline__ Best scan_active(const MergeParams& M, i64 n, i64 first, i64 stride) {
+    Best v{0, -1, 0, 0, 0};
+    // 4 independent (act -> count, key) chains in flight per thread: the scan is latency bound.
+    // __ldcg: counts are updated by atomics (L2); the leader loop has no fence that would drop a stale L1 line.
+    for (i64 i0 = first; i0 < n; i0 += 4 * stride) {
+        int32_t sl[4]; i64 cc[4]; u64 kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { i64 i = i0 + u * stride; sl[u] = i < n ? M.act[i] : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { cc[u] = sl[u] >= 0 ? __ldcg(&M.pcnt[sl[u]]) : 0; kk[u] = sl[u] >= 0 ? __ldcg(&M.pkey[sl[u]]) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (cc[u] <= 0 || cc[u] < v.cnt) continue;
+            Best t{cc[u], sl[u], (int32_t)((kk[u] >> 32) & 0x7fffffff), (int32_t)(kk[u] & 0xffffffffu), 0};
+            if (best_gt(M, t, v)) v = t;
+        }
+    }
+    return v;
+}
+
+// block-wide best: max count first (cheap), the byte-wise tie-break only among equal counts
+__device__ Best block_best_fast(const MergeParams& M, Best v, Best* sh, i64* sh_cnt) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    i64 c = v.slot >= 0 ? v.cnt : 0;
+    for (int o = 16; o > 0; o >>= 1) { i64 t = __shfl_xor_sync(0xffffffffu, c, o); if (t > c) c = t; }
+    if (lane == 0) sh_cnt[wid] = c;
+    __syncthreads();
+    i64 mx = lane < (int)(blockDim.x >> 5) ? sh_cnt[lane] : 0;
+    for (int o = 16; o > 0; o >>= 1) { i64 t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
+    const bool cand = v.slot >= 0 && mx > 0 && v.cnt == mx;
+    const int ncand = __syncthreads_count(cand);
+    if (ncand == 0) return Best{0, -1, 0, 0, 0};
+    if (ncand == 1) {
+        if (cand) sh[0] = v;
+        __syncthreads();
+        Best r = sh[0];
+        __syncthreads();
+        return r;
+    }
+    return block_best(M, cand ? v : Best{0, -1, 0, 0, 0}, sh);
+}
+
 // grid-wide argmax over the active set; every block returns the same result
 __device__ Best grid_argmax(const MergeParams& M, cg::grid_group& grid, Best* sh) {
-    i64 n = M.state[MS_ACT_N];
-    Best v{0, -1, 0, 0, 0};
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-        int32_t slot = M.act[i];
-        i64 c = M.pcnt[slot];
-        if (c <= 0 || c < v.cnt) continue;
-        u64 k = M.pkey[slot];
-        Best t{c, slot, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
-        if (best_gt(M, t, v)) v = t;
-    }
+    Best v = scan_active(M, M.state[MS_ACT_N], (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
     v = block_best(M, v, sh);
     if (threadIdx.x == 0) M.partial[blockIdx.x] = v;
     grid.sync();
@@ -219,12 +285,15 @@ __device__ void rebuild_active(const MergeParams& M, cg::grid_group& grid, i64 T
         }
     }
     grid.sync();
+    if (gtid == 0) M.state[MS_ACT_BASE] = M.state[MS_ACT_N];
 }
 
 // CSR postings: for every pair slot the words that contain it (duplicates allowed)
-__device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* sh_scan) {
+__device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* sh_scan, i64 m_now) {
     i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     for (i64 i = gtid; i < M.pcap; i += gstride) M.icnt[i] = 0;
+    // forget the affected-log segments: the CSR built below covers everything
+    for (i64 mm = M.state[MS_LAST_REBUILD_M] + gtid; mm < m_now; mm += gstride) M.tok_first[M.merge_new[mm]] = -1;
     grid.sync();
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
         int32_t w = M.sym_word[i];
@@ -239,6 +308,7 @@ __device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* s
     // exclusive scan of icnt -> ioff, one contiguous chunk per block
     i64 chunk = (M.pcap + gridDim.x - 1) / gridDim.x;
     i64 lo = chunk * blockIdx.x, hi = lo + chunk < M.pcap ? lo + chunk : M.pcap;
+    if (lo > hi) lo = hi;
     {
         i64 s = 0;
         for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) s += M.icnt[i];
@@ -257,7 +327,6 @@ __device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* s
         for (i64 t0 = lo; t0 < hi; t0 += blockDim.x) {
             i64 i = t0 + threadIdx.x;
             i64 v = i < hi ? M.icnt[i] : 0;
-            // block inclusive scan
             i64 inc = v;
             int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
             for (int o = 1; o < 32; o <<= 1) { i64 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -270,7 +339,6 @@ __device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* s
             __syncthreads();
         }
         if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) M.ioff[M.pcap] = (uint32_t)base;
-        if (hi == M.pcap && lo < hi && blockIdx.x != gridDim.x - 1 && threadIdx.x == 0) M.ioff[M.pcap] = (uint32_t)base;
     }
     grid.sync();
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
@@ -281,7 +349,7 @@ __device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* s
             if (s >= 0) { uint32_t r = atomicSub(&M.icnt[s], 1u) - 1; M.ipost[M.ioff[s] + r] = w; }
         }
     }
-    if (gtid == 0) { M.state[MS_DLOG_N] = 0; M.state[MS_DLOG_OVF] = 0; M.state[MS_REBUILDS]++; }
+    if (gtid == 0) { M.state[MS_ALOG_N] = 0; M.state[MS_LAST_REBUILD_M] = m_now; M.state[MS_REBUILDS]++; }
     grid.sync();
 }
 
@@ -290,8 +358,15 @@ __device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t x, int32_
     if (s >= 0) atomicAdd((u64*)&M.pcnt[s], (u64)(-f));
     else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);
 }
-__device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, int32_t w, i64 T) {
-    i64 s = pair_upsert(M, PAIR_KEY(x, y));
+// Leader-mode "top list" (shared memory): every pair with count >= T2.  Scanning the whole active
+// set every merge is bound by one SM's gather rate (one 128-byte line per cycle); the top list keeps
+// the per-merge scan to a few hundred entries and is rebuilt only when its best falls below T2.
+#define ML_TOP_N 512
+struct LeaderTop { u64 key[ML_TOP_N]; int32_t slot[ML_TOP_N]; int n; int ovf; i64 T2; };
+
+__device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, LeaderTop* lt) {
+    const u64 key = PAIR_KEY(x, y);
+    i64 s = pair_upsert(M, key);
     if (s < 0) return;
     i64 now = (i64)atomicAdd((u64*)&M.pcnt[s], (u64)f) + f;
     if (now >= T) {
@@ -300,32 +375,386 @@ __device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_
             i64 idx = (i64)atomicAdd((u64*)&M.state[MS_ACT_N], 1ULL);
             M.act[idx] = (int32_t)s;
         }
+        if (lt && now >= lt->T2) {
+            if (!(atomicOr(&M.intop[s >> 5], bit) & bit)) {
+                int idx = atomicAdd(&lt->n, 1);
+                if (idx < ML_TOP_N) { lt->slot[idx] = (int32_t)s; lt->key[idx] = key; }
+                else { atomicAnd(&M.intop[s >> 5], ~bit); lt->ovf = 1; }
+            }
+        }
     }
-    i64 d = (i64)atomicAdd((u64*)&M.state[MS_DLOG_N], 1ULL);
-    if (d < M.dlog_cap) { M.dlog_slot[d] = (int32_t)s; M.dlog_word[d] = w; }
-    else M.state[MS_DLOG_OVF] = 1;
+}
+__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w) {
+    i64 d = (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL);
+    if (d < M.alog_cap) M.alog_word[d] = w;
+    else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);     // callers reserve space up front
 }
 
-// rewrite one word in place (left->right, non-overlapping) and apply the pair-count deltas
-__device__ void rewrite_word(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T) {
+// one thread rewrites one word in place (left->right, non-overlapping) and applies the deltas
+__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, LeaderTop* lt) {
     int32_t* s = M.wsym + M.woff[w];
     int n = M.wlen[w];
     i64 f = M.wcnt[w];
     int o = 0, j = 0;
     int32_t prev_old = -1, prev_new = -1;
-    bool prev_changed = false;
+    bool prev_changed = false, any = false;
     while (j < n) {
         int32_t x = s[j];
         if (j + 1 < n && x == a && s[j + 1] == b) {
-            if (o > 0) { pair_sub(M, prev_old, a, f); pair_add(M, prev_new, c, f, w, T); }
+            if (o > 0) { pair_sub(M, prev_old, a, f); pair_add(M, prev_new, c, f, T, lt); }
             pair_sub(M, a, b, f);
-            s[o++] = c; prev_old = b; prev_new = c; prev_changed = true; j += 2;
+            s[o++] = c; prev_old = b; prev_new = c; prev_changed = true; any = true; j += 2;
         } else {
-            if (o > 0 && prev_changed) { pair_sub(M, prev_old, x, f); pair_add(M, prev_new, x, f, w, T); }
+            if (o > 0 && prev_changed) { pair_sub(M, prev_old, x, f); pair_add(M, prev_new, x, f, T, lt); }
             s[o++] = x; prev_old = x; prev_new = x; prev_changed = false; j += 1;
         }
     }
-    M.wlen[w] = o;
+    if (any) { M.wlen[w] = o; alog_append(M, w); }
+}
+
+// one warp rewrites one word (a != b): every lane owns one old position per 32-symbol chunk, so the
+// pair-count updates of a word are issued in parallel instead of as one dependent chain
+__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T) {
+    const int lane = threadIdx.x & 31;
+    int32_t* s = M.wsym + M.woff[w];
+    const int n = M.wlen[w];
+    const i64 f = M.wcnt[w];
+    int out = 0;
+    bool any = false;
+    int32_t carry_prev = -1;                       // old symbol at position base-1 (may already be overwritten)
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        int32_t xm1 = -1, x0 = -1, x1 = -1, x2 = -1, x3 = -1;
+        if (j < n) x0 = s[j];
+        if (j + 1 < n) x1 = s[j + 1];
+        if (j + 2 < n) x2 = s[j + 2];
+        if (j + 3 < n) x3 = s[j + 3];
+        xm1 = __shfl_up_sync(0xffffffffu, x0, 1);
+        if (lane == 0) xm1 = carry_prev;
+        carry_prev = __shfl_sync(0xffffffffu, x0, 31);
+        __syncwarp();
+        const bool valid = j < n;
+        const bool sel0 = valid && x0 == a && x1 == b;          // merge site starts here
+        const bool rem0 = valid && xm1 == a && x0 == b;         // second half of a site: removed
+        const bool sel1 = x1 == a && x2 == b;
+        const bool keep = valid && !rem0;
+        const unsigned keepmask = __ballot_sync(0xffffffffu, keep);
+        any |= __any_sync(0xffffffffu, sel0);
+        // old pair (j, j+1) disappears when either side is part of a site
+        if (valid && j + 1 < n && (sel0 || rem0 || sel1 || /*rem1*/ sel0)) pair_sub(M, x0, x1, f);
+        // new pair starting at kept position j
+        if (keep) {
+            const int jn = sel0 ? j + 2 : j + 1;              // next kept old position
+            if (jn < n) {
+                const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
+                const bool seln = xn == a && xnn == b;
+                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, nullptr);
+            }
+        }
+        __syncwarp();
+        if (keep) s[out + __popc(keepmask & ((1u << lane) - 1))] = sel0 ? c : x0;
+        out += __popc(keepmask);
+        __syncwarp();
+    }
+    if (any && lane == 0) { M.wlen[w] = out; alog_append(M, w); }
+}
+
+// four words per warp, one per 8-lane group (words are short: ~6 symbols on average).  Group-local
+// version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes must call it together.
+__device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
+                                 int32_t a, int32_t b, int32_t c, i64 T, LeaderTop* lt) {
+    const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & 24;
+    int32_t* s = M.wsym + (w >= 0 ? off : 0);
+    if (w < 0) n = 0;
+    int out = 0;
+    bool any = false;
+    int32_t carry_prev = -1;
+    for (int base = 0; __any_sync(0xffffffffu, base < n); base += 8) {
+        const int j = base + gl;
+        int32_t x0 = -1, x1 = -1, x2 = -1, x3 = -1;
+        if (j < n) x0 = s[j];
+        if (j + 1 < n) x1 = s[j + 1];
+        if (j + 2 < n) x2 = s[j + 2];
+        if (j + 3 < n) x3 = s[j + 3];
+        int32_t xm1 = __shfl_up_sync(0xffffffffu, x0, 1, 8);
+        if (gl == 0) xm1 = carry_prev;
+        carry_prev = __shfl_sync(0xffffffffu, x0, 7, 8);
+        __syncwarp();
+        const bool valid = j < n;
+        const bool sel0 = valid && x0 == a && x1 == b;
+        const bool rem0 = valid && xm1 == a && x0 == b;
+        const bool sel1 = x1 == a && x2 == b;
+        const bool keep = valid && !rem0;
+        const unsigned keepmask = (__ballot_sync(0xffffffffu, keep) >> gshift) & 0xffu;
+        any |= ((__ballot_sync(0xffffffffu, sel0) >> gshift) & 0xffu) != 0;
+        if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, x0, x1, f);
+        if (keep) {
+            const int jn = sel0 ? j + 2 : j + 1;
+            if (jn < n) {
+                const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
+                const bool seln = xn == a && xnn == b;
+                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, lt);
+            }
+        }
+        __syncwarp();
+        if (keep) s[out + __popc(keepmask & ((1u << gl) - 1))] = sel0 ? c : x0;
+        out += __popc(keepmask);
+        __syncwarp();
+    }
+    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w); }
+}
+
+// candidate ranges for pair (a, b) at slot: CSR postings + affected-log segments of the merges that
+// produced a or b since the last index rebuild.  Returns the number of ranges, or -1 if too many.
+struct Ranges { const int32_t* base[ML_MAX_RANGES]; int len[ML_MAX_RANGES]; int n; i64 total; };
+
+__device__ void build_ranges(const MergeParams& M, int32_t slot, int32_t a, int32_t b, Ranges* R) {
+    int n = 0; i64 total = 0;
+    uint32_t p0 = M.ioff[slot], p1 = M.ioff[slot + 1];
+    if (p1 > p0) { R->base[n] = M.ipost + p0; R->len[n] = (int)(p1 - p0); total += p1 - p0; n++; }
+    for (int side = 0; side < 2; side++) {
+        int32_t t = side == 0 ? a : b;
+        if (side == 1 && b == a) break;
+        for (int32_t mm = M.tok_first[t]; mm >= 0; mm = M.merge_next[mm]) {
+            int ln = M.seg_end[mm] - M.seg_start[mm];
+            if (ln <= 0) continue;
+            if (n >= ML_MAX_RANGES) { R->n = -1; R->total = total; return; }
+            R->base[n] = M.alog_word + M.seg_start[mm]; R->len[n] = ln; total += ln; n++;
+        }
+    }
+    R->n = n; R->total = total;
+}
+__device__ __forceinline__ int32_t range_item(const Ranges& R, i64 it) {
+    for (int r = 0; r < R.n; r++) { if (it < R.len[r]) return R.base[r][it]; it -= R.len[r]; }
+    return -1;
+}
+
+// merged token id for (a, b): existing id when the bytes are already a token, else n_tok
+__device__ int32_t lookup_merged(const MergeParams& M, int32_t a, int32_t b, int32_t n_tok) {
+    u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
+    i64 oa = M.tok_off[a], ob = M.tok_off[b];
+    i64 la = M.tok_off[a + 1] - oa, lb = M.tok_off[b + 1] - ob;
+    u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
+    for (;;) {
+        u64 e = *(volatile u64*)&M.tset[slot];
+        if (e == 0) return n_tok;
+        int32_t id = (int32_t)(e & 0xffffffffu) - 1;
+        if ((e >> 32) == (H >> 32) && id < n_tok && M.tok_hash[id] == H && M.tok_off[id + 1] - M.tok_off[id] == la + lb) {
+            const uint8_t* pc = M.tok_bytes + M.tok_off[id];
+            const uint8_t* pa = M.tok_bytes + oa;
+            const uint8_t* pb = M.tok_bytes + ob;
+            bool eq = true;
+            for (i64 k = 0; k < la && eq; k++) eq = pc[k] == pa[k];
+            for (i64 k = 0; k < lb && eq; k++) eq = pc[la + k] == pb[k];
+            if (eq) return id;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+
+// record merge m and (when the bytes are new) create token c; executed by ONE block
+__device__ void commit_merge(const MergeParams& M, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 alog_start) {
+    if (threadIdx.x == 0) {
+        M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c;
+        M.seg_start[m] = (int32_t)alog_start;
+        M.merge_next[m] = M.tok_first[c];
+    }
+    if (is_new) {
+        i64 oa = M.tok_off[a], ob = M.tok_off[b], oc = M.tok_off[c];
+        i64 la = M.tok_off[a + 1] - oa, lb = M.tok_off[b + 1] - ob;
+        if (oc + la + lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
+            if (threadIdx.x == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL);
+        } else {
+            for (i64 k = threadIdx.x; k < la; k += blockDim.x) M.tok_bytes[oc + k] = M.tok_bytes[oa + k];
+            for (i64 k = threadIdx.x; k < lb; k += blockDim.x) M.tok_bytes[oc + la + k] = M.tok_bytes[ob + k];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
+                M.tok_off[c + 1] = oc + la + lb;
+                M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
+                M.tok_first[c] = -1;
+                __threadfence();
+                u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
+                while (M.tset[slot] != 0) slot = (slot + 1) & mask;
+                atomicExch(&M.tset[slot], (H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1));
+                M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + la + lb;
+            }
+        }
+    }
+}
+// the same, executed by ONE WARP (leader mode: overlaps with the rewrite done by the other warps)
+__device__ void commit_merge_warp(const MergeParams& M, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 alog_start) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c;
+        M.seg_start[m] = (int32_t)alog_start;
+        M.merge_next[m] = is_new ? -1 : M.tok_first[c];
+    }
+    if (is_new) {
+        i64 oa = M.tok_off[a], ob = M.tok_off[b], oc = M.tok_off[c];
+        i64 la = M.tok_off[a + 1] - oa, lb = M.tok_off[b + 1] - ob;
+        if (oc + la + lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
+            if (lane == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL);
+        } else {
+            for (i64 k = lane; k < la; k += 32) M.tok_bytes[oc + k] = M.tok_bytes[oa + k];
+            for (i64 k = lane; k < lb; k += 32) M.tok_bytes[oc + la + k] = M.tok_bytes[ob + k];
+            __syncwarp();
+            if (lane == 0) {
+                u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
+                M.tok_off[c + 1] = oc + la + lb;
+                M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
+                M.tok_first[c] = -1;
+                __threadfence();
+                u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
+                while (M.tset[slot] != 0) slot = (slot + 1) & mask;
+                atomicExch(&M.tset[slot], (H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1));
+                M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + la + lb;
+            }
+        }
+    }
+}
+// after the rewrite of merge m finished: close its segment and link it to its product token
+__device__ __forceinline__ void close_merge(const MergeParams& M, i64 m, int32_t c) {
+    M.seg_end[m] = (int32_t)__ldcg(&M.state[MS_ALOG_N]);
+    M.tok_first[c] = (int32_t)m;
+    M.state[MS_NMERGES] = m + 1;
+}
+
+// ---- leader mode: CTA 0 runs merges alone, block barriers only ---------------------------------
+struct ClaimedWord { i64 off; i64 f; int32_t w; int32_t n; };
+
+// leader: drop the top list (its dedupe bits must not outlive it)
+__device__ void top_clear(const MergeParams& M, LeaderTop* LT) {
+    __syncthreads();
+    const int n = LT->n < ML_TOP_N ? LT->n : ML_TOP_N;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { int32_t sl = LT->slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
+    __syncthreads();
+    if (threadIdx.x == 0) { LT->n = 0; LT->ovf = 0; }
+    __syncthreads();
+}
+
+// leader: rebuild the top list from the active set.  Returns false when grid mode has to take over
+// (no pair with count >= T, or more than ML_TOP_N pairs tie for the maximum).
+__device__ bool top_rebuild(const MergeParams& M, LeaderTop* LT, i64 act_n, i64 T, Best* sh_best, i64* sh_cnt) {
+    top_clear(M, LT);
+    Best am = block_best_fast(M, scan_active(M, act_n, threadIdx.x, blockDim.x), sh_best, sh_cnt);
+    if (am.slot < 0 || am.cnt < T) return false;
+    i64 T2 = am.cnt - am.cnt / 4; if (T2 < T) T2 = T;
+    for (int round = 0; round < 40; round++) {
+        if (threadIdx.x == 0) LT->T2 = T2;
+        __syncthreads();
+        for (i64 i = threadIdx.x; i < act_n; i += blockDim.x) {
+            int32_t sl = M.act[i];
+            if (__ldcg(&M.pcnt[sl]) >= T2) {
+                int idx = atomicAdd(&LT->n, 1);
+                if (idx < ML_TOP_N) { LT->slot[idx] = sl; LT->key[idx] = __ldcg(&M.pkey[sl]); atomicOr(&M.intop[sl >> 5], 1u << (sl & 31)); }
+                else LT->ovf = 1;
+            }
+        }
+        __syncthreads();
+        if (!LT->ovf) return true;
+        if (T2 >= am.cnt) break;                       // > ML_TOP_N pairs tie for the maximum
+        top_clear(M, LT);
+        T2 = T2 + (am.cnt - T2 + 1) / 2;
+    }
+    top_clear(M, LT);
+    return false;
+}
+
+__device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin) {
+    __shared__ Ranges R;
+    __shared__ int32_t sh_c;
+    __shared__ ClaimedWord sh_list[ML_LEADER_ITEMS_MAX];
+    __shared__ int sh_nlist;
+    __shared__ i64 sh_cnt[ML_THREADS / 32];
+    __shared__ i64 sh_state[3];                      // act_n, alog_n, error: refreshed once per merge by thread 0
+    __shared__ LeaderTop LT;
+    i64 m = M.state[MS_NMERGES];
+    int32_t n_tok = (int32_t)M.state[MS_NTOK];
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    long long t_arg = 0, t_rng = 0, t_claim = 0, t_rw = 0, t_close = 0, s_act = 0, s_items = 0, s_words = 0, n_done = 0, n_top = 0;
+    if (threadIdx.x == 0) {
+        sh_state[0] = __ldcg(&M.state[MS_ACT_N]); sh_state[1] = __ldcg(&M.state[MS_ALOG_N]); sh_state[2] = __ldcg(&M.state[MS_ERROR]);
+        LT.n = 0; LT.ovf = 0; LT.T2 = INT64_MAX;
+    }
+    __syncthreads();
+    for (int iter = 0; iter < ML_LEADER_BATCH && m < M.num_merges; iter++) {
+        long long c0 = clock64();
+        const i64 act_n = sh_state[0], alog_n = sh_state[1];
+        if (sh_state[2] || act_n > ML_LEADER_ACT_MAX) break;
+        // ---- best pair: scan the top list; rebuild it when it cannot prove the maximum
+        Best best{0, -1, 0, 0, 0};
+        bool ok = true;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            Best mine{0, -1, 0, 0, 0};
+            const int tn = LT.n < ML_TOP_N ? LT.n : ML_TOP_N;
+            if (!LT.ovf && (int)threadIdx.x < tn) {
+                const int32_t sl = LT.slot[threadIdx.x];
+                const i64 cnt = __ldcg(&M.pcnt[sl]);
+                const u64 k = LT.key[threadIdx.x];
+                if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
+            }
+            best = block_best_fast(M, mine, sh_best, sh_cnt);
+            if (!LT.ovf && best.slot >= 0 && best.cnt >= LT.T2) break;
+            if (attempt == 1) { ok = false; break; }
+            n_top++;
+            if (!top_rebuild(M, &LT, act_n, T, sh_best, sh_cnt)) { ok = false; break; }
+        }
+        if (!ok || best.cnt < T || best.cnt < Tmin) break;                // threshold step / termination: grid mode
+        long long c1 = clock64();
+        if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); sh_nlist = 0; }
+        if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok);
+        __syncthreads();
+        if (R.n < 0 || R.total > ML_LEADER_ITEMS_MAX || alog_n + R.total > M.alog_cap) break;
+        long long c2 = clock64();
+        const int32_t a = best.a, b = best.b, c = sh_c;
+        const bool is_new = c == n_tok;
+        const int32_t stamp = (int32_t)(m + 1);
+        // the last warp records the merge / creates the token while the others claim the candidate words
+        if (warp == nwarps - 1) commit_merge_warp(M, m, a, b, c, is_new, alog_n);
+        else {
+            for (i64 it = threadIdx.x; it < R.total; it += blockDim.x - 32) {
+                int32_t w = range_item(R, it);
+                if (atomicExch(&M.wstamp[w], stamp) != stamp) {
+                    ClaimedWord cw; cw.w = w; cw.off = M.woff[w]; cw.n = M.wlen[w]; cw.f = M.wcnt[w];
+                    sh_list[atomicAdd(&sh_nlist, 1)] = cw;
+                }
+            }
+        }
+        if (is_new) n_tok++;
+        __syncthreads();
+        long long c3 = clock64();
+        const int nlist = sh_nlist;
+        if (a != b) {
+            for (int kb = warp * 4; kb < nlist; kb += nwarps * 4) {
+                const int k = kb + (lane >> 3);
+                ClaimedWord cw; cw.w = -1; cw.off = 0; cw.n = 0; cw.f = 0;
+                if (k < nlist) cw = sh_list[k];
+                rewrite_words_g8(M, cw.w, cw.off, cw.n, cw.f, a, b, c, T, &LT);
+            }
+        } else {
+            for (int k = threadIdx.x; k < nlist; k += blockDim.x) rewrite_word_thread(M, sh_list[k].w, a, b, c, T, &LT);
+        }
+        __syncthreads();
+        long long c4 = clock64();
+        if (threadIdx.x == 0) {
+            // one L2 round trip: the counters the rewrite just bumped with atomics
+            const i64 an = __ldcg(&M.state[MS_ACT_N]), ln = __ldcg(&M.state[MS_ALOG_N]), er = __ldcg(&M.state[MS_ERROR]);
+            M.seg_end[m] = (int32_t)ln; M.tok_first[c] = (int32_t)m; M.state[MS_NMERGES] = m + 1;
+            sh_state[0] = an; sh_state[1] = ln; sh_state[2] = er;
+        }
+        __syncthreads();
+        long long c5 = clock64();
+        t_arg += c1 - c0; t_rng += c2 - c1; t_claim += c3 - c2; t_rw += c4 - c3; t_close += c5 - c4;
+        s_act += act_n; s_items += R.total; s_words += nlist; n_done++;
+        m++;
+    }
+    top_clear(M, &LT);
+    if (threadIdx.x == 0) {
+        M.state[20] += t_arg; M.state[21] += t_rng; M.state[22] += t_claim; M.state[23] += t_rw; M.state[24] += t_close;
+        M.state[25] += s_act; M.state[26] += s_items; M.state[27] += s_words; M.state[28] += n_top;
+        M.state[MS_LEADER_MERGES] += n_done;
+    }
 }
 
 __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
@@ -333,6 +762,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     __shared__ Best sh_best[ML_THREADS / 32];
     __shared__ i64 sh_scan[1 + ML_THREADS / 32];
     __shared__ int32_t sh_c;
+    __shared__ Ranges R;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
 
     // ---- K4: pair histogram (trainer.py:228-235)
@@ -344,110 +774,102 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             if (s >= 0) atomicAdd((u64*)&M.pcnt[s], (u64)M.wcnt[w]);
         }
     }
+    for (i64 t = gtid; t < M.max_tokens; t += gstride) M.tok_first[t] = -1;
     grid.sync();
-    // global max count -> first threshold
     {
         i64 mx = 0;
         for (i64 s = gtid; s < M.pcap; s += gstride) { i64 c = M.pcnt[s]; if (c > mx) mx = c; }
         for (int o = 16; o > 0; o >>= 1) { i64 t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
         if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax((i64*)&M.state[MS_MAXCNT], mx);
     }
-    rebuild_index(M, grid, sh_scan);      // starts and ends with grid-wide syncs
-    i64 Tmin = M.min_freq > 1 ? M.min_freq : 1;
-    i64 T = M.state[MS_MAXCNT] / 4; if (T < Tmin) T = Tmin;
+    rebuild_index(M, grid, sh_scan, 0);      // starts and ends with grid-wide syncs
+    const i64 Tmin = M.min_freq > 1 ? M.min_freq : 1;
+    i64 T = M.state[MS_MAXCNT] / 2; if (T < Tmin) T = Tmin;
     rebuild_active(M, grid, T);
 
-    int32_t n_tok = (int32_t)M.state[MS_NTOK];   // every block tracks the token count identically
-    i64 m = 0;
-    for (; m < M.num_merges; m++) {
-        if (M.state[MS_ERROR]) break;             // uniform: read right after a grid sync
-        // ---- phase 1: best pair
+    int skip = 0, backoff = 1;
+    for (;;) {
+        // ---- every CTA reads the shared state right after a grid barrier
+        i64 m = M.state[MS_NMERGES];
+        int32_t n_tok = (int32_t)M.state[MS_NTOK];
+        i64 alog_n = M.state[MS_ALOG_N];
+        const i64 act_n = M.state[MS_ACT_N];
+        const i64 gen = M.state[MS_LEADER_GEN];
+        if (m >= M.num_merges || M.state[MS_ERROR] || M.state[MS_DONE]) break;
+
+        // ---- leader mode while the work per merge is small
+        if (skip > 0) skip--;
+        else if (act_n <= ML_LEADER_ACT_MAX && alog_n + ML_LEADER_ITEMS_MAX <= M.alog_cap) {
+            const i64 m0 = m;
+            grid.sync();                                    // everyone has read the state the leader is about to change
+            if (blockIdx.x == 0) {
+                leader_loop(M, sh_best, T, Tmin);
+                __syncthreads();
+                if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
+            } else {
+                if (threadIdx.x == 0) while (*(volatile i64*)&M.state[MS_LEADER_GEN] == gen) __nanosleep(2000);
+                __syncthreads();
+            }
+            grid.sync();
+            m = M.state[MS_NMERGES];
+            n_tok = (int32_t)M.state[MS_NTOK];
+            alog_n = M.state[MS_ALOG_N];
+            if (m == m0) { backoff = backoff < 64 ? backoff * 2 : 64; skip = backoff; } else backoff = 1;
+            if (m >= M.num_merges || M.state[MS_ERROR]) break;
+            grid.sync();                                    // everyone has re-read the state
+        }
+
+        // ---- one merge in grid mode (also handles threshold steps, compaction, termination)
+        if (M.state[MS_ACT_N] > ML_LEADER_ACT_MAX && M.state[MS_ACT_N] > 2 * M.state[MS_ACT_BASE]) {
+            grid.sync();
+            rebuild_active(M, grid, T);                     // drop entries that fell below T
+        }
         Best best = grid_argmax(M, grid, sh_best);
         bool stop = false;
         while (best.slot < 0 || best.cnt < T) {
-            if (T <= Tmin) { stop = true; break; }   // nothing left with count >= max(1, min_frequency)
-            T = T / 4; if (T < Tmin) T = Tmin;
-            grid.sync();                            // everyone has read partial[] / act before it is rebuilt
+            if (T <= Tmin) { stop = true; break; }          // nothing left with count >= max(1, min_frequency)
+            T = T / 2; if (T < Tmin) T = Tmin;
+            grid.sync();                                    // everyone has read partial[] / act before it is rebuilt
             rebuild_active(M, grid, T);
             best = grid_argmax(M, grid, sh_best);
         }
-        if (stop) break;
+        if (stop) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
         const int32_t a = best.a, b = best.b;
-
-        // ---- phase 2: merged token id (existing id when the bytes are already a token)
-        if (threadIdx.x == 0) {
-            u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
-            i64 la = M.tok_off[a + 1] - M.tok_off[a], lb = M.tok_off[b + 1] - M.tok_off[b];
-            int32_t c = n_tok;
-            u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
-            for (;;) {
-                u64 e = *(volatile u64*)&M.tset[slot];
-                if (e == 0) break;
-                int32_t id = (int32_t)(e & 0xffffffffu) - 1;
-                if ((e >> 32) == (H >> 32) && id < n_tok && M.tok_hash[id] == H && M.tok_off[id + 1] - M.tok_off[id] == la + lb) {
-                    const uint8_t* pc = M.tok_bytes + M.tok_off[id];
-                    const uint8_t* pa = M.tok_bytes + M.tok_off[a];
-                    const uint8_t* pb = M.tok_bytes + M.tok_off[b];
-                    bool eq = true;
-                    for (i64 k = 0; k < la && eq; k++) eq = pc[k] == pa[k];
-                    for (i64 k = 0; k < lb && eq; k++) eq = pc[la + k] == pb[k];
-                    if (eq) { c = id; break; }
-                }
-                slot = (slot + 1) & mask;
-            }
-            sh_c = c;
-        }
+        if (threadIdx.x == 0) { build_ranges(M, best.slot, a, b, &R); sh_c = lookup_merged(M, a, b, n_tok); }
         __syncthreads();
+        if (R.n < 0 || alog_n + R.total > M.alog_cap) {
+            // fold the affected log into the CSR index first, then look the candidates up again
+            grid.sync();
+            rebuild_index(M, grid, sh_scan, m);
+            alog_n = 0;
+            if (threadIdx.x == 0) build_ranges(M, best.slot, a, b, &R);
+            __syncthreads();
+        }
         const int32_t c = sh_c;
         const bool is_new = c == n_tok;
-        if (blockIdx.x == 0) {
-            if (threadIdx.x == 0) { M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c; }
-            if (is_new) {
-                i64 oa = M.tok_off[a], ob = M.tok_off[b], oc = M.tok_off[c];
-                i64 la = M.tok_off[a + 1] - oa, lb = M.tok_off[b + 1] - ob;
-                if (oc + la + lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
-                    if (threadIdx.x == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL);
-                } else {
-                    for (i64 k = threadIdx.x; k < la; k += blockDim.x) M.tok_bytes[oc + k] = M.tok_bytes[oa + k];
-                    for (i64 k = threadIdx.x; k < lb; k += blockDim.x) M.tok_bytes[oc + la + k] = M.tok_bytes[ob + k];
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
-                        M.tok_off[c + 1] = oc + la + lb;
-                        M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
-                        __threadfence();
-                        u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
-                        while (M.tset[slot] != 0) slot = (slot + 1) & mask;
-                        atomicExch(&M.tset[slot], (H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1));
-                        M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + la + lb;
-                    }
-                }
+        if (blockIdx.x == 0) commit_merge(M, m, a, b, c, is_new, alog_n);
+        const int32_t stamp = (int32_t)(m + 1);
+        if (a != b && R.total * 32 <= gstride * 4) {
+            const i64 gw = gtid >> 5, nw = gstride >> 5;
+            for (i64 it = gw; it < R.total; it += nw) {
+                int32_t w = range_item(R, it);
+                int32_t old = 0;
+                if ((threadIdx.x & 31) == 0) old = atomicExch(&M.wstamp[w], stamp);
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == stamp) continue;
+                rewrite_word_warp(M, w, a, b, c, T);
             }
-            if (threadIdx.x == 0) M.state[MS_NMERGES] = m + 1;
-        }
-        if (is_new) n_tok++;
-
-        // ---- phase 3: rewrite the words that contain (a, b)
-        {
-            const i64 p0 = M.ioff[best.slot], npost = (i64)M.ioff[best.slot + 1] - p0;
-            i64 nlog = M.state[MS_DLOG_N]; if (nlog > M.dlog_cap) nlog = M.dlog_cap;
-            grid.sync();     // snapshot of dlog_n taken by every block before anyone appends
-            const int32_t stamp = (int32_t)(m + 1);
-            for (i64 it = gtid; it < npost + nlog; it += gstride) {
-                int32_t w;
-                if (it < npost) w = M.ipost[p0 + it];
-                else { i64 d = it - npost; w = M.dlog_slot[d] == best.slot ? M.dlog_word[d] : -1; }
-                if (w < 0) continue;
+        } else {
+            for (i64 it = gtid; it < R.total; it += gstride) {
+                int32_t w = range_item(R, it);
                 if (atomicExch(&M.wstamp[w], stamp) == stamp) continue;
-                rewrite_word(M, w, a, b, c, T);
+                rewrite_word_thread(M, w, a, b, c, T, nullptr);
             }
         }
         grid.sync();
-        // ---- maintenance: fold the delta log into the CSR index when it fills up
-        if (M.state[MS_DLOG_OVF] || M.state[MS_DLOG_N] > M.dlog_cap / 2) {
-            grid.sync();
-            rebuild_index(M, grid, sh_scan);
-        }
+        // every CTA writes the same values: no further barrier needed before the next iteration
+        if (threadIdx.x == 0) close_merge(M, m, c);
+        if (gtid == 0) M.state[MS_GRID_MERGES]++;
+        __syncthreads();
     }
-    (void)m;
 }

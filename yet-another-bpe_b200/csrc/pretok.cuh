@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(256) k_resolve_specials(PretokParams P, i64 lo
 __device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) { return mix64(k0 * 0x9e3779b97f4a7c15ULL ^ mix64(k1)); }
 
 // returns slot (>=0) and adds `add` to its count; *created = 1 when this call created the entry
-__device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 cap, u64 k0, u64 k1, i64 add, int* created) {
+__device__ __forceinline__ i64 short_insert_h(ulonglong2* keys, i64* counts, i64 cap, u64 h, u64 k0, u64 k1, i64 add, int* created) {
     u64 mask = (u64)cap - 1;
-    u64 slot = short_hash(k0, k1) & mask;
+    u64 slot = h & mask;
     *created = 0;
     for (int probe = 0; probe < 8192; probe++) {
         u64* kp = (u64*)&keys[slot];
@@ -173,6 +173,32 @@ __device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 c
         slot = (slot + 1) & mask;
     }
     return -1;
+}
+
+__device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 cap, u64 k0, u64 k1, i64 add, int* created) {
+    return short_insert_h(keys, counts, cap, short_hash(k0, k1), k0, k1, add, created);
+}
+
+// Per-CTA pre-aggregation cache in shared memory: hot pre-tokens (Zipf head) are counted with
+// shared-memory atomics and reach the global table once per CTA, at the end of the kernel.
+#define PT_CACHE_N 2048
+#define PT_CACHE_PROBES 4
+#define PT_CACHE_BYTES (PT_CACHE_N * 20)
+
+__device__ __forceinline__ bool cache_add(u64* ck0, u64* ck1, uint32_t* cc, u64 h, u64 k0, u64 k1) {
+    uint32_t ci = (uint32_t)(h >> 40) & (PT_CACHE_N - 1);
+#pragma unroll
+    for (int p = 0; p < PT_CACHE_PROBES; p++) {
+        u64 c0 = *(volatile u64*)&ck0[ci];
+        if (c0 == 0) { c0 = atomicCAS(&ck0[ci], 0ULL, k0); if (c0 == 0) c0 = k0; }
+        if (c0 == k0) {
+            u64 c1 = *(volatile u64*)&ck1[ci];
+            if (c1 == 0) { c1 = atomicCAS(&ck1[ci], 0ULL, k1); if (c1 == 0) c1 = k1; }
+            if (c1 == k1) { atomicAdd(&cc[ci], 1u); return true; }
+        }
+        ci = (ci + 1) & (PT_CACHE_N - 1);
+    }
+    return false;
 }
 
 // read-only lookup (encode passes); -1 when absent
@@ -500,6 +526,11 @@ __device__ __forceinline__ void init_tile_smem(TileSmem& S) {
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
     __shared__ TileSmem S;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    u64* ck0 = (u64*)dyn_smem;
+    u64* ck1 = ck0 + PT_CACHE_N;
+    uint32_t* cc = (uint32_t*)(ck1 + PT_CACHE_N);
+    for (int i = threadIdx.x; i < PT_CACHE_N; i += PT_THREADS) { ck0[i] = 0; ck1[i] = 0; cc[i] = 0; }
     init_tile_smem(S);
     const int tid = threadIdx.x;
     u64 my_tok = 0, my_us = 0, my_ul = 0, my_ub = 0;
@@ -532,8 +563,11 @@ __global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
             if (len <= PT_SHORT_MAX) {
                 u64 k0, k1;
                 pack_short_key(txt, s, len, &k0, &k1);
-                if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
-                if (created) { my_us++; my_ub += len; }
+                u64 h = short_hash(k0, k1);
+                if (!cache_add(ck0, ck1, cc, h, k0, k1)) {
+                    if (short_insert_h(P.skeys, P.scounts, P.scap, h, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                    if (created) { my_us++; my_ub += len; }
+                }
             } else {
                 u64 h = 0;
                 for (int j = 0; j < len; j++) h += long_hash_term(txt[s + j], j);
@@ -542,6 +576,16 @@ __global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
             }
         }
         __syncthreads();     // everyone is done with txt[buf] and S before the next iteration reuses them
+    }
+    // flush the pre-aggregation cache
+    __syncthreads();
+    for (int i = tid; i < PT_CACHE_N; i += PT_THREADS) {
+        u64 k1 = ck1[i];
+        if (k1 == 0) continue;
+        u64 k0 = ck0[i];
+        int created;
+        if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, (i64)cc[i], &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+        if (created) { my_us++; my_ub += (u64)(k0 >> 56); }
     }
     // block-level reduction of the statistics
     for (int o = 16; o > 0; o >>= 1) {

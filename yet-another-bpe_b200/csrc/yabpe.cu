@@ -145,9 +145,17 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
         if (rc) return rc;
     }
     if (P.n_tiles > 0 && (stages & 2)) {
-        int grid = num_sms() * 4;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_pretok_count, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_CACHE_BYTES));
+            attr_set = true;
+        }
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pretok_count, PT_THREADS, PT_CACHE_BYTES));
+        if (per_sm < 1) per_sm = 1;
+        int grid = num_sms() * per_sm;
         if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
-        k_pretok_count<<<grid, PT_THREADS, 0, st>>>(P); LAUNCHED();
+        k_pretok_count<<<grid, PT_THREADS, PT_CACHE_BYTES, st>>>(P); LAUNCHED();
         CUDA_TRY(cudaGetLastError());
     }
     if (P.n_tiles > 0 && (stages & 4)) {
@@ -188,8 +196,10 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.tok_hash = (u64*)m->tok_hash; M.tok_pow = (u64*)m->tok_pow; M.tset = (u64*)m->tset; M.tset_cap = m->tset_cap;
     M.max_tokens = m->max_tokens;
     M.pkey = (u64*)m->pkey; M.pcnt = (i64*)m->pcnt; M.pcap = m->pcap;
-    M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = m->ipost; M.inact = m->inact; M.act = m->act;
-    M.dlog_slot = m->dlog_slot; M.dlog_word = m->dlog_word; M.dlog_cap = m->dlog_cap;
+    M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = m->ipost; M.inact = m->inact; M.intop = m->intop; M.act = m->act;
+    M.alog_word = m->alog_word; M.alog_cap = m->alog_cap; M.seg_start = m->seg_start; M.seg_end = m->seg_end;
+    M.merge_next = m->merge_next; M.tok_first = m->tok_first;
+    ARG_CHECK(m->alog_cap >= 2 * m->n_words + ML_LEADER_ITEMS_MAX);
     M.partial = (Best*)m->partial; M.bsum = (i64*)m->bsum;
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
     M.num_merges = m->num_merges; M.min_freq = m->min_frequency;
@@ -197,7 +207,7 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, 0));
     ARG_CHECK(per_sm >= 1);
-    if (per_sm > 2) per_sm = 2;
+    per_sm = 1;
     int grid = num_sms() * per_sm;
     if (grid > 1024) grid = 1024;
     void* args[] = {&M};

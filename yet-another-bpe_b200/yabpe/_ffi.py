@@ -17,6 +17,7 @@ ABI_VERSION = 1
 ST_NTOK, ST_UNIQ_SHORT, ST_UNIQ_LONG, ST_UNIQ_BYTES, ST_ERR_POS, ST_TABLE_FULL, ST_OVF_N = 0, 1, 2, 3, 4, 5, 6
 ST_NSPECIAL = 8
 MS_NMERGES, MS_NTOK, MS_ERROR, MS_NPAIRS, MS_POOL_USED, MS_REBUILDS, MS_TREBUILDS = 0, 1, 2, 6, 8, 9, 10
+MS_LEADER_MERGES, MS_GRID_MERGES = 15, 16
 ME_PAIR_TABLE_FULL, ME_TOK_POOL_FULL, ME_INTERNAL = 1, 2, 4
 INT64_MAX = (1 << 63) - 1
 
@@ -64,8 +65,9 @@ class MergeArgs(C.Structure):
         ("tok_off", C.c_void_p), ("tok_hash", C.c_void_p), ("tok_pow", C.c_void_p),
         ("tset", C.c_void_p), ("tset_cap", C.c_int64), ("max_tokens", C.c_int64),
         ("pkey", C.c_void_p), ("pcnt", C.c_void_p), ("pcap", C.c_int64),
-        ("ioff", C.c_void_p), ("icnt", C.c_void_p), ("ipost", C.c_void_p), ("inact", C.c_void_p), ("act", C.c_void_p),
-        ("dlog_slot", C.c_void_p), ("dlog_word", C.c_void_p), ("dlog_cap", C.c_int64),
+        ("ioff", C.c_void_p), ("icnt", C.c_void_p), ("ipost", C.c_void_p), ("inact", C.c_void_p), ("intop", C.c_void_p), ("act", C.c_void_p),
+        ("alog_word", C.c_void_p), ("alog_cap", C.c_int64), ("seg_start", C.c_void_p), ("seg_end", C.c_void_p),
+        ("merge_next", C.c_void_p), ("tok_first", C.c_void_p),
         ("partial", C.c_void_p), ("bsum", C.c_void_p),
         ("merges", C.c_void_p), ("merge_new", C.c_void_p), ("state", C.c_void_p),
         ("num_merges", C.c_int64), ("min_frequency", C.c_int64),

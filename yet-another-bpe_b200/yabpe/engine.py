@@ -190,7 +190,7 @@ class MergeResult:
 
 
 def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: int, min_frequency: int,
-               pcap: int | None = None, pool_cap: int | None = None, dlog_cap: int | None = None,
+               pcap: int | None = None, pool_cap: int | None = None,
                restore=None, timing: dict | None = None) -> MergeResult:
     """Run the persistent merge kernel.  `restore()` must rebuild `words` in place for a retry."""
     L = _ffi.load()
@@ -202,8 +202,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
             pcap = _pow2_at_least(min(max(4 * words.n_syms, 1 << 16), 1 << 26))
         if pool_cap is None:
             pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
-        if dlog_cap is None:
-            dlog_cap = min(max(words.n_syms, 1 << 16), 1 << 24)
+        alog_cap = max(2 * words.n_words, 1 << 16) + 4096
         tset_cap = _pow2_at_least(4 * max_tokens)
         # base tokens on the host
         tok_bytes = np.zeros(pool_cap, dtype=np.uint8)
@@ -230,7 +229,11 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         ioff, icnt = z(pcap + 1, torch.int32), z(pcap, torch.int32)
         ipost = z(words.n_syms + 8, torch.int32)
         inact, act = z((pcap + 31) // 32 + 1, torch.int32), z(pcap, torch.int32)
-        dlog_slot, dlog_word = z(dlog_cap, torch.int32), z(dlog_cap, torch.int32)
+        intop = z((pcap + 31) // 32 + 1, torch.int32)
+        alog_word = z(alog_cap, torch.int32)
+        nm1 = max(num_merges, 1)
+        seg_start, seg_end, merge_next = z(nm1, torch.int32), z(nm1, torch.int32), z(nm1, torch.int32)
+        tok_first = z(max_tokens, torch.int32)
         partial, bsum = z(1024 * 3, torch.int64), z(1024, torch.int64)
         merges, merge_new = z(2 * max(num_merges, 1), torch.int32), z(max(num_merges, 1), torch.int32)
         state_np = np.zeros(32, dtype=np.int64)
@@ -244,8 +247,10 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.tset = d_tset.data_ptr(); m.tset_cap = tset_cap; m.max_tokens = max_tokens
         m.pkey = pkey.data_ptr(); m.pcnt = pcnt.data_ptr(); m.pcap = pcap
         m.ioff = ioff.data_ptr(); m.icnt = icnt.data_ptr(); m.ipost = ipost.data_ptr()
-        m.inact = inact.data_ptr(); m.act = act.data_ptr()
-        m.dlog_slot = dlog_slot.data_ptr(); m.dlog_word = dlog_word.data_ptr(); m.dlog_cap = dlog_cap
+        m.inact = inact.data_ptr(); m.intop = intop.data_ptr(); m.act = act.data_ptr()
+        m.alog_word = alog_word.data_ptr(); m.alog_cap = alog_cap
+        m.seg_start = seg_start.data_ptr(); m.seg_end = seg_end.data_ptr()
+        m.merge_next = merge_next.data_ptr(); m.tok_first = tok_first.data_ptr()
         m.partial = partial.data_ptr(); m.bsum = bsum.data_ptr()
         m.merges = merges.data_ptr(); m.merge_new = merge_new.data_ptr(); m.state = state.data_ptr()
         m.num_merges = num_merges; m.min_frequency = min_frequency

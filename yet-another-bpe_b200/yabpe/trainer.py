@@ -83,6 +83,8 @@ class TrainStats:
     n_pairs: int = 0
     n_specials: int = 0
     launches: int = 0
+    leader_merges: int = 0
+    grid_merges: int = 0
 
 
 class BBPETrainer:
@@ -194,6 +196,9 @@ class BBPETrainer:
         stats.index_rebuilds = int(mr.state[_ffi.MS_REBUILDS])
         stats.threshold_rebuilds = int(mr.state[_ffi.MS_TREBUILDS])
         stats.n_pairs = int(mr.state[_ffi.MS_NPAIRS])
+        stats.leader_merges = int(mr.state[_ffi.MS_LEADER_MERGES])
+        stats.grid_merges = int(mr.state[_ffi.MS_GRID_MERGES])
+        self.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]]
         stats.launches = _ffi.launch_count() - launches0
         self.last_stats = stats
         if self.profile and ev and len(ev) == 4:
