@@ -28,7 +28,6 @@ namespace cg = cooperative_groups;
 #define MS_ERROR 2
 #define MS_ALOG_N 3
 #define MS_ACT_N 4
-#define MS_T 5
 #define MS_NPAIRS 6
 #define MS_DONE 7
 #define MS_POOL_USED 8
@@ -41,6 +40,11 @@ namespace cg = cooperative_groups;
 #define MS_LEADER_MERGES 15
 #define MS_GRID_MERGES 16
 #define MS_LEADER_GEN 17
+#define MS_TOP_N 18
+#define MS_TOP_OVF 19
+#define MS_T2 5
+#define MS_LEADER_REASON 31
+#define MS_TOP_REBUILDS 28
 
 #define ME_PAIR_TABLE_FULL 1
 #define ME_TOK_POOL_FULL 2
@@ -132,6 +136,7 @@ struct MergeParams {
     // pairs
     u64* pkey; i64* pcnt; i64 pcap;
     uint32_t* ioff; uint32_t* icnt; int32_t* ipost; uint32_t* inact; uint32_t* intop; int32_t* act;
+    int32_t* top_slot; u64* top_key; int* hist;
     // affected-word log: alog_word[seg_start[m] .. seg_end[m]) = words rewritten by merge m
     int32_t* alog_word; i64 alog_cap;
     int32_t* seg_start; int32_t* seg_end;      // per merge
@@ -358,13 +363,15 @@ __device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t x, int32_
     if (s >= 0) atomicAdd((u64*)&M.pcnt[s], (u64)(-f));
     else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);
 }
-// Leader-mode "top list" (shared memory): every pair with count >= T2.  Scanning the whole active
-// set every merge is bound by one SM's gather rate (one 128-byte line per cycle); the top list keeps
-// the per-merge scan to a few hundred entries and is rebuilt only when its best falls below T2.
+// "Top list": every pair with count >= T2, kept in global memory (at most ML_TOP_N entries) and
+// maintained by pair_add in both modes.  Scanning the whole active set every merge is bound by the
+// gather rate of the SMs involved (one 128-byte line per cycle per SM); the top list keeps the
+// per-merge scan to a few hundred entries.  It is rebuilt (grid-wide) when its best entry falls
+// below T2 or when it overflows.  state[MS_T2]: > 0 valid threshold, 0 = rebuild needed,
+// -1 = disabled for this merge (more than ML_TOP_N pairs tie for the maximum).
 #define ML_TOP_N 512
-struct LeaderTop { u64 key[ML_TOP_N]; int32_t slot[ML_TOP_N]; int n; int ovf; i64 T2; };
 
-__device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, LeaderTop* lt) {
+__device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, i64 T2) {
     const u64 key = PAIR_KEY(x, y);
     i64 s = pair_upsert(M, key);
     if (s < 0) return;
@@ -375,11 +382,11 @@ __device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_
             i64 idx = (i64)atomicAdd((u64*)&M.state[MS_ACT_N], 1ULL);
             M.act[idx] = (int32_t)s;
         }
-        if (lt && now >= lt->T2) {
+        if (T2 > 0 && now >= T2) {
             if (!(atomicOr(&M.intop[s >> 5], bit) & bit)) {
-                int idx = atomicAdd(&lt->n, 1);
-                if (idx < ML_TOP_N) { lt->slot[idx] = (int32_t)s; lt->key[idx] = key; }
-                else { atomicAnd(&M.intop[s >> 5], ~bit); lt->ovf = 1; }
+                i64 idx = (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
+                if (idx < ML_TOP_N) { M.top_slot[idx] = (int32_t)s; M.top_key[idx] = key; }
+                else { atomicAnd(&M.intop[s >> 5], ~bit); M.state[MS_TOP_OVF] = 1; }
             }
         }
     }
@@ -391,7 +398,7 @@ __device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w) {
 }
 
 // one thread rewrites one word in place (left->right, non-overlapping) and applies the deltas
-__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, LeaderTop* lt) {
+__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2) {
     int32_t* s = M.wsym + M.woff[w];
     int n = M.wlen[w];
     i64 f = M.wcnt[w];
@@ -401,11 +408,11 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
     while (j < n) {
         int32_t x = s[j];
         if (j + 1 < n && x == a && s[j + 1] == b) {
-            if (o > 0) { pair_sub(M, prev_old, a, f); pair_add(M, prev_new, c, f, T, lt); }
+            if (o > 0) { pair_sub(M, prev_old, a, f); pair_add(M, prev_new, c, f, T, T2); }
             pair_sub(M, a, b, f);
             s[o++] = c; prev_old = b; prev_new = c; prev_changed = true; any = true; j += 2;
         } else {
-            if (o > 0 && prev_changed) { pair_sub(M, prev_old, x, f); pair_add(M, prev_new, x, f, T, lt); }
+            if (o > 0 && prev_changed) { pair_sub(M, prev_old, x, f); pair_add(M, prev_new, x, f, T, T2); }
             s[o++] = x; prev_old = x; prev_new = x; prev_changed = false; j += 1;
         }
     }
@@ -414,7 +421,7 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
 
 // one warp rewrites one word (a != b): every lane owns one old position per 32-symbol chunk, so the
 // pair-count updates of a word are issued in parallel instead of as one dependent chain
-__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T) {
+__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2) {
     const int lane = threadIdx.x & 31;
     int32_t* s = M.wsym + M.woff[w];
     const int n = M.wlen[w];
@@ -448,7 +455,7 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
             if (jn < n) {
                 const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
                 const bool seln = xn == a && xnn == b;
-                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, nullptr);
+                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2);
             }
         }
         __syncwarp();
@@ -462,7 +469,7 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
 // four words per warp, one per 8-lane group (words are short: ~6 symbols on average).  Group-local
 // version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes must call it together.
 __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
-                                 int32_t a, int32_t b, int32_t c, i64 T, LeaderTop* lt) {
+                                 int32_t a, int32_t b, int32_t c, i64 T, i64 T2) {
     const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & 24;
     int32_t* s = M.wsym + (w >= 0 ? off : 0);
     if (w < 0) n = 0;
@@ -493,7 +500,7 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
             if (jn < n) {
                 const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
                 const bool seln = xn == a && xnn == b;
-                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, lt);
+                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2);
             }
         }
         __syncwarp();
@@ -623,84 +630,61 @@ __device__ __forceinline__ void close_merge(const MergeParams& M, i64 m, int32_t
 // ---- leader mode: CTA 0 runs merges alone, block barriers only ---------------------------------
 struct ClaimedWord { i64 off; i64 f; int32_t w; int32_t n; };
 
-// leader: drop the top list (its dedupe bits must not outlive it)
-__device__ void top_clear(const MergeParams& M, LeaderTop* LT) {
-    __syncthreads();
-    const int n = LT->n < ML_TOP_N ? LT->n : ML_TOP_N;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { int32_t sl = LT->slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
-    __syncthreads();
-    if (threadIdx.x == 0) { LT->n = 0; LT->ovf = 0; }
-    __syncthreads();
-}
-
-// leader: rebuild the top list from the active set.  Returns false when grid mode has to take over
-// (no pair with count >= T, or more than ML_TOP_N pairs tie for the maximum).
-__device__ bool top_rebuild(const MergeParams& M, LeaderTop* LT, i64 act_n, i64 T, Best* sh_best, i64* sh_cnt) {
-    top_clear(M, LT);
-    Best am = block_best_fast(M, scan_active(M, act_n, threadIdx.x, blockDim.x), sh_best, sh_cnt);
-    if (am.slot < 0 || am.cnt < T) return false;
-    i64 T2 = am.cnt - am.cnt / 4; if (T2 < T) T2 = T;
-    for (int round = 0; round < 40; round++) {
-        if (threadIdx.x == 0) LT->T2 = T2;
-        __syncthreads();
-        for (i64 i = threadIdx.x; i < act_n; i += blockDim.x) {
-            int32_t sl = M.act[i];
-            if (__ldcg(&M.pcnt[sl]) >= T2) {
-                int idx = atomicAdd(&LT->n, 1);
-                if (idx < ML_TOP_N) { LT->slot[idx] = sl; LT->key[idx] = __ldcg(&M.pkey[sl]); atomicOr(&M.intop[sl >> 5], 1u << (sl & 31)); }
-                else LT->ovf = 1;
-            }
-        }
-        __syncthreads();
-        if (!LT->ovf) return true;
-        if (T2 >= am.cnt) break;                       // > ML_TOP_N pairs tie for the maximum
-        top_clear(M, LT);
-        T2 = T2 + (am.cnt - T2 + 1) / 2;
+// best entry of the top list, computed by ONE block (every block gets the same answer when all call it)
+__device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh_cnt) {
+    Best mine{0, -1, 0, 0, 0};
+    const int tn = top_n < ML_TOP_N ? (int)top_n : ML_TOP_N;
+    if ((int)threadIdx.x < tn) {
+        const int32_t sl = M.top_slot[threadIdx.x];
+        const u64 k = M.top_key[threadIdx.x];
+        const i64 cnt = __ldcg(&M.pcnt[sl]);
+        if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
     }
-    top_clear(M, LT);
-    return false;
+    return block_best_fast(M, mine, sh_best, sh_cnt);
 }
 
-__device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin) {
+#define LR_TOP 1      // leader stopped: top list exhausted / overflowed
+#define LR_OTHER 2    // leader stopped: the next merge needs the whole grid (or nothing is left to do)
+
+__device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin, const i64 T2) {
     __shared__ Ranges R;
     __shared__ int32_t sh_c;
     __shared__ ClaimedWord sh_list[ML_LEADER_ITEMS_MAX];
     __shared__ int sh_nlist;
     __shared__ i64 sh_cnt[ML_THREADS / 32];
-    __shared__ i64 sh_state[3];                      // act_n, alog_n, error: refreshed once per merge by thread 0
-    __shared__ LeaderTop LT;
+    __shared__ i64 sh_state[5];          // act_n, alog_n, error, top_n, top_ovf: refreshed once per merge by thread 0
+    __shared__ int32_t sh_tslot[ML_TOP_N];
+    __shared__ u64 sh_tkey[ML_TOP_N];
     i64 m = M.state[MS_NMERGES];
     int32_t n_tok = (int32_t)M.state[MS_NTOK];
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    long long t_arg = 0, t_rng = 0, t_claim = 0, t_rw = 0, t_close = 0, s_act = 0, s_items = 0, s_words = 0, n_done = 0, n_top = 0;
+    long long t_arg = 0, t_rng = 0, t_claim = 0, t_rw = 0, t_close = 0, s_act = 0, s_items = 0, s_words = 0, n_done = 0;
+    int reason = LR_OTHER;
+    int cached = 0;                      // entries of the top list already copied to shared memory
     if (threadIdx.x == 0) {
         sh_state[0] = __ldcg(&M.state[MS_ACT_N]); sh_state[1] = __ldcg(&M.state[MS_ALOG_N]); sh_state[2] = __ldcg(&M.state[MS_ERROR]);
-        LT.n = 0; LT.ovf = 0; LT.T2 = INT64_MAX;
+        sh_state[3] = __ldcg(&M.state[MS_TOP_N]); sh_state[4] = __ldcg(&M.state[MS_TOP_OVF]);
     }
     __syncthreads();
     for (int iter = 0; iter < ML_LEADER_BATCH && m < M.num_merges; iter++) {
         long long c0 = clock64();
         const i64 act_n = sh_state[0], alog_n = sh_state[1];
-        if (sh_state[2] || act_n > ML_LEADER_ACT_MAX) break;
-        // ---- best pair: scan the top list; rebuild it when it cannot prove the maximum
-        Best best{0, -1, 0, 0, 0};
-        bool ok = true;
-        for (int attempt = 0; attempt < 2; attempt++) {
-            Best mine{0, -1, 0, 0, 0};
-            const int tn = LT.n < ML_TOP_N ? LT.n : ML_TOP_N;
-            if (!LT.ovf && (int)threadIdx.x < tn) {
-                const int32_t sl = LT.slot[threadIdx.x];
-                const i64 cnt = __ldcg(&M.pcnt[sl]);
-                const u64 k = LT.key[threadIdx.x];
-                if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
-            }
-            best = block_best_fast(M, mine, sh_best, sh_cnt);
-            if (!LT.ovf && best.slot >= 0 && best.cnt >= LT.T2) break;
-            if (attempt == 1) { ok = false; break; }
-            n_top++;
-            if (!top_rebuild(M, &LT, act_n, T, sh_best, sh_cnt)) { ok = false; break; }
+        if (sh_state[2]) break;
+        if (sh_state[4] || sh_state[3] > ML_TOP_N) { reason = LR_TOP; break; }
+        // ---- best pair: scan the top list (slot / key cached in shared memory)
+        const int tn = (int)sh_state[3];
+        Best mine{0, -1, 0, 0, 0};
+        if ((int)threadIdx.x < tn) {
+            if ((int)threadIdx.x >= cached) { sh_tslot[threadIdx.x] = M.top_slot[threadIdx.x]; sh_tkey[threadIdx.x] = M.top_key[threadIdx.x]; }
+            const int32_t sl = sh_tslot[threadIdx.x];
+            const u64 k = sh_tkey[threadIdx.x];
+            const i64 cnt = __ldcg(&M.pcnt[sl]);
+            if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
         }
-        if (!ok || best.cnt < T || best.cnt < Tmin) break;                // threshold step / termination: grid mode
+        cached = tn;
+        Best best = block_best_fast(M, mine, sh_best, sh_cnt);
+        if (best.slot < 0 || best.cnt < T2) { reason = LR_TOP; break; }
+        if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
         long long c1 = clock64();
         if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); sh_nlist = 0; }
         if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok);
@@ -717,7 +701,19 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 int32_t w = range_item(R, it);
                 if (atomicExch(&M.wstamp[w], stamp) != stamp) {
                     ClaimedWord cw; cw.w = w; cw.off = M.woff[w]; cw.n = M.wlen[w]; cw.f = M.wcnt[w];
-                    sh_list[atomicAdd(&sh_nlist, 1)] = cw;
+                    // candidates are a superset (stale postings, whole-token segments): keep real matches only
+                    bool hit = cw.n > 64;
+                    if (!hit) {
+                        const int32_t* sp = M.wsym + cw.off;
+                        int32_t prev = -1;
+                        for (int j0 = 0; j0 < cw.n; j0 += 4) {
+                            int32_t v0 = sp[j0], v1 = j0 + 1 < cw.n ? sp[j0 + 1] : -1, v2 = j0 + 2 < cw.n ? sp[j0 + 2] : -1,
+                                    v3 = j0 + 3 < cw.n ? sp[j0 + 3] : -1;
+                            hit |= (prev == a && v0 == b) | (v0 == a && v1 == b) | (v1 == a && v2 == b) | (v2 == a && v3 == b);
+                            prev = v3;
+                        }
+                    }
+                    if (hit) sh_list[atomicAdd(&sh_nlist, 1)] = cw;
                 }
             }
         }
@@ -730,37 +726,101 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 const int k = kb + (lane >> 3);
                 ClaimedWord cw; cw.w = -1; cw.off = 0; cw.n = 0; cw.f = 0;
                 if (k < nlist) cw = sh_list[k];
-                rewrite_words_g8(M, cw.w, cw.off, cw.n, cw.f, a, b, c, T, &LT);
+                rewrite_words_g8(M, cw.w, cw.off, cw.n, cw.f, a, b, c, T, T2);
             }
         } else {
-            for (int k = threadIdx.x; k < nlist; k += blockDim.x) rewrite_word_thread(M, sh_list[k].w, a, b, c, T, &LT);
+            for (int k = threadIdx.x; k < nlist; k += blockDim.x) rewrite_word_thread(M, sh_list[k].w, a, b, c, T, T2);
         }
         __syncthreads();
         long long c4 = clock64();
         if (threadIdx.x == 0) {
             // one L2 round trip: the counters the rewrite just bumped with atomics
             const i64 an = __ldcg(&M.state[MS_ACT_N]), ln = __ldcg(&M.state[MS_ALOG_N]), er = __ldcg(&M.state[MS_ERROR]);
+            const i64 tn2 = __ldcg(&M.state[MS_TOP_N]), tov = __ldcg(&M.state[MS_TOP_OVF]);
             M.seg_end[m] = (int32_t)ln; M.tok_first[c] = (int32_t)m; M.state[MS_NMERGES] = m + 1;
-            sh_state[0] = an; sh_state[1] = ln; sh_state[2] = er;
+            sh_state[0] = an; sh_state[1] = ln; sh_state[2] = er; sh_state[3] = tn2; sh_state[4] = tov;
         }
         __syncthreads();
         long long c5 = clock64();
         t_arg += c1 - c0; t_rng += c2 - c1; t_claim += c3 - c2; t_rw += c4 - c3; t_close += c5 - c4;
-        s_act += act_n; s_items += R.total; s_words += nlist; n_done++;
+        s_act += sh_state[1] - alog_n; s_items += R.total; s_words += nlist; n_done++;
         m++;
     }
-    top_clear(M, &LT);
     if (threadIdx.x == 0) {
         M.state[20] += t_arg; M.state[21] += t_rng; M.state[22] += t_claim; M.state[23] += t_rw; M.state[24] += t_close;
-        M.state[25] += s_act; M.state[26] += s_items; M.state[27] += s_words; M.state[28] += n_top;
+        M.state[25] += s_act; M.state[26] += s_items; M.state[27] += s_words;
         M.state[MS_LEADER_MERGES] += n_done;
+        M.state[MS_LEADER_REASON] = reason;
+        if (reason == LR_TOP) M.state[MS_T2] = 0;
     }
+}
+
+// grid-wide rebuild of the top list.  On return state[MS_T2] holds the new threshold (> 0), or -1 when
+// more than ML_TOP_N pairs tie near the maximum (the caller then scans the whole active set for one
+// merge).  Lowers T (and rebuilds the active set) while no pair reaches it; returns false when no pair
+// with count >= Tmin is left.  Must be entered by all CTAs right after a grid barrier.
+__device__ bool grid_top_rebuild(const MergeParams& M, cg::grid_group& grid, i64& T, i64 Tmin, Best* sh_best, int* sh_hist) {
+    const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
+    {
+        i64 n_old = M.state[MS_TOP_N]; if (n_old > ML_TOP_N) n_old = ML_TOP_N;
+        for (i64 i = gtid; i < n_old; i += gstride) { int32_t sl = M.top_slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
+        for (i64 i = gtid; i < 1024; i += gstride) M.hist[i] = 0;
+    }
+    grid.sync();
+    if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_TOP_REBUILDS]++; }
+    Best am;
+    for (;;) {
+        am = grid_argmax(M, grid, sh_best);              // contains a grid barrier
+        if (am.slot >= 0 && am.cnt >= T) break;
+        if (T <= Tmin) return false;
+        T = T / 2; if (T < Tmin) T = Tmin;
+        grid.sync();
+        rebuild_active(M, grid, T);
+    }
+    const i64 hi = am.cnt, span = hi - T, act_n = M.state[MS_ACT_N];
+    for (i64 i = gtid; i < act_n; i += gstride) {
+        i64 c = __ldcg(&M.pcnt[M.act[i]]);
+        if (c < T) continue;
+        int bin = span > 0 ? (int)(((c - T) * 1023) / span) : 1023;
+        atomicAdd(&M.hist[bin], 1);
+    }
+    grid.sync();
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh_hist[i] = M.hist[i];
+    __syncthreads();
+    i64 T2;
+    {
+        int acc = 0, b = 1023;
+        while (b >= 0 && acc + sh_hist[b] <= (ML_TOP_N * 3) / 4) { acc += sh_hist[b]; b--; }
+        T2 = b < 0 ? T : (b >= 1023 ? hi : T + ((i64)(b + 1) * span + 1022) / 1023);
+        if (T2 < T) T2 = T;
+    }
+    for (i64 i = gtid; i < act_n; i += gstride) {
+        int32_t sl = M.act[i];
+        if (__ldcg(&M.pcnt[sl]) >= T2) {
+            i64 idx = (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
+            if (idx < ML_TOP_N) { M.top_slot[idx] = sl; M.top_key[idx] = __ldcg(&M.pkey[sl]); atomicOr(&M.intop[sl >> 5], 1u << (sl & 31)); }
+            else M.state[MS_TOP_OVF] = 1;
+        }
+    }
+    grid.sync();
+    const bool ovf = M.state[MS_TOP_OVF] != 0;
+    grid.sync();                                         // everyone has seen the overflow flag
+    if (ovf) {
+        i64 n_old = M.state[MS_TOP_N]; if (n_old > ML_TOP_N) n_old = ML_TOP_N;
+        for (i64 i = gtid; i < n_old; i += gstride) { int32_t sl = M.top_slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
+        grid.sync();
+        if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_T2] = -1; }
+    } else if (gtid == 0) M.state[MS_T2] = T2;
+    grid.sync();
+    return true;
 }
 
 __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     cg::grid_group grid = cg::this_grid();
     __shared__ Best sh_best[ML_THREADS / 32];
     __shared__ i64 sh_scan[1 + ML_THREADS / 32];
+    __shared__ i64 sh_cnt[ML_THREADS / 32];
+    __shared__ int sh_hist[1024];
     __shared__ int32_t sh_c;
     __shared__ Ranges R;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
@@ -795,15 +855,25 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         i64 alog_n = M.state[MS_ALOG_N];
         const i64 act_n = M.state[MS_ACT_N];
         const i64 gen = M.state[MS_LEADER_GEN];
+        i64 T2 = M.state[MS_T2];
+        const i64 top_n = M.state[MS_TOP_N];
+        const bool top_ovf = M.state[MS_TOP_OVF] != 0;
         if (m >= M.num_merges || M.state[MS_ERROR] || M.state[MS_DONE]) break;
+
+        // ---- (re)build the top list when it cannot prove the maximum any more
+        if (T2 == 0 || (T2 > 0 && top_ovf)) {
+            grid.sync();                                    // everyone has read the state
+            if (!grid_top_rebuild(M, grid, T, Tmin, sh_best, sh_hist)) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
+            continue;
+        }
 
         // ---- leader mode while the work per merge is small
         if (skip > 0) skip--;
-        else if (act_n <= ML_LEADER_ACT_MAX && alog_n + ML_LEADER_ITEMS_MAX <= M.alog_cap) {
+        else if (T2 > 0 && alog_n + ML_LEADER_ITEMS_MAX <= M.alog_cap) {
             const i64 m0 = m;
             grid.sync();                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
-                leader_loop(M, sh_best, T, Tmin);
+                leader_loop(M, sh_best, T, Tmin, T2);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
             } else {
@@ -814,26 +884,34 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             m = M.state[MS_NMERGES];
             n_tok = (int32_t)M.state[MS_NTOK];
             alog_n = M.state[MS_ALOG_N];
-            if (m == m0) { backoff = backoff < 64 ? backoff * 2 : 64; skip = backoff; } else backoff = 1;
+            const i64 reason = M.state[MS_LEADER_REASON];
+            if (m == m0 && reason != LR_TOP) { backoff = backoff < 64 ? backoff * 2 : 64; skip = backoff; } else backoff = 1;
             if (m >= M.num_merges || M.state[MS_ERROR]) break;
             grid.sync();                                    // everyone has re-read the state
+            if (reason == LR_TOP) continue;                 // top list exhausted: rebuild it first
         }
 
-        // ---- one merge in grid mode (also handles threshold steps, compaction, termination)
-        if (M.state[MS_ACT_N] > ML_LEADER_ACT_MAX && M.state[MS_ACT_N] > 2 * M.state[MS_ACT_BASE]) {
-            grid.sync();
-            rebuild_active(M, grid, T);                     // drop entries that fell below T
-        }
-        Best best = grid_argmax(M, grid, sh_best);
-        bool stop = false;
-        while (best.slot < 0 || best.cnt < T) {
-            if (T <= Tmin) { stop = true; break; }          // nothing left with count >= max(1, min_frequency)
-            T = T / 2; if (T < Tmin) T = Tmin;
-            grid.sync();                                    // everyone has read partial[] / act before it is rebuilt
-            rebuild_active(M, grid, T);
+        // ---- one merge in grid mode.  With a valid top list every CTA finds the best pair on its own
+        //      (same data, same answer): no grid barrier for the argmax.
+        Best best;
+        if (T2 > 0) {
+            best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
+            if (best.slot < 0 || best.cnt < T2 || best.cnt < T) {
+                grid.sync();                                // everyone has finished reading the list
+                if (gtid == 0) M.state[MS_T2] = 0;
+                grid.sync();
+                continue;
+            }
+        } else {
+            // top list disabled (massive ties): full scan of the active set for this merge
             best = grid_argmax(M, grid, sh_best);
+            if (best.slot < 0 || best.cnt < T) {            // cannot happen right after a rebuild; be safe
+                grid.sync();
+                if (gtid == 0) M.state[MS_T2] = 0;
+                grid.sync();
+                continue;
+            }
         }
-        if (stop) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
         const int32_t a = best.a, b = best.b;
         if (threadIdx.x == 0) { build_ranges(M, best.slot, a, b, &R); sh_c = lookup_merged(M, a, b, n_tok); }
         __syncthreads();
@@ -849,6 +927,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         const bool is_new = c == n_tok;
         if (blockIdx.x == 0) commit_merge(M, m, a, b, c, is_new, alog_n);
         const int32_t stamp = (int32_t)(m + 1);
+        const i64 T2u = T2 > 0 ? T2 : 0;
         if (a != b && R.total * 32 <= gstride * 4) {
             const i64 gw = gtid >> 5, nw = gstride >> 5;
             for (i64 it = gw; it < R.total; it += nw) {
@@ -857,18 +936,18 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if ((threadIdx.x & 31) == 0) old = atomicExch(&M.wstamp[w], stamp);
                 old = __shfl_sync(0xffffffffu, old, 0);
                 if (old == stamp) continue;
-                rewrite_word_warp(M, w, a, b, c, T);
+                rewrite_word_warp(M, w, a, b, c, T, T2u);
             }
         } else {
             for (i64 it = gtid; it < R.total; it += gstride) {
                 int32_t w = range_item(R, it);
                 if (atomicExch(&M.wstamp[w], stamp) == stamp) continue;
-                rewrite_word_thread(M, w, a, b, c, T, nullptr);
+                rewrite_word_thread(M, w, a, b, c, T, T2u);
             }
         }
         grid.sync();
         // every CTA writes the same values: no further barrier needed before the next iteration
-        if (threadIdx.x == 0) close_merge(M, m, c);
+        if (threadIdx.x == 0) { close_merge(M, m, c); if (T2 < 0) M.state[MS_T2] = 0; }
         if (gtid == 0) M.state[MS_GRID_MERGES]++;
         __syncthreads();
     }

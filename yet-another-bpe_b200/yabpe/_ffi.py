@@ -65,7 +65,8 @@ class MergeArgs(C.Structure):
         ("tok_off", C.c_void_p), ("tok_hash", C.c_void_p), ("tok_pow", C.c_void_p),
         ("tset", C.c_void_p), ("tset_cap", C.c_int64), ("max_tokens", C.c_int64),
         ("pkey", C.c_void_p), ("pcnt", C.c_void_p), ("pcap", C.c_int64),
-        ("ioff", C.c_void_p), ("icnt", C.c_void_p), ("ipost", C.c_void_p), ("inact", C.c_void_p), ("intop", C.c_void_p), ("act", C.c_void_p),
+        ("ioff", C.c_void_p), ("icnt", C.c_void_p), ("ipost", C.c_void_p), ("inact", C.c_void_p), ("intop", C.c_void_p), ("top_slot", C.c_void_p), ("top_key", C.c_void_p), ("hist", C.c_void_p),
+        ("act", C.c_void_p),
         ("alog_word", C.c_void_p), ("alog_cap", C.c_int64), ("seg_start", C.c_void_p), ("seg_end", C.c_void_p),
         ("merge_next", C.c_void_p), ("tok_first", C.c_void_p),
         ("partial", C.c_void_p), ("bsum", C.c_void_p),

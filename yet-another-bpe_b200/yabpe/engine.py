@@ -230,6 +230,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         ipost = z(words.n_syms + 8, torch.int32)
         inact, act = z((pcap + 31) // 32 + 1, torch.int32), z(pcap, torch.int32)
         intop = z((pcap + 31) // 32 + 1, torch.int32)
+        top_slot, top_key, hist = z(512, torch.int32), z(512, torch.int64), z(1024, torch.int32)
         alog_word = z(alog_cap, torch.int32)
         nm1 = max(num_merges, 1)
         seg_start, seg_end, merge_next = z(nm1, torch.int32), z(nm1, torch.int32), z(nm1, torch.int32)
@@ -248,6 +249,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.pkey = pkey.data_ptr(); m.pcnt = pcnt.data_ptr(); m.pcap = pcap
         m.ioff = ioff.data_ptr(); m.icnt = icnt.data_ptr(); m.ipost = ipost.data_ptr()
         m.inact = inact.data_ptr(); m.intop = intop.data_ptr(); m.act = act.data_ptr()
+        m.top_slot = top_slot.data_ptr(); m.top_key = top_key.data_ptr(); m.hist = hist.data_ptr()
         m.alog_word = alog_word.data_ptr(); m.alog_cap = alog_cap
         m.seg_start = seg_start.data_ptr(); m.seg_end = seg_end.data_ptr()
         m.merge_next = merge_next.data_ptr(); m.tok_first = tok_first.data_ptr()
