@@ -90,6 +90,20 @@ def test_pretok_counts_fuzz_and_adversarial(yabpe):
         assert _device_counts(text, sp, mode="encode") == _oracle_counts(text, sp, mode="encode"), sp
 
 
+def test_pretok_fast_path_large_fuzz(yabpe):
+    """Interior tiles take the register-resident fast path: hammer it with every event kind at every alignment."""
+    rng = random.Random(321)
+    heavy = ALPHABET + ["'s", "'t", "'re", " 'll", "\u00a0", "\u3000", "\u2003", "x'", "''", "<|endoftext|>'s", "é's"]
+    for sp, mode in (([], "train"), (["<|endoftext|>"], "train"), (["<|e|>", "<|endoftext|>"], "train"),
+                     (["<|endoftext|>"], "encode"), (["<|e|>", "<|endoftext|>", "<|endoftext|><|endoftext|>"], "encode")):
+        text = "".join(rng.choice(heavy) for _ in range(400_000)).encode("utf-8")
+        assert _device_counts(text, sp, mode=mode) == _oracle_counts(text, sp, mode=mode), (sp, mode)
+    # mostly-ASCII prose with sparse events
+    words = ["the", "a", "don't", "we've", "I'll", "it's", "naïve", "café", "中文", "x", "1234", "...", "\n", "\n\n", " ", "  "]
+    text = " ".join(rng.choice(words) for _ in range(500_000)).encode("utf-8")
+    assert _device_counts(text, ["<|endoftext|>"]) == _oracle_counts(text, ["<|endoftext|>"])
+
+
 def test_pretok_long_tokens_and_tile_edges(yabpe):
     """Tokens straddling tile boundaries, longer than the tile window, and MB-long runs."""
     parts = [b"x" * 8191, b" ", b"y" * 9000, b"\n", "中".encode() * 5000, b" 1234567890" * 3, b"!" * 20000, b" ",

@@ -25,7 +25,10 @@ NVCC_FLAGS = [
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return OUT
-    cmd = ["nvcc", *NVCC_FLAGS] + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(OUT), str(SRC)]
+    import os
+    import shlex
+    extra = shlex.split(os.environ.get("YABPE_NVCC_EXTRA", ""))      # tuning experiments only
+    cmd = ["nvcc", *NVCC_FLAGS, *extra] + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(OUT), str(SRC)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
         i64 next = tile + gridDim.x;
         if (next < P.n_tiles && tid == 0) tile_issue_load(P, S, next, buf ^ 1);
         mbar_wait(&S.bar[buf], phase[buf]); phase[buf] ^= 1;
-        tile_scan(P, S, tile, buf);
+        bool has_cut;
+        tile_scan(P, S, tile, buf, &has_cut);
         const uint8_t* txt = S.txt[buf];
         const i64 g0 = (P.tile_base + tile) * PT_TILE - PT_HL;
         const int ntok = S.ntok_own, ntot = S.ntok_total;
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
         if (ntok > 0 && ntok >= ntot) {
             int k = ntok - 1;
             i64 gpos = g0 + S.tokpos[k];
-            if (gpos >= P.own_lo && gpos < P.own_hi && !(S.info[S.tokpos[k]] & IB_IN)) {
+            const int sk = S.tokpos[k];
+            if (gpos >= P.own_lo && gpos < P.own_hi && !(P.n_sp > 0 && ((S.recw[(sk >> 5) + 4] >> (sk & 31)) & 1))) {
                 i64 e = block_find_token_end(P, gpos, &sh_min);
                 u64 h = block_long_hash(P.text, gpos, e - gpos, &sh_acc);
                 int created;
@@ -198,8 +200,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
                 live = gpos >= P.own_lo && gpos < P.own_hi;
             }
             if (live) {
-                uint8_t v = S.info[s];
-                if (v & IB_IN) {                       // recognised special: its id, or dropped (tokenizer.py:177-181)
+                if (P.n_sp > 0 && ((S.recw[(s >> 5) + 4] >> (s & 31)) & 1)) {   // recognised special: its id, or dropped (tokenizer.py:177-181)
                     int sp = special_match(P.text, gpos, P.n);
                     spid = sp >= 0 ? E.sp_ids[sp] : -1;
                     cnt = spid >= 0 ? 1 : 0;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
             int off = block_exclusive_scan(cnt, S.scan_tmp, &total);
             if (WRITE && live) {
                 i64 dst = sh_base + running + off;
-                if ((S.info[s] & IB_FR) && O.doc_off) {          // first token of a document?
+                if (has_cut && O.doc_off) {                     // first token of a document?
                     int lo = 0, hi = P.n_cuts;
                     while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] < gpos) lo = mid + 1; else hi = mid; }
                     if (lo < P.n_cuts && P.cuts[lo] == gpos) O.doc_off[lo + 1] = dst;

@@ -14,15 +14,19 @@
 
 #include "common.cuh"
 
+#ifndef PT_TILE
 #define PT_TILE 8192
+#endif
 #define PT_HL 32
 #define PT_HR 256
-#define PT_SLACK 16
-#define PT_WIN (PT_HL + PT_TILE + PT_HR + PT_SLACK)       // 8496 bytes, multiple of 16
+#define PT_SLACK 48
+#define PT_WIN (PT_HL + PT_TILE + PT_HR + PT_SLACK)       // 8528 bytes, multiple of 16
 #define PT_THREADS 256
 #define PT_NBITS (PT_TILE + PT_HR + 1)                    // start bits for window offsets [HL, HL+TILE+HR]
 #define PT_NMASK ((PT_NBITS + 31) / 32)                   // 265 words
 #define PT_SHORT_MAX 14
+#define PT_MAXMISS 4
+#define PT_NSEG (PT_NMASK)                                  // 32-byte segments per tile incl. the right halo
 
 // stats slots (device int64[16])
 #define ST_NTOK 0
@@ -181,7 +185,9 @@ __device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 c
 
 // Per-CTA pre-aggregation cache in shared memory: hot pre-tokens (Zipf head) are counted with
 // shared-memory atomics and reach the global table once per CTA, at the end of the kernel.
-#define PT_CACHE_N 2048
+#ifndef PT_CACHE_N
+#define PT_CACHE_N 1024
+#endif
 #define PT_CACHE_PROBES 4
 #define PT_CACHE_BYTES (PT_CACHE_N * 20)
 
@@ -272,14 +278,18 @@ __device__ i64 long_find(const LongEntry* ent, i64 cap, const uint8_t* text, u64
 // ---------------------------------------------------------------------------------
 struct TileSmem {
     alignas(128) uint8_t txt[2][PT_WIN];
-    alignas(16) uint8_t info[PT_WIN];
+    union {                                   // info: generic passes A-C only; tokpos: from pass D1 on
+        alignas(16) uint8_t info[PT_WIN];
+        uint16_t tokpos[PT_TILE + 8];
+    };
     uint32_t smask[PT_NMASK + 7];
-    uint16_t tokpos[PT_NBITS + 3];
     uint8_t lut[256];
     alignas(8) uint64_t bar[2];
     int scan_tmp[PT_THREADS / 32];
     int scan_carry;
     int ntok_total, ntok_own;
+    // fast (pure-ASCII interior tile) path
+    uint32_t recw[PT_WIN / 32 + 8];      // encode mode: recognised-special bits; word i covers window offsets [32(i-4), 32(i-3))
 };
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* tmp, int* total) {
@@ -314,8 +324,8 @@ __device__ __forceinline__ void info_or(uint8_t* info, int x, uint32_t bits) {
     atomicOr((uint32_t*)(info + (x & ~3)), bits << ((x & 3) * 8));
 }
 
-// Passes A-D1 for one tile.  On return S.smask / S.tokpos / S.ntok_* describe the tile's tokens.
-__device__ void tile_scan(const PretokParams& P, TileSmem& S, i64 tile, int buf) {
+// Generic path, passes A-C: any text (multi-byte code points, hard cuts, buffer ends).  Writes S.smask.
+__device__ void tile_scan_generic(const PretokParams& P, TileSmem& S, i64 tile, int buf) {
     const int tid = threadIdx.x;
     const i64 t0 = (P.tile_base + tile) * PT_TILE;
     const i64 g0 = t0 - PT_HL;
@@ -469,23 +479,287 @@ __device__ void tile_scan(const PretokParams& P, TileSmem& S, i64 tile, int buf)
         if ((tid & 31) == 0 && (b >> 5) < PT_NMASK) S.smask[b >> 5] = m;
     }
     __syncthreads();
+}
 
-    // ---- pass D1: compact start positions
-    if (tid == 0) S.scan_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < PT_NMASK; base += PT_THREADS) {
-        int wi = base + tid;
-        uint32_t m = wi < PT_NMASK ? S.smask[wi] : 0;
-        int cnt = __popc(m), total;
-        int off = block_exclusive_scan(cnt, S.scan_tmp, &total) + S.scan_carry;
-        if (wi == PT_TILE / 32) S.ntok_own = off;        // starts with bit index < TILE
-        while (m) { int bit = __ffs(m) - 1; m &= m - 1; S.tokpos[off++] = (uint16_t)(PT_HL + wi * 32 + bit); }
-        __syncthreads();
-        if (tid == 0) S.scan_carry += total;
-        __syncthreads();
+// ---------------------------------------------------------------------------------
+// Fast path: interior tile, pure ASCII.  One thread scans one 32-byte segment entirely in
+// registers: SWAR classification of the 8 words, predicate bits gathered into "transposed"
+// 32-bit masks (bit 8k+j = byte k of word j), the start rule as ~25 bitwise operations, and
+// rare per-thread events (recognised specials, live contractions) patched in afterwards.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool rec_bit_g(const PretokParams& P, i64 q) { return P.n_sp > 0 && ((P.rec[q >> 5] >> (q & 31)) & 1); }
+__device__ __forceinline__ uint32_t tbit(int p) { return 1u << (((p & 3) << 3) | (p >> 2)); }       // segment position -> mask bit
+__device__ __forceinline__ uint32_t prevT(uint32_t m, uint32_t carry) { return (m << 8) | (((m >> 24) << 1) & 0xffu) | carry; }
+__device__ __forceinline__ uint32_t nextT(uint32_t m, uint32_t carry) { return (m >> 8) | (((m & 0xffu) >> 1) << 24) | (carry << 31); }
+__device__ __forceinline__ uint32_t spread8(uint32_t b) {     // bit j -> bit 4j
+    b = (b | (b << 12)) & 0x000f000fu;
+    b = (b | (b << 6)) & 0x03030303u;
+    b = (b | (b << 3)) & 0x11111111u;
+    return b;
+}
+__device__ __forceinline__ uint32_t untranspose(uint32_t t) {
+    return spread8(t & 0xff) | (spread8((t >> 8) & 0xff) << 1) | (spread8((t >> 16) & 0xff) << 2) | (spread8(t >> 24) << 3);
+}
+__device__ __forceinline__ int ascii_kclass(uint32_t b) {
+    if (((b | 0x20) - 'a') < 26u) return KC_L;
+    if ((b - '0') < 10u) return KC_N;
+    if (b == 0x20) return KC_SP;
+    if ((b - 9) < 5u) return KC_S;
+    return KC_O;
+}
+
+// class of the code point that window byte `pos` belongs to (multi-byte aware; O when ill-formed)
+__device__ int smem_kclass(const uint8_t* txt, int pos) {
+    uint8_t b = txt[pos];
+    if (b < 0x80) return ascii_kclass(b);
+    int y = pos;
+    while ((txt[y] & 0xC0) == 0x80 && pos - y < 3) y--;
+    b = txt[y];
+    if (b < 0xC0) return KC_O;
+    int len;
+    if (!utf8_seq_ok(txt + y, 8, &len) || y + len <= pos) return KC_O;
+    return kclass_of_cp(utf8_decode(txt + y, len));
+}
+
+// window touches offset 0 / n or contains a hard cut -> generic path (every thread computes the same answer)
+__device__ __forceinline__ bool tile_is_boundary(const PretokParams& P, i64 g0, bool* has_cut) {
+    bool cut = false;
+    if (P.n_cuts > 0) {
+        int lo = 0, hi = P.n_cuts;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] < g0) lo = mid + 1; else hi = mid; }
+        cut = lo < P.n_cuts && P.cuts[lo] <= g0 + PT_WIN;
     }
-    if (tid == 0) S.ntok_total = S.scan_carry;
+    *has_cut = cut;
+    return cut || g0 <= 0 || g0 + PT_WIN >= P.n;
+}
+
+// encode mode: stage the recognised-special bits of the window (consumed by the token loops after pass D1)
+__device__ __forceinline__ void tile_stage_rec(const PretokParams& P, TileSmem& S, i64 g0) {
+    if (P.mode != 1 || P.n_sp == 0) return;
+    const i64 nrec = (P.n + 63) / 32 + 1;
+    for (int i = threadIdx.x; i < PT_WIN / 32 + 8; i += PT_THREADS) {
+        i64 wi = (g0 >> 5) - 4 + i;              // g0 is a multiple of 32
+        S.recw[i] = (wi >= 0 && wi < nrec) ? P.rec[wi] : 0u;
+    }
+}
+
+// scan one 32-byte segment (index sgi, window offset x0 = HL + 32*sgi); returns the start mask in natural
+// bit order, *na != 0 when a non-ASCII byte was seen (the tile then falls back to the generic path)
+__device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const uint8_t* txt, i64 g0, int sgi, uint32_t* na_out) {
+    const int x0 = PT_HL + 32 * sgi;
+    const uint4* p4 = (const uint4*)(txt + x0);
+    const uint4 A = p4[0], B = p4[1];
+    const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    const uint32_t pw = ((const uint32_t*)txt)[x0 / 4 - 1], nw = ((const uint32_t*)txt)[x0 / 4 + 8];
+    uint32_t na = (pw | nw) & 0x80808080u;
+    uint32_t Lm = 0, Nm = 0, Sm = 0, SPm = 0, APm = 0, NAm = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        na |= w[j] & 0x80808080u;
+        NAm |= (w[j] & 0x80808080u) >> (7 - j);
+        const uint32_t x = w[j] & 0x7f7f7f7fu, y = x | 0x20202020u;
+        const uint32_t fL = (y + 0x1f1f1f1fu) & ~(y + 0x05050505u) & 0x80808080u;
+        const uint32_t fN = (x + 0x50505050u) & ~(x + 0x46464646u) & 0x80808080u;
+        const uint32_t fSP = ~((x ^ 0x20202020u) + 0x7f7f7f7fu) & 0x80808080u;
+        const uint32_t fS = ((x + 0x77777777u) & ~(x + 0x72727272u) & 0x80808080u) | fSP;
+        const uint32_t fAP = ~((x ^ 0x27272727u) + 0x7f7f7f7fu) & 0x80808080u;
+        Lm |= fL >> (7 - j); Nm |= fN >> (7 - j); Sm |= fS >> (7 - j); SPm |= fSP >> (7 - j); APm |= fAP >> (7 - j);
+    }
+    (void)na_out;
+    const uint32_t pb = pw >> 24, nb = nw & 0xffu;
+    int pk = ascii_kclass(pb);
+    uint32_t nS_in = (nb == 0x20 || (nb - 9) < 5u) ? 1u : 0u;
+    uint32_t FL = 0, SUP = 0, NOEXT = 0, APkill = 0, CONT = 0, wsleads = 0;
+    // ---- events: non-ASCII code points (decoded one by one; classes from the two-stage Unicode table)
+    if (na) {
+        Lm &= ~NAm; Nm &= ~NAm; Sm &= ~NAm; SPm &= ~NAm; APm &= ~NAm;     // the SWAR tests looked at the low 7 bits only
+        uint32_t covered = 0;
+        uint32_t nat = untranspose(NAm);
+        for (int it = -3; it < 32; it++) {
+            if (it >= 0) { if (!nat) break; it = __ffs(nat) - 1; nat &= nat - 1; }
+            const int x = x0 + it;
+            const uint8_t b = txt[x];
+            if (b < 0xC0) continue;                                   // ASCII or continuation byte
+            int len;
+            const bool ok = utf8_seq_ok(txt + x, P.n - (g0 + x), &len);
+            if (it < 0 && len <= -it) continue;                       // ends before the segment
+            if (!ok) { if (it >= 0) atomicMin((i64*)&P.stats[ST_ERR_POS], g0 + x); continue; }
+            const int kc = kclass_of_cp(utf8_decode(txt + x, len));
+            for (int t = 0; t < len; t++) {
+                const int pos = it + t;
+                if (pos < 0 || pos >= 32) continue;
+                const uint32_t tb = tbit(pos);
+                covered |= tb;
+                if (t > 0) CONT |= tb;
+                if (kc == KC_L) Lm |= tb; else if (kc == KC_N) Nm |= tb; else if (kc == KC_S) Sm |= tb;
+            }
+            if (kc == KC_S && it >= 0) wsleads |= tbit(it);
+        }
+        uint32_t stray = untranspose(NAm & ~covered);                 // bytes >= 0x80 not part of a well-formed sequence
+        if (stray) atomicMin((i64*)&P.stats[ST_ERR_POS], g0 + x0 + __ffs(stray) - 1);
+        if (pb >= 0x80) pk = smem_kclass(txt, x0 - 1);
+        if (nb >= 0x80) nS_in = smem_kclass(txt, x0 + 32) >= KC_S ? 1u : 0u;
+    }
+    uint32_t flprev = 0, killprev = 0;           // bit d-1: position x0-d (d = 1..3) is a forced start / inside a special
+    // ---- events: recognised specials that touch [x0-3, x0+32] (bits of the rec bitmap, read from L2)
+    if (P.n_sp > 0) {
+        const i64 g = g0 + x0;                                   // multiple of 32
+        const i64 wi0 = g >> 5;
+        int kprev = (c_sp.max_len + 3 + 31) >> 5;
+        if (kprev > wi0) kprev = (int)wi0;
+        for (int j = -kprev; j <= 1; j++) {
+            uint32_t rw = P.rec[wi0 + j];
+            if (j == 1) rw &= 1u;                                // only a special starting right after the segment matters
+            while (rw) {
+                const int bit = __ffs(rw) - 1; rw &= rw - 1;
+                const int q = x0 + 32 * j + bit;                 // window offset, may be negative
+                int m;
+                if (c_sp.n == 1) m = c_sp.offs[1];
+                else { int sp = special_match(P.text, g0 + q, P.n); m = sp >= 0 ? c_sp.offs[sp + 1] - c_sp.offs[sp] : 1; }
+                const int e = q + m;
+                if (e < x0 - 3 || q > x0 + 32) continue;
+                for (int pp = (q > x0 - 3 ? q : x0 - 3); pp < e && pp < x0 + 32; pp++) {
+                    if (pp >= x0) { APkill |= tbit(pp - x0); if (pp != q) SUP |= tbit(pp - x0); }
+                    else killprev |= 1u << (x0 - pp - 1);
+                }
+                if (q >= x0 && q < x0 + 32) FL |= tbit(q - x0);
+                if (e >= x0 && e < x0 + 32) FL |= tbit(e - x0);
+                else if (e >= x0 - 3 && e < x0) flprev |= 1u << (x0 - e - 1);
+                if (P.mode == 1) {                  // encode: the text before a special ends at it
+                    if (q - 1 >= x0 && q - 1 < x0 + 32) NOEXT |= tbit(q - 1 - x0);
+                    if (q == x0 + 32) nS_in = 1u;
+                }
+            }
+        }
+    }
+    const uint32_t pL = prevT(Lm, pk == KC_L), pN = prevT(Nm, pk == KC_N), pS = prevT(Sm, pk >= KC_S), pSP = prevT(SPm, pk == KC_SP);
+    // ---- events: live contractions whose effects reach this segment (apostrophe at x0-3 .. x0+31)
+    uint32_t apprev = 0;
+    if (((pw >> 8) & 0xff) == '\'') apprev |= 4u;      // x0-3
+    if (((pw >> 16) & 0xff) == '\'') apprev |= 2u;     // x0-2
+    if ((pw >> 24) == '\'') apprev |= 1u;              // x0-1
+    apprev &= ~killprev;
+    uint32_t apm = APm & ~APkill;
+    if (apm | apprev) {
+        uint32_t nat = untranspose(apm);
+        for (int d = 3; d >= 1; d--) {
+            if (!(apprev & (1u << (d - 1)))) continue;
+            const int a = x0 - d;
+            const uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
+            int clen = 0;
+            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
+            else if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) clen = 3;
+            if (P.mode == 1 && clen) {          // the contraction may not reach into a special (text ends there)
+                if (rec_bit_g(P, g0 + a + 1)) clen = 0;
+                else if (clen == 3 && (rec_bit_g(P, g0 + a + 2))) clen = 0;
+            }
+            if (clen <= d) continue;             // ends before this segment... unless the forced start lands on x0
+            bool live = (flprev >> (d - 1)) & 1;
+            if (!live) { int k = smem_kclass(txt, a - 1); live = (k == KC_L || k == KC_N || k == KC_S); }
+            if (!live) continue;
+            for (int t = 1; t < clen; t++) if (a + t >= x0) SUP |= tbit(a + t - x0);
+            if (a + clen >= x0) FL |= tbit(a + clen - x0);
+        }
+        // contraction ending exactly at x0 (clen == d): forced start at x0
+        for (int d = 3; d >= 2; d--) {
+            if (!(apprev & (1u << (d - 1)))) continue;
+            const int a = x0 - d;
+            const uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
+            int clen = 0;
+            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
+            else if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) clen = 3;
+            if (clen != d) continue;
+            if (P.mode == 1) {
+                if (rec_bit_g(P, g0 + a + 1)) continue;
+                if (clen == 3 && (rec_bit_g(P, g0 + a + 2))) continue;
+            }
+            bool live = (flprev >> (d - 1)) & 1;
+            if (!live) { int k = smem_kclass(txt, a - 1); live = (k == KC_L || k == KC_N || k == KC_S); }
+            if (live) FL |= tbit(0);
+        }
+        while (nat) {
+            const int ap = __ffs(nat) - 1; nat &= nat - 1;
+            const int a = x0 + ap;
+            const uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
+            int clen = 0;
+            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
+            else if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) clen = 3;
+            if (!clen) continue;
+            if (P.mode == 1) {
+                if (rec_bit_g(P, g0 + a + 1)) continue;
+                if (clen == 3 && (rec_bit_g(P, g0 + a + 2))) continue;
+            }
+            const uint32_t tb = tbit(ap);
+            const bool live = (FL & tb) || (pL & tb) || (pN & tb) || ((pS & tb) && !(pSP & tb));
+            if (!live) continue;
+            for (int t = 1; t < clen; t++) if (ap + t < 32) SUP |= tbit(ap + t);
+            if (ap + clen < 32) FL |= tbit(ap + clen);
+        }
+    }
+    // ---- the start rule, 32 positions at once
+    const uint32_t Om = ~(Lm | Nm | Sm), pO = ~(pL | pN | pS);
+    const uint32_t same = (Lm & pL) | (Nm & pN) | (Om & pO);
+    const uint32_t NS = nextT(Sm, nS_in) | NOEXT;
+    uint32_t st = (((~Sm & ~pSP & (pS | ~same)) | (Sm & (~pS | ~NS))) & ~SUP & ~CONT) | FL;
+    // multi-byte whitespace (U+00A0, U+2003, U+3000, ...): the look-ahead is the next CODE POINT, not the next byte
+    if (wsleads) {
+        uint32_t nat = untranspose(wsleads);
+        while (nat) {
+            const int pos = __ffs(nat) - 1; nat &= nat - 1;
+            const uint32_t tb = tbit(pos);
+            if ((FL & tb) || (SUP & tb) || !(pS & tb)) continue;     // already decided by the generic formula
+            const int nx = x0 + pos + utf8_len_from_lead(txt[x0 + pos]);
+            const bool exists = !(P.mode == 1 && rec_bit_g(P, g0 + nx));
+            const bool start = exists && smem_kclass(txt, nx) < KC_S;
+            st = start ? (st | tb) : (st & ~tb);
+        }
+    }
+    return untranspose(st);
+}
+
+// Fast path, whole tile.  Returns false when the tile needs the generic path (smask is then rewritten).
+__device__ bool tile_scan_fast(const PretokParams& P, TileSmem& S, i64 g0, int buf) {
+    const uint8_t* txt = S.txt[buf];
+    uint32_t na = 0;
+    for (int sgi = threadIdx.x; sgi < PT_NSEG; sgi += PT_THREADS) {
+        uint32_t m = segment_scan(P, txt, g0, sgi, &na);
+        S.smask[sgi] = sgi == PT_NSEG - 1 ? (m & 1u) : m;
+    }
     __syncthreads();
+    return true;
+}
+
+// pass D1: compact the start positions of S.smask into S.tokpos.  Only starts inside the tile become
+// tokens; the first start in the right halo is kept as the end of the last one.
+__device__ void tile_compact(TileSmem& S) {
+    const int tid = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < PT_TILE / 32; base += PT_THREADS) {
+        int wi = base + tid;
+        uint32_t m = wi < PT_TILE / 32 ? S.smask[wi] : 0;
+        int cnt = __popc(m), total;
+        int off = block_exclusive_scan(cnt, S.scan_tmp, &total) + carry;
+        while (m) { int bit = __ffs(m) - 1; m &= m - 1; S.tokpos[off++] = (uint16_t)(PT_HL + wi * 32 + bit); }
+        carry += total;
+    }
+    if (tid == 0) {
+        int sentinel = -1;
+        for (int wi = PT_TILE / 32; wi < PT_NMASK && sentinel < 0; wi++) { uint32_t m = S.smask[wi]; if (m) sentinel = PT_HL + wi * 32 + __ffs(m) - 1; }
+        S.ntok_own = carry;
+        S.ntok_total = carry + (sentinel >= 0 ? 1 : 0);
+        if (sentinel >= 0) S.tokpos[carry] = (uint16_t)sentinel;
+    }
+    __syncthreads();
+}
+
+// Passes A-D1 for one tile.  On return S.tokpos / S.ntok_* describe the tile's tokens.
+__device__ void tile_scan(const PretokParams& P, TileSmem& S, i64 tile, int buf, bool* has_cut) {
+    const i64 g0 = (P.tile_base + tile) * PT_TILE - PT_HL;
+    tile_stage_rec(P, S, g0);
+    bool done = false;
+    if (!tile_is_boundary(P, g0, has_cut)) done = tile_scan_fast(P, S, g0, buf);
+    if (!done) tile_scan_generic(P, S, tile, buf);
+    tile_compact(S);
 }
 
 // 16 bytes of the window starting at offset s (unaligned) as two u64
@@ -524,7 +798,10 @@ __device__ __forceinline__ void init_tile_smem(TileSmem& S) {
 // ---------------------------------------------------------------------------------
 // K1+K2: count pre-tokens into the hash tables
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS) k_pretok_count(PretokParams P) {
     __shared__ TileSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     u64* ck0 = (u64*)dyn_smem;
@@ -542,16 +819,21 @@ __global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
         i64 next = tile + gridDim.x;
         if (next < P.n_tiles && tid == 0) tile_issue_load(P, S, next, buf ^ 1);
         mbar_wait(&S.bar[buf], phase[buf]); phase[buf] ^= 1;
-        tile_scan(P, S, tile, buf);
+        bool has_cut;
+        tile_scan(P, S, tile, buf, &has_cut);
 
         const uint8_t* txt = S.txt[buf];
         const i64 g0 = (P.tile_base + tile) * PT_TILE - PT_HL;
         const int ntok = S.ntok_own, ntot = S.ntok_total;
+        // cache misses are collected and sent to the global table together, so that their
+        // probe latencies overlap instead of adding up
+        u64 mk0[PT_MAXMISS], mk1[PT_MAXMISS], mh[PT_MAXMISS];
+        int nmiss = 0;
         for (int k = tid; k < ntok; k += PT_THREADS) {
             int s = S.tokpos[k];
             i64 gpos = g0 + s;
             if (gpos < P.own_lo || gpos >= P.own_hi) continue;
-            if (P.mode == 1 && (S.info[s] & IB_IN)) continue;        // encode: specials are not words
+            if (P.mode == 1 && P.n_sp > 0 && ((S.recw[(s >> 5) + 4] >> (s & 31)) & 1)) continue;   // encode: specials are not words
             my_tok++;
             if (k + 1 >= ntot) {                                      // end not inside the window
                 u64 idx = atomicAdd((u64*)&P.stats[ST_OVF_N], 1ULL);
@@ -565,14 +847,36 @@ __global__ void __launch_bounds__(PT_THREADS) k_pretok_count(PretokParams P) {
                 pack_short_key(txt, s, len, &k0, &k1);
                 u64 h = short_hash(k0, k1);
                 if (!cache_add(ck0, ck1, cc, h, k0, k1)) {
-                    if (short_insert_h(P.skeys, P.scounts, P.scap, h, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
-                    if (created) { my_us++; my_ub += len; }
+                    if (nmiss < PT_MAXMISS) {
+#pragma unroll
+                        for (int i = 0; i < PT_MAXMISS; i++) if (i == nmiss) { mk0[i] = k0; mk1[i] = k1; mh[i] = h; }
+                        nmiss++;
+                    } else {
+                        if (short_insert_h(P.skeys, P.scounts, P.scap, h, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                        if (created) { my_us++; my_ub += len; }
+                    }
                 }
             } else {
                 u64 h = 0;
                 for (int j = 0; j < len; j++) h += long_hash_term(txt[s + j], j);
                 if (long_insert(P.lent, P.lcap, P.text, long_hash_fix(h), gpos, len, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
                 if (created) { my_ul++; my_ub += len; }
+            }
+        }
+        {
+            ulonglong2 kv[PT_MAXMISS];
+            const u64 smask_ = (u64)P.scap - 1;
+#pragma unroll
+            for (int i = 0; i < PT_MAXMISS; i++) if (i < nmiss) kv[i] = __ldcg(&P.skeys[mh[i] & smask_]);
+#pragma unroll
+            for (int i = 0; i < PT_MAXMISS; i++) {
+                if (i >= nmiss) continue;
+                if (kv[i].x == mk0[i] && kv[i].y == mk1[i]) atomicAdd((u64*)&P.scounts[mh[i] & smask_], 1ULL);
+                else {
+                    int created;
+                    if (short_insert_h(P.skeys, P.scounts, P.scap, mh[i], mk0[i], mk1[i], 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                    if (created) { my_us++; my_ub += (u64)(mk0[i] >> 56); }
+                }
             }
         }
         __syncthreads();     // everyone is done with txt[buf] and S before the next iteration reuses them

@@ -15,7 +15,7 @@ from . import _ffi
 
 TOK_HASH_B = 0x100000001B3
 MASK64 = (1 << 64) - 1
-PT_TILE = 8192
+PT_TILE = 2048          # lower bound of the kernel's tile size (sizes the over-long token list)
 
 
 def _pow2_at_least(x: int) -> int:
