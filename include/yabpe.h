@@ -118,6 +118,13 @@ typedef struct {
 
 int yabpe_compact_words(const yabpe_pretok_args* a, const yabpe_word_table* w, void* stream);
 
+/* Multi-GPU exchange: add `n_words` packed pre-tokens (bytes a->text[offs[i] .. offs[i]+lens[i]), occurrence
+ * counts[i]) to the tables in `a` (a->text is the packed byte blob; long entries reference it).  Used
+ * after the NCCL all-to-all of hash-partitioned (word, count) lists; merges duplicates from different
+ * ranks exactly like trainer.py:221-225 merges occurrences.  has_long != 0 when some lens[i] > 256. */
+int yabpe_insert_words(const yabpe_pretok_args* a, const int64_t* offs, const int32_t* lens, const int64_t* counts,
+                       int64_t n_words, int32_t has_long, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Merge loop.  Replaces trainer.py:216-302 (_merge_loop): pair histogram, best-pair selection
  * max(count, (left_bytes, right_bytes)), left-to-right rewrite, incremental deltas.  One

@@ -165,6 +165,62 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
     return YABPE_OK;
 }
 
+// ---- merge packed (bytes, offsets, lengths, counts) words into the tables (multi-GPU exchange) ----
+__global__ void __launch_bounds__(256) k_insert_words(PretokParams P, const i64* offs, const int32_t* lens, const i64* cnts, i64 nw) {
+    u64 my_us = 0, my_ul = 0, my_ub = 0;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += stride) {
+        const int len = lens[w];
+        const i64 pos = offs[w], c = cnts[w];
+        int created = 0;
+        if (len <= 0) continue;
+        if (len <= PT_SHORT_MAX) {
+            u64 lo = 0, hi = 0;
+            for (int k = 0; k < len; k++) { u64 b = P.text[pos + k]; if (k < 8) lo |= b << (8 * k); else hi |= b << (8 * (k - 8)); }
+            const u64 k0 = (lo & 0x00FFFFFFFFFFFFFFULL) | ((u64)len << 56), k1 = (lo >> 56) | (hi << 8) | (1ULL << 56);
+            if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, c, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+            if (created) { my_us++; my_ub += len; }
+        } else if (len <= 256) {
+            u64 h = 0;
+            for (int j = 0; j < len; j++) h += long_hash_term(P.text[pos + j], j);
+            if (long_insert(P.lent, P.lcap, P.text, long_hash_fix(h), pos, len, c, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+            if (created) { my_ul++; my_ub += len; }
+        }
+    }
+    if (my_us) atomicAdd((u64*)&P.stats[ST_UNIQ_SHORT], my_us);
+    if (my_ul) atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], my_ul);
+    if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
+}
+__global__ void __launch_bounds__(256) k_insert_words_long(PretokParams P, const i64* offs, const int32_t* lens, const i64* cnts, i64 nw) {
+    __shared__ u64 sh_acc; __shared__ i64 sh[4];
+    for (i64 w = blockIdx.x; w < nw; w += gridDim.x) {
+        const i64 len = lens[w];
+        if (len <= 256) continue;
+        u64 h = block_long_hash(P.text, offs[w], len, &sh_acc);
+        int created;
+        i64 slot = block_long_upsert(P.lent, P.lcap, P.text, h, offs[w], len, cnts[w], false, &created, sh);
+        if (threadIdx.x == 0) {
+            if (slot < 0) P.stats[ST_TABLE_FULL] = 1;
+            if (created) { atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], 1ULL); atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], (u64)len); }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int yabpe_insert_words(const yabpe_pretok_args* a, const int64_t* offs, const int32_t* lens, const int64_t* counts,
+                                  int64_t n_words, int32_t has_long, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokParams P;
+    int rc = make_params(a, &P);
+    if (rc) return rc;
+    ARG_CHECK(offs && lens && counts && n_words >= 0 && a->stats);
+    if (n_words == 0) return YABPE_OK;
+    k_insert_words<<<num_sms() * 8, 256, 0, st>>>(P, (const i64*)offs, lens, (const i64*)counts, n_words); LAUNCHED();
+    if (has_long) { k_insert_words_long<<<num_sms() * 2, 256, 0, st>>>(P, (const i64*)offs, lens, (const i64*)counts, n_words); LAUNCHED(); }
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
 static WordTable make_words(const yabpe_word_table* w) {
     WordTable W;
     W.wsym = w->wsym; W.sym_word = w->sym_word; W.woff = (i64*)w->woff; W.wlen = w->wlen; W.wcnt = (i64*)w->wcnt;

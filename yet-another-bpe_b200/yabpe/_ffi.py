@@ -24,7 +24,7 @@ INT64_MAX = (1 << 63) - 1
 EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
-    "yabpe_launch_count",
+    "yabpe_launch_count", "yabpe_insert_words",
 ]
 
 
@@ -110,6 +110,8 @@ def load() -> C.CDLL:
     L.yabpe_pretok_count.argtypes = [C.POINTER(PretokArgs), C.c_void_p]
     L.yabpe_compact_words.restype = C.c_int
     L.yabpe_compact_words.argtypes = [C.POINTER(PretokArgs), C.POINTER(WordTable), C.c_void_p]
+    L.yabpe_insert_words.restype = C.c_int
+    L.yabpe_insert_words.argtypes = [C.POINTER(PretokArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.yabpe_merge_loop.restype = C.c_int
     L.yabpe_merge_loop.argtypes = [C.POINTER(MergeArgs), C.c_void_p]
     L.yabpe_encode_words.restype = C.c_int

@@ -71,6 +71,31 @@ def chunk_cuts(data: np.ndarray, chunk_size: int) -> list[int]:
     return cuts
 
 
+def device_chunk_cuts(text_dev, n: int, chunk_size: int) -> list[int]:
+    """`chunk_cuts` for bytes resident on the device: reads only the <= 5 bytes around each cut."""
+    cuts: list[int] = []
+    if n <= chunk_size:
+        return cuts
+    start = 0
+    while start < n:
+        tentative = min(start + chunk_size, n)
+        if tentative < n:
+            bstart = max(0, tentative - 4)
+            window = text_dev[bstart:tentative + 1].cpu().numpy()
+            pos = tentative - bstart
+            while pos > 0 and (int(window[pos]) & 0xC0) == 0x80:
+                pos -= 1
+            actual = bstart + pos
+        else:
+            actual = n
+        if actual > start:
+            cuts.append(actual)
+            start = actual
+        else:
+            start += 1
+    return [c for c in cuts if 0 < c < n]
+
+
 @dataclass
 class TrainStats:
     n_bytes: int = 0
@@ -133,26 +158,7 @@ class BBPETrainer:
         torch = _ffi.require_cuda()
         if n == 0:
             return self._finish(self._init_base_vocab(), [])
-        cs = int(self.config.chunk_size_bytes)
-        cuts: list[int] = []
-        if n > cs:                                                        # trainer.py:172-198 on device bytes
-            start = 0
-            while start < n:
-                tentative = min(start + cs, n)
-                if tentative < n:
-                    bstart = max(0, tentative - 4)
-                    window = text_dev[bstart:tentative + 1].cpu().numpy()
-                    pos = tentative - bstart
-                    while pos > 0 and (int(window[pos]) & 0xC0) == 0x80:
-                        pos -= 1
-                    actual = bstart + pos
-                else:
-                    actual = n
-                if actual > start:
-                    cuts.append(actual)
-                    start = actual
-                else:
-                    start += 1
+        cuts = device_chunk_cuts(text_dev, n, int(self.config.chunk_size_bytes))
         return self._train_on_device(torch, text_dev, n, cuts, [0], [name])
 
     def _train_on_device(self, torch, text_dev, n: int, cuts: list[int], file_starts: list[int],
