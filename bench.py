@@ -38,6 +38,7 @@ WORKLOADS = {
     "owt-1g-v32k": ("owt", 1_000_000_000, 32_000, 20260102),
 }
 SPECIALS = ["<|endoftext|>"]
+NCU_TRAFFIC_RATIO = 1.27          # (dram__bytes_read + dram__bytes_write) / corpus bytes, profiles/r1_ncu_pretok_*.txt
 METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
 UNIT = "MB/s"
 
@@ -95,6 +96,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def _trim_utf8(b: bytes) -> bytes:
+    while b and (b[-1] & 0xC0) == 0x80:
+        b = b[:-1]
+    if b and b[-1] >= 0xC0:
+        b = b[:-1]
+    return b
+
+
 def cpu_port_run(sample: bytes, vocab: int) -> tuple[float, int]:
     """One timed run of the oracle port on `sample`; returns (seconds, merges)."""
     from oracle import oracle
@@ -112,8 +121,20 @@ def run_reference(args) -> None:
     sys.path.insert(0, str(ROOT / "tests"))
     import common
     sample_bytes = args.cpu_sample_mb << 20
-    gen = common.synth_tinystories if kind == "tinystories" else common.synth_owt
-    sample = gen(sample_bytes, seed=seed)
+    sample = None
+    try:                                      # same generator as the GPU arm when a device is present
+        import torch
+        if torch.cuda.is_available():
+            from synth_gpu import synth_corpus_device
+            dev_text, dn = synth_corpus_device(torch, sample_bytes, kind, seed, piece_bytes=min(sample_bytes, 256 << 20))
+            sample = _trim_utf8(dev_text[:dn].cpu().numpy().tobytes())
+            del dev_text
+            torch.cuda.empty_cache()
+    except Exception:
+        sample = None
+    if sample is None:
+        gen = common.synth_tinystories if kind == "tinystories" else common.synth_owt
+        sample = gen(sample_bytes, seed=seed)
     for _ in range(args.warmup):
         cpu_port_run(sample[: 1 << 20], vocab)
     t = 0.0
@@ -149,6 +170,8 @@ def main() -> None:
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--encode-mb", type=int, default=256)
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("YABPE_BENCH_WATCHDOG_S", "600")), exit=True)   # never hang a GPU box
     if args.impl == "reference":
         run_reference(args)
         return
@@ -157,7 +180,8 @@ def main() -> None:
     import torch
     import yabpe
     from synth_gpu import synth_corpus_device
-    from yabpe import _ffi
+    from yabpe import _ffi, engine
+    from yabpe.distributed import train_device_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +206,6 @@ def main() -> None:
         tr = yabpe.BBPETrainer(cfg)
         tr.profile = profile
         if world > 1:
-            from yabpe.distributed import train_device_sharded
             model = train_device_sharded(tr, text_dev, n)
         else:
             model = tr.train_device(text_dev, n)
@@ -220,27 +243,37 @@ def main() -> None:
     if tile_ms:
         achieved = n / (tile_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_pretok_count", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+                    "frac": round(achieved / peak, 4), "traffic": int(n * NCU_TRAFFIC_RATIO), "peak_source": peak_kind,
+                    "traffic_source": "dram bytes per algorithmic byte from the committed ncu --set full capture (profiles/), scaled to this launch",
                     "algorithmic_bytes_per_launch": n, "ms_per_launch": round(tile_ms, 3)}
 
-    # e2e: pinned host bytes -> H2D -> train -> D2H results
+    # e2e: pinned host bytes -> H2D -> train -> D2H results (every rank copies its own shard)
     e2e = None
-    if not args.skip_e2e and world == 1:
+    if not args.skip_e2e:
         host = torch.empty(n, dtype=torch.uint8).pin_memory()
         host.copy_(text_dev[:n])
         host_np = host.numpy()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         reps = max(1, min(args.steps, 2))
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(reps):
             tr2 = yabpe.BBPETrainer(cfg)
-            m2 = tr2.train_from_buffers([host_np])
-        torch.cuda.synchronize()
+            if world > 1:
+                dev2, n2 = engine.to_device_text(torch, host, non_blocking=True)
+                m2 = train_device_sharded(tr2, dev2, n2)
+            else:
+                m2 = tr2.train_from_buffers([host_np])
+        barrier()
         dt = (time.perf_counter() - t0) / reps
-        d2h = sum(len(a) + len(b) for a, b in m2.merges) + sum(len(k) for k in m2.vocab)
-        e2e = {"value": round(n / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": round(dt * 1e3, 2)}
-        assert m2.merges == model.merges
+        if world > 1:
+            tmax = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax.item())
+        if rank == 0:
+            d2h = sum(len(a) + len(b) for a, b in m2.merges) + sum(len(k) for k in m2.vocab)
+            e2e = {"value": round(total_bytes / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(total_bytes),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 2)}
+            assert m2.merges == model.merges
         del host, host_np
 
     # secondary: encode MB/s with the trained model on a slice of the corpus (device-resident in, ids out)

@@ -162,6 +162,20 @@ def test_train_synthetic_vs_oracle(yabpe, tmp_path, kind, size, vocab):
     assert got_vocab == want_vocab
 
 
+def test_train_medium_corpus_vs_oracle_and_deterministic(yabpe, tmp_path):
+    """Big enough for many grid-mode merges, index rebuilds and threshold steps; run twice (races show up
+    as run-to-run differences) and check against the oracle."""
+    data = common.synth_owt(24_000_000, seed=77)
+    p = tmp_path / "m.txt"
+    p.write_bytes(data)
+    want = oracle.train_bpe(p, 2500, ["<|endoftext|>"], fast=True)
+    got1 = yabpe.train_bpe(p, 2500, ["<|endoftext|>"])
+    got2 = yabpe.train_bpe(p, 2500, ["<|endoftext|>"])
+    assert got1[1] == got2[1]
+    assert got1[1] == want[1]
+    assert got1[0] == want[0]
+
+
 def test_train_edge_cases(yabpe, tmp_path):
     p = tmp_path / "e.txt"
     p.write_bytes(b"")

@@ -100,6 +100,8 @@ struct SpecialSet {
     int offs[YABPE_MAX_SPECIALS + 1];
     unsigned char blob[YABPE_MAX_SPECIAL_BYTES];
     unsigned char first_byte_mask[32];   // 256-bit set of first bytes
+    int n_first;                         // distinct first bytes (<= 8 listed; more -> generic scan)
+    unsigned char first[8];
 };
 __constant__ SpecialSet c_sp;
 

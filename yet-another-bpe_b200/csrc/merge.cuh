@@ -892,12 +892,13 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         }
 
         // ---- one merge in grid mode.  With a valid top list every CTA finds the best pair on its own
-        //      (same data, same answer): no grid barrier for the argmax.
+        //      (same data, same answer); the barrier only keeps the rewrite (which changes the counts)
+        //      from starting before every CTA has read them.
         Best best;
         if (T2 > 0) {
             best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
+            grid.sync();
             if (best.slot < 0 || best.cnt < T2 || best.cnt < T) {
-                grid.sync();                                // everyone has finished reading the list
                 if (gtid == 0) M.state[MS_T2] = 0;
                 grid.sync();
                 continue;

@@ -90,12 +90,34 @@ __device__ __forceinline__ i64 logical_end_after(const PretokParams& P, i64 i) {
 }
 
 __global__ void __launch_bounds__(256) k_special_candidates(PretokParams P, i64 lo, i64 hi) {
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-        uint8_t b = P.text[i];
-        if (!((c_sp.first_byte_mask[b >> 3] >> (b & 7)) & 1)) continue;
-        i64 lim = logical_end_after(P, i);
-        if (special_match(P.text, i, lim) >= 0) atomicOr(&P.cand[i >> 5], 1u << (i & 31));
+    // 16 bytes per thread and step; a SWAR zero-byte test finds the (rare) first bytes of specials
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 c0 = lo >> 4, c1 = (hi + 15) >> 4;
+    const bool generic = c_sp.n_first > 8;
+    for (i64 c = c0 + (i64)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += stride) {
+        const uint4 v = ((const uint4*)P.text)[c];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t hit = 0;                                   // bit 4j+k: byte k of word j starts like a special
+        if (!generic) {
+            for (int f = 0; f < c_sp.n_first; f++) {
+                const uint32_t F = 0x01010101u * c_sp.first[f];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t z = w[j] ^ F;
+                    uint32_t m = ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z) & 0x80808080u;     // exact zero-byte flags
+                    while (m) { int b = __ffs(m) - 1; m &= m - 1; hit |= 1u << (4 * j + (b >> 3)); }
+                }
+            }
+        } else hit = 0xffffu;
+        while (hit) {
+            const int k = __ffs(hit) - 1; hit &= hit - 1;
+            const i64 i = (c << 4) + k;
+            if (i < lo || i >= hi) continue;
+            const uint8_t b = P.text[i];
+            if (!((c_sp.first_byte_mask[b >> 3] >> (b & 7)) & 1)) continue;
+            const i64 lim = logical_end_after(P, i);
+            if (special_match(P.text, i, lim) >= 0) atomicOr(&P.cand[i >> 5], 1u << (i & 31));
+        }
     }
 }
 

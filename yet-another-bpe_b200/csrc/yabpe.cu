@@ -67,6 +67,10 @@ static int upload_specials(const uint8_t* blob, const int32_t* offs, int32_t n, 
         ARG_CHECK(len <= PT_HR / 2);
         if (len > h.max_len) h.max_len = len;
         unsigned char b = blob[offs[i]];
+        if (!((h.first_byte_mask[b >> 3] >> (b & 7)) & 1)) {
+            if (h.n_first < 8) h.first[h.n_first] = b;
+            h.n_first++;
+        }
         h.first_byte_mask[b >> 3] |= (unsigned char)(1u << (b & 7));
     }
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_sp, &h, sizeof h, 0, cudaMemcpyHostToDevice, st));

@@ -76,10 +76,10 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
     L = _ffi.load()
     dev = text_dev.device
-    if short_cap is None:
-        short_cap = _pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26))
-    if long_cap is None:
-        long_cap = _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24))
+    if short_cap is None or long_cap is None:
+        est_s, est_l = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode)
+        short_cap = short_cap or est_s
+        long_cap = long_cap or est_l
     n_cuts = 0 if cuts is None else int(len(cuts))
     cuts_t = torch.from_numpy(np.ascontiguousarray(cuts, dtype=np.int64)).to(dev) if n_cuts else None
     blob, offs = pack_specials(specials)
@@ -119,6 +119,30 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
                 ev = torch.cuda.Event(enable_timing=True); ev.record(); stage_events.append(ev)
             a.stages = 0
     return res
+
+
+_SAMPLE_BYTES = 16 << 20
+
+
+def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple[int, int]:
+    """Hash-table capacities.  Small inputs: proportional to n.  Large inputs: count the unique
+    pre-tokens of a 16 MB prefix and extrapolate (Heaps' law, exponent 0.75), so that a 2 GB corpus
+    with 10^5 word types does not zero and scan GB-sized tables.  Overflow is detected and retried."""
+    if n <= 4 * _SAMPLE_BYTES:
+        return (_pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26)), _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24)))
+    m = _SAMPLE_BYTES
+    while m > 0 and (int(text_dev[m].item()) & 0xC0) == 0x80:
+        m -= 1
+    sub_cuts = None if cuts is None else np.asarray([c for c in cuts if 0 < c < m], dtype=np.int64)
+    res = pretok_count(torch, text_dev, m, sub_cuts if sub_cuts is not None and len(sub_cuts) else None, specials, mode,
+                       short_cap=1 << 22, long_cap=1 << 20)     # the prefix as a text of its own: an estimate only
+    st = res.stats_host()
+    scale = (n / m) ** 0.75
+    us = max(int(st[_ffi.ST_UNIQ_SHORT]), 1 << 10) * scale
+    ul = max(int(st[_ffi.ST_UNIQ_LONG]), 1 << 6) * scale
+    if st[_ffi.ST_TABLE_FULL] != 0:
+        us, ul = 1 << 24, 1 << 22
+    return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))))
 
 
 def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None) -> tuple[PretokResult, np.ndarray]:
