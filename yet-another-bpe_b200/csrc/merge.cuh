@@ -12,13 +12,18 @@
 // with incremental pair-count deltas.  See "merge loop" below for the two execution modes.
 #pragma once
 
-#include <cooperative_groups.h>
-
 #include "pretok.cuh"
 
-namespace cg = cooperative_groups;
-
 #define ML_THREADS 1024
+#ifndef ML_DEFER_NPAIRS
+#define ML_DEFER_NPAIRS 1
+#endif
+#ifndef ML_NPAIRS_CHECK_D
+#define ML_NPAIRS_CHECK_D 1
+#endif
+#ifndef ML_NPAIRS_CHECK_E
+#define ML_NPAIRS_CHECK_E 1
+#endif
 #define PAIR_KEY(a, b) (0x8000000000000000ULL | ((u64)(uint32_t)(a) << 32) | (u64)(uint32_t)(b))
 #define TOK_HASH_B 0x100000001b3ULL
 
@@ -45,6 +50,8 @@ namespace cg = cooperative_groups;
 #define MS_T2 5
 #define MS_LEADER_REASON 31
 #define MS_TOP_REBUILDS 28
+#define MS_BAR_COUNT 29
+#define MS_BAR_GEN 30
 
 #define ME_PAIR_TABLE_FULL 1
 #define ME_TOK_POOL_FULL 2
@@ -120,6 +127,7 @@ __global__ void __launch_bounds__(256) k_compact_long(const LongEntry* ent, i64 
 //               other CTAs wait at one grid barrier; used while the active set and the
 //               affected word lists are small (the common case after the first few hundred merges)
 struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
+#define ML_TOP_N 512
 
 #define ML_MAX_RANGES 12
 #define ML_LEADER_ACT_MAX 32768
@@ -129,6 +137,7 @@ struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
 struct MergeParams {
     // words
     int32_t* wsym; const int32_t* sym_word; i64 n_syms;
+    int32_t* wslot;                              // per symbol slot: pair-table slot of (sym[j], sym[j+1])
     const i64* woff; int32_t* wlen; const i64* wcnt; i64 n_words; int32_t* wstamp;
     // tokens (ids < n_base are prepared by the host: 256 bytes + specials)
     uint8_t* tok_bytes; i64 tok_bytes_cap; i64* tok_off; u64* tok_hash; u64* tok_pow;
@@ -148,6 +157,27 @@ struct MergeParams {
     i64 num_merges; i64 min_freq;
 };
 
+// Grid-wide barrier on two words of the state array (arrival counter + generation).  The kernel is
+// launched cooperatively, so all CTAs are co-resident and spinning is safe.  Thread 0's fences order the
+// CTA's earlier writes before the arrival and drop stale L1 lines after the release.
+__device__ __forceinline__ void grid_barrier(const MergeParams& M) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile i64* gen = &M.state[MS_BAR_GEN];
+        const i64 g = *gen;
+        __threadfence();
+        if (atomicAdd((u64*)&M.state[MS_BAR_COUNT], 1ULL) == (u64)gridDim.x - 1) {
+            *(volatile i64*)&M.state[MS_BAR_COUNT] = 0;
+            __threadfence();
+            atomicAdd((u64*)&M.state[MS_BAR_GEN], 1ULL);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ i64 pair_find(const MergeParams& M, u64 key) {
     u64 mask = (u64)M.pcap - 1;
     u64 slot = mix64(key) & mask;
@@ -163,14 +193,18 @@ __device__ __forceinline__ i64 pair_upsert(const MergeParams& M, u64 key) {
     u64 mask = (u64)M.pcap - 1;
     u64 slot = mix64(key) & mask;
     for (i64 probes = 0; probes < M.pcap; probes++) {
-        u64 k = *(volatile u64*)&M.pkey[slot];
+        u64 k = M.pkey[slot];                       // keys are write-once: a cached value is either right or empty
         if (k == 0) {
             k = atomicCAS(&M.pkey[slot], 0ULL, key);
+#if ML_DEFER_NPAIRS
+            if (k == 0) { atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL); return (i64)slot; }   // load factor: checked once per merge
+#else
             if (k == 0) {
                 u64 np = atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL);
                 if ((i64)np * 4 > M.pcap * 3) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL);
                 return (i64)slot;
             }
+#endif
         }
         if (k == key) return (i64)slot;
         slot = (slot + 1) & mask;
@@ -267,21 +301,21 @@ __device__ Best block_best_fast(const MergeParams& M, Best v, Best* sh, i64* sh_
 }
 
 // grid-wide argmax over the active set; every block returns the same result
-__device__ Best grid_argmax(const MergeParams& M, cg::grid_group& grid, Best* sh) {
+__device__ Best grid_argmax(const MergeParams& M, Best* sh) {
     Best v = scan_active(M, M.state[MS_ACT_N], (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
     v = block_best(M, v, sh);
     if (threadIdx.x == 0) M.partial[blockIdx.x] = v;
-    grid.sync();
+    grid_barrier(M);
     Best w{0, -1, 0, 0, 0};
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { Best t = M.partial[i]; if (best_gt(M, t, w)) w = t; }
     return block_best(M, w, sh);
 }
 
-__device__ void rebuild_active(const MergeParams& M, cg::grid_group& grid, i64 T) {
+__device__ void rebuild_active(const MergeParams& M, i64 T) {
     i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     for (i64 i = gtid; i < (M.pcap + 31) / 32; i += gstride) M.inact[i] = 0;
     if (gtid == 0) { M.state[MS_ACT_N] = 0; M.state[MS_TREBUILDS]++; }
-    grid.sync();
+    grid_barrier(M);
     for (i64 s = gtid; s < M.pcap; s += gstride) {
         if (M.pkey[s] != 0 && M.pcnt[s] >= T) {
             atomicOr(&M.inact[s >> 5], 1u << (s & 31));
@@ -289,27 +323,23 @@ __device__ void rebuild_active(const MergeParams& M, cg::grid_group& grid, i64 T
             M.act[idx] = (int32_t)s;
         }
     }
-    grid.sync();
+    grid_barrier(M);
     if (gtid == 0) M.state[MS_ACT_BASE] = M.state[MS_ACT_N];
 }
 
 // CSR postings: for every pair slot the words that contain it (duplicates allowed)
-__device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* sh_scan, i64 m_now) {
+__device__ void rebuild_index(const MergeParams& M, i64* sh_scan, i64 m_now) {
     i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     for (i64 i = gtid; i < M.pcap; i += gstride) M.icnt[i] = 0;
     // forget the affected-log segments: the CSR built below covers everything
     for (i64 mm = M.state[MS_LAST_REBUILD_M] + gtid; mm < m_now; mm += gstride) M.tok_first[M.merge_new[mm]] = -1;
-    grid.sync();
+    grid_barrier(M);
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
         int32_t w = M.sym_word[i];
         i64 j = i - M.woff[w];
-        if (j + 1 < M.wlen[w]) {
-            i64 s = pair_find(M, PAIR_KEY(M.wsym[i], M.wsym[i + 1]));
-            if (s >= 0) atomicAdd(&M.icnt[s], 1u);
-            else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);
-        }
+        if (j + 1 < M.wlen[w]) atomicAdd(&M.icnt[M.wslot[i]], 1u);
     }
-    grid.sync();
+    grid_barrier(M);
     // exclusive scan of icnt -> ioff, one contiguous chunk per block
     i64 chunk = (M.pcap + gridDim.x - 1) / gridDim.x;
     i64 lo = chunk * blockIdx.x, hi = lo + chunk < M.pcap ? lo + chunk : M.pcap;
@@ -324,7 +354,7 @@ __device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* s
         __syncthreads();
         if (threadIdx.x == 0) M.bsum[blockIdx.x] = sh_scan[0];
     }
-    grid.sync();
+    grid_barrier(M);
     {
         i64 base = 0;
         for (int b = 0; b < (int)blockIdx.x; b++) base += M.bsum[b];
@@ -345,23 +375,52 @@ __device__ void rebuild_index(const MergeParams& M, cg::grid_group& grid, i64* s
         }
         if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) M.ioff[M.pcap] = (uint32_t)base;
     }
-    grid.sync();
+    grid_barrier(M);
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
         int32_t w = M.sym_word[i];
         i64 j = i - M.woff[w];
-        if (j + 1 < M.wlen[w]) {
-            i64 s = pair_find(M, PAIR_KEY(M.wsym[i], M.wsym[i + 1]));
-            if (s >= 0) { uint32_t r = atomicSub(&M.icnt[s], 1u) - 1; M.ipost[M.ioff[s] + r] = w; }
-        }
+        if (j + 1 < M.wlen[w]) { const int32_t s = M.wslot[i]; uint32_t r = atomicSub(&M.icnt[s], 1u) - 1; M.ipost[M.ioff[s] + r] = w; }
     }
     if (gtid == 0) { M.state[MS_ALOG_N] = 0; M.state[MS_LAST_REBUILD_M] = m_now; M.state[MS_REBUILDS]++; }
-    grid.sync();
+    grid_barrier(M);
 }
 
-__device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t x, int32_t y, i64 f) {
-    i64 s = pair_find(M, PAIR_KEY(x, y));
-    if (s >= 0) atomicAdd((u64*)&M.pcnt[s], (u64)(-f));
-    else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);
+// Leader mode keeps the counts of the top-list pairs mirrored in shared memory (the leader is the only
+// writer while it runs), so the per-merge argmax needs no global gather at all.
+#ifndef ML_NEW_COMMIT
+#define ML_NEW_COMMIT 1
+#endif
+#ifndef ML_USE_MIRROR
+#define ML_USE_MIRROR 1
+#endif
+struct LeaderMirror { i64 cnt[ML_TOP_N]; int32_t mkey[2 * ML_TOP_N]; int16_t mval[2 * ML_TOP_N]; };
+
+__device__ __forceinline__ int mirror_find(const LeaderMirror* lm, int32_t slot) {
+    uint32_t h = ((uint32_t)slot * 2654435761u) >> 22;          // 10 bits (2 * ML_TOP_N = 1024 entries)
+    for (;;) {
+        const int32_t k = lm->mkey[h];
+        if (k == slot + 1) return lm->mval[h];
+        if (k == 0) return -1;
+        h = (h + 1) & (2 * ML_TOP_N - 1);
+    }
+}
+__device__ __forceinline__ void mirror_insert(LeaderMirror* lm, int32_t slot, int idx) {
+    uint32_t h = ((uint32_t)slot * 2654435761u) >> 22;
+    for (;;) {
+        const int32_t old = atomicCAS(&lm->mkey[h], 0, slot + 1);
+        if (old == 0) { lm->mval[h] = (int16_t)idx; return; }
+        h = (h + 1) & (2 * ML_TOP_N - 1);
+    }
+}
+__device__ __forceinline__ void mirror_add(LeaderMirror* lm, int32_t slot, i64 d) {
+    if (!lm) return;
+    const int idx = mirror_find(lm, slot);
+    if (idx >= 0) atomicAdd((u64*)&lm->cnt[idx], (u64)d);
+}
+
+__device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t slot, i64 f, LeaderMirror* lm) {
+    atomicAdd((u64*)&M.pcnt[slot], (u64)(-f));     // the slot of every adjacency is cached in wslot: no probe
+    mirror_add(lm, slot, -f);
 }
 // "Top list": every pair with count >= T2, kept in global memory (at most ML_TOP_N entries) and
 // maintained by pair_add in both modes.  Scanning the whole active set every merge is bound by the
@@ -369,13 +428,13 @@ __device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t x, int32_
 // per-merge scan to a few hundred entries.  It is rebuilt (grid-wide) when its best entry falls
 // below T2 or when it overflows.  state[MS_T2]: > 0 valid threshold, 0 = rebuild needed,
 // -1 = disabled for this merge (more than ML_TOP_N pairs tie for the maximum).
-#define ML_TOP_N 512
 
-__device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, i64 T2) {
+__device__ __forceinline__ int32_t pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, i64 T2, LeaderMirror* lm) {
     const u64 key = PAIR_KEY(x, y);
     i64 s = pair_upsert(M, key);
-    if (s < 0) return;
+    if (s < 0) return 0;
     i64 now = (i64)atomicAdd((u64*)&M.pcnt[s], (u64)f) + f;
+    mirror_add(lm, (int32_t)s, f);
     if (now >= T) {
         uint32_t bit = 1u << (s & 31);
         if (!(atomicOr(&M.inact[s >> 5], bit) & bit)) {
@@ -390,6 +449,7 @@ __device__ __forceinline__ void pair_add(const MergeParams& M, int32_t x, int32_
             }
         }
     }
+    return (int32_t)s;
 }
 __device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w) {
     i64 d = (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL);
@@ -398,22 +458,29 @@ __device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w) {
 }
 
 // one thread rewrites one word in place (left->right, non-overlapping) and applies the deltas
-__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2) {
-    int32_t* s = M.wsym + M.woff[w];
+__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderMirror* lm) {
+    const i64 off = M.woff[w];
+    int32_t* s = M.wsym + off;
+    int32_t* ws = M.wslot + off;
     int n = M.wlen[w];
     i64 f = M.wcnt[w];
     int o = 0, j = 0;
-    int32_t prev_old = -1, prev_new = -1;
+    int32_t prev_new = -1;
     bool prev_changed = false, any = false;
     while (j < n) {
         int32_t x = s[j];
         if (j + 1 < n && x == a && s[j + 1] == b) {
-            if (o > 0) { pair_sub(M, prev_old, a, f); pair_add(M, prev_new, c, f, T, T2); }
-            pair_sub(M, a, b, f);
-            s[o++] = c; prev_old = b; prev_new = c; prev_changed = true; any = true; j += 2;
+            const int32_t sl_ab = ws[j];
+            if (o > 0) { pair_sub(M, ws[j - 1], f, lm); ws[o - 1] = pair_add(M, prev_new, c, f, T, T2, lm); }
+            pair_sub(M, sl_ab, f, lm);
+            s[o++] = c; prev_new = c; prev_changed = true; any = true; j += 2;
         } else {
-            if (o > 0 && prev_changed) { pair_sub(M, prev_old, x, f); pair_add(M, prev_new, x, f, T, T2); }
-            s[o++] = x; prev_old = x; prev_new = x; prev_changed = false; j += 1;
+            if (o > 0) {
+                const int32_t sl_old = ws[j - 1];
+                if (prev_changed) { pair_sub(M, sl_old, f, lm); ws[o - 1] = pair_add(M, prev_new, x, f, T, T2, lm); }
+                else ws[o - 1] = sl_old;
+            }
+            s[o++] = x; prev_new = x; prev_changed = false; j += 1;
         }
     }
     if (any) { M.wlen[w] = o; alog_append(M, w); }
@@ -421,9 +488,11 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
 
 // one warp rewrites one word (a != b): every lane owns one old position per 32-symbol chunk, so the
 // pair-count updates of a word are issued in parallel instead of as one dependent chain
-__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2) {
+__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderMirror* lm) {
     const int lane = threadIdx.x & 31;
-    int32_t* s = M.wsym + M.woff[w];
+    const i64 woff_ = M.woff[w];
+    int32_t* s = M.wsym + woff_;
+    int32_t* ws = M.wslot + woff_;
     const int n = M.wlen[w];
     const i64 f = M.wcnt[w];
     int out = 0;
@@ -431,8 +500,9 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
     int32_t carry_prev = -1;                       // old symbol at position base-1 (may already be overwritten)
     for (int base = 0; base < n; base += 32) {
         const int j = base + lane;
-        int32_t xm1 = -1, x0 = -1, x1 = -1, x2 = -1, x3 = -1;
+        int32_t xm1 = -1, x0 = -1, x1 = -1, x2 = -1, x3 = -1, ps0 = 0;
         if (j < n) x0 = s[j];
+        if (j + 1 < n) ps0 = ws[j];
         if (j + 1 < n) x1 = s[j + 1];
         if (j + 2 < n) x2 = s[j + 2];
         if (j + 3 < n) x3 = s[j + 3];
@@ -448,18 +518,24 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
         const unsigned keepmask = __ballot_sync(0xffffffffu, keep);
         any |= __any_sync(0xffffffffu, sel0);
         // old pair (j, j+1) disappears when either side is part of a site
-        if (valid && j + 1 < n && (sel0 || rem0 || sel1 || /*rem1*/ sel0)) pair_sub(M, x0, x1, f);
+        if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, ps0, f, lm);
         // new pair starting at kept position j
+        int32_t nslot = ps0; bool has_pair = false;
         if (keep) {
             const int jn = sel0 ? j + 2 : j + 1;              // next kept old position
             if (jn < n) {
+                has_pair = true;
                 const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
                 const bool seln = xn == a && xnn == b;
-                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2);
+                if (sel0 || seln) nslot = pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2, lm);
             }
         }
         __syncwarp();
-        if (keep) s[out + __popc(keepmask & ((1u << lane) - 1))] = sel0 ? c : x0;
+        if (keep) {
+            const int ni = out + __popc(keepmask & ((1u << lane) - 1));
+            s[ni] = sel0 ? c : x0;
+            if (has_pair) ws[ni] = nslot;
+        }
         out += __popc(keepmask);
         __syncwarp();
     }
@@ -469,18 +545,19 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
 // four words per warp, one per 8-lane group (words are short: ~6 symbols on average).  Group-local
 // version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes must call it together.
 __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
-                                 int32_t a, int32_t b, int32_t c, i64 T, i64 T2) {
+                                 int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderMirror* lm) {
     const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & 24;
     int32_t* s = M.wsym + (w >= 0 ? off : 0);
+    int32_t* ws = M.wslot + (w >= 0 ? off : 0);
     if (w < 0) n = 0;
     int out = 0;
     bool any = false;
     int32_t carry_prev = -1;
     for (int base = 0; __any_sync(0xffffffffu, base < n); base += 8) {
         const int j = base + gl;
-        int32_t x0 = -1, x1 = -1, x2 = -1, x3 = -1;
+        int32_t x0 = -1, x1 = -1, x2 = -1, x3 = -1, ps0 = 0;
         if (j < n) x0 = s[j];
-        if (j + 1 < n) x1 = s[j + 1];
+        if (j + 1 < n) { x1 = s[j + 1]; ps0 = ws[j]; }
         if (j + 2 < n) x2 = s[j + 2];
         if (j + 3 < n) x3 = s[j + 3];
         int32_t xm1 = __shfl_up_sync(0xffffffffu, x0, 1, 8);
@@ -494,17 +571,23 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
         const bool keep = valid && !rem0;
         const unsigned keepmask = (__ballot_sync(0xffffffffu, keep) >> gshift) & 0xffu;
         any |= ((__ballot_sync(0xffffffffu, sel0) >> gshift) & 0xffu) != 0;
-        if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, x0, x1, f);
+        if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, ps0, f, lm);
+        int32_t nslot = ps0; bool has_pair = false;
         if (keep) {
             const int jn = sel0 ? j + 2 : j + 1;
             if (jn < n) {
+                has_pair = true;
                 const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
                 const bool seln = xn == a && xnn == b;
-                if (sel0 || seln) pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2);
+                if (sel0 || seln) nslot = pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2, lm);
             }
         }
         __syncwarp();
-        if (keep) s[out + __popc(keepmask & ((1u << gl) - 1))] = sel0 ? c : x0;
+        if (keep) {
+            const int ni = out + __popc(keepmask & ((1u << gl) - 1));
+            s[ni] = sel0 ? c : x0;
+            if (has_pair) ws[ni] = nslot;
+        }
         out += __popc(keepmask);
         __syncwarp();
     }
@@ -537,14 +620,18 @@ __device__ __forceinline__ int32_t range_item(const Ranges& R, i64 it) {
 }
 
 // merged token id for (a, b): existing id when the bytes are already a token, else n_tok
-__device__ int32_t lookup_merged(const MergeParams& M, int32_t a, int32_t b, int32_t n_tok) {
-    u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
+struct MergedInfo { u64 H, P; i64 oa, ob, la, lb, tslot; };
+
+__device__ int32_t lookup_merged(const MergeParams& M, int32_t a, int32_t b, int32_t n_tok, MergedInfo* info = nullptr) {
+    const u64 ha = M.tok_hash[a], hb = M.tok_hash[b], pa_ = M.tok_pow[a], pb_ = M.tok_pow[b];
+    u64 H = ha * pb_ + hb;
     i64 oa = M.tok_off[a], ob = M.tok_off[b];
     i64 la = M.tok_off[a + 1] - oa, lb = M.tok_off[b + 1] - ob;
     u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
+    if (info) { info->H = H; info->P = pa_ * pb_; info->oa = oa; info->ob = ob; info->la = la; info->lb = lb; }
     for (;;) {
         u64 e = *(volatile u64*)&M.tset[slot];
-        if (e == 0) return n_tok;
+        if (e == 0) { if (info) info->tslot = (i64)slot; return n_tok; }
         int32_t id = (int32_t)(e & 0xffffffffu) - 1;
         if ((e >> 32) == (H >> 32) && id < n_tok && M.tok_hash[id] == H && M.tok_off[id + 1] - M.tok_off[id] == la + lb) {
             const uint8_t* pc = M.tok_bytes + M.tok_off[id];
@@ -620,6 +707,30 @@ __device__ void commit_merge_warp(const MergeParams& M, i64 m, int32_t a, int32_
         }
     }
 }
+// leader-mode commit by one warp; MI comes from lookup_merged, oc = current end of the token byte pool
+__device__ void commit_merge_leader(const MergeParams& M, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 alog_start,
+                                    const MergedInfo& MI, i64 oc) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c;
+        M.seg_start[m] = (int32_t)alog_start;
+        M.merge_next[m] = is_new ? -1 : M.tok_first[c];
+    }
+    if (!is_new) return;
+    if (oc + MI.la + MI.lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
+        if (lane == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL);
+        return;
+    }
+    for (i64 k = lane; k < MI.la; k += 32) M.tok_bytes[oc + k] = M.tok_bytes[MI.oa + k];
+    for (i64 k = lane; k < MI.lb; k += 32) M.tok_bytes[oc + MI.la + k] = M.tok_bytes[MI.ob + k];
+    if (lane == 0) {
+        M.tok_off[c + 1] = oc + MI.la + MI.lb;
+        M.tok_hash[c] = MI.H; M.tok_pow[c] = MI.P;
+        M.tok_first[c] = -1;
+        *(volatile u64*)&M.tset[MI.tslot] = (MI.H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1);
+        M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + MI.la + MI.lb;
+    }
+}
 // after the rewrite of merge m finished: close its segment and link it to its product token
 __device__ __forceinline__ void close_merge(const MergeParams& M, i64 m, int32_t c) {
     M.seg_end[m] = (int32_t)__ldcg(&M.state[MS_ALOG_N]);
@@ -653,6 +764,10 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
     __shared__ int sh_nlist;
     __shared__ i64 sh_cnt[ML_THREADS / 32];
     __shared__ i64 sh_state[5];          // act_n, alog_n, error, top_n, top_ovf: refreshed once per merge by thread 0
+    __shared__ MergedInfo MI;
+    __shared__ LeaderMirror LM;
+    for (int i = threadIdx.x; i < 2 * ML_TOP_N; i += blockDim.x) LM.mkey[i] = 0;
+    i64 pool_end = M.tok_off[(int32_t)M.state[MS_NTOK]];
     __shared__ int32_t sh_tslot[ML_TOP_N];
     __shared__ u64 sh_tkey[ML_TOP_N];
     i64 m = M.state[MS_NMERGES];
@@ -675,10 +790,15 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         const int tn = (int)sh_state[3];
         Best mine{0, -1, 0, 0, 0};
         if ((int)threadIdx.x < tn) {
-            if ((int)threadIdx.x >= cached) { sh_tslot[threadIdx.x] = M.top_slot[threadIdx.x]; sh_tkey[threadIdx.x] = M.top_key[threadIdx.x]; }
+            if ((int)threadIdx.x >= cached) {          // new entry: fetch it once, from then on its count is mirrored
+                const int32_t nsl = M.top_slot[threadIdx.x];
+                sh_tslot[threadIdx.x] = nsl; sh_tkey[threadIdx.x] = M.top_key[threadIdx.x];
+                LM.cnt[threadIdx.x] = __ldcg(&M.pcnt[nsl]);
+                mirror_insert(&LM, nsl, threadIdx.x);
+            }
             const int32_t sl = sh_tslot[threadIdx.x];
             const u64 k = sh_tkey[threadIdx.x];
-            const i64 cnt = __ldcg(&M.pcnt[sl]);
+            const i64 cnt = ML_USE_MIRROR ? LM.cnt[threadIdx.x] : __ldcg(&M.pcnt[sl]);
             if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
         }
         cached = tn;
@@ -687,7 +807,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
         long long c1 = clock64();
         if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); sh_nlist = 0; }
-        if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok);
+        if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok, &MI);
         __syncthreads();
         if (R.n < 0 || R.total > ML_LEADER_ITEMS_MAX || alog_n + R.total > M.alog_cap) break;
         long long c2 = clock64();
@@ -695,7 +815,11 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         const bool is_new = c == n_tok;
         const int32_t stamp = (int32_t)(m + 1);
         // the last warp records the merge / creates the token while the others claim the candidate words
+#if ML_NEW_COMMIT
+        if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
+#else
         if (warp == nwarps - 1) commit_merge_warp(M, m, a, b, c, is_new, alog_n);
+#endif
         else {
             for (i64 it = threadIdx.x; it < R.total; it += blockDim.x - 32) {
                 int32_t w = range_item(R, it);
@@ -717,7 +841,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 }
             }
         }
-        if (is_new) n_tok++;
+        if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }
         __syncthreads();
         long long c3 = clock64();
         const int nlist = sh_nlist;
@@ -726,17 +850,19 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 const int k = kb + (lane >> 3);
                 ClaimedWord cw; cw.w = -1; cw.off = 0; cw.n = 0; cw.f = 0;
                 if (k < nlist) cw = sh_list[k];
-                rewrite_words_g8(M, cw.w, cw.off, cw.n, cw.f, a, b, c, T, T2);
+                rewrite_words_g8(M, cw.w, cw.off, cw.n, cw.f, a, b, c, T, T2, ML_USE_MIRROR ? &LM : nullptr);
             }
         } else {
-            for (int k = threadIdx.x; k < nlist; k += blockDim.x) rewrite_word_thread(M, sh_list[k].w, a, b, c, T, T2);
+            for (int k = threadIdx.x; k < nlist; k += blockDim.x) rewrite_word_thread(M, sh_list[k].w, a, b, c, T, T2, ML_USE_MIRROR ? &LM : nullptr);
         }
         __syncthreads();
         long long c4 = clock64();
         if (threadIdx.x == 0) {
             // one L2 round trip: the counters the rewrite just bumped with atomics
-            const i64 an = __ldcg(&M.state[MS_ACT_N]), ln = __ldcg(&M.state[MS_ALOG_N]), er = __ldcg(&M.state[MS_ERROR]);
+            const i64 an = __ldcg(&M.state[MS_ACT_N]), ln = __ldcg(&M.state[MS_ALOG_N]);
             const i64 tn2 = __ldcg(&M.state[MS_TOP_N]), tov = __ldcg(&M.state[MS_TOP_OVF]);
+            i64 er = __ldcg(&M.state[MS_ERROR]);
+            if (ML_NPAIRS_CHECK_D && __ldcg(&M.state[MS_NPAIRS]) * 4 > M.pcap * 3) { atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); er |= ME_PAIR_TABLE_FULL; }
             M.seg_end[m] = (int32_t)ln; M.tok_first[c] = (int32_t)m; M.state[MS_NMERGES] = m + 1;
             sh_state[0] = an; sh_state[1] = ln; sh_state[2] = er; sh_state[3] = tn2; sh_state[4] = tov;
         }
@@ -746,6 +872,10 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         s_act += sh_state[1] - alog_n; s_items += R.total; s_words += nlist; n_done++;
         m++;
     }
+    // the mirror must agree with the table (cheap self-check, once per leader session)
+    __syncthreads();
+    if (ML_USE_MIRROR && (int)threadIdx.x < cached && LM.cnt[threadIdx.x] != __ldcg(&M.pcnt[sh_tslot[threadIdx.x]]))
+        atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);
     if (threadIdx.x == 0) {
         M.state[20] += t_arg; M.state[21] += t_rng; M.state[22] += t_claim; M.state[23] += t_rw; M.state[24] += t_close;
         M.state[25] += s_act; M.state[26] += s_items; M.state[27] += s_words;
@@ -759,23 +889,23 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
 // more than ML_TOP_N pairs tie near the maximum (the caller then scans the whole active set for one
 // merge).  Lowers T (and rebuilds the active set) while no pair reaches it; returns false when no pair
 // with count >= Tmin is left.  Must be entered by all CTAs right after a grid barrier.
-__device__ bool grid_top_rebuild(const MergeParams& M, cg::grid_group& grid, i64& T, i64 Tmin, Best* sh_best, int* sh_hist) {
+__device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* sh_best, int* sh_hist) {
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     {
         i64 n_old = M.state[MS_TOP_N]; if (n_old > ML_TOP_N) n_old = ML_TOP_N;
         for (i64 i = gtid; i < n_old; i += gstride) { int32_t sl = M.top_slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
         for (i64 i = gtid; i < 1024; i += gstride) M.hist[i] = 0;
     }
-    grid.sync();
+    grid_barrier(M);
     if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_TOP_REBUILDS]++; }
     Best am;
     for (;;) {
-        am = grid_argmax(M, grid, sh_best);              // contains a grid barrier
+        am = grid_argmax(M, sh_best);              // contains a grid barrier
         if (am.slot >= 0 && am.cnt >= T) break;
         if (T <= Tmin) return false;
         T = T / 2; if (T < Tmin) T = Tmin;
-        grid.sync();
-        rebuild_active(M, grid, T);
+        grid_barrier(M);
+        rebuild_active(M, T);
     }
     const i64 hi = am.cnt, span = hi - T, act_n = M.state[MS_ACT_N];
     for (i64 i = gtid; i < act_n; i += gstride) {
@@ -784,7 +914,7 @@ __device__ bool grid_top_rebuild(const MergeParams& M, cg::grid_group& grid, i64
         int bin = span > 0 ? (int)(((c - T) * 1023) / span) : 1023;
         atomicAdd(&M.hist[bin], 1);
     }
-    grid.sync();
+    grid_barrier(M);
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh_hist[i] = M.hist[i];
     __syncthreads();
     i64 T2;
@@ -802,21 +932,20 @@ __device__ bool grid_top_rebuild(const MergeParams& M, cg::grid_group& grid, i64
             else M.state[MS_TOP_OVF] = 1;
         }
     }
-    grid.sync();
+    grid_barrier(M);
     const bool ovf = M.state[MS_TOP_OVF] != 0;
-    grid.sync();                                         // everyone has seen the overflow flag
+    grid_barrier(M);                                         // everyone has seen the overflow flag
     if (ovf) {
         i64 n_old = M.state[MS_TOP_N]; if (n_old > ML_TOP_N) n_old = ML_TOP_N;
         for (i64 i = gtid; i < n_old; i += gstride) { int32_t sl = M.top_slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
-        grid.sync();
+        grid_barrier(M);
         if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_T2] = -1; }
     } else if (gtid == 0) M.state[MS_T2] = T2;
-    grid.sync();
+    grid_barrier(M);
     return true;
 }
 
 __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ Best sh_best[ML_THREADS / 32];
     __shared__ i64 sh_scan[1 + ML_THREADS / 32];
     __shared__ i64 sh_cnt[ML_THREADS / 32];
@@ -831,21 +960,21 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         i64 j = i - M.woff[w];
         if (j + 1 < M.wlen[w]) {
             i64 s = pair_upsert(M, PAIR_KEY(M.wsym[i], M.wsym[i + 1]));
-            if (s >= 0) atomicAdd((u64*)&M.pcnt[s], (u64)M.wcnt[w]);
+            if (s >= 0) { atomicAdd((u64*)&M.pcnt[s], (u64)M.wcnt[w]); M.wslot[i] = (int32_t)s; }
         }
     }
     for (i64 t = gtid; t < M.max_tokens; t += gstride) M.tok_first[t] = -1;
-    grid.sync();
+    grid_barrier(M);
     {
         i64 mx = 0;
         for (i64 s = gtid; s < M.pcap; s += gstride) { i64 c = M.pcnt[s]; if (c > mx) mx = c; }
         for (int o = 16; o > 0; o >>= 1) { i64 t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
         if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax((i64*)&M.state[MS_MAXCNT], mx);
     }
-    rebuild_index(M, grid, sh_scan, 0);      // starts and ends with grid-wide syncs
+    rebuild_index(M, sh_scan, 0);      // starts and ends with grid-wide syncs
     const i64 Tmin = M.min_freq > 1 ? M.min_freq : 1;
     i64 T = M.state[MS_MAXCNT] / 2; if (T < Tmin) T = Tmin;
-    rebuild_active(M, grid, T);
+    rebuild_active(M, T);
 
     int skip = 0, backoff = 1;
     for (;;) {
@@ -859,11 +988,12 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         const i64 top_n = M.state[MS_TOP_N];
         const bool top_ovf = M.state[MS_TOP_OVF] != 0;
         if (m >= M.num_merges || M.state[MS_ERROR] || M.state[MS_DONE]) break;
+        if (ML_NPAIRS_CHECK_E && M.state[MS_NPAIRS] * 4 > M.pcap * 3) { if (gtid == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); break; }
 
         // ---- (re)build the top list when it cannot prove the maximum any more
         if (T2 == 0 || (T2 > 0 && top_ovf)) {
-            grid.sync();                                    // everyone has read the state
-            if (!grid_top_rebuild(M, grid, T, Tmin, sh_best, sh_hist)) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
+            grid_barrier(M);                                    // everyone has read the state
+            if (!grid_top_rebuild(M, T, Tmin, sh_best, sh_hist)) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
             continue;
         }
 
@@ -871,7 +1001,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         if (skip > 0) skip--;
         else if (T2 > 0 && alog_n + ML_LEADER_ITEMS_MAX <= M.alog_cap) {
             const i64 m0 = m;
-            grid.sync();                                    // everyone has read the state the leader is about to change
+            grid_barrier(M);                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
                 leader_loop(M, sh_best, T, Tmin, T2);
                 __syncthreads();
@@ -880,14 +1010,14 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if (threadIdx.x == 0) while (*(volatile i64*)&M.state[MS_LEADER_GEN] == gen) __nanosleep(2000);
                 __syncthreads();
             }
-            grid.sync();
+            grid_barrier(M);
             m = M.state[MS_NMERGES];
             n_tok = (int32_t)M.state[MS_NTOK];
             alog_n = M.state[MS_ALOG_N];
             const i64 reason = M.state[MS_LEADER_REASON];
             if (m == m0 && reason != LR_TOP) { backoff = backoff < 64 ? backoff * 2 : 64; skip = backoff; } else backoff = 1;
             if (m >= M.num_merges || M.state[MS_ERROR]) break;
-            grid.sync();                                    // everyone has re-read the state
+            grid_barrier(M);                                    // everyone has re-read the state
             if (reason == LR_TOP) continue;                 // top list exhausted: rebuild it first
         }
 
@@ -897,19 +1027,19 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         Best best;
         if (T2 > 0) {
             best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
-            grid.sync();
+            grid_barrier(M);
             if (best.slot < 0 || best.cnt < T2 || best.cnt < T) {
                 if (gtid == 0) M.state[MS_T2] = 0;
-                grid.sync();
+                grid_barrier(M);
                 continue;
             }
         } else {
             // top list disabled (massive ties): full scan of the active set for this merge
-            best = grid_argmax(M, grid, sh_best);
+            best = grid_argmax(M, sh_best);
             if (best.slot < 0 || best.cnt < T) {            // cannot happen right after a rebuild; be safe
-                grid.sync();
+                grid_barrier(M);
                 if (gtid == 0) M.state[MS_T2] = 0;
-                grid.sync();
+                grid_barrier(M);
                 continue;
             }
         }
@@ -918,8 +1048,8 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         __syncthreads();
         if (R.n < 0 || alog_n + R.total > M.alog_cap) {
             // fold the affected log into the CSR index first, then look the candidates up again
-            grid.sync();
-            rebuild_index(M, grid, sh_scan, m);
+            grid_barrier(M);
+            rebuild_index(M, sh_scan, m);
             alog_n = 0;
             if (threadIdx.x == 0) build_ranges(M, best.slot, a, b, &R);
             __syncthreads();
@@ -937,16 +1067,16 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if ((threadIdx.x & 31) == 0) old = atomicExch(&M.wstamp[w], stamp);
                 old = __shfl_sync(0xffffffffu, old, 0);
                 if (old == stamp) continue;
-                rewrite_word_warp(M, w, a, b, c, T, T2u);
+                rewrite_word_warp(M, w, a, b, c, T, T2u, nullptr);
             }
         } else {
             for (i64 it = gtid; it < R.total; it += gstride) {
                 int32_t w = range_item(R, it);
                 if (atomicExch(&M.wstamp[w], stamp) == stamp) continue;
-                rewrite_word_thread(M, w, a, b, c, T, T2u);
+                rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr);
             }
         }
-        grid.sync();
+        grid_barrier(M);
         // every CTA writes the same values: no further barrier needed before the next iteration
         if (threadIdx.x == 0) { close_merge(M, m, c); if (T2 < 0) M.state[MS_T2] = 0; }
         if (gtid == 0) M.state[MS_GRID_MERGES]++;

@@ -191,6 +191,10 @@ def compact_words(torch, res: PretokResult, st: np.ndarray, with_maps: bool) -> 
     w.counters = counters.data_ptr()
     if n_words > 0:
         _ffi.check(L.yabpe_compact_words(C.byref(res.args), C.byref(w), _ffi.stream_ptr(torch)))
+    import os
+    if os.environ.get("YABPE_DEBUG_SYNC"):
+        torch.cuda.synchronize()
+        print(f"[yabpe debug] compact ok: n_words={n_words} n_syms={n_syms} counters={counters.tolist()}", flush=True)
     return WordArrays(table=w, n_words=n_words, n_syms=n_syms,
                       keep=[wsym, sym_word, woff, wlen, wcnt, sword, lword, counters],
                       wsym=wsym, woff=woff, wlen=wlen, wcnt=wcnt)
@@ -249,6 +253,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         d_tok_bytes, d_tok_off, d_th, d_tp, d_tset = t(tok_bytes), t(tok_off), t(th.view(np.int64)), t(tp.view(np.int64)), t(tset.view(np.int64))
         z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
         wstamp = z(words.n_words + 1, torch.int32)
+        wslot = z(words.n_syms + 8, torch.int32)
         pkey, pcnt = z(pcap, torch.int64), z(pcap, torch.int64)
         ioff, icnt = z(pcap + 1, torch.int32), z(pcap, torch.int32)
         ipost = z(words.n_syms + 8, torch.int32)
@@ -266,7 +271,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         state = t(state_np)
         m = _ffi.MergeArgs()
         m.words = words.table; m.n_words = words.n_words; m.n_syms = words.n_syms
-        m.wstamp = wstamp.data_ptr()
+        m.wstamp = wstamp.data_ptr(); m.wslot = wslot.data_ptr()
         m.tok_bytes = d_tok_bytes.data_ptr(); m.tok_bytes_cap = pool_cap
         m.tok_off = d_tok_off.data_ptr(); m.tok_hash = d_th.data_ptr(); m.tok_pow = d_tp.data_ptr()
         m.tset = d_tset.data_ptr(); m.tset_cap = tset_cap; m.max_tokens = max_tokens
@@ -282,6 +287,10 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.num_merges = num_merges; m.min_frequency = min_frequency
         if timing is not None:
             t0 = torch.cuda.Event(enable_timing=True); t0.record()
+        import os
+        if os.environ.get("YABPE_DEBUG_SYNC"):
+            torch.cuda.synchronize()
+            print("[yabpe debug] before merge loop: ok", flush=True)
         _ffi.check(L.yabpe_merge_loop(C.byref(m), _ffi.stream_ptr(torch)))
         if timing is not None:
             t1 = torch.cuda.Event(enable_timing=True); t1.record()
