@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YABPE_ABI_VERSION 1
+#define YABPE_ABI_VERSION 2
 
 #define YABPE_OK 0
 #define YABPE_ERR_CUDA (-1)
@@ -42,6 +42,8 @@ extern "C" {
 #define YABPE_ST_TABLE_FULL 5  /* != 0: a hash table overflowed, retry with larger tables */
 #define YABPE_ST_OVF_N 6       /* pre-tokens longer than the tile window                  */
 #define YABPE_ST_NSPECIAL 8    /* recognised special-token occurrences                    */
+#define YABPE_ST_SLOW_N 9      /* boundary work items the warp kernel left to the generic kernel */
+#define YABPE_ST_CACHE_HIT 10  /* pre-tokens counted in shared memory by the warp kernel   */
 
 /* indices into the int64[32] merge-loop state array */
 #define YABPE_MS_NMERGES 0
@@ -81,7 +83,8 @@ typedef struct {
     const int32_t* sp_offs;     /* HOST: n_sp + 1 offsets into sp_blob                            */
     int32_t n_sp;
     int32_t stages;             /* 0 = all; else bit 0: special resolution, bit 1: tile kernel,   */
-                                /*   bit 2: over-long pre-tokens (lets a caller time each stage)  */
+                                /*   bit 2: over-long pre-tokens (lets a caller time each stage), */
+                                /*   bit 3: generic tile kernel only (no warp kernel; for tests)  */
     int64_t own_lo, own_hi;     /* only pre-tokens starting in [own_lo, own_hi) are counted       */
     uint32_t* cand_bits;        /* device, (n + 63) / 32 words, zeroed; may be NULL when n_sp = 0 */
     uint32_t* rec_bits;         /* device, same size, zeroed: recognised special starts (output)  */
@@ -93,6 +96,8 @@ typedef struct {
     int64_t* ovf_pos;           /* device scratch for over-long pre-token starts                  */
     int64_t ovf_cap;
     int64_t* stats;             /* device int64[16]; caller zeroes it and sets [ERR_POS]=INT64_MAX */
+    int64_t* work;              /* device scratch, 3 * work_cap int64 (boundary work items), or NULL */
+    int64_t work_cap;           /*   >= 4 * n_cuts + 16 enables the warp kernel in trainer mode   */
 } yabpe_pretok_args;
 
 /* Stage 1: special-token candidates + resolution (skipped when n_sp == 0).

@@ -104,6 +104,28 @@ def test_pretok_fast_path_large_fuzz(yabpe):
     assert _device_counts(text, ["<|endoftext|>"]) == _oracle_counts(text, ["<|endoftext|>"])
 
 
+def test_pretok_warp_kernel_vs_generic_kernel(yabpe):
+    """Trainer mode runs the warp-autonomous kernel on interior 992-byte chunks and the generic tile kernel on
+    the rest; stages bit 3 forces the generic kernel everywhere.  Both must give the oracle's table, and the
+    warp kernel must actually have run (cache hits > 0, only a handful of boundary work items)."""
+    from yabpe.trainer import pretoken_counts
+    rng = random.Random(99)
+    heavy = ALPHABET + ["'s", "'t", "'re", " the", " and", " of", "\n\n", ". ", "<|endoftext|>\n", "\u00a0", "tion", "ing"]
+    text = "".join(rng.choice(heavy) for _ in range(700_000)).encode("utf-8")
+    for sp, cs in (([], 1 << 30), (["<|endoftext|>"], 1 << 30), (["<|endoftext|>"], 200_003), (["<|e|>", "<|endoftext|>"], 1 << 30)):
+        st = {}
+        fast = pretoken_counts(text, sp, chunk_size_bytes=cs, stats_out=st)
+        slow = pretoken_counts(text, sp, chunk_size_bytes=cs, generic_only=True)
+        assert fast == slow, (sp, cs)
+        assert st["cache_hits"] > 0 and 0 < st["slow_items"] <= 4 * (len(text) // cs) + 16, st
+        fast.pop("__n_pretokens__")
+        assert fast == _oracle_counts(text, sp, chunk_size=cs), (sp, cs)
+    # pre-tokens of 15..100 bytes everywhere (long-table path of the warp kernel), and chunk-straddling ones
+    words = ["x" * n for n in (15, 16, 17, 31, 32, 33, 40, 64, 100)] + ["ab", "the", "1234567890123456"]
+    text = " ".join(rng.choice(words) for _ in range(120_000)).encode()
+    assert _device_counts(text, ["<|endoftext|>"]) == _oracle_counts(text, ["<|endoftext|>"])
+
+
 def test_pretok_long_tokens_and_tile_edges(yabpe):
     """Tokens straddling tile boundaries, longer than the tile window, and MB-long runs."""
     parts = [b"x" * 8191, b" ", b"y" * 9000, b"\n", "中".encode() * 5000, b" 1234567890" * 3, b"!" * 20000, b" ",

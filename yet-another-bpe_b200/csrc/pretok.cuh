@@ -38,6 +38,8 @@
 #define ST_OVF_N 6
 #define ST_CHAIN_FAIL 7
 #define ST_NSPECIAL 8
+#define ST_SLOW_N 9        // work items the warp kernel left to the generic tile kernel
+#define ST_CACHE_HIT 10    // warp kernel: pre-tokens counted in the shared-memory cache (diagnostic)
 
 struct LongEntry { u64 h; i64 pos; i64 len; i64 count; };
 
@@ -52,6 +54,8 @@ struct PretokParams {
     i64* ovf_pos; i64 ovf_cap;
     i64* stats;
     i64 tile_base; i64 n_tiles;
+    i64* work; i64 work_cap;        // (tile, own_lo, own_hi) triples: chunks the warp kernel hands to the generic kernel
+    int list_mode;                  // generic kernel: iterate over `work` instead of all tiles
 };
 
 // ---------------------------------------------------------------------------------
@@ -180,7 +184,18 @@ __global__ void __launch_bounds__(256) k_resolve_specials(PretokParams P, i64 lo
 // ---------------------------------------------------------------------------------
 // hash-table inserts
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) { return mix64(k0 * 0x9e3779b97f4a7c15ULL ^ mix64(k1)); }
+// 32-bit multiply-add of the four key words + murmur3 finaliser: ~13 integer instructions (the 64-bit
+// mix it replaces cost ~60).  Table slot = low bits, shared-memory cache index = high bits.
+__device__ __forceinline__ uint32_t short_hash_w(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t x = a * 0x9E3779B1u + b * 0x85EBCA77u;
+    uint32_t y = c * 0xC2B2AE3Du + d * 0x27D4EB2Fu;
+    x ^= (y << 13) | (y >> 19);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) {
+    return short_hash_w((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
+}
 
 // returns slot (>=0) and adds `add` to its count; *created = 1 when this call created the entry
 __device__ __forceinline__ i64 short_insert_h(ulonglong2* keys, i64* counts, i64 cap, u64 h, u64 k0, u64 k1, i64 add, int* created) {
@@ -214,7 +229,7 @@ __device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 c
 #define PT_CACHE_BYTES (PT_CACHE_N * 20)
 
 __device__ __forceinline__ bool cache_add(u64* ck0, u64* ck1, uint32_t* cc, u64 h, u64 k0, u64 k1) {
-    uint32_t ci = (uint32_t)(h >> 40) & (PT_CACHE_N - 1);
+    uint32_t ci = (uint32_t)(h >> 16) & (PT_CACHE_N - 1);
 #pragma unroll
     for (int p = 0; p < PT_CACHE_PROBES; p++) {
         u64 c0 = *(volatile u64*)&ck0[ci];
@@ -834,12 +849,20 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS) k_pretok_count(Pret
     const int tid = threadIdx.x;
     u64 my_tok = 0, my_us = 0, my_ul = 0, my_ub = 0;
     uint32_t phase[2] = {0, 0};
-    i64 tile = blockIdx.x;
-    if (tile < P.n_tiles && tid == 0) tile_issue_load(P, S, tile, 0);
+    // list mode: the items are (absolute tile, own_lo, own_hi) triples written by k_pretok_warp
+    i64 n_items = P.n_tiles;
+    if (P.list_mode) {
+        n_items = P.stats[ST_SLOW_N];
+        if (n_items > P.work_cap) { if (tid == 0 && blockIdx.x == 0) P.stats[ST_TABLE_FULL] = 4; n_items = P.work_cap; }
+    }
+    i64 item = blockIdx.x;
+    if (item < n_items && tid == 0) tile_issue_load(P, S, P.list_mode ? P.work[3 * item] - P.tile_base : item, 0);
     int buf = 0;
-    for (; tile < P.n_tiles; tile += gridDim.x, buf ^= 1) {
-        i64 next = tile + gridDim.x;
-        if (next < P.n_tiles && tid == 0) tile_issue_load(P, S, next, buf ^ 1);
+    for (; item < n_items; item += gridDim.x, buf ^= 1) {
+        const i64 next = item + gridDim.x;
+        if (next < n_items && tid == 0) tile_issue_load(P, S, P.list_mode ? P.work[3 * next] - P.tile_base : next, buf ^ 1);
+        const i64 tile = P.list_mode ? P.work[3 * item] - P.tile_base : item;
+        const i64 own_lo = P.list_mode ? P.work[3 * item + 1] : P.own_lo, own_hi = P.list_mode ? P.work[3 * item + 2] : P.own_hi;
         mbar_wait(&S.bar[buf], phase[buf]); phase[buf] ^= 1;
         bool has_cut;
         tile_scan(P, S, tile, buf, &has_cut);
@@ -854,7 +877,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS) k_pretok_count(Pret
         for (int k = tid; k < ntok; k += PT_THREADS) {
             int s = S.tokpos[k];
             i64 gpos = g0 + s;
-            if (gpos < P.own_lo || gpos >= P.own_hi) continue;
+            if (gpos < own_lo || gpos >= own_hi) continue;
             if (P.mode == 1 && P.n_sp > 0 && ((S.recw[(s >> 5) + 4] >> (s & 31)) & 1)) continue;   // encode: specials are not words
             my_tok++;
             if (k + 1 >= ntot) {                                      // end not inside the window

@@ -5,6 +5,7 @@
 
 #include "../../include/yabpe.h"
 #include "encode.cuh"
+#include "pretok_fast.cuh"
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
@@ -92,6 +93,7 @@ static int make_params(const yabpe_pretok_args* a, PretokParams* P) {
     P->lent = (LongEntry*)a->long_entries; P->lcap = a->long_cap;
     P->ovf_pos = (i64*)a->ovf_pos; P->ovf_cap = a->ovf_cap;
     P->stats = (i64*)a->stats;
+    P->work = (i64*)a->work; P->work_cap = a->work ? a->work_cap : 0; P->list_mode = 0;
     P->tile_base = a->own_lo / PT_TILE;
     P->n_tiles = a->own_hi > a->own_lo ? (a->own_hi - 1) / PT_TILE - P->tile_base + 1 : 0;
     return YABPE_OK;
@@ -140,7 +142,8 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
     int rc = make_params(a, &P);
     if (rc) return rc;
     ARG_CHECK(a->ovf_pos && a->ovf_cap > 0 && a->stats);
-    const int stages = a->stages ? a->stages : 7;
+    int stages = a->stages;
+    if ((stages & 7) == 0) stages |= 7;
     if (stages & 1) {
         rc = run_specials(a, P, st);
         if (rc) return rc;
@@ -152,14 +155,32 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
         static bool attr_set = false;
         if (!attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_pretok_count, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_CACHE_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(k_pretok_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
             attr_set = true;
         }
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pretok_count, PT_THREADS, PT_CACHE_BYTES));
         if (per_sm < 1) per_sm = 1;
-        int grid = num_sms() * per_sm;
-        if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
-        k_pretok_count<<<grid, PT_THREADS, PT_CACHE_BYTES, st>>>(P); LAUNCHED();
+        // Trainer mode, interior text: the warp-autonomous kernel; it leaves the chunks that touch a hard cut,
+        // the ends of the text or the edge of the owned range in P.work for the generic kernel (list mode).
+        // Dense cuts (tiny reference chunk sizes) or a missing work list: the generic kernel does everything.
+        const i64 c_lo = P.own_lo / PW_CH, c_hi = (P.own_hi - 1) / PW_CH + 1;
+        const bool warp_path = a->mode == 0 && !(stages & 8) && P.work && P.work_cap >= 4 * (i64)P.n_cuts + 16 &&
+                               c_hi - c_lo >= 4 && 8 * (i64)P.n_cuts < c_hi - c_lo;
+        if (warp_path) {
+            i64 grid_w = (c_hi - c_lo + PW_WARPS - 1) / PW_WARPS;
+            if (grid_w > num_sms()) grid_w = num_sms();
+            k_pretok_warp<<<(int)grid_w, PW_THREADS, PW_SMEM_BYTES, st>>>(P, c_lo, c_hi); LAUNCHED();
+            PretokParams PL = P;
+            PL.list_mode = 1;
+            i64 grid = (i64)num_sms() * per_sm;
+            if (grid > P.work_cap) grid = P.work_cap;
+            k_pretok_count<<<(int)grid, PT_THREADS, PT_CACHE_BYTES, st>>>(PL); LAUNCHED();
+        } else {
+            int grid = num_sms() * per_sm;
+            if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
+            k_pretok_count<<<grid, PT_THREADS, PT_CACHE_BYTES, st>>>(P); LAUNCHED();
+        }
         CUDA_TRY(cudaGetLastError());
     }
     if (P.n_tiles > 0 && (stages & 4)) {

@@ -11,11 +11,11 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libyabpe.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # stats / state slots (include/yabpe.h)
 ST_NTOK, ST_UNIQ_SHORT, ST_UNIQ_LONG, ST_UNIQ_BYTES, ST_ERR_POS, ST_TABLE_FULL, ST_OVF_N = 0, 1, 2, 3, 4, 5, 6
-ST_NSPECIAL = 8
+ST_NSPECIAL, ST_SLOW_N, ST_CACHE_HIT = 8, 9, 10
 MS_NMERGES, MS_NTOK, MS_ERROR, MS_NPAIRS, MS_POOL_USED, MS_REBUILDS, MS_TREBUILDS = 0, 1, 2, 6, 8, 9, 10
 MS_LEADER_MERGES, MS_GRID_MERGES = 15, 16
 ME_PAIR_TABLE_FULL, ME_TOK_POOL_FULL, ME_INTERNAL = 1, 2, 4
@@ -47,6 +47,7 @@ class PretokArgs(C.Structure):
         ("long_entries", C.c_void_p), ("long_cap", C.c_int64),
         ("ovf_pos", C.c_void_p), ("ovf_cap", C.c_int64),
         ("stats", C.c_void_p),
+        ("work", C.c_void_p), ("work_cap", C.c_int64),
     ]
 
 

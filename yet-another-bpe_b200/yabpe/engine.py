@@ -72,7 +72,8 @@ class PretokResult:
 
 def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: list[bytes], mode: int,
                  own: tuple[int, int] | None = None, short_cap: int | None = None,
-                 long_cap: int | None = None, stage_events: list | None = None) -> PretokResult:
+                 long_cap: int | None = None, stage_events: list | None = None,
+                 generic_only: bool = False) -> PretokResult:
     """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
     L = _ffi.load()
     dev = text_dev.device
@@ -89,8 +90,10 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     skeys = torch.zeros(short_cap * 2, dtype=torch.int64, device=dev)
     scounts = torch.zeros(short_cap, dtype=torch.int64, device=dev)
     lent = torch.zeros(long_cap * 4, dtype=torch.int64, device=dev)
-    ovf_cap = n // PT_TILE + 16
+    ovf_cap = n // 992 + 16         # at most one over-long pre-token per 992-byte chunk of the warp kernel
     ovf = torch.empty(ovf_cap, dtype=torch.int64, device=dev)
+    work_cap = 4 * n_cuts + 64
+    work = torch.empty(3 * work_cap, dtype=torch.int64, device=dev)
     stats_np = np.zeros(16, dtype=np.int64)
     stats_np[_ffi.ST_ERR_POS] = _ffi.INT64_MAX
     stats = torch.from_numpy(stats_np).to(dev)
@@ -105,16 +108,19 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     a.long_entries = lent.data_ptr(); a.long_cap = long_cap
     a.ovf_pos = ovf.data_ptr(); a.ovf_cap = ovf_cap
     a.stats = stats.data_ptr()
-    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf], stats=stats,
+    a.work = work.data_ptr(); a.work_cap = work_cap
+    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work], stats=stats,
                        short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n)
     if n > 0:
+        extra = 8 if generic_only else 0        # stages bit 3: generic tile kernel only (A/B parity tests)
+        a.stages = extra
         if stage_events is None:
             _ffi.check(L.yabpe_pretok_count(C.byref(a), _ffi.stream_ptr(torch)))
         else:
             # one call per stage with a CUDA event after each (bench: per-kernel durations)
             ev = torch.cuda.Event(enable_timing=True); ev.record(); stage_events.append(ev)
             for bit in (1, 2, 4):
-                a.stages = bit
+                a.stages = bit | extra
                 _ffi.check(L.yabpe_pretok_count(C.byref(a), _ffi.stream_ptr(torch)))
                 ev = torch.cuda.Event(enable_timing=True); ev.record(); stage_events.append(ev)
             a.stages = 0
@@ -145,11 +151,12 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple
     return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))))
 
 
-def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None) -> tuple[PretokResult, np.ndarray]:
+def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None,
+                         generic_only: bool = False) -> tuple[PretokResult, np.ndarray]:
     """pretok_count + one host sync; grows the tables and retries when they overflow."""
     short_cap = long_cap = None
     for _ in range(8):
-        res = pretok_count(torch, text_dev, n, cuts, specials, mode, own, short_cap, long_cap)
+        res = pretok_count(torch, text_dev, n, cuts, specials, mode, own, short_cap, long_cap, generic_only=generic_only)
         st = res.stats_host()
         if st[_ffi.ST_TABLE_FULL] == 0:
             return res, st

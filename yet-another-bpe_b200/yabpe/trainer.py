@@ -256,7 +256,8 @@ def train_bpe(input_path: str | os.PathLike, vocab_size: int, special_tokens: li
 
 
 def pretoken_counts(data: bytes | np.ndarray, special_tokens: Sequence[str] = (), *, mode: str = "train",
-                    chunk_size_bytes: int = 1 << 30, cuts: Sequence[int] | None = None) -> dict[bytes, int]:
+                    chunk_size_bytes: int = 1 << 30, cuts: Sequence[int] | None = None,
+                    generic_only: bool = False, stats_out: dict | None = None) -> dict[bytes, int]:
     """Device word-count table of `data` as a dict (the multiset trainer.py:221-225 builds).
     mode="encode" applies the tokenizer's special handling (specials split first and not counted)."""
     torch = _ffi.require_cuda()
@@ -272,7 +273,9 @@ def pretoken_counts(data: bytes | np.ndarray, special_tokens: Sequence[str] = ()
     cut_list = [c for c in cut_list if 0 < c < raw.size]
     text_dev, n = engine.to_device_text(torch, raw)
     res, st = engine.pretok_count_checked(torch, text_dev, n, np.asarray(cut_list, dtype=np.int64) if cut_list else None,
-                                          sp, 0 if mode == "train" else 1)
+                                          sp, 0 if mode == "train" else 1, generic_only=generic_only)
+    if stats_out is not None:
+        stats_out.update(slow_items=int(st[_ffi.ST_SLOW_N]), cache_hits=int(st[_ffi.ST_CACHE_HIT]), n_tok=int(st[_ffi.ST_NTOK]))
     if int(st[_ffi.ST_ERR_POS]) != _ffi.INT64_MAX:
         raise ValueError(f"invalid UTF-8 at position {int(st[_ffi.ST_ERR_POS])}")
     words = engine.compact_words(torch, res, st, with_maps=False)
