@@ -14,4 +14,4 @@ for it in range(3):
     torch.cuda.synchronize()
     st = res.stats_host()
     print("iter", it, "specials %.3f ms tiles %.3f ms long %.3f ms" % (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])),
-          "GB/s %.1f" % (n / ev[1].elapsed_time(ev[2]) / 1e6), "ntok", st[0], "uniq", st[1], st[2])
+          "GB/s %.1f" % (n / ev[1].elapsed_time(ev[2]) / 1e6), "ntok", st[0], "uniq", st[1], st[2], "cache-hit %.3f slow-items %d" % (st[10] / max(st[0], 1), st[9]))

@@ -184,13 +184,11 @@ __global__ void __launch_bounds__(256) k_resolve_specials(PretokParams P, i64 lo
 // ---------------------------------------------------------------------------------
 // hash-table inserts
 // ---------------------------------------------------------------------------------
-// 32-bit multiply-add of the four key words + murmur3 finaliser: ~13 integer instructions (the 64-bit
+// multiply-add of the four 32-bit key words + one multiply-xorshift round: 9 integer instructions (the 64-bit
 // mix it replaces cost ~60).  Table slot = low bits, shared-memory cache index = high bits.
 __device__ __forceinline__ uint32_t short_hash_w(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t x = a * 0x9E3779B1u + b * 0x85EBCA77u;
-    uint32_t y = c * 0xC2B2AE3Du + d * 0x27D4EB2Fu;
-    x ^= (y << 13) | (y >> 19);
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    uint32_t x = a * 0x9E3779B1u + b * 0x85EBCA77u + c * 0xC2B2AE3Du + d * 0x27D4EB2Fu;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15;
     return x;
 }
 __device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) {
@@ -202,6 +200,7 @@ __device__ __forceinline__ i64 short_insert_h(ulonglong2* keys, i64* counts, i64
     u64 mask = (u64)cap - 1;
     u64 slot = h & mask;
     *created = 0;
+#pragma unroll 1
     for (int probe = 0; probe < 8192; probe++) {
         u64* kp = (u64*)&keys[slot];
         u64 c0 = *(volatile u64*)kp;
@@ -326,7 +325,7 @@ struct TileSmem {
     int scan_carry;
     int ntok_total, ntok_own;
     // fast (pure-ASCII interior tile) path
-    uint32_t recw[PT_WIN / 32 + 8];      // encode mode: recognised-special bits; word i covers window offsets [32(i-4), 32(i-3))
+    uint32_t recw[PT_WIN / 32 + 8];      // recognised-special bits; word i covers window offsets [32(i-4), 32(i-3))
 };
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* tmp, int* total) {
@@ -570,9 +569,9 @@ __device__ __forceinline__ bool tile_is_boundary(const PretokParams& P, i64 g0, 
     return cut || g0 <= 0 || g0 + PT_WIN >= P.n;
 }
 
-// encode mode: stage the recognised-special bits of the window (consumed by the token loops after pass D1)
+// stage the recognised-special bits of the window (segment_scan; encode mode: also the token loops after pass D1)
 __device__ __forceinline__ void tile_stage_rec(const PretokParams& P, TileSmem& S, i64 g0) {
-    if (P.mode != 1 || P.n_sp == 0) return;
+    if (P.n_sp == 0) return;
     const i64 nrec = (P.n + 63) / 32 + 1;
     for (int i = threadIdx.x; i < PT_WIN / 32 + 8; i += PT_THREADS) {
         i64 wi = (g0 >> 5) - 4 + i;              // g0 is a multiple of 32
@@ -581,8 +580,19 @@ __device__ __forceinline__ void tile_stage_rec(const PretokParams& P, TileSmem& 
 }
 
 // scan one 32-byte segment (index sgi, window offset x0 = HL + 32*sgi); returns the start mask in natural
-// bit order, *na != 0 when a non-ASCII byte was seen (the tile then falls back to the generic path)
-__device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const uint8_t* txt, i64 g0, int sgi, uint32_t* na_out) {
+// bit order.  recw = recognised-special bits of the window staged in shared memory: word (x >> 5) + 4 covers
+// window offsets [x & ~31, (x & ~31) + 32) (the window base is a multiple of 32; four words of history).
+// Class masks are "transposed" (tbit); the rare-event masks FL / SUP / KILL are in natural bit order so that
+// a special or a contraction patches a bit RANGE with two shifts instead of a per-byte loop.
+__device__ __forceinline__ uint32_t range_mask(int lo, int hi) {        // bits [lo, hi), 0 <= lo < hi <= 32
+    return (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
+}
+__device__ __forceinline__ int contraction_len(uint8_t c1, uint8_t c2) {
+    if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') return 2;
+    if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) return 3;
+    return 0;
+}
+__device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const uint8_t* txt, const uint32_t* recw, i64 g0, int sgi) {
     const int x0 = PT_HL + 32 * sgi;
     const uint4* p4 = (const uint4*)(txt + x0);
     const uint4 A = p4[0], B = p4[1];
@@ -602,11 +612,11 @@ __device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const ui
         const uint32_t fAP = ~((x ^ 0x27272727u) + 0x7f7f7f7fu) & 0x80808080u;
         Lm |= fL >> (7 - j); Nm |= fN >> (7 - j); Sm |= fS >> (7 - j); SPm |= fSP >> (7 - j); APm |= fAP >> (7 - j);
     }
-    (void)na_out;
     const uint32_t pb = pw >> 24, nb = nw & 0xffu;
     int pk = ascii_kclass(pb);
     uint32_t nS_in = (nb == 0x20 || (nb - 9) < 5u) ? 1u : 0u;
-    uint32_t FL = 0, SUP = 0, NOEXT = 0, APkill = 0, CONT = 0, wsleads = 0;
+    uint32_t FLn = 0, SUPn = 0, KILLn = 0;          // natural order: forced starts, suppressed starts, bytes of specials
+    uint32_t NOEXT = 0, CONT = 0, wsleads = 0;      // transposed order
     // ---- events: non-ASCII code points (decoded one by one; classes from the two-stage Unicode table)
     if (na) {
         Lm &= ~NAm; Nm &= ~NAm; Sm &= ~NAm; SPm &= ~NAm; APm &= ~NAm;     // the SWAR tests looked at the low 7 bits only
@@ -638,33 +648,41 @@ __device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const ui
         if (nb >= 0x80) nS_in = smem_kclass(txt, x0 + 32) >= KC_S ? 1u : 0u;
     }
     uint32_t flprev = 0, killprev = 0;           // bit d-1: position x0-d (d = 1..3) is a forced start / inside a special
-    // ---- events: recognised specials that touch [x0-3, x0+32] (bits of the rec bitmap, read from L2)
+    // ---- events: recognised specials that touch [x0-3, x0+32]
     if (P.n_sp > 0) {
-        const i64 g = g0 + x0;                                   // multiple of 32
-        const i64 wi0 = g >> 5;
-        int kprev = (c_sp.max_len + 3 + 31) >> 5;
-        if (kprev > wi0) kprev = (int)wi0;
-        for (int j = -kprev; j <= 1; j++) {
-            uint32_t rw = P.rec[wi0 + j];
-            if (j == 1) rw &= 1u;                                // only a special starting right after the segment matters
-            while (rw) {
-                const int bit = __ffs(rw) - 1; rw &= rw - 1;
-                const int q = x0 + 32 * j + bit;                 // window offset, may be negative
-                int m;
-                if (c_sp.n == 1) m = c_sp.offs[1];
-                else { int sp = special_match(P.text, g0 + q, P.n); m = sp >= 0 ? c_sp.offs[sp + 1] - c_sp.offs[sp] : 1; }
-                const int e = q + m;
-                if (e < x0 - 3 || q > x0 + 32) continue;
-                for (int pp = (q > x0 - 3 ? q : x0 - 3); pp < e && pp < x0 + 32; pp++) {
-                    if (pp >= x0) { APkill |= tbit(pp - x0); if (pp != q) SUP |= tbit(pp - x0); }
-                    else killprev |= 1u << (x0 - pp - 1);
-                }
-                if (q >= x0 && q < x0 + 32) FL |= tbit(q - x0);
-                if (e >= x0 && e < x0 + 32) FL |= tbit(e - x0);
-                else if (e >= x0 - 3 && e < x0) flprev |= 1u << (x0 - e - 1);
-                if (P.mode == 1) {                  // encode: the text before a special ends at it
-                    if (q - 1 >= x0 && q - 1 < x0 + 32) NOEXT |= tbit(q - 1 - x0);
-                    if (q == x0 + 32) nS_in = 1u;
+        const int wi = (x0 >> 5) + 4;
+        const int kprev = (c_sp.max_len + 3 + 31) >> 5;              // <= 5 (specials are at most 128 bytes)
+        uint32_t any = recw[wi] | (recw[wi + 1] & 1u) | recw[wi - 1];
+#pragma unroll 1
+        for (int j = 2; j <= kprev; j++) any |= recw[wi - j];
+        if (any) {
+#pragma unroll 1
+            for (int j = -kprev; j <= 1; j++) {
+                uint32_t rw = recw[wi + j];
+                if (j == 1) rw &= 1u;                                // only a special starting right after the segment matters
+                while (rw) {
+                    const int bit = __ffs(rw) - 1; rw &= rw - 1;
+                    const int q = x0 + 32 * j + bit;                 // window offset
+                    int m;
+                    if (c_sp.n == 1) m = c_sp.offs[1];
+                    else { int sp = special_match(P.text, g0 + q, P.n); m = sp >= 0 ? c_sp.offs[sp + 1] - c_sp.offs[sp] : 1; }
+                    const int e = q + m;
+                    if (e < x0 - 3 || q > x0 + 32) continue;
+                    const int lo = (q > x0 ? q : x0) - x0, hi = (e < x0 + 32 ? e : x0 + 32) - x0;
+                    if (hi > lo) {
+                        const uint32_t r = range_mask(lo, hi);
+                        KILLn |= r;
+                        SUPn |= q >= x0 ? (r & ~(1u << lo)) : r;
+                    }
+#pragma unroll
+                    for (int d = 1; d <= 3; d++) if (q <= x0 - d && x0 - d < e) killprev |= 1u << (d - 1);
+                    if (q >= x0 && q < x0 + 32) FLn |= 1u << (q - x0);
+                    if (e >= x0 && e < x0 + 32) FLn |= 1u << (e - x0);
+                    else if (e >= x0 - 3 && e < x0) flprev |= 1u << (x0 - e - 1);
+                    if (P.mode == 1) {                  // encode: the text before a special ends at it
+                        if (q - 1 >= x0 && q - 1 < x0 + 32) NOEXT |= tbit(q - 1 - x0);
+                        if (q == x0 + 32) nS_in = 1u;
+                    }
                 }
             }
         }
@@ -676,90 +694,66 @@ __device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const ui
     if (((pw >> 16) & 0xff) == '\'') apprev |= 2u;     // x0-2
     if ((pw >> 24) == '\'') apprev |= 1u;              // x0-1
     apprev &= ~killprev;
-    uint32_t apm = APm & ~APkill;
-    if (apm | apprev) {
-        uint32_t nat = untranspose(apm);
+    if (APm | apprev) {
+        uint32_t nat = untranspose(APm) & ~KILLn;
         for (int d = 3; d >= 1; d--) {
             if (!(apprev & (1u << (d - 1)))) continue;
             const int a = x0 - d;
-            const uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
-            int clen = 0;
-            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
-            else if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) clen = 3;
+            int clen = contraction_len(txt[a + 1], txt[a + 2]);
             if (P.mode == 1 && clen) {          // the contraction may not reach into a special (text ends there)
                 if (rec_bit_g(P, g0 + a + 1)) clen = 0;
                 else if (clen == 3 && (rec_bit_g(P, g0 + a + 2))) clen = 0;
             }
-            if (clen <= d) continue;             // ends before this segment... unless the forced start lands on x0
+            if (clen < d) continue;              // ends before this segment
             bool live = (flprev >> (d - 1)) & 1;
             if (!live) { int k = smem_kclass(txt, a - 1); live = (k == KC_L || k == KC_N || k == KC_S); }
             if (!live) continue;
-            for (int t = 1; t < clen; t++) if (a + t >= x0) SUP |= tbit(a + t - x0);
-            if (a + clen >= x0) FL |= tbit(a + clen - x0);
-        }
-        // contraction ending exactly at x0 (clen == d): forced start at x0
-        for (int d = 3; d >= 2; d--) {
-            if (!(apprev & (1u << (d - 1)))) continue;
-            const int a = x0 - d;
-            const uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
-            int clen = 0;
-            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
-            else if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) clen = 3;
-            if (clen != d) continue;
-            if (P.mode == 1) {
-                if (rec_bit_g(P, g0 + a + 1)) continue;
-                if (clen == 3 && (rec_bit_g(P, g0 + a + 2))) continue;
-            }
-            bool live = (flprev >> (d - 1)) & 1;
-            if (!live) { int k = smem_kclass(txt, a - 1); live = (k == KC_L || k == KC_N || k == KC_S); }
-            if (live) FL |= tbit(0);
+            if (clen > d) SUPn |= range_mask(0, clen - d);     // positions a+1 .. a+clen-1 that fall into the segment
+            if (a + clen < x0 + 32) FLn |= 1u << (a + clen - x0);   // the position after a contraction is a forced start
         }
         while (nat) {
             const int ap = __ffs(nat) - 1; nat &= nat - 1;
             const int a = x0 + ap;
-            const uint8_t c1 = txt[a + 1], c2 = txt[a + 2];
-            int clen = 0;
-            if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') clen = 2;
-            else if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) clen = 3;
+            const int clen = contraction_len(txt[a + 1], txt[a + 2]);
             if (!clen) continue;
             if (P.mode == 1) {
                 if (rec_bit_g(P, g0 + a + 1)) continue;
                 if (clen == 3 && (rec_bit_g(P, g0 + a + 2))) continue;
             }
             const uint32_t tb = tbit(ap);
-            const bool live = (FL & tb) || (pL & tb) || (pN & tb) || ((pS & tb) && !(pSP & tb));
+            const bool live = ((FLn >> ap) & 1u) || (pL & tb) || (pN & tb) || ((pS & tb) && !(pSP & tb));
             if (!live) continue;
-            for (int t = 1; t < clen; t++) if (ap + t < 32) SUP |= tbit(ap + t);
-            if (ap + clen < 32) FL |= tbit(ap + clen);
+            const int hi = ap + clen < 32 ? ap + clen : 32;
+            if (hi > ap + 1) SUPn |= range_mask(ap + 1, hi);
+            if (ap + clen < 32) FLn |= 1u << (ap + clen);
         }
     }
     // ---- the start rule, 32 positions at once
     const uint32_t Om = ~(Lm | Nm | Sm), pO = ~(pL | pN | pS);
     const uint32_t same = (Lm & pL) | (Nm & pN) | (Om & pO);
     const uint32_t NS = nextT(Sm, nS_in) | NOEXT;
-    uint32_t st = (((~Sm & ~pSP & (pS | ~same)) | (Sm & (~pS | ~NS))) & ~SUP & ~CONT) | FL;
+    uint32_t st = (untranspose(((~Sm & ~pSP & (pS | ~same)) | (Sm & (~pS | ~NS))) & ~CONT) & ~SUPn) | FLn;
     // multi-byte whitespace (U+00A0, U+2003, U+3000, ...): the look-ahead is the next CODE POINT, not the next byte
     if (wsleads) {
         uint32_t nat = untranspose(wsleads);
         while (nat) {
             const int pos = __ffs(nat) - 1; nat &= nat - 1;
-            const uint32_t tb = tbit(pos);
-            if ((FL & tb) || (SUP & tb) || !(pS & tb)) continue;     // already decided by the generic formula
+            if (((FLn | SUPn) >> pos) & 1u) continue;                // already decided
+            if (!(pS & tbit(pos))) continue;                         // previous is not whitespace: a start, as computed
             const int nx = x0 + pos + utf8_len_from_lead(txt[x0 + pos]);
             const bool exists = !(P.mode == 1 && rec_bit_g(P, g0 + nx));
             const bool start = exists && smem_kclass(txt, nx) < KC_S;
-            st = start ? (st | tb) : (st & ~tb);
+            st = start ? (st | (1u << pos)) : (st & ~(1u << pos));
         }
     }
-    return untranspose(st);
+    return st;
 }
 
 // Fast path, whole tile.  Returns false when the tile needs the generic path (smask is then rewritten).
 __device__ bool tile_scan_fast(const PretokParams& P, TileSmem& S, i64 g0, int buf) {
     const uint8_t* txt = S.txt[buf];
-    uint32_t na = 0;
     for (int sgi = threadIdx.x; sgi < PT_NSEG; sgi += PT_THREADS) {
-        uint32_t m = segment_scan(P, txt, g0, sgi, &na);
+        uint32_t m = segment_scan(P, txt, S.recw, g0, sgi);
         S.smask[sgi] = sgi == PT_NSEG - 1 ? (m & 1u) : m;
     }
     __syncthreads();
@@ -793,6 +787,7 @@ __device__ void tile_compact(TileSmem& S) {
 __device__ void tile_scan(const PretokParams& P, TileSmem& S, i64 tile, int buf, bool* has_cut) {
     const i64 g0 = (P.tile_base + tile) * PT_TILE - PT_HL;
     tile_stage_rec(P, S, g0);
+    if (P.n_sp > 0) __syncthreads();
     bool done = false;
     if (!tile_is_boundary(P, g0, has_cut)) done = tile_scan_fast(P, S, g0, buf);
     if (!done) tile_scan_generic(P, S, tile, buf);

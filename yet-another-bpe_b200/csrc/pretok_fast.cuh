@@ -22,14 +22,14 @@
 #define PW_HL 32                           // left context in the window (= PT_HL: segment_scan uses it)
 #define PW_WIN 1088                        // 32 + 992 + 32 (look-ahead segment) + 32 (slack for its own look-ahead)
 #ifndef PW_WARPS
-#define PW_WARPS 24
+#define PW_WARPS 28
 #endif
 #define PW_THREADS (PW_WARPS * 32)
 #ifndef PW_NC
 #define PW_NC 4096                         // cache entries per CTA (power of two)
 #endif
-#define PW_NC_LOG2 (PW_NC == 4096 ? 12 : (PW_NC == 2048 ? 11 : (PW_NC == 8192 ? 13 : 10)))
-#define PW_QCAP 96                         // per-warp miss queue
+#define PW_NC_LOG2 (PW_NC == 4096 ? 12 : (PW_NC == 2048 ? 11 : (PW_NC == 8192 ? 13 : (PW_NC == 1024 ? 10 : 9))))
+#define PW_LQCAP 64                        // per-warp queue of long (> 14 byte) pre-tokens
 #define PW_TOKCAP 1024
 
 static_assert(PW_HL == PT_HL, "segment_scan assumes PT_HL bytes of left context");
@@ -37,33 +37,26 @@ static_assert((PW_NC & (PW_NC - 1)) == 0, "cache size must be a power of two");
 
 struct WarpSmem {
     alignas(128) uint8_t txt[2][PW_WIN];
-    alignas(16) ulonglong2 queue[PW_QCAP];
+    u64 lqueue[PW_LQCAP];                  // long pre-tokens: global position | length << 40
     uint16_t tokpos[PW_TOKCAP];
     alignas(8) uint64_t bar[2];
-    uint8_t pad_[96];
+    uint32_t recw[2][PW_WIN / 32 + 8];     // recognised-special bits of the window (+4 words of history, +4 slack)
+    uint8_t pad_[128 - (16 + 2 * 4 * (PW_WIN / 32 + 8)) % 128];
 };
 static_assert(sizeof(WarpSmem) % 128 == 0, "warp areas stay 128-byte aligned");
 
 #define PW_SMEM_BYTES (PW_NC * 20 + 256 + PW_WARPS * (int)sizeof(WarpSmem))
 
-// no cut inside [g0, g1]?  (all lanes ask the same question: the loads broadcast)
-__device__ __forceinline__ bool pw_no_cut(const PretokParams& P, i64 g0, i64 g1) {
-    if (P.n_cuts == 0) return true;
+// first cut >= g (or INT64_MAX)
+__device__ __forceinline__ i64 pw_next_cut(const PretokParams& P, i64 g) {
     int lo = 0, hi = P.n_cuts;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] < g0) lo = mid + 1; else hi = mid; }
-    return !(lo < P.n_cuts && P.cuts[lo] <= g1);
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] < g) lo = mid + 1; else hi = mid; }
+    return lo < P.n_cuts ? P.cuts[lo] : INT64_MAX;
 }
 
-__device__ __forceinline__ bool pw_chunk_is_fast(const PretokParams& P, i64 c) {
-    const i64 A = c * PW_CH, g0 = A - PW_HL;
-    if (A < P.own_lo || A + PW_CH > P.own_hi) return false;
-    if (g0 <= 0 || g0 + PW_WIN >= P.n) return false;
-    return pw_no_cut(P, g0, g0 + PW_WIN);
-}
-
-// hand the owned part of chunk c to the generic kernel, split at its 8 KiB tile boundaries
-__device__ void pw_emit_slow(const PretokParams& P, i64 c) {
-    i64 lo = c * PW_CH, hi = lo + PW_CH;
+// hand the owned part of the chunk at byte offset A to the generic kernel, split at its 8 KiB tile boundaries
+__device__ void pw_emit_slow(const PretokParams& P, i64 A) {
+    i64 lo = A, hi = lo + PW_CH;
     if (lo < P.own_lo) lo = P.own_lo;
     if (hi > P.own_hi) hi = P.own_hi;
     if (lo >= hi) return;
@@ -74,41 +67,17 @@ __device__ void pw_emit_slow(const PretokParams& P, i64 c) {
     }
 }
 
-// drain the warp's miss queue into the global tables; the key loads of four entries per lane are in
-// flight together so that their latencies overlap
-__device__ void pw_drain(const PretokParams& P, const ulonglong2* queue, int qn, u64& my_us, u64& my_ul, u64& my_ub) {
-    const int lane = threadIdx.x & 31;
-    const u64 smask = (u64)P.scap - 1;
-    for (int base = 0; base < qn; base += 128) {
-        ulonglong2 e[4], kv[4];
-        u64 sl[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = base + u * 32 + lane;
-            e[u].x = 0; e[u].y = 0; sl[u] = 0; kv[u].x = 0; kv[u].y = 0;
-            if (i < qn) {
-                e[u] = queue[i];
-                if ((e[u].y >> 56) == 1) { sl[u] = short_hash(e[u].x, e[u].y) & smask; kv[u] = __ldcg(&P.skeys[sl[u]]); }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (e[u].y == 0) continue;
-            int created = 0;
-            if ((e[u].y >> 56) == 1) {
-                if (kv[u].x == e[u].x && kv[u].y == e[u].y) atomicAdd((u64*)&P.scounts[sl[u]], 1ULL);
-                else {
-                    if (short_insert_h(P.skeys, P.scounts, P.scap, sl[u], e[u].x, e[u].y, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
-                    if (created) { my_us++; my_ub += e[u].x >> 56; }
-                }
-            } else {
-                const i64 pos = (i64)e[u].x, len = (i64)(e[u].y & 0xffffffffULL);
-                u64 h = 0;
-                for (i64 j = 0; j < len; j++) h += long_hash_term(P.text[pos + j], j);
-                if (long_insert(P.lent, P.lcap, P.text, long_hash_fix(h), pos, len, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
-                if (created) { my_ul++; my_ub += (u64)len; }
-            }
-        }
+// long pre-tokens (15 bytes .. one chunk): one lane each, bytes read back from global memory (L2-hot)
+__device__ void pw_drain_long(const PretokParams& P, const u64* lqueue, int qn, u64& my_ul, u64& my_ub) {
+    for (int i = threadIdx.x & 31; i < qn; i += 32) {
+        const u64 e = lqueue[i];
+        const i64 pos = (i64)(e & ((1ULL << 40) - 1)), len = (i64)(e >> 40);
+        if (len == 0) continue;                  // placeholder of an over-long pre-token (handled by k_long_tokens_dyn)
+        u64 h = 0;
+        for (i64 j = 0; j < len; j++) h += long_hash_term(P.text[pos + j], j);
+        int created;
+        if (long_insert(P.lent, P.lcap, P.text, long_hash_fix(h), pos, len, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+        if (created) { my_ul++; my_ub += (u64)len; }
     }
 }
 
@@ -132,35 +101,75 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     if (lane == 0) { mbar_init(&W.bar[0], 1); mbar_init(&W.bar[1], 1); mbar_fence_init(); }
     __syncthreads();
 
-    u64 my_tok = 0, my_us = 0, my_ul = 0, my_ub = 0, my_hit = 0;
-    int qn = 0;
+    u64 my_us = 0, my_ul = 0, my_ub = 0;
+    uint32_t my_tok = 0, my_miss = 0;              // warp-uniform
+    int lqn = 0;
     uint32_t phase0 = 0, phase1 = 0;
-    const i64 nw = (i64)gridDim.x * PW_WARPS;
+    const i64 stepA = (i64)gridDim.x * PW_WARPS * PW_CH, endA = c_hi * PW_CH;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const i64 nrec = (P.n + 63) / 32 + 1;
+    const u64 smask = (u64)P.scap - 1;
+    // chunks whose offset A lies in [fastA_lo, fastA_hi] are fully owned and away from both ends of the text
+    const i64 fastA_lo = P.own_lo > PW_HL + 1 ? P.own_lo : PW_HL + 1;
+    const i64 fastA_hi = (P.own_hi - PW_CH < P.n - 1 - PW_WIN + PW_HL) ? P.own_hi - PW_CH : P.n - 1 - PW_WIN + PW_HL;
+    i64 next_cut = P.n_cuts ? -1 : INT64_MAX;      // first cut >= the current window start (refreshed lazily)
 
-    // the next fast chunk at or after c (slow chunks on the way are handed to the generic kernel)
-    auto advance = [&](i64 c) -> i64 {
-        while (c < c_hi && !pw_chunk_is_fast(P, c)) { if (lane == 0) pw_emit_slow(P, c); c += nw; }
-        return c;
-    };
-    auto issue = [&](i64 c, int buf) {
-        mbar_expect_tx(&W.bar[buf], PW_WIN);
-        tma_load_1d(W.txt[buf], P.text + (c * PW_CH - PW_HL), PW_WIN, &W.bar[buf]);
+    // a global-table probe in flight: issued when a pre-token misses the cache, consumed one round later
+    bool pend = false;
+    uint32_t pkx = 0, pky = 0, pkz = 0, pkw = 0, pslot = 0;
+    ulonglong2 pkv; pkv.x = 0; pkv.y = 0;
+    auto consume = [&]() {
+        if (pend) {
+            const u64 k0 = (u64)pkx | ((u64)pky << 32), k1 = (u64)pkz | ((u64)pkw << 32);
+            if (pkv.x == k0 && pkv.y == k1) atomicAdd((u64*)&P.scounts[pslot], 1ULL);
+            else {
+                int created;
+                if (short_insert_h(P.skeys, P.scounts, P.scap, pslot, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                if (created) { my_us++; my_ub += pky >> 24; }
+            }
+            pend = false;
+        }
     };
 
-    i64 c = advance(c_lo + (i64)blockIdx.x * PW_WARPS + warp);
-    if (c < c_hi && lane == 0) issue(c, 0);
+    // the next fast chunk at or after offset A (slow chunks on the way are handed to the generic kernel)
+    auto advance = [&](i64 A) -> i64 {
+        for (; A < endA; A += stepA) {
+            if (A >= fastA_lo && A <= fastA_hi) {
+                if (next_cut < A - PW_HL) next_cut = pw_next_cut(P, A - PW_HL);
+                if (next_cut > A - PW_HL + PW_WIN) break;
+            }
+            if (lane == 0) pw_emit_slow(P, A);
+        }
+        return A;
+    };
+
+    i64 A = advance((c_lo + (i64)blockIdx.x * PW_WARPS + warp) * PW_CH);
+    if (A < endA) {
+        if (lane == 0) { mbar_expect_tx(&W.bar[0], PW_WIN); tma_load_1d(W.txt[0], P.text + (A - PW_HL), PW_WIN, &W.bar[0]); }
+        if (P.n_sp > 0) {
+            const i64 wi = ((A - PW_HL) >> 5) - 4 + lane;
+            W.recw[0][lane] = wi >= 0 ? P.rec[wi] : 0u;
+            if (lane < PW_WIN / 32 + 8 - 32) W.recw[0][32 + lane] = wi + 32 < nrec ? P.rec[wi + 32] : 0u;
+        }
+    }
     int buf = 0;
-    while (c < c_hi) {
-        const i64 cn = advance(c + nw);
-        if (cn < c_hi && lane == 0) issue(cn, buf ^ 1);
+    while (A < endA) {
+        const i64 An = advance(A + stepA);
+        uint32_t nr0 = 0, nr1 = 0;                 // next window's recognised-special bits: loaded now, stored after this chunk
+        if (An < endA) {
+            if (lane == 0) { mbar_expect_tx(&W.bar[buf ^ 1], PW_WIN); tma_load_1d(W.txt[buf ^ 1], P.text + (An - PW_HL), PW_WIN, &W.bar[buf ^ 1]); }
+            if (P.n_sp > 0) {
+                const i64 wi = ((An - PW_HL) >> 5) - 4 + lane;
+                nr0 = P.rec[wi];                   // wi >= 0: An > A >= PW_HL + 1 + stepA
+                if (lane < PW_WIN / 32 + 8 - 32 && wi + 32 < nrec) nr1 = P.rec[wi + 32];
+            }
+        }
         if (buf == 0) { mbar_wait(&W.bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&W.bar[1], phase1); phase1 ^= 1; }
         const uint8_t* txt = W.txt[buf];
-        const i64 g0 = c * PW_CH - PW_HL;
+        const i64 g0 = A - PW_HL;
 
         // ---- token starts of this lane's segment
-        uint32_t na_unused;
-        const uint32_t m = segment_scan(P, txt, g0, lane, &na_unused);
+        const uint32_t m = segment_scan(P, txt, W.recw[buf], g0, lane);
         const bool own = lane < 31;
         const int cnt = own ? __popc(m) : 0;
         int inc = cnt;
@@ -176,59 +185,75 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             W.tokpos[total] = m ? (uint16_t)(PW_HL + PW_CH + __ffs(m) - 1) : (uint16_t)0xFFFF;
         }
         __syncwarp();
+        my_tok += (uint32_t)total;
 
         // ---- one lane per pre-token
         const uint32_t* tw = (const uint32_t*)txt;
         for (int base = 0; base < total; base += 32) {
             const int k = base + lane;
+            int s = 0, len = 0;
+            if (k < total) { s = W.tokpos[k]; len = (int)W.tokpos[k + 1] - s; }      // sentinel 0xFFFF: len > 14
+            uint32_t kx = 0, ky = 0, kz = 0, kw = 0, h = 0;
             bool miss = false;
-            ulonglong2 ent; ent.x = 0; ent.y = 0;
-            if (k < total) {
-                const int s = W.tokpos[k], e = W.tokpos[k + 1];
-                my_tok++;
-                if (e == 0xFFFF) {                                    // ends beyond the look-ahead segment
-                    const u64 idx = atomicAdd((u64*)&P.stats[ST_OVF_N], 1ULL);
-                    if ((i64)idx < P.ovf_cap) P.ovf_pos[idx] = g0 + s;
-                } else {
-                    const int len = e - s;
-                    if (len <= PT_SHORT_MAX) {
-                        const int wi = s >> 2, sh = (s & 3) * 8;
-                        const uint32_t a0 = tw[wi], a1 = tw[wi + 1], a2 = tw[wi + 2], a3 = tw[wi + 3], a4 = tw[wi + 4];
-                        const uint4 mk = lut[len];
-                        const uint32_t b0 = __funnelshift_r(a0, a1, sh) & mk.x, b1 = __funnelshift_r(a1, a2, sh) & mk.y;
-                        const uint32_t b2 = __funnelshift_r(a2, a3, sh) & mk.z, b3 = __funnelshift_r(a3, a4, sh) & mk.w;
-                        // key words (same layout as pack_short_key): k0 = 7 bytes | len << 56, k1 = 7 bytes | 1 << 56
-                        const uint32_t kx = b0, ky = (b1 & 0x00ffffffu) | ((uint32_t)len << 24);
-                        const uint32_t kz = (b1 >> 24) | (b2 << 8), kw = (b2 >> 24) | (b3 << 8) | (1u << 24);
-                        const uint32_t h = short_hash_w(kx, ky, kz, kw);
-                        uint32_t ci = h >> (32 - PW_NC_LOG2);
-                        bool done = false;
-#pragma unroll
-                        for (int probe = 0; probe < 2 && !done; probe++) {
-                            const uint4 a = ckeys[ci];
-                            if (a.x == kx && a.y == ky && a.z == kz && a.w == kw) { atomicAdd(&ccnt[ci], 1u); done = true; }
-                            else if (a.w == 0 && atomicCAS(&ccnt[ci], 0u, 0x80000001u) == 0u) { ckeys[ci] = make_uint4(kx, ky, kz, kw); done = true; }
-                            else ci ^= 1u;
-                        }
-                        if (done) my_hit++;
-                        else { miss = true; ent.x = (u64)kx | ((u64)ky << 32); ent.y = (u64)kz | ((u64)kw << 32); }
-                    } else {
-                        miss = true; ent.x = (u64)(g0 + s); ent.y = (2ULL << 56) | (u64)len;
-                    }
+            const bool is_short = (unsigned)(len - 1) < (unsigned)PT_SHORT_MAX;
+            if (is_short) {
+                const int wi = s >> 2, sh = (s & 3) * 8;
+                const uint32_t a0 = tw[wi], a1 = tw[wi + 1], a2 = tw[wi + 2], a3 = tw[wi + 3], a4 = tw[wi + 4];
+                const uint4 mk = lut[len];
+                const uint32_t b0 = __funnelshift_r(a0, a1, sh) & mk.x, b1 = __funnelshift_r(a1, a2, sh) & mk.y;
+                const uint32_t b2 = __funnelshift_r(a2, a3, sh) & mk.z, b3 = __funnelshift_r(a3, a4, sh) & mk.w;
+                // key words (same layout as pack_short_key): k0 = 7 bytes | len << 56, k1 = 7 bytes | 1 << 56
+                kx = b0; ky = (b1 & 0x00ffffffu) | ((uint32_t)len << 24);
+                kz = __funnelshift_r(b1, b2, 24); kw = __funnelshift_r(b2, b3, 24) | (1u << 24);
+                h = short_hash_w(kx, ky, kz, kw);
+                const uint32_t ci = h >> (32 - PW_NC_LOG2);
+                const uint4 a = ckeys[ci];
+                if (((a.x ^ kx) | (a.y ^ ky) | (a.z ^ kz) | (a.w ^ kw)) == 0) atomicAdd(&ccnt[ci], 1u);
+                else miss = true;
+            }
+            if (miss) {                            // second cache way, or claim an empty one
+                uint32_t ci = h >> (32 - PW_NC_LOG2);
+                if (ckeys[ci].w == 0 && atomicCAS(&ccnt[ci], 0u, 0x80000001u) == 0u) { ckeys[ci] = make_uint4(kx, ky, kz, kw); miss = false; }
+                else {
+                    ci ^= 1u;
+                    const uint4 a = ckeys[ci];
+                    if (((a.x ^ kx) | (a.y ^ ky) | (a.z ^ kz) | (a.w ^ kw)) == 0) { atomicAdd(&ccnt[ci], 1u); miss = false; }
+                    else if (a.w == 0 && atomicCAS(&ccnt[ci], 0u, 0x80000001u) == 0u) { ckeys[ci] = make_uint4(kx, ky, kz, kw); miss = false; }
                 }
             }
-            const uint32_t mm = __ballot_sync(0xffffffffu, miss);
-            if (mm) {
-                if (miss) W.queue[qn + __popc(mm & lt_mask)] = ent;
-                qn += __popc(mm);
-                if (qn > PW_QCAP - 32) { __syncwarp(); pw_drain(P, W.queue, qn, my_us, my_ul, my_ub); qn = 0; __syncwarp(); }
+            consume();                             // the probe issued one round ago has landed by now
+            if (miss) {
+                pend = true; pkx = kx; pky = ky; pkz = kz; pkw = kw;
+                pslot = (uint32_t)(h & smask);
+                pkv = __ldcg(&P.skeys[pslot]);
+            }
+            my_miss += __popc(__ballot_sync(0xffffffffu, miss));
+            // long (15 bytes .. one chunk) and over-long pre-tokens
+            const bool is_long = k < total && !is_short;
+            const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+            if (lm) {
+                if (is_long) {
+                    if (len + s == 0xFFFF) {                          // ends beyond the look-ahead segment
+                        const u64 idx = atomicAdd((u64*)&P.stats[ST_OVF_N], 1ULL);
+                        if ((i64)idx < P.ovf_cap) P.ovf_pos[idx] = g0 + s;
+                        W.lqueue[lqn + __popc(lm & lt_mask)] = 0;     // placeholder (length 0: ignored by the drain)
+                    } else W.lqueue[lqn + __popc(lm & lt_mask)] = (u64)(g0 + s) | ((u64)len << 40);
+                }
+                lqn += __popc(lm);
+                my_miss += __popc(lm);
+                if (lqn > PW_LQCAP - 32) { __syncwarp(); pw_drain_long(P, W.lqueue, lqn, my_ul, my_ub); lqn = 0; __syncwarp(); }
             }
         }
-        __syncwarp();        // every lane is done with txt[buf] and tokpos before they are reused
-        c = cn; buf ^= 1;
+        if (P.n_sp > 0 && An < endA) {
+            W.recw[buf ^ 1][lane] = nr0;
+            if (lane < PW_WIN / 32 + 8 - 32) W.recw[buf ^ 1][32 + lane] = nr1;
+        }
+        __syncwarp();        // every lane is done with txt[buf], recw[buf] and tokpos before they are reused
+        A = An; buf ^= 1;
     }
+    consume();
     __syncwarp();
-    pw_drain(P, W.queue, qn, my_us, my_ul, my_ub);
+    pw_drain_long(P, W.lqueue, lqn, my_ul, my_ub);
 
     // ---- flush the cache
     __syncthreads();
@@ -242,15 +267,14 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         if (created) { my_us++; my_ub += k0 >> 56; }
     }
     for (int o = 16; o > 0; o >>= 1) {
-        my_tok += __shfl_xor_sync(0xffffffffu, my_tok, o); my_us += __shfl_xor_sync(0xffffffffu, my_us, o);
+        my_us += __shfl_xor_sync(0xffffffffu, my_us, o);
         my_ul += __shfl_xor_sync(0xffffffffu, my_ul, o); my_ub += __shfl_xor_sync(0xffffffffu, my_ub, o);
-        my_hit += __shfl_xor_sync(0xffffffffu, my_hit, o);
     }
     if (lane == 0) {
-        if (my_tok) atomicAdd((u64*)&P.stats[ST_NTOK], my_tok);
+        if (my_tok) atomicAdd((u64*)&P.stats[ST_NTOK], (u64)my_tok);
         if (my_us) atomicAdd((u64*)&P.stats[ST_UNIQ_SHORT], my_us);
         if (my_ul) atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], my_ul);
         if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
-        if (my_hit) atomicAdd((u64*)&P.stats[ST_CACHE_HIT], my_hit);
+        if (my_tok > my_miss) atomicAdd((u64*)&P.stats[ST_CACHE_HIT], (u64)(my_tok - my_miss));
     }
 }
