@@ -139,6 +139,7 @@ typedef struct {
     yabpe_word_table words; int64_t n_words, n_syms;
     int32_t* wstamp;            /* device, n_words, zeroed                                        */
     int32_t* wslot;             /* device, n_syms + 8: cached pair-table slot of every adjacency  */
+    int32_t* newp;              /* device, n_syms + 8: scratch (pairs created by one merge)        */
     uint8_t* tok_bytes; int64_t tok_bytes_cap;   /* token byte pool; base tokens filled by host   */
     int64_t* tok_off;           /* device, max_tokens + 1; [0..n_base] filled by the host         */
     uint64_t* tok_hash;         /* device, max_tokens; polynomial hash (base 0x100000001b3, +1)   */

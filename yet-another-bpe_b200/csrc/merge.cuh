@@ -15,6 +15,18 @@
 #include "pretok.cuh"
 
 #define ML_THREADS 1024
+#ifndef ML_TIMING
+#define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
+#endif
+#if ML_TIMING
+#define ML_CLOCK(v) long long v = clock64()
+#define ML_T0(v) long long v = clock64()
+#define ML_TACC(slot, from) do { if (threadIdx.x == 0) { long long _t = clock64(); sh_tacc[slot] += _t - (from); (from) = _t; } } while (0)
+#else
+#define ML_CLOCK(v)
+#define ML_T0(v)
+#define ML_TACC(slot, from)
+#endif
 #ifndef ML_DEFER_NPAIRS
 #define ML_DEFER_NPAIRS 1
 #endif
@@ -138,6 +150,7 @@ struct MergeParams {
     // words
     int32_t* wsym; const int32_t* sym_word; i64 n_syms;
     int32_t* wslot;                              // per symbol slot: pair-table slot of (sym[j], sym[j+1])
+    int32_t* newp;                               // n_syms entries: spill of the leader's per-merge list of new pairs
     const i64* woff; int32_t* wlen; const i64* wcnt; i64 n_words; int32_t* wstamp;
     // tokens (ids < n_base are prepared by the host: 256 bytes + specials)
     uint8_t* tok_bytes; i64 tok_bytes_cap; i64* tok_off; u64* tok_hash; u64* tok_pow;
@@ -189,22 +202,20 @@ __device__ __forceinline__ i64 pair_find(const MergeParams& M, u64 key) {
     }
     return -1;
 }
-__device__ __forceinline__ i64 pair_upsert(const MergeParams& M, u64 key) {
+// expect_new: the key is very likely absent (it contains a token created by the current merge), so the probe
+// starts with the CAS instead of a load: one L2 round trip less on the critical path of every merge.
+// created_ctr: shared-memory counter of new pairs (leader mode), else the global MS_NPAIRS is bumped.
+__device__ __forceinline__ i64 pair_upsert(const MergeParams& M, u64 key, bool expect_new = false, int* created_ctr = nullptr) {
     u64 mask = (u64)M.pcap - 1;
     u64 slot = mix64(key) & mask;
     for (i64 probes = 0; probes < M.pcap; probes++) {
-        u64 k = M.pkey[slot];                       // keys are write-once: a cached value is either right or empty
+        u64 k = expect_new ? 0ULL : M.pkey[slot];   // keys are write-once: a cached value is either right or empty
         if (k == 0) {
             k = atomicCAS(&M.pkey[slot], 0ULL, key);
-#if ML_DEFER_NPAIRS
-            if (k == 0) { atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL); return (i64)slot; }   // load factor: checked once per merge
-#else
-            if (k == 0) {
-                u64 np = atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL);
-                if ((i64)np * 4 > M.pcap * 3) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL);
+            if (k == 0) {                           // load factor: checked once per merge
+                if (created_ctr) atomicAdd(created_ctr, 1); else atomicAdd((u64*)&M.state[MS_NPAIRS], 1ULL);
                 return (i64)slot;
             }
-#endif
         }
         if (k == key) return (i64)slot;
         slot = (slot + 1) & mask;
@@ -324,7 +335,7 @@ __device__ void rebuild_active(const MergeParams& M, i64 T) {
         }
     }
     grid_barrier(M);
-    if (gtid == 0) M.state[MS_ACT_BASE] = M.state[MS_ACT_N];
+
 }
 
 // CSR postings: for every pair slot the words that contain it (duplicates allowed)
@@ -393,7 +404,11 @@ __device__ void rebuild_index(const MergeParams& M, i64* sh_scan, i64 m_now) {
 #ifndef ML_USE_MIRROR
 #define ML_USE_MIRROR 1
 #endif
-struct LeaderMirror { i64 cnt[ML_TOP_N]; int32_t mkey[2 * ML_TOP_N]; int16_t mval[2 * ML_TOP_N]; };
+// Counts are kept as two 32-bit halves: shared memory has native 32-bit atomic adds, while a 64-bit add is a
+// compare-and-swap loop (~145 cycles uncontended, far worse when every rewrite site hits the same entry).
+struct LeaderMirror { uint32_t lo[ML_TOP_N], hi[ML_TOP_N]; uint8_t pending[ML_TOP_N]; int32_t mkey[2 * ML_TOP_N]; int16_t mval[2 * ML_TOP_N]; };
+__device__ __forceinline__ i64 mirror_get(const LeaderMirror* lm, int idx) { return (i64)(((u64)lm->hi[idx] << 32) | lm->lo[idx]); }
+__device__ __forceinline__ void mirror_set(LeaderMirror* lm, int idx, i64 v) { lm->lo[idx] = (uint32_t)(u64)v; lm->hi[idx] = (uint32_t)((u64)v >> 32); lm->pending[idx] = 0; }
 
 __device__ __forceinline__ int mirror_find(const LeaderMirror* lm, int32_t slot) {
     uint32_t h = ((uint32_t)slot * 2654435761u) >> 22;          // 10 bits (2 * ML_TOP_N = 1024 entries)
@@ -412,15 +427,51 @@ __device__ __forceinline__ void mirror_insert(LeaderMirror* lm, int32_t slot, in
         h = (h + 1) & (2 * ML_TOP_N - 1);
     }
 }
-__device__ __forceinline__ void mirror_add(LeaderMirror* lm, int32_t slot, i64 d) {
-    if (!lm) return;
-    const int idx = mirror_find(lm, slot);
-    if (idx >= 0) atomicAdd((u64*)&lm->cnt[idx], (u64)d);
+
+// Leader-mode context (shared memory of CTA 0).  While the leader runs it is the only writer of the merge
+// state, so the counters the rewrite bumps (active set, affected log, top list, new pairs) live here and
+// are written back to M.state once, when the leader hands control back to the grid.
+#define ML_DEDUPE_N 2048
+#define ML_NEWP_N 1024
+struct LeaderCtx {
+    LeaderMirror LM;
+    int32_t tslot[ML_TOP_N]; u64 tkey[ML_TOP_N];
+    u64 dedupe[ML_DEDUPE_N];                     // (merge stamp << 32 | word): candidate words already taken this merge
+    int32_t newp[ML_NEWP_N];                     // slots of the pairs created by the current merge (spill: M.newp)
+    int top_n, top_ovf, act_n, alog_n, npairs_new, error, nnew;
+    int32_t cur_slot;                            // pair-table slot of the pair being merged
+};
+
+__device__ __forceinline__ void mirror_add(LeaderCtx* lc, int32_t slot, i64 d) {
+    if (!lc) return;
+    const int idx = mirror_find(&lc->LM, slot);
+    if (idx >= 0) {
+        const uint32_t dlo = (uint32_t)(u64)d, dhi = (uint32_t)((u64)d >> 32);
+        const uint32_t old = atomicAdd(&lc->LM.lo[idx], dlo);
+        const uint32_t carry = (uint32_t)(((u64)old + dlo) >> 32);
+        if (dhi + carry) atomicAdd(&lc->LM.hi[idx], dhi + carry);
+    }
 }
 
-__device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t slot, i64 f, LeaderMirror* lm) {
+// true when this call took word w for merge `stamp` (first claim wins; stale entries of older merges are overwritten)
+__device__ __forceinline__ bool dedupe_claim(LeaderCtx* lc, int32_t w, uint32_t stamp) {
+    const u64 mine = ((u64)stamp << 32) | (uint32_t)w;
+    uint32_t h = ((uint32_t)w * 2654435761u) >> 21;             // 11 bits
+    for (;;) {
+        const u64 cur = lc->dedupe[h];
+        if (cur == mine) return false;
+        if ((uint32_t)(cur >> 32) != stamp) {
+            if (atomicCAS(&lc->dedupe[h], cur, mine) == cur) return true;
+            continue;                                            // somebody else changed this entry: look again
+        }
+        h = (h + 1) & (ML_DEDUPE_N - 1);
+    }
+}
+
+__device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t slot, i64 f, LeaderCtx* lc) {
     atomicAdd((u64*)&M.pcnt[slot], (u64)(-f));     // the slot of every adjacency is cached in wslot: no probe
-    mirror_add(lm, slot, -f);
+    // the merged pair itself is decremented by EVERY site: its mirrored count is re-read once after the rewrite instead
+    if (lc && slot != lc->cur_slot) mirror_add(lc, slot, -f);
 }
 // "Top list": every pair with count >= T2, kept in global memory (at most ML_TOP_N entries) and
 // maintained by pair_add in both modes.  Scanning the whole active set every merge is bound by the
@@ -428,37 +479,87 @@ __device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t slot, i64
 // per-merge scan to a few hundred entries.  It is rebuilt (grid-wide) when its best entry falls
 // below T2 or when it overflows.  state[MS_T2]: > 0 valid threshold, 0 = rebuild needed,
 // -1 = disabled for this merge (more than ML_TOP_N pairs tie for the maximum).
-
-__device__ __forceinline__ int32_t pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, i64 T2, LeaderMirror* lm) {
+// Membership (active set: count >= T, top list: count >= T2) is updated by the add that CROSSES the
+// threshold upwards (before < T <= after): exactly one add sees each crossing, so most adds end with the
+// atomic that returns the new count and never touch the membership bitmaps.
+__device__ __forceinline__ int32_t pair_add(const MergeParams& M, int32_t x, int32_t y, i64 f, i64 T, i64 T2, LeaderCtx* lc, bool expect_new) {
     const u64 key = PAIR_KEY(x, y);
-    i64 s = pair_upsert(M, key);
+    if (lc && expect_new) {
+        // Leader mode, new product token: every pair that GAINS in this merge contains the new token, i.e. was
+        // created by this merge.  The creator notes the slot; the count is added without waiting for the result
+        // and the thresholds are checked once per new pair after the rewrite (leader_new_pairs).
+        const u64 mask = (u64)M.pcap - 1;
+        u64 slot = mix64(key) & mask;
+        for (i64 probes = 0; probes < M.pcap; probes++) {
+            const u64 k = atomicCAS(&M.pkey[slot], 0ULL, key);
+            if (k == 0) {
+                const int idx = atomicAdd(&lc->nnew, 1);
+                if (idx < ML_NEWP_N) lc->newp[idx] = (int32_t)slot; else M.newp[idx - ML_NEWP_N] = (int32_t)slot;
+                break;
+            }
+            if (k == key) break;
+            slot = (slot + 1) & mask;
+        }
+        atomicAdd((u64*)&M.pcnt[slot], (u64)f);
+        return (int32_t)slot;
+    }
+    i64 s = pair_upsert(M, key, expect_new, lc ? &lc->npairs_new : nullptr);
     if (s < 0) return 0;
-    i64 now = (i64)atomicAdd((u64*)&M.pcnt[s], (u64)f) + f;
-    mirror_add(lm, (int32_t)s, f);
-    if (now >= T) {
-        uint32_t bit = 1u << (s & 31);
+    const i64 now = (i64)atomicAdd((u64*)&M.pcnt[s], (u64)f) + f;
+    mirror_add(lc, (int32_t)s, f);
+    if (now >= T && now - f < T) {
+        const uint32_t bit = 1u << (s & 31);
         if (!(atomicOr(&M.inact[s >> 5], bit) & bit)) {
-            i64 idx = (i64)atomicAdd((u64*)&M.state[MS_ACT_N], 1ULL);
+            const i64 idx = lc ? (i64)atomicAdd(&lc->act_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_ACT_N], 1ULL);
             M.act[idx] = (int32_t)s;
         }
-        if (T2 > 0 && now >= T2) {
-            if (!(atomicOr(&M.intop[s >> 5], bit) & bit)) {
-                i64 idx = (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
-                if (idx < ML_TOP_N) { M.top_slot[idx] = (int32_t)s; M.top_key[idx] = key; }
-                else { atomicAnd(&M.intop[s >> 5], ~bit); M.state[MS_TOP_OVF] = 1; }
+    }
+    if (T2 > 0 && now >= T2 && now - f < T2) {
+        const uint32_t bit = 1u << (s & 31);
+        if (!(atomicOr(&M.intop[s >> 5], bit) & bit)) {
+            const i64 idx = lc ? (i64)atomicAdd(&lc->top_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
+            if (idx < ML_TOP_N) {
+                M.top_slot[idx] = (int32_t)s; M.top_key[idx] = key;
+                if (lc) { lc->tslot[idx] = (int32_t)s; lc->tkey[idx] = key; lc->LM.pending[idx] = 1; }
+            } else {
+                atomicAnd(&M.intop[s >> 5], ~bit);
+                if (lc) lc->top_ovf = 1; else M.state[MS_TOP_OVF] = 1;
             }
         }
     }
     return (int32_t)s;
 }
-__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w) {
-    i64 d = (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL);
+// Leader mode, after the rewrite of a merge with a new product token: thresholds of the pairs it created.
+// Each new pair is visited exactly once, so the membership bits need no test-and-set.
+__device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx* lc, i64 T, i64 T2) {
+    const int n = lc->nnew;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int32_t s = i < ML_NEWP_N ? lc->newp[i] : M.newp[i - ML_NEWP_N];
+        const i64 cnt = __ldcg(&M.pcnt[s]);
+        const u64 key = __ldcg(&M.pkey[s]);
+        if (cnt < T) continue;
+        const uint32_t bit = 1u << (s & 31);
+        atomicOr(&M.inact[s >> 5], bit);
+        M.act[atomicAdd(&lc->act_n, 1)] = s;
+        if (cnt >= T2) {
+            const int idx = atomicAdd(&lc->top_n, 1);
+            if (idx < ML_TOP_N) {
+                atomicOr(&M.intop[s >> 5], bit);
+                M.top_slot[idx] = s; M.top_key[idx] = key;
+                lc->tslot[idx] = s; lc->tkey[idx] = key; mirror_set(&lc->LM, idx, cnt);
+                mirror_insert(&lc->LM, s, idx);
+            } else lc->top_ovf = 1;
+        }
+    }
+}
+__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, LeaderCtx* lc) {
+    const i64 d = lc ? (i64)atomicAdd(&lc->alog_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL);
     if (d < M.alog_cap) M.alog_word[d] = w;
     else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);     // callers reserve space up front
 }
 
 // one thread rewrites one word in place (left->right, non-overlapping) and applies the deltas
-__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderMirror* lm) {
+__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew) {
     const i64 off = M.woff[w];
     int32_t* s = M.wsym + off;
     int32_t* ws = M.wslot + off;
@@ -471,24 +572,24 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
         int32_t x = s[j];
         if (j + 1 < n && x == a && s[j + 1] == b) {
             const int32_t sl_ab = ws[j];
-            if (o > 0) { pair_sub(M, ws[j - 1], f, lm); ws[o - 1] = pair_add(M, prev_new, c, f, T, T2, lm); }
+            if (o > 0) { pair_sub(M, ws[j - 1], f, lm); ws[o - 1] = pair_add(M, prev_new, c, f, T, T2, lm, xnew); }
             pair_sub(M, sl_ab, f, lm);
             s[o++] = c; prev_new = c; prev_changed = true; any = true; j += 2;
         } else {
             if (o > 0) {
                 const int32_t sl_old = ws[j - 1];
-                if (prev_changed) { pair_sub(M, sl_old, f, lm); ws[o - 1] = pair_add(M, prev_new, x, f, T, T2, lm); }
+                if (prev_changed) { pair_sub(M, sl_old, f, lm); ws[o - 1] = pair_add(M, prev_new, x, f, T, T2, lm, xnew); }
                 else ws[o - 1] = sl_old;
             }
             s[o++] = x; prev_new = x; prev_changed = false; j += 1;
         }
     }
-    if (any) { M.wlen[w] = o; alog_append(M, w); }
+    if (any) { M.wlen[w] = o; alog_append(M, w, lm); }
 }
 
 // one warp rewrites one word (a != b): every lane owns one old position per 32-symbol chunk, so the
 // pair-count updates of a word are issued in parallel instead of as one dependent chain
-__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderMirror* lm) {
+__device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew) {
     const int lane = threadIdx.x & 31;
     const i64 woff_ = M.woff[w];
     int32_t* s = M.wsym + woff_;
@@ -527,25 +628,25 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
                 has_pair = true;
                 const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
                 const bool seln = xn == a && xnn == b;
-                if (sel0 || seln) nslot = pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2, lm);
+                if (sel0 || seln) nslot = pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2, lm, xnew);
             }
         }
         __syncwarp();
         if (keep) {
             const int ni = out + __popc(keepmask & ((1u << lane) - 1));
-            s[ni] = sel0 ? c : x0;
-            if (has_pair) ws[ni] = nslot;
+            if (ni != j || sel0) s[ni] = sel0 ? c : x0;           // untouched prefix of the word: nothing to store
+            if (has_pair && (ni != j || nslot != ps0)) ws[ni] = nslot;
         }
         out += __popc(keepmask);
         __syncwarp();
     }
-    if (any && lane == 0) { M.wlen[w] = out; alog_append(M, w); }
+    if (any && lane == 0) { M.wlen[w] = out; alog_append(M, w, lm); }
 }
 
 // four words per warp, one per 8-lane group (words are short: ~6 symbols on average).  Group-local
 // version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes must call it together.
 __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
-                                 int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderMirror* lm) {
+                                 int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew) {
     const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & 24;
     int32_t* s = M.wsym + (w >= 0 ? off : 0);
     int32_t* ws = M.wslot + (w >= 0 ? off : 0);
@@ -553,13 +654,22 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
     int out = 0;
     bool any = false;
     int32_t carry_prev = -1;
+    // the symbols of chunk k+1 are loaded before the atomics of chunk k are issued (software pipelining: a word
+    // longer than 8 symbols would otherwise pay the L2 round trips of every chunk one after the other);
+    // chunk k only stores to positions < 8(k+1), chunk k+1 only loads positions >= 8(k+1)
+    int32_t nx0 = -1, nx1 = -1, nx2 = -1, nx3 = -1, nps0 = 0;
+    if (gl < n) nx0 = s[gl];
+    if (gl + 1 < n) { nx1 = s[gl + 1]; nps0 = ws[gl]; }
+    if (gl + 2 < n) nx2 = s[gl + 2];
+    if (gl + 3 < n) nx3 = s[gl + 3];
     for (int base = 0; __any_sync(0xffffffffu, base < n); base += 8) {
         const int j = base + gl;
-        int32_t x0 = -1, x1 = -1, x2 = -1, x3 = -1, ps0 = 0;
-        if (j < n) x0 = s[j];
-        if (j + 1 < n) { x1 = s[j + 1]; ps0 = ws[j]; }
-        if (j + 2 < n) x2 = s[j + 2];
-        if (j + 3 < n) x3 = s[j + 3];
+        const int32_t x0 = nx0, x1 = nx1, x2 = nx2, x3 = nx3, ps0 = nps0;
+        nx0 = -1; nx1 = -1; nx2 = -1; nx3 = -1; nps0 = 0;
+        if (j + 8 < n) nx0 = s[j + 8];
+        if (j + 9 < n) { nx1 = s[j + 9]; nps0 = ws[j + 8]; }
+        if (j + 10 < n) nx2 = s[j + 10];
+        if (j + 11 < n) nx3 = s[j + 11];
         int32_t xm1 = __shfl_up_sync(0xffffffffu, x0, 1, 8);
         if (gl == 0) xm1 = carry_prev;
         carry_prev = __shfl_sync(0xffffffffu, x0, 7, 8);
@@ -579,19 +689,19 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
                 has_pair = true;
                 const int32_t xn = sel0 ? x2 : x1, xnn = sel0 ? x3 : x2;
                 const bool seln = xn == a && xnn == b;
-                if (sel0 || seln) nslot = pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2, lm);
+                if (sel0 || seln) nslot = pair_add(M, sel0 ? c : x0, seln ? c : xn, f, T, T2, lm, xnew);
             }
         }
         __syncwarp();
         if (keep) {
             const int ni = out + __popc(keepmask & ((1u << gl) - 1));
-            s[ni] = sel0 ? c : x0;
-            if (has_pair) ws[ni] = nslot;
+            if (ni != j || sel0) s[ni] = sel0 ? c : x0;           // untouched prefix of the word: nothing to store
+            if (has_pair && (ni != j || nslot != ps0)) ws[ni] = nslot;
         }
         out += __popc(keepmask);
         __syncwarp();
     }
-    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w); }
+    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w, lm); }
 }
 
 // candidate ranges for pair (a, b) at slot: CSR postings + affected-log segments of the merges that
@@ -757,128 +867,168 @@ __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh
 #define LR_TOP 1      // leader stopped: top list exhausted / overflowed
 #define LR_OTHER 2    // leader stopped: the next merge needs the whole grid (or nothing is left to do)
 
+// Leader loop.  Per merge (every stage is bounded by dependent L2 round trips, not by bandwidth):
+//   A  argmax over the top list: counts mirrored in shared memory, warp max -> shared atomicMax -> candidates
+//   B  candidate ranges (thread 0) and merged-token lookup (thread 32), side by side
+//   C  the last warp records the merge / creates the token while every other 8-lane group takes ONE candidate
+//      item, claims its word in a shared-memory set (no global stamp), loads the word and rewrites it
+//   D  thread 0 closes the merge's affected-log segment (plain stores; all counters are in shared memory)
 __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin, const i64 T2) {
     __shared__ Ranges R;
     __shared__ int32_t sh_c;
-    __shared__ ClaimedWord sh_list[ML_LEADER_ITEMS_MAX];
-    __shared__ int sh_nlist;
-    __shared__ i64 sh_cnt[ML_THREADS / 32];
-    __shared__ i64 sh_state[5];          // act_n, alog_n, error, top_n, top_ovf: refreshed once per merge by thread 0
     __shared__ MergedInfo MI;
-    __shared__ LeaderMirror LM;
-    for (int i = threadIdx.x; i < 2 * ML_TOP_N; i += blockDim.x) LM.mkey[i] = 0;
+    __shared__ LeaderCtx C;
+    __shared__ i64 sh_wmax[ML_THREADS / 32];    // stage A: per-warp maximum count
+#if ML_TIMING
+    __shared__ long long sh_tacc[8];
+    if (threadIdx.x < 8) sh_tacc[threadIdx.x] = 0;
+#endif
+    __shared__ int sh_ncand;
+    __shared__ Best sh_cand[32];
+    for (int i = threadIdx.x; i < 2 * ML_TOP_N; i += blockDim.x) C.LM.mkey[i] = 0;
+    for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
     i64 pool_end = M.tok_off[(int32_t)M.state[MS_NTOK]];
-    __shared__ int32_t sh_tslot[ML_TOP_N];
-    __shared__ u64 sh_tkey[ML_TOP_N];
     i64 m = M.state[MS_NMERGES];
     int32_t n_tok = (int32_t)M.state[MS_NTOK];
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    long long t_arg = 0, t_rng = 0, t_claim = 0, t_rw = 0, t_close = 0, s_act = 0, s_items = 0, s_words = 0, n_done = 0;
+    #if ML_TIMING
+    long long t_arg = 0, t_rng = 0, t_rw = 0, t_close = 0;
+#endif
+    int s_act = 0, s_items = 0, n_done = 0;
     int reason = LR_OTHER;
-    int cached = 0;                      // entries of the top list already copied to shared memory
+    int cached = 0;                      // entries of the top list whose count is mirrored in shared memory
+    const i64 npairs0 = __ldcg(&M.state[MS_NPAIRS]);
     if (threadIdx.x == 0) {
-        sh_state[0] = __ldcg(&M.state[MS_ACT_N]); sh_state[1] = __ldcg(&M.state[MS_ALOG_N]); sh_state[2] = __ldcg(&M.state[MS_ERROR]);
-        sh_state[3] = __ldcg(&M.state[MS_TOP_N]); sh_state[4] = __ldcg(&M.state[MS_TOP_OVF]);
+        C.act_n = (int)__ldcg(&M.state[MS_ACT_N]); C.alog_n = (int)__ldcg(&M.state[MS_ALOG_N]);
+        C.error = (int)__ldcg(&M.state[MS_ERROR]);
+        C.top_n = (int)__ldcg(&M.state[MS_TOP_N]); C.top_ovf = (int)__ldcg(&M.state[MS_TOP_OVF]);
+        C.npairs_new = 0; C.nnew = 0;
+        sh_ncand = 0; C.cur_slot = -1;
+    }
+    __syncthreads();
+    {
+        const int tn0 = C.top_n < ML_TOP_N ? C.top_n : ML_TOP_N;
+        if ((int)threadIdx.x < tn0) { C.tslot[threadIdx.x] = M.top_slot[threadIdx.x]; C.tkey[threadIdx.x] = M.top_key[threadIdx.x]; C.LM.pending[threadIdx.x] = 1; }
     }
     __syncthreads();
     for (int iter = 0; iter < ML_LEADER_BATCH && m < M.num_merges; iter++) {
-        long long c0 = clock64();
-        const i64 act_n = sh_state[0], alog_n = sh_state[1];
-        if (sh_state[2]) break;
-        if (sh_state[4] || sh_state[3] > ML_TOP_N) { reason = LR_TOP; break; }
-        // ---- best pair: scan the top list (slot / key cached in shared memory)
-        const int tn = (int)sh_state[3];
+        ML_CLOCK(c0);
+        const int alog_n = C.alog_n;
+        if (C.error) break;
+        if (C.top_ovf || C.top_n > ML_TOP_N) { reason = LR_TOP; break; }
+        if ((npairs0 + C.npairs_new + C.nnew) * 4 > M.pcap * 3) { if (threadIdx.x == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); break; }
+        // ---- A: best pair of the top list
+        const int tn = C.top_n;
         Best mine{0, -1, 0, 0, 0};
         if ((int)threadIdx.x < tn) {
-            if ((int)threadIdx.x >= cached) {          // new entry: fetch it once, from then on its count is mirrored
-                const int32_t nsl = M.top_slot[threadIdx.x];
-                sh_tslot[threadIdx.x] = nsl; sh_tkey[threadIdx.x] = M.top_key[threadIdx.x];
-                LM.cnt[threadIdx.x] = __ldcg(&M.pcnt[nsl]);
-                mirror_insert(&LM, nsl, threadIdx.x);
+            const int32_t sl = C.tslot[threadIdx.x];
+            if ((int)threadIdx.x >= cached && C.LM.pending[threadIdx.x]) {   // entry without a mirrored count yet
+                mirror_set(&C.LM, threadIdx.x, __ldcg(&M.pcnt[sl]));
+                mirror_insert(&C.LM, sl, threadIdx.x);
             }
-            const int32_t sl = sh_tslot[threadIdx.x];
-            const u64 k = sh_tkey[threadIdx.x];
-            const i64 cnt = ML_USE_MIRROR ? LM.cnt[threadIdx.x] : __ldcg(&M.pcnt[sl]);
+            const u64 k = C.tkey[threadIdx.x];
+            const i64 cnt = mirror_get(&C.LM, threadIdx.x);
             if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
         }
         cached = tn;
-        Best best = block_best_fast(M, mine, sh_best, sh_cnt);
+        {
+            i64 wm = mine.cnt;
+            for (int o = 16; o > 0; o >>= 1) { const i64 t = __shfl_xor_sync(0xffffffffu, wm, o); if (t > wm) wm = t; }
+            if (lane == 0) sh_wmax[warp] = wm;
+        }
+        __syncthreads();
+        i64 mx = lane < nwarps ? sh_wmax[lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) { const i64 t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
+        if (mine.slot >= 0 && mine.cnt == mx) { const int ci = atomicAdd(&sh_ncand, 1); if (ci < 32) sh_cand[ci] = mine; }
+        __syncthreads();
+        Best best{0, -1, 0, 0, 0};
+        const int ncand = sh_ncand;
+        if (mx > 0) {
+            if (ncand == 1) best = sh_cand[0];
+            else if (ncand <= 32) {                     // ties: byte-wise comparison, every warp redundantly (no barrier)
+                Best t = lane < ncand ? sh_cand[lane] : Best{0, -1, 0, 0, 0};
+                for (int o = 16; o > 0; o >>= 1) { const Best u = shfl_best(t, o); if (best_gt(M, u, t)) t = u; }
+                best = t;
+            } else {
+                __syncthreads();
+                best = block_best(M, (mine.slot >= 0 && mine.cnt == mx) ? mine : Best{0, -1, 0, 0, 0}, sh_best);
+            }
+        }
         if (best.slot < 0 || best.cnt < T2) { reason = LR_TOP; break; }
         if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
-        long long c1 = clock64();
-        if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); sh_nlist = 0; }
+        ML_CLOCK(c1);
+        // ---- B: candidate ranges + merged token
+        if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); C.cur_slot = best.slot; }
         if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok, &MI);
         __syncthreads();
+        if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
         if (R.n < 0 || R.total > ML_LEADER_ITEMS_MAX || alog_n + R.total > M.alog_cap) break;
-        long long c2 = clock64();
+        ML_CLOCK(c2);
         const int32_t a = best.a, b = best.b, c = sh_c;
         const bool is_new = c == n_tok;
-        const int32_t stamp = (int32_t)(m + 1);
-        // the last warp records the merge / creates the token while the others claim the candidate words
-#if ML_NEW_COMMIT
+        const uint32_t stamp = (uint32_t)(m + 1);
+        // ---- C: commit (last warp) || claim + rewrite (one 8-lane group per candidate item)
         if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
-#else
-        if (warp == nwarps - 1) commit_merge_warp(M, m, a, b, c, is_new, alog_n);
-#endif
         else {
-            for (i64 it = threadIdx.x; it < R.total; it += blockDim.x - 32) {
-                int32_t w = range_item(R, it);
-                if (atomicExch(&M.wstamp[w], stamp) != stamp) {
-                    ClaimedWord cw; cw.w = w; cw.off = M.woff[w]; cw.n = M.wlen[w]; cw.f = M.wcnt[w];
-                    // candidates are a superset (stale postings, whole-token segments): keep real matches only
-                    bool hit = cw.n > 64;
-                    if (!hit) {
-                        const int32_t* sp = M.wsym + cw.off;
-                        int32_t prev = -1;
-                        for (int j0 = 0; j0 < cw.n; j0 += 4) {
-                            int32_t v0 = sp[j0], v1 = j0 + 1 < cw.n ? sp[j0 + 1] : -1, v2 = j0 + 2 < cw.n ? sp[j0 + 2] : -1,
-                                    v3 = j0 + 3 < cw.n ? sp[j0 + 3] : -1;
-                            hit |= (prev == a && v0 == b) | (v0 == a && v1 == b) | (v1 == a && v2 == b) | (v2 == a && v3 == b);
-                            prev = v3;
-                        }
-                    }
-                    if (hit) sh_list[atomicAdd(&sh_nlist, 1)] = cw;
+            const int ngroups = (nwarps - 1) * 4, gl = lane & 7;
+            const int total = (int)R.total;
+            for (int base = 0; base < total; base += ngroups) {
+                const int it = base + warp * 4 + (lane >> 3);
+                int32_t w = -1;
+                int take = 0;
+                ML_T0(q);
+                if (it < total) {
+                    w = range_item(R, it);
+                    if (gl == 0) take = dedupe_claim(&C, w, stamp) ? 1 : 0;
                 }
+                take = __shfl_sync(0xffffffffu, take, lane & 24);
+                if (!take) w = -1;
+                ML_TACC(0, q);
+                i64 off = 0, f = 0; int n = 0;
+                if (w >= 0) { off = M.woff[w]; n = M.wlen[w]; f = M.wcnt[w]; }
+#if ML_TIMING
+                if (n < 0) M.state[MS_SCRATCH] = off + f;
+#endif
+                ML_TACC(1, q);
+                if (a != b) rewrite_words_g8(M, w, off, n, f, a, b, c, T, T2, &C, is_new);
+                else if (w >= 0 && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, &C, is_new);
+                ML_TACC(2, q);
+#if ML_TIMING
+                if (threadIdx.x == 0) sh_tacc[3] += 1;
+#endif
             }
         }
         if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }
+        ML_T0(qb);
         __syncthreads();
-        long long c3 = clock64();
-        const int nlist = sh_nlist;
-        if (a != b) {
-            for (int kb = warp * 4; kb < nlist; kb += nwarps * 4) {
-                const int k = kb + (lane >> 3);
-                ClaimedWord cw; cw.w = -1; cw.off = 0; cw.n = 0; cw.f = 0;
-                if (k < nlist) cw = sh_list[k];
-                rewrite_words_g8(M, cw.w, cw.off, cw.n, cw.f, a, b, c, T, T2, ML_USE_MIRROR ? &LM : nullptr);
-            }
-        } else {
-            for (int k = threadIdx.x; k < nlist; k += blockDim.x) rewrite_word_thread(M, sh_list[k].w, a, b, c, T, T2, ML_USE_MIRROR ? &LM : nullptr);
-        }
+        ML_TACC(4, qb);
+        ML_CLOCK(c3);
+        // ---- D: close the merge; thresholds of the pairs it created
+        if (threadIdx.x == 0) { M.seg_end[m] = C.alog_n; M.tok_first[c] = (int32_t)m; }
+        if (threadIdx.x == 32) { const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, __ldcg(&M.pcnt[best.slot])); }
+        if (is_new) leader_new_pairs(M, &C, T, T2);
         __syncthreads();
-        long long c4 = clock64();
-        if (threadIdx.x == 0) {
-            // one L2 round trip: the counters the rewrite just bumped with atomics
-            const i64 an = __ldcg(&M.state[MS_ACT_N]), ln = __ldcg(&M.state[MS_ALOG_N]);
-            const i64 tn2 = __ldcg(&M.state[MS_TOP_N]), tov = __ldcg(&M.state[MS_TOP_OVF]);
-            i64 er = __ldcg(&M.state[MS_ERROR]);
-            if (ML_NPAIRS_CHECK_D && __ldcg(&M.state[MS_NPAIRS]) * 4 > M.pcap * 3) { atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); er |= ME_PAIR_TABLE_FULL; }
-            M.seg_end[m] = (int32_t)ln; M.tok_first[c] = (int32_t)m; M.state[MS_NMERGES] = m + 1;
-            sh_state[0] = an; sh_state[1] = ln; sh_state[2] = er; sh_state[3] = tn2; sh_state[4] = tov;
-        }
-        __syncthreads();
-        long long c5 = clock64();
-        t_arg += c1 - c0; t_rng += c2 - c1; t_claim += c3 - c2; t_rw += c4 - c3; t_close += c5 - c4;
-        s_act += sh_state[1] - alog_n; s_items += R.total; s_words += nlist; n_done++;
+        ML_CLOCK(c4);
+#if ML_TIMING
+        t_arg += c1 - c0; t_rng += c2 - c1; t_rw += c3 - c2; t_close += c4 - c3;
+#endif
+        s_act += C.alog_n - alog_n; s_items += (int)R.total; n_done++;
         m++;
     }
-    // the mirror must agree with the table (cheap self-check, once per leader session)
     __syncthreads();
-    if (ML_USE_MIRROR && (int)threadIdx.x < cached && LM.cnt[threadIdx.x] != __ldcg(&M.pcnt[sh_tslot[threadIdx.x]]))
+    // the mirror must agree with the table (cheap self-check, once per leader session)
+    if ((int)threadIdx.x < cached && mirror_get(&C.LM, threadIdx.x) != __ldcg(&M.pcnt[C.tslot[threadIdx.x]]))
         atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);
     if (threadIdx.x == 0) {
-        M.state[20] += t_arg; M.state[21] += t_rng; M.state[22] += t_claim; M.state[23] += t_rw; M.state[24] += t_close;
-        M.state[25] += s_act; M.state[26] += s_items; M.state[27] += s_words;
+        M.state[MS_NMERGES] = m;
+        M.state[MS_ACT_N] = C.act_n; M.state[MS_ALOG_N] = C.alog_n;
+        M.state[MS_TOP_N] = C.top_n; M.state[MS_TOP_OVF] = C.top_ovf;
+        if (C.npairs_new + C.nnew) atomicAdd((u64*)&M.state[MS_NPAIRS], (u64)(C.npairs_new + C.nnew));
+#if ML_TIMING
+        M.state[20] += t_arg; M.state[21] += t_rng; M.state[23] += t_rw; M.state[24] += t_close;
+        M.state[22] += sh_tacc[2]; M.state[27] += sh_tacc[3]; M.state[28] += sh_tacc[4]; M.state[12] += sh_tacc[0]; M.state[13] += sh_tacc[1];
+#endif
+        M.state[25] += s_act; M.state[26] += s_items;
         M.state[MS_LEADER_MERGES] += n_done;
         M.state[MS_LEADER_REASON] = reason;
         if (reason == LR_TOP) M.state[MS_T2] = 0;
@@ -1067,13 +1217,13 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if ((threadIdx.x & 31) == 0) old = atomicExch(&M.wstamp[w], stamp);
                 old = __shfl_sync(0xffffffffu, old, 0);
                 if (old == stamp) continue;
-                rewrite_word_warp(M, w, a, b, c, T, T2u, nullptr);
+                rewrite_word_warp(M, w, a, b, c, T, T2u, nullptr, is_new);
             }
         } else {
             for (i64 it = gtid; it < R.total; it += gstride) {
                 int32_t w = range_item(R, it);
                 if (atomicExch(&M.wstamp[w], stamp) == stamp) continue;
-                rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr);
+                rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr, is_new);
             }
         }
         grid_barrier(M);

@@ -61,7 +61,7 @@ class WordTable(C.Structure):
 class MergeArgs(C.Structure):
     _fields_ = [
         ("words", WordTable), ("n_words", C.c_int64), ("n_syms", C.c_int64),
-        ("wstamp", C.c_void_p), ("wslot", C.c_void_p),
+        ("wstamp", C.c_void_p), ("wslot", C.c_void_p), ("newp", C.c_void_p),
         ("tok_bytes", C.c_void_p), ("tok_bytes_cap", C.c_int64),
         ("tok_off", C.c_void_p), ("tok_hash", C.c_void_p), ("tok_pow", C.c_void_p),
         ("tset", C.c_void_p), ("tset_cap", C.c_int64), ("max_tokens", C.c_int64),

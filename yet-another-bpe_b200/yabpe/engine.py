@@ -234,7 +234,8 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
     max_tokens = n_base + num_merges + 2
     for attempt in range(6):
         if pcap is None:
-            pcap = _pow2_at_least(min(max(4 * words.n_syms, 1 << 16), 1 << 26))
+            import os as _os
+            pcap = _pow2_at_least(min(max(int(float(_os.environ.get('YABPE_PCAP_FACTOR', '4')) * words.n_syms), 1 << 16), 1 << 26))
         if pool_cap is None:
             pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
         alog_cap = max(2 * words.n_words, 1 << 16) + 4096
@@ -261,6 +262,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
         wstamp = z(words.n_words + 1, torch.int32)
         wslot = z(words.n_syms + 8, torch.int32)
+        newp = torch.empty(words.n_syms + 8, dtype=torch.int32, device=dev)
         pkey, pcnt = z(pcap, torch.int64), z(pcap, torch.int64)
         ioff, icnt = z(pcap + 1, torch.int32), z(pcap, torch.int32)
         ipost = z(words.n_syms + 8, torch.int32)
@@ -278,7 +280,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         state = t(state_np)
         m = _ffi.MergeArgs()
         m.words = words.table; m.n_words = words.n_words; m.n_syms = words.n_syms
-        m.wstamp = wstamp.data_ptr(); m.wslot = wslot.data_ptr()
+        m.wstamp = wstamp.data_ptr(); m.wslot = wslot.data_ptr(); m.newp = newp.data_ptr()
         m.tok_bytes = d_tok_bytes.data_ptr(); m.tok_bytes_cap = pool_cap
         m.tok_off = d_tok_off.data_ptr(); m.tok_hash = d_th.data_ptr(); m.tok_pow = d_tp.data_ptr()
         m.tset = d_tset.data_ptr(); m.tset_cap = tset_cap; m.max_tokens = max_tokens
