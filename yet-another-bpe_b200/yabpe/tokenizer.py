@@ -117,10 +117,20 @@ class BBPETokenizer:
             return torch.empty(0, dtype=torch.int32, device="cuda"), None
         e = self._device_model(torch)
         launches0 = _ffi.launch_count()
+        prof = getattr(self, "profile", False)
+        evs = []
+
+        def mark():
+            if prof:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); evs.append(ev)
+
+        mark()
         res, st = engine.pretok_count_checked(torch, text_dev, n, cuts, self._sp_bytes, mode=1, own=own)
+        mark()
         words = engine.compact_words(torch, res, st, with_maps=True)
         stream = _ffi.stream_ptr(torch)
         _ffi.check(L.yabpe_encode_words(C.byref(e), C.byref(words.table), words.n_words, stream))
+        mark()
         lo, hi = own if own is not None else (0, n)
         n_tiles = int(L.yabpe_num_tiles(lo, hi))
         tile_count = torch.zeros(n_tiles + 1, dtype=torch.int64, device="cuda")
@@ -130,11 +140,18 @@ class BBPETokenizer:
         o.tile_count = tile_count.data_ptr(); o.out_ids = None; o.out_cap = 0
         o.doc_off = doc_off.data_ptr() if n_cuts else None
         _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 0, stream))
+        mark()
         total = int(tile_count[n_tiles].item())
         ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
         o.out_ids = ids.data_ptr(); o.out_cap = total
         _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
+        mark()
         self.last_launches = _ffi.launch_count() - launches0
+        if prof:
+            torch.cuda.synchronize()
+            names = ["pretok_count_ms", "words_ms", "count_pass_ms", "write_pass_ms"]
+            self.timing = {k: evs[i].elapsed_time(evs[i + 1]) for i, k in enumerate(names)}
+            self.timing["unique_words"] = words.n_words
         self._keep = (res, words, tile_count)
         return ids[:total], doc_off
 
