@@ -15,6 +15,9 @@
 #include "pretok.cuh"
 
 #define ML_THREADS 1024
+#ifndef ML_BATCH_STATS
+#define ML_BATCH_STATS 0
+#endif
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
 #endif
@@ -143,7 +146,9 @@ struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
 
 #define ML_MAX_RANGES 12
 #define ML_LEADER_ACT_MAX 32768
+#ifndef ML_LEADER_ITEMS_MAX
 #define ML_LEADER_ITEMS_MAX 1024
+#endif
 #define ML_LEADER_BATCH 4096
 
 struct MergeParams {
@@ -431,12 +436,12 @@ __device__ __forceinline__ void mirror_insert(LeaderMirror* lm, int32_t slot, in
 // Leader-mode context (shared memory of CTA 0).  While the leader runs it is the only writer of the merge
 // state, so the counters the rewrite bumps (active set, affected log, top list, new pairs) live here and
 // are written back to M.state once, when the leader hands control back to the grid.
-#define ML_DEDUPE_N 2048
+#define ML_DEDUPE_N (2 * ML_LEADER_ITEMS_MAX)
 #define ML_NEWP_N 1024
 struct LeaderCtx {
     LeaderMirror LM;
     int32_t tslot[ML_TOP_N]; u64 tkey[ML_TOP_N];
-    u64 dedupe[ML_DEDUPE_N];                     // (merge stamp << 32 | word): candidate words already taken this merge
+    int32_t dedupe[ML_DEDUPE_N];                 // word + 1: candidate words already taken by the current merge (0 = free)
     int32_t newp[ML_NEWP_N];                     // slots of the pairs created by the current merge (spill: M.newp)
     int top_n, top_ovf, act_n, alog_n, npairs_new, error, nnew;
     int32_t cur_slot;                            // pair-table slot of the pair being merged
@@ -453,17 +458,13 @@ __device__ __forceinline__ void mirror_add(LeaderCtx* lc, int32_t slot, i64 d) {
     }
 }
 
-// true when this call took word w for merge `stamp` (first claim wins; stale entries of older merges are overwritten)
-__device__ __forceinline__ bool dedupe_claim(LeaderCtx* lc, int32_t w, uint32_t stamp) {
-    const u64 mine = ((u64)stamp << 32) | (uint32_t)w;
-    uint32_t h = ((uint32_t)w * 2654435761u) >> 21;             // 11 bits
+// true when this call took word w for the current merge (first claim wins); the set is cleared once per merge
+__device__ __forceinline__ bool dedupe_claim(LeaderCtx* lc, int32_t w) {
+    uint32_t h = (((uint32_t)w * 2654435761u) >> 8) & (ML_DEDUPE_N - 1);
     for (;;) {
-        const u64 cur = lc->dedupe[h];
-        if (cur == mine) return false;
-        if ((uint32_t)(cur >> 32) != stamp) {
-            if (atomicCAS(&lc->dedupe[h], cur, mine) == cur) return true;
-            continue;                                            // somebody else changed this entry: look again
-        }
+        const int32_t old = atomicCAS(&lc->dedupe[h], 0, w + 1);
+        if (old == 0) return true;
+        if (old == w + 1) return false;
         h = (h + 1) & (ML_DEDUPE_N - 1);
     }
 }
@@ -867,6 +868,54 @@ __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh
 #define LR_TOP 1      // leader stopped: top list exhausted / overflowed
 #define LR_OTHER 2    // leader stopped: the next merge needs the whole grid (or nothing is left to do)
 
+
+// ---- batch selection -------------------------------------------------------------------------------
+// The ML_BATCH_MAX + 1 largest entries of the top list in strictly descending (count, then list index) order.
+// key = count << 9 | (511 - index); 0 = none.  Phase 1: every warp extracts the five largest keys of its 32
+// lanes (redux.sync); phase 2 (after ONE block barrier): every warp redundantly extracts the five largest of
+// the per-warp lists, so all warps hold the same result without a second barrier.
+#define ML_BATCH_MAX 4
+#define ML_SEL (ML_BATCH_MAX + 1)
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return ((u64)mhi << 32) | mlo;
+}
+__device__ __forceinline__ void select_top(u64 key, u64* sh_keys /* [32][ML_SEL] */, u64* out /* [ML_SEL] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    u64 k = key;
+#pragma unroll
+    for (int r = 0; r < ML_SEL; r++) {
+        const u64 m = warp_max_u64(k);
+        if (k == m) k = 0;                        // keys are unique (the index is part of the key)
+        if (lane == r) sh_keys[warp * ML_SEL + r] = m;
+    }
+    __syncthreads();
+    // nwarps * ML_SEL <= 160 keys: five per lane
+    u64 v[ML_SEL];
+#pragma unroll
+    for (int u = 0; u < ML_SEL; u++) { const int i = lane + 32 * u; v[u] = i < nwarps * ML_SEL ? sh_keys[i] : 0; }
+#pragma unroll
+    for (int r = 0; r < ML_SEL; r++) {
+        u64 lm = v[0];
+#pragma unroll
+        for (int u = 1; u < ML_SEL; u++) lm = v[u] > lm ? v[u] : lm;
+        const u64 m = warp_max_u64(lm);
+        out[r] = m;
+#pragma unroll
+        for (int u = 0; u < ML_SEL; u++) if (v[u] == m) v[u] = 0;
+    }
+}
+
+// warp-wide maximum of non-negative 64-bit values with two redux.sync (32-bit) instead of ten shuffles
+__device__ __forceinline__ i64 warp_max_i64(i64 v) {
+    const uint32_t hi = (uint32_t)((u64)v >> 32), lo = (uint32_t)(u64)v;
+    const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return (i64)(((u64)mhi << 32) | mlo);
+}
+
 // Leader loop.  Per merge (every stage is bounded by dependent L2 round trips, not by bandwidth):
 //   A  argmax over the top list: counts mirrored in shared memory, warp max -> shared atomicMax -> candidates
 //   B  candidate ranges (thread 0) and merged-token lookup (thread 32), side by side
@@ -879,6 +928,11 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
     __shared__ MergedInfo MI;
     __shared__ LeaderCtx C;
     __shared__ i64 sh_wmax[ML_THREADS / 32];    // stage A: per-warp maximum count
+#if ML_BATCH_STATS
+    __shared__ u64 sh_selkeys[32 * ML_SEL];
+    __shared__ int sh_skip;
+    if (threadIdx.x == 0) sh_skip = 0;
+#endif
 #if ML_TIMING
     __shared__ long long sh_tacc[8];
     if (threadIdx.x < 8) sh_tacc[threadIdx.x] = 0;
@@ -931,14 +985,39 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
             if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
         }
         cached = tn;
+#if ML_BATCH_STATS
         {
-            i64 wm = mine.cnt;
-            for (int o = 16; o > 0; o >>= 1) { const i64 t = __shfl_xor_sync(0xffffffffu, wm, o); if (t > wm) wm = t; }
+            u64 topk[ML_SEL];
+            select_top(mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL, sh_selkeys, topk);
+            if (threadIdx.x == 0) {
+                int k = 0;
+                int32_t ta[ML_SEL], tb[ML_SEL]; i64 tc[ML_SEL];
+                for (int j = 0; j < ML_SEL; j++) {
+                    tc[j] = (i64)(topk[j] >> 9);
+                    const int idx = 511 - (int)(topk[j] & 511);
+                    const u64 kk = topk[j] ? C.tkey[idx] : 0;
+                    ta[j] = (int32_t)((kk >> 32) & 0x7fffffff); tb[j] = (int32_t)(kk & 0xffffffffu);
+                }
+                for (k = 0; k < ML_BATCH_MAX; k++) {
+                    if (tc[k] < T2 || tc[k] < T || tc[k] <= tc[k + 1]) break;        // strict drop after member k
+                    if (k > 0 && ta[k] == tb[k]) break;
+                    bool clash = false;
+                    for (int i = 0; i < k; i++) clash |= ta[i] == ta[k] || ta[i] == tb[k] || tb[i] == ta[k] || tb[i] == tb[k];
+                    if (clash) break;
+                }
+                if (k == 0) k = 1;
+                if (ta[0] == tb[0]) k = 1;
+                if (sh_skip > 0) sh_skip--; else { M.state[12] += k; M.state[13] += 1; sh_skip = k - 1; }
+            }
+            __syncthreads();
+        }
+#endif
+        {
+            const i64 wm = warp_max_i64(mine.cnt);
             if (lane == 0) sh_wmax[warp] = wm;
         }
         __syncthreads();
-        i64 mx = lane < nwarps ? sh_wmax[lane] : 0;
-        for (int o = 16; o > 0; o >>= 1) { const i64 t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
+        const i64 mx = warp_max_i64(lane < nwarps ? sh_wmax[lane] : 0);
         if (mine.slot >= 0 && mine.cnt == mx) { const int ci = atomicAdd(&sh_ncand, 1); if (ci < 32) sh_cand[ci] = mine; }
         __syncthreads();
         Best best{0, -1, 0, 0, 0};
@@ -960,26 +1039,26 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         // ---- B: candidate ranges + merged token
         if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); C.cur_slot = best.slot; }
         if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok, &MI);
+        for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
         if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
         if (R.n < 0 || R.total > ML_LEADER_ITEMS_MAX || alog_n + R.total > M.alog_cap) break;
         ML_CLOCK(c2);
         const int32_t a = best.a, b = best.b, c = sh_c;
         const bool is_new = c == n_tok;
-        const uint32_t stamp = (uint32_t)(m + 1);
         // ---- C: commit (last warp) || claim + rewrite (one 8-lane group per candidate item)
         if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
         else {
             const int ngroups = (nwarps - 1) * 4, gl = lane & 7;
             const int total = (int)R.total;
-            for (int base = 0; base < total; base += ngroups) {
+            for (int base = 0; base + warp * 4 < total; base += ngroups) {     // warps without a candidate go straight to the barrier
                 const int it = base + warp * 4 + (lane >> 3);
                 int32_t w = -1;
                 int take = 0;
                 ML_T0(q);
                 if (it < total) {
                     w = range_item(R, it);
-                    if (gl == 0) take = dedupe_claim(&C, w, stamp) ? 1 : 0;
+                    if (gl == 0) take = dedupe_claim(&C, w) ? 1 : 0;
                 }
                 take = __shfl_sync(0xffffffffu, take, lane & 24);
                 if (!take) w = -1;

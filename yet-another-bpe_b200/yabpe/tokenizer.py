@@ -107,10 +107,13 @@ class BBPETokenizer:
             self._dev = (dev, e, tensors)
         return self._dev[1]
 
-    def encode_device(self, text_dev, n: int, cuts: np.ndarray | None = None, own: tuple[int, int] | None = None):
+    def encode_device(self, text_dev, n: int, cuts: np.ndarray | None = None, own: tuple[int, int] | None = None,
+                      reuse_output: bool = False):
         """Encode `n` bytes resident on the device; `cuts` = interior document boundaries.
         Returns (ids tensor int32 on device, doc_off tensor int64 or None).  One host sync
-        (table sizes) + one (id count)."""
+        (table sizes) + one (id count).  reuse_output=True writes the ids into a buffer kept by the
+        tokenizer (sized from the previous call, grown on demand): no allocation and no host sync between
+        the two tile passes; the returned view is valid until the next call."""
         torch = _ffi.require_cuda()
         L = _ffi.load()
         if n == 0:
@@ -141,10 +144,25 @@ class BBPETokenizer:
         o.doc_off = doc_off.data_ptr() if n_cuts else None
         _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 0, stream))
         mark()
-        total = int(tile_count[n_tiles].item())
-        ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
-        o.out_ids = ids.data_ptr(); o.out_cap = total
-        _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
+        if reuse_output:
+            buf = getattr(self, "_ids_buf", None)
+            want = n // 2 + 4096
+            if buf is None or buf.numel() < want:
+                buf = torch.empty(want, dtype=torch.int32, device="cuda")
+            while True:                                   # writes beyond out_cap are dropped by the kernel
+                o.out_ids = buf.data_ptr(); o.out_cap = buf.numel()
+                _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
+                total = int(tile_count[n_tiles].item())
+                if total <= buf.numel():
+                    break
+                buf = torch.empty(total + total // 8, dtype=torch.int32, device="cuda")
+            self._ids_buf = buf
+            ids = buf
+        else:
+            total = int(tile_count[n_tiles].item())
+            ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+            o.out_ids = ids.data_ptr(); o.out_cap = total
+            _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
         mark()
         self.last_launches = _ffi.launch_count() - launches0
         if prof:
