@@ -144,6 +144,7 @@ typedef struct {
     int64_t* tok_off;           /* device, max_tokens + 1; [0..n_base] filled by the host         */
     uint64_t* tok_hash;         /* device, max_tokens; polynomial hash (base 0x100000001b3, +1)   */
     uint64_t* tok_pow;          /* device, max_tokens; base^len                                   */
+    uint64_t* tok_pre;          /* device, max_tokens; scratch (8-byte big-endian prefix per token) */
     uint64_t* tset; int64_t tset_cap;            /* device hash set of token hashes, pow2         */
     int64_t max_tokens;
     uint64_t* pkey; int64_t* pcnt; int64_t pcap; /* pair table, pow2, zeroed                      */

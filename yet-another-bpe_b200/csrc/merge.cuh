@@ -159,6 +159,7 @@ struct MergeParams {
     const i64* woff; int32_t* wlen; const i64* wcnt; i64 n_words; int32_t* wstamp;
     // tokens (ids < n_base are prepared by the host: 256 bytes + specials)
     uint8_t* tok_bytes; i64 tok_bytes_cap; i64* tok_off; u64* tok_hash; u64* tok_pow;
+    u64* tok_pre;                                // first 8 bytes of every token, big-endian, zero padded (tie-break fast path)
     u64* tset; i64 tset_cap; i64 max_tokens;
     // pairs
     u64* pkey; i64* pcnt; i64 pcap;
@@ -240,6 +241,19 @@ __device__ int tok_cmp(const MergeParams& M, int32_t x, int32_t y) {
         if (d) return d;
     }
     return lx < ly ? -1 : (lx > ly ? 1 : 0);
+}
+// first 8 bytes, big-endian: for DIFFERENT prefixes the unsigned order of the prefixes is the bytes order of the tokens
+// (a shorter token is zero padded: "ab" < "ab\x01"); EQUAL prefixes decide nothing (fall back to tok_cmp)
+__device__ __forceinline__ u64 tok_prefix_of_bytes(const uint8_t* p, i64 len) {
+    u64 v = 0;
+    for (int k = 0; k < 8; k++) v = (v << 8) | (k < len ? (u64)p[k] : 0ULL);
+    return v;
+}
+__device__ __forceinline__ u64 tok_prefix_concat(u64 pa, i64 la, u64 pb) { return la >= 8 ? pa : (pa | (pb >> (8 * la))); }
+__device__ __forceinline__ int tok_cmp_pre(const MergeParams& M, int32_t x, u64 px, int32_t y, u64 py) {
+    if (x == y) return 0;
+    if (px != py) return px > py ? 1 : -1;
+    return tok_cmp(M, x, y);
 }
 __device__ __forceinline__ bool best_gt(const MergeParams& M, const Best& p, const Best& q) {
     if (p.cnt != q.cnt) return p.cnt > q.cnt;
@@ -441,6 +455,7 @@ __device__ __forceinline__ void mirror_insert(LeaderMirror* lm, int32_t slot, in
 struct LeaderCtx {
     LeaderMirror LM;
     int32_t tslot[ML_TOP_N]; u64 tkey[ML_TOP_N];
+    u64 tpa[ML_TOP_N], tpb[ML_TOP_N];            // 8-byte prefixes of the two tokens of every entry (tie-break without global loads)
     int32_t dedupe[ML_DEDUPE_N];                 // word + 1: candidate words already taken by the current merge (0 = free)
     int32_t newp[ML_NEWP_N];                     // slots of the pairs created by the current merge (spill: M.newp)
     int top_n, top_ovf, act_n, alog_n, npairs_new, error, nnew;
@@ -548,6 +563,7 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
                 atomicOr(&M.intop[s >> 5], bit);
                 M.top_slot[idx] = s; M.top_key[idx] = key;
                 lc->tslot[idx] = s; lc->tkey[idx] = key; mirror_set(&lc->LM, idx, cnt);
+                lc->tpa[idx] = M.tok_pre[(int32_t)((key >> 32) & 0x7fffffff)]; lc->tpb[idx] = M.tok_pre[(int32_t)(key & 0xffffffffu)];
                 mirror_insert(&lc->LM, s, idx);
             } else lc->top_ovf = 1;
         }
@@ -777,6 +793,7 @@ __device__ void commit_merge(const MergeParams& M, i64 m, int32_t a, int32_t b, 
                 u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
                 M.tok_off[c + 1] = oc + la + lb;
                 M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
+                M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], la, M.tok_pre[b]);
                 M.tok_first[c] = -1;
                 __threadfence();
                 u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
@@ -808,6 +825,7 @@ __device__ void commit_merge_warp(const MergeParams& M, i64 m, int32_t a, int32_
                 u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
                 M.tok_off[c + 1] = oc + la + lb;
                 M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
+                M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], la, M.tok_pre[b]);
                 M.tok_first[c] = -1;
                 __threadfence();
                 u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
@@ -837,6 +855,7 @@ __device__ void commit_merge_leader(const MergeParams& M, i64 m, int32_t a, int3
     if (lane == 0) {
         M.tok_off[c + 1] = oc + MI.la + MI.lb;
         M.tok_hash[c] = MI.H; M.tok_pow[c] = MI.P;
+        M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], MI.la, M.tok_pre[b]);
         M.tok_first[c] = -1;
         *(volatile u64*)&M.tset[MI.tslot] = (MI.H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1);
         M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + MI.la + MI.lb;
@@ -976,13 +995,14 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         Best mine{0, -1, 0, 0, 0};
         if ((int)threadIdx.x < tn) {
             const int32_t sl = C.tslot[threadIdx.x];
+            const u64 k = C.tkey[threadIdx.x];
             if ((int)threadIdx.x >= cached && C.LM.pending[threadIdx.x]) {   // entry without a mirrored count yet
                 mirror_set(&C.LM, threadIdx.x, __ldcg(&M.pcnt[sl]));
                 mirror_insert(&C.LM, sl, threadIdx.x);
+                C.tpa[threadIdx.x] = M.tok_pre[(int32_t)((k >> 32) & 0x7fffffff)]; C.tpb[threadIdx.x] = M.tok_pre[(int32_t)(k & 0xffffffffu)];
             }
-            const u64 k = C.tkey[threadIdx.x];
             const i64 cnt = mirror_get(&C.LM, threadIdx.x);
-            if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), 0};
+            if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
         }
         cached = tn;
 #if ML_BATCH_STATS
@@ -1026,7 +1046,18 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
             if (ncand == 1) best = sh_cand[0];
             else if (ncand <= 32) {                     // ties: byte-wise comparison, every warp redundantly (no barrier)
                 Best t = lane < ncand ? sh_cand[lane] : Best{0, -1, 0, 0, 0};
-                for (int o = 16; o > 0; o >>= 1) { const Best u = shfl_best(t, o); if (best_gt(M, u, t)) t = u; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    Best u = shfl_best(t, o);
+                    u.pad = __shfl_xor_sync(0xffffffffu, t.pad, o);
+                    bool gt = false;                                      // equal counts: (left bytes, right bytes)
+                    if (u.slot >= 0 && t.slot < 0) gt = true;
+                    else if (u.slot >= 0 && u.slot != t.slot) {
+                        int r = tok_cmp_pre(M, u.a, C.tpa[u.pad], t.a, C.tpa[t.pad]);
+                        if (r == 0) r = tok_cmp_pre(M, u.b, C.tpb[u.pad], t.b, C.tpb[t.pad]);
+                        gt = r > 0;
+                    }
+                    if (gt) t = u;
+                }
                 best = t;
             } else {
                 __syncthreads();
@@ -1193,6 +1224,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         }
     }
     for (i64 t = gtid; t < M.max_tokens; t += gstride) M.tok_first[t] = -1;
+    for (i64 t = gtid; t < M.state[MS_NTOK]; t += gstride) M.tok_pre[t] = tok_prefix_of_bytes(M.tok_bytes + M.tok_off[t], M.tok_off[t + 1] - M.tok_off[t]);
     grid_barrier(M);
     {
         i64 mx = 0;

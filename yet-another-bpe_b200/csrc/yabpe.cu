@@ -274,7 +274,7 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.wsym = m->words.wsym; M.sym_word = m->words.sym_word; M.n_syms = m->n_syms;
     M.woff = (const i64*)m->words.woff; M.wlen = m->words.wlen; M.wcnt = (const i64*)m->words.wcnt; M.n_words = m->n_words; M.wstamp = m->wstamp; M.wslot = m->wslot; M.newp = m->newp;
     M.tok_bytes = m->tok_bytes; M.tok_bytes_cap = m->tok_bytes_cap; M.tok_off = (i64*)m->tok_off;
-    M.tok_hash = (u64*)m->tok_hash; M.tok_pow = (u64*)m->tok_pow; M.tset = (u64*)m->tset; M.tset_cap = m->tset_cap;
+    M.tok_hash = (u64*)m->tok_hash; M.tok_pow = (u64*)m->tok_pow; M.tok_pre = (u64*)m->tok_pre; M.tset = (u64*)m->tset; M.tset_cap = m->tset_cap;
     M.max_tokens = m->max_tokens;
     M.pkey = (u64*)m->pkey; M.pcnt = (i64*)m->pcnt; M.pcap = m->pcap;
     M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = m->ipost; M.inact = m->inact; M.intop = m->intop; M.act = m->act;

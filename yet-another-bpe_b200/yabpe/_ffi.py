@@ -63,7 +63,7 @@ class MergeArgs(C.Structure):
         ("words", WordTable), ("n_words", C.c_int64), ("n_syms", C.c_int64),
         ("wstamp", C.c_void_p), ("wslot", C.c_void_p), ("newp", C.c_void_p),
         ("tok_bytes", C.c_void_p), ("tok_bytes_cap", C.c_int64),
-        ("tok_off", C.c_void_p), ("tok_hash", C.c_void_p), ("tok_pow", C.c_void_p),
+        ("tok_off", C.c_void_p), ("tok_hash", C.c_void_p), ("tok_pow", C.c_void_p), ("tok_pre", C.c_void_p),
         ("tset", C.c_void_p), ("tset_cap", C.c_int64), ("max_tokens", C.c_int64),
         ("pkey", C.c_void_p), ("pcnt", C.c_void_p), ("pcap", C.c_int64),
         ("ioff", C.c_void_p), ("icnt", C.c_void_p), ("ipost", C.c_void_p), ("inact", C.c_void_p), ("intop", C.c_void_p), ("top_slot", C.c_void_p), ("top_key", C.c_void_p), ("hist", C.c_void_p),

@@ -283,6 +283,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.wstamp = wstamp.data_ptr(); m.wslot = wslot.data_ptr(); m.newp = newp.data_ptr()
         m.tok_bytes = d_tok_bytes.data_ptr(); m.tok_bytes_cap = pool_cap
         m.tok_off = d_tok_off.data_ptr(); m.tok_hash = d_th.data_ptr(); m.tok_pow = d_tp.data_ptr()
+        tok_pre = z(max_tokens, torch.int64); m.tok_pre = tok_pre.data_ptr()
         m.tset = d_tset.data_ptr(); m.tset_cap = tset_cap; m.max_tokens = max_tokens
         m.pkey = pkey.data_ptr(); m.pcnt = pcnt.data_ptr(); m.pcap = pcap
         m.ioff = ioff.data_ptr(); m.icnt = icnt.data_ptr(); m.ipost = ipost.data_ptr()
