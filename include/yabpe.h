@@ -200,6 +200,10 @@ int64_t yabpe_num_tiles(int64_t own_lo, int64_t own_hi);
 /* kernels launched by this library since load (the bench's `gpu_launches`) */
 int64_t yabpe_launch_count(void);
 
+/* sizeof() of the argument structs as compiled (0 pretok_args, 1 word_table, 2 merge_args, 3 encode_model,
+ * 4 encode_out): lets a binding check its own struct layout against the library it loaded. */
+int64_t yabpe_sizeof(int32_t which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -284,3 +284,52 @@ def test_encode_roundtrip_property_large(yabpe):
     ids = t.encode(text)
     assert t.decode(ids) == text
     assert min(ids) >= 0 and max(ids) < 50257
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_train_properties_at_bench_scale(yabpe):
+    """Size-independent properties at a size no CPU oracle handles in seconds (256 MB of the bench generator,
+    crossing no reference chunk cut, and 1.2 GB crossing one): conservation of pre-token occurrences, run-to-run
+    determinism, dense ids, every merge result present, and agreement of the sharded table with the whole."""
+    import sys
+    import torch
+    sys.path.insert(0, str(common.ROOT / "tools"))
+    from synth_gpu import synth_corpus_device
+    from yabpe import _ffi, engine
+    text, n = synth_corpus_device(torch, 256_000_000, "tinystories", 4242)
+    cfg = yabpe.BBPETrainerConfig(vocab_size=3000, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
+                                  special_tokens=["<|endoftext|>"])
+    m1 = yabpe.BBPETrainer(cfg).train_device(text, n)
+    tr2 = yabpe.BBPETrainer(cfg)
+    m2 = tr2.train_device(text, n)
+    assert m1.merges == m2.merges and m1.vocab == m2.vocab
+    assert sorted(m1.vocab.values()) == list(range(len(m1.vocab)))
+    assert len(m1.merges) == 3000 - 257
+    for a, b in m1.merges:
+        assert a in m1.vocab and b in m1.vocab and a + b in m1.vocab
+    # conservation: the table of the whole text == the sum of the tables of two owned halves (the shard edge is NOT a cut)
+    sp = [b"<|endoftext|>"]
+    whole, st = engine.pretok_count_checked(torch, text, n, None, sp, 0)
+    half = (n // 2) | 7
+    tot = 0
+    for own in ((0, half), (half, n)):
+        part, st_p = engine.pretok_count_checked(torch, text, n, None, sp, 0, own=own)
+        tot += int(st_p[_ffi.ST_NTOK])
+    assert tot == int(st[_ffi.ST_NTOK]) == tr2.last_stats.n_pretokens
+    # the generic kernel alone gives the same statistics as the warp kernel + boundary list
+    gen, st_g = engine.pretok_count_checked(torch, text, n, None, sp, 0, generic_only=True)
+    for k in (_ffi.ST_NTOK, _ffi.ST_UNIQ_SHORT, _ffi.ST_UNIQ_LONG, _ffi.ST_UNIQ_BYTES, _ffi.ST_NSPECIAL):
+        assert int(st_g[k]) == int(st[k]), k
+    assert int(st[_ffi.ST_CACHE_HIT]) > 0 and int(st_g[_ffi.ST_CACHE_HIT]) == 0
+
+
+def test_train_adversarial_large_vocab(yabpe, tmp_path):
+    """BASELINE.json configs[4] at a size the oracle still finishes: tie farms, dense specials, long runs, odd
+    whitespace -- many merges, so the late low-count phase (ties decided by token bytes) is covered."""
+    data = common.synth_adversarial(1_500_000, seed=99)
+    p = tmp_path / "adv.txt"
+    p.write_bytes(data)
+    want = oracle.train_bpe(p, 6000, ["<|endoftext|>"], fast=True)
+    got = yabpe.train_bpe(p, 6000, ["<|endoftext|>"])
+    assert got[1] == want[1]
+    assert got[0] == want[0]

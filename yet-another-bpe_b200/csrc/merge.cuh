@@ -14,7 +14,9 @@
 
 #include "pretok.cuh"
 
+#ifndef ML_THREADS
 #define ML_THREADS 1024
+#endif
 #ifndef ML_BATCH_STATS
 #define ML_BATCH_STATS 0
 #endif
@@ -1082,30 +1084,38 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         else {
             const int ngroups = (nwarps - 1) * 4, gl = lane & 7;
             const int total = (int)R.total;
-            for (int base = 0; base + warp * 4 < total; base += ngroups) {     // warps without a candidate go straight to the barrier
-                const int it = base + warp * 4 + (lane >> 3);
-                int32_t w = -1;
-                int take = 0;
-                ML_T0(q);
-                if (it < total) {
-                    w = range_item(R, it);
-                    if (gl == 0) take = dedupe_claim(&C, w) ? 1 : 0;
-                }
+            // Software pipeline over the passes of this group: the candidate of pass p+2 and the word header of pass
+            // p+1 are loaded while pass p is rewritten, so only the first pass pays those round trips in full
+            // (the word arrays of a large corpus do not fit the L2: every round trip is a DRAM access).
+            const int it0 = warp * 4 + (lane >> 3);
+            int32_t w_cur = it0 < total ? range_item(R, it0) : -1;
+            int32_t w_nx = it0 + ngroups < total ? range_item(R, it0 + ngroups) : -1;
+            {
+                int take = (w_cur >= 0 && gl == 0) ? (dedupe_claim(&C, w_cur) ? 1 : 0) : 0;
                 take = __shfl_sync(0xffffffffu, take, lane & 24);
-                if (!take) w = -1;
+                if (!take) w_cur = -1;
+            }
+            uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
+            if (w_cur >= 0) { off_cur = (uint32_t)M.woff[w_cur]; n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur]; }
+            for (int base = 0; base + warp * 4 < total; base += ngroups) {     // warps without a candidate go straight to the barrier
+                ML_T0(q);
+                const int it2 = base + it0 + 2 * ngroups;
+                const int32_t w_nx2 = it2 < total ? range_item(R, it2) : -1;
+                {
+                    int take = (w_nx >= 0 && gl == 0) ? (dedupe_claim(&C, w_nx) ? 1 : 0) : 0;
+                    take = __shfl_sync(0xffffffffu, take, lane & 24);
+                    if (!take) w_nx = -1;
+                }
+                uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
+                if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
                 ML_TACC(0, q);
-                i64 off = 0, f = 0; int n = 0;
-                if (w >= 0) { off = M.woff[w]; n = M.wlen[w]; f = M.wcnt[w]; }
-#if ML_TIMING
-                if (n < 0) M.state[MS_SCRATCH] = off + f;
-#endif
-                ML_TACC(1, q);
-                if (a != b) rewrite_words_g8(M, w, off, n, f, a, b, c, T, T2, &C, is_new);
-                else if (w >= 0 && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, &C, is_new);
+                if (a != b) rewrite_words_g8(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
+                else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new);
                 ML_TACC(2, q);
 #if ML_TIMING
                 if (threadIdx.x == 0) sh_tacc[3] += 1;
 #endif
+                w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = w_nx2;
             }
         }
         if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }

@@ -39,6 +39,16 @@ static int num_sms() {
 extern "C" const char* yabpe_last_error(void) { return g_err; }
 extern "C" int yabpe_abi_version(void) { return YABPE_ABI_VERSION; }
 extern "C" int64_t yabpe_launch_count(void) { return g_launches; }
+extern "C" int64_t yabpe_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return (int64_t)sizeof(yabpe_pretok_args);
+        case 1: return (int64_t)sizeof(yabpe_word_table);
+        case 2: return (int64_t)sizeof(yabpe_merge_args);
+        case 3: return (int64_t)sizeof(yabpe_encode_model);
+        case 4: return (int64_t)sizeof(yabpe_encode_out);
+        default: return -1;
+    }
+}
 
 extern "C" int yabpe_class_of(uint32_t cp) {
     if (cp >= 0x110000) return 0;

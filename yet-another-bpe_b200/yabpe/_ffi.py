@@ -24,7 +24,7 @@ INT64_MAX = (1 << 63) - 1
 EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
-    "yabpe_launch_count", "yabpe_insert_words",
+    "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof",
 ]
 
 
@@ -123,6 +123,11 @@ def load() -> C.CDLL:
     L.yabpe_num_tiles.restype = C.c_int64
     L.yabpe_num_tiles.argtypes = [C.c_int64, C.c_int64]
     L.yabpe_launch_count.restype = C.c_int64
+    L.yabpe_sizeof.restype = C.c_int64
+    L.yabpe_sizeof.argtypes = [C.c_int32]
+    for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut)):
+        if L.yabpe_sizeof(which) != C.sizeof(st):
+            raise YabpeUnavailable(f"{st.__name__}: ctypes layout ({C.sizeof(st)} B) != libyabpe.so ({L.yabpe_sizeof(which)} B); rebuild")
     if L.yabpe_abi_version() != ABI_VERSION:
         raise YabpeUnavailable(f"libyabpe.so ABI {L.yabpe_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L
