@@ -145,40 +145,69 @@ __device__ bool any_bit(const uint32_t* bm, i64 lo, i64 hi) {   // any set bit i
 //   trainer: candidate q is recognised iff q is a token start given the previous recognised
 //            special end as a fresh-text fence
 //   encode : leftmost, priority order, non-overlapping (tokenizer.py:97-102,171)
-__global__ void __launch_bounds__(256) k_resolve_specials(PretokParams P, i64 lo, i64 hi, i64 ctx_lo) {
-    const int D = P.mode == 0 ? c_sp.max_len + 16 : c_sp.max_len - 1;
-    i64 nwords_lo = lo >> 5, nwords_hi = (hi + 31) >> 5;
-    i64 stride = (i64)gridDim.x * blockDim.x;
+// Candidates are sparse (about one per 30 bitmap words on document-separated text) while resolving one costs
+// dozens of dependent loads: a thread-per-word scan would run that slow path with one or two active lanes in
+// every warp iteration.  Each warp therefore first gathers candidate positions into its own shared-memory list
+// (ballot + prefix) and runs the slow path 32 candidates at a time with all lanes busy.
+__device__ __forceinline__ int resolve_candidate(const PretokParams& P, i64 q, i64 ctx_lo, int D) {
+    // chain head?  no candidate in [q-D, q)
+    if (D > 0 && any_bit(P.cand, q - D, q - 1)) return 0;      // resolved by the walk of its chain's head
+    (void)ctx_lo;
     GlobalText G{P.text, P.n, P.cuts, P.n_cuts, nullptr, -1, P.mode};
-    for (i64 wi = nwords_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; wi < nwords_hi; wi += stride) {
-        uint32_t w = P.cand[wi];
-        while (w) {
-            int bit = __ffs(w) - 1; w &= w - 1;
-            i64 q = (wi << 5) + bit;
-            if (q < lo || q >= hi) continue;
-            // chain head?  no candidate in [q-D, q)
-            if (D > 0 && any_bit(P.cand, q - D, q - 1)) {
-                // a chain that started before the available left context cannot be resolved here
-                if (q - D < ctx_lo && ctx_lo > 0 && !any_bit(P.cand, ctx_lo, q - 1)) { /* head is before ctx */ }
-                continue;
-            }
-            i64 e = -1, cur = q;
-            for (;;) {
-                i64 lim = logical_end_after(P, cur);
-                int s = special_match(P.text, cur, lim);
-                int m = c_sp.offs[s + 1] - c_sp.offs[s];
-                bool ok = false;
-                if (cur >= e) {
-                    if (P.mode == 1) ok = true;
-                    else { G.fence_fl = e; ok = is_token_start(G, cur); }
-                }
-                if (ok) { atomicOr(&P.rec[cur >> 5], 1u << (cur & 31)); e = cur + m; atomicAdd((u64*)&P.stats[ST_NSPECIAL], 1ULL); }
-                i64 nx = D > 0 ? next_bit(P.cand, cur, cur + D < P.n - 1 ? cur + D : P.n - 1) : -1;
-                if (nx < 0) break;
-                cur = nx;
+    int n_rec = 0;
+    i64 e = -1, cur = q;
+    for (;;) {
+        i64 lim = logical_end_after(P, cur);
+        int s = special_match(P.text, cur, lim);
+        int m = c_sp.offs[s + 1] - c_sp.offs[s];
+        bool ok = false;
+        if (cur >= e) {
+            if (P.mode == 1) ok = true;
+            else { G.fence_fl = e; ok = is_token_start(G, cur); }
+        }
+        if (ok) { atomicOr(&P.rec[cur >> 5], 1u << (cur & 31)); e = cur + m; n_rec++; }
+        i64 nx = D > 0 ? next_bit(P.cand, cur, cur + D < P.n - 1 ? cur + D : P.n - 1) : -1;
+        if (nx < 0) break;
+        cur = nx;
+    }
+    return n_rec;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_specials(PretokParams P, i64 lo, i64 hi, i64 ctx_lo) {
+    __shared__ i64 sh_list[8][64];
+    const int D = P.mode == 0 ? c_sp.max_len + 16 : c_sp.max_len - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    i64* list = sh_list[warp];
+    int cnt = 0;                                     // warp-uniform
+    int my_rec = 0;
+    const i64 nwords_lo = lo >> 5, nwords_hi = (hi + 31) >> 5;
+    const i64 stride = (i64)gridDim.x * 8 * 32;
+    for (i64 base = nwords_lo + ((i64)blockIdx.x * 8 + warp) * 32; base < nwords_hi; base += stride) {
+        const i64 wi = base + lane;
+        uint32_t w = wi < nwords_hi ? P.cand[wi] : 0u;
+        while (__any_sync(0xffffffffu, w != 0)) {
+            bool has = w != 0;
+            i64 q = 0;
+            if (has) { const int bit = __ffs(w) - 1; w &= w - 1; q = (wi << 5) + bit; has = q >= lo && q < hi; }
+            const uint32_t m = __ballot_sync(0xffffffffu, has);
+            if (has) list[cnt + __popc(m & lt)] = q;
+            cnt += __popc(m);
+            __syncwarp();
+            if (cnt >= 32) {
+                my_rec += resolve_candidate(P, list[lane], ctx_lo, D);
+                __syncwarp();
+                const i64 t = lane + 32 < cnt ? list[lane + 32] : 0;
+                __syncwarp();
+                if (lane + 32 < cnt) list[lane] = t;
+                cnt -= 32;
+                __syncwarp();
             }
         }
     }
+    if (lane < cnt) my_rec += resolve_candidate(P, list[lane], ctx_lo, D);
+    for (int o = 16; o > 0; o >>= 1) my_rec += __shfl_xor_sync(0xffffffffu, my_rec, o);
+    if (lane == 0 && my_rec) atomicAdd((u64*)&P.stats[ST_NSPECIAL], (u64)my_rec);
 }
 
 // ---------------------------------------------------------------------------------
