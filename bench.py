@@ -179,7 +179,7 @@ def run_encode(args) -> None:
     vocab, merges = common.gpt2_vocab_and_merges()
     tok = yabpe.Tokenizer(vocab, merges, SPECIALS).inner
     shard = nbytes // world                                  # documents are independent: shard by document, no exchange
-    text_dev, n = synth_corpus_device(torch, shard, kind, seed + rank)
+    text_dev, n = synth_corpus_device(torch, shard, kind, seed + rank, lex_seed=seed)
     torch.cuda.synchronize()
 
     def barrier():
@@ -299,7 +299,7 @@ def main() -> None:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, nbytes, vocab, seed = WORKLOADS[args.workload]
-    text_dev, n = synth_corpus_device(torch, nbytes, kind, seed + rank)
+    text_dev, n = synth_corpus_device(torch, nbytes, kind, seed + rank, lex_seed=seed)     # one corpus: shared lexicon, own text
     torch.cuda.synchronize()
 
     cfg = yabpe.BBPETrainerConfig(vocab_size=vocab, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
@@ -417,7 +417,7 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/int64", "data": f"synthetic ({kind}-shaped, torch generator, seed {seed})",
+            "vs_baseline": None, "dtype": "u8/int64", "data": f"synthetic ({kind}-shaped, torch generator, lexicon seed {seed}, text seed {seed}+rank)",
             "config": {"workload": args.workload, "corpus_bytes_per_gpu": n, "vocab_size": vocab, "special_tokens": SPECIALS,
                        "l2": "inputs (>= 256 MB) larger than the 126 MB L2", "n_pretokens": stats.n_pretokens,
                        "unique_words": stats.n_words, "merges": stats.n_merges},

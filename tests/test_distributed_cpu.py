@@ -1,4 +1,4 @@
-"""World-size-2 gloo test (CPU) of the multi-GPU exchange logic in yabpe/distributed.py.
+"""World-size-2 and -4 gloo tests (CPU) of the multi-GPU exchange logic in yabpe/distributed.py.
 
 The CUDA-only pieces (local counting, duplicate merge) are replaced by the oracle / a Python dict;
 everything else -- hashing, partitioning, the variable-size all-to-all, the gather on rank 0 and the
@@ -90,11 +90,15 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def test_shard_exchange_world2_gloo(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_shard_exchange_gloo(tmp_path, world):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=str(ROOT)))
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

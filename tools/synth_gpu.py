@@ -57,12 +57,14 @@ def _lexicon(kind: str, n_types: int, seed: int) -> tuple[np.ndarray, np.ndarray
 
 
 def synth_corpus_device(torch, n_bytes: int, kind: str = "tinystories", seed: int = 20260101,
-                        n_types: int | None = None, piece_bytes: int = 256 << 20):
-    """Return (uint8 device tensor with capacity round_up(n,16)+64, n)."""
+                        n_types: int | None = None, piece_bytes: int = 256 << 20, lex_seed: int | None = None):
+    """Return (uint8 device tensor with capacity round_up(n,16)+64, n).
+    `seed` drives the text; `lex_seed` (default: seed) the lexicon -- shards of ONE corpus share the lexicon
+    and differ in their text, so a multi-GPU run passes lex_seed=<corpus seed>, seed=<corpus seed> + rank."""
     dev = torch.device("cuda")
     if n_types is None:
         n_types = 40_000 if kind == "tinystories" else 5_000_000
-    lex_np, len_np = _lexicon(kind, n_types, seed)
+    lex_np, len_np = _lexicon(kind, n_types, seed if lex_seed is None else lex_seed)
     lex = torch.from_numpy(lex_np).to(dev)
     lex_len = torch.from_numpy(len_np).to(dev)
     ranks = np.arange(1, n_types + 1, dtype=np.float64)

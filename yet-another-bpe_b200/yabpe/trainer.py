@@ -204,7 +204,7 @@ class BBPETrainer:
         stats.n_pairs = int(mr.state[_ffi.MS_NPAIRS])
         stats.leader_merges = int(mr.state[_ffi.MS_LEADER_MERGES])
         stats.grid_merges = int(mr.state[_ffi.MS_GRID_MERGES])
-        self.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13])]
+        self.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13]), int(mr.state[17])]
         stats.launches = _ffi.launch_count() - launches0
         self.last_stats = stats
         if self.profile and ev and len(ev) == 4:
