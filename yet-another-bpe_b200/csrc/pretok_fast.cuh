@@ -29,6 +29,9 @@
 #define PW_NC 4096                         // cache entries per CTA (power of two)
 #endif
 #define PW_NC_LOG2 (PW_NC == 4096 ? 12 : (PW_NC == 2048 ? 11 : (PW_NC == 8192 ? 13 : (PW_NC == 1024 ? 10 : 9))))
+#ifndef PW_TWO_WAY
+#define PW_TWO_WAY 0      // a second cache way costs more instructions per round than its extra hits save
+#endif
 #define PW_LQCAP 64                        // per-warp queue of long (> 14 byte) pre-tokens
 #define PW_TOKCAP 1024
 
@@ -214,12 +217,14 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             if (miss) {                            // second cache way, or claim an empty one
                 uint32_t ci = h >> (32 - PW_NC_LOG2);
                 if (ckeys[ci].w == 0 && atomicCAS(&ccnt[ci], 0u, 0x80000001u) == 0u) { ckeys[ci] = make_uint4(kx, ky, kz, kw); miss = false; }
+#if PW_TWO_WAY
                 else {
                     ci ^= 1u;
                     const uint4 a = ckeys[ci];
                     if (((a.x ^ kx) | (a.y ^ ky) | (a.z ^ kz) | (a.w ^ kw)) == 0) { atomicAdd(&ccnt[ci], 1u); miss = false; }
                     else if (a.w == 0 && atomicCAS(&ccnt[ci], 0u, 0x80000001u) == 0u) { ckeys[ci] = make_uint4(kx, ky, kz, kw); miss = false; }
                 }
+#endif
             }
             consume();                             // the probe issued one round ago has landed by now
             if (miss) {
