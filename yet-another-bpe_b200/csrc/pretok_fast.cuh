@@ -89,8 +89,14 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     uint4* ckeys = (uint4*)pw_smem;                                   // 16-byte keys (k0 = x,y  k1 = z,w)
     uint32_t* ccnt = (uint32_t*)(pw_smem + PW_NC * 16);               // bit 31 = claimed, low bits = occurrences
     uint4* lut = (uint4*)(pw_smem + PW_NC * 20);                      // byte masks per pre-token length
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem& W = *(WarpSmem*)(pw_smem + PW_NC * 20 + 256 + warp * sizeof(WarpSmem));
+    // lane id and the warp's shared-memory area are made opaque to the compiler: otherwise it re-derives them from
+    // threadIdx (S2R + integer ops) all over the inner loops instead of spending two registers (6 % of all instructions)
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    WarpSmem* Wp = (WarpSmem*)(pw_smem + PW_NC * 20 + 256 + warp * sizeof(WarpSmem));
+    asm volatile("" : "+l"(Wp));
+    WarpSmem& W = *Wp;
 
     for (int i = threadIdx.x; i < PW_NC; i += PW_THREADS) { ckeys[i] = make_uint4(0, 0, 0, 0); ccnt[i] = 0; }
     if (threadIdx.x < 16) {

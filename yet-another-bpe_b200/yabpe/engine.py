@@ -234,8 +234,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
     max_tokens = n_base + num_merges + 2
     for attempt in range(6):
         if pcap is None:
-            import os as _os
-            pcap = _pow2_at_least(min(max(int(float(_os.environ.get('YABPE_PCAP_FACTOR', '4')) * words.n_syms), 1 << 16), 1 << 26))
+            pcap = _pow2_at_least(min(max(4 * words.n_syms, 1 << 16), 1 << 26))
         if pool_cap is None:
             pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
         alog_cap = max(2 * words.n_words, 1 << 16) + 4096
