@@ -32,15 +32,6 @@
 #define ML_T0(v)
 #define ML_TACC(slot, from)
 #endif
-#ifndef ML_DEFER_NPAIRS
-#define ML_DEFER_NPAIRS 1
-#endif
-#ifndef ML_NPAIRS_CHECK_D
-#define ML_NPAIRS_CHECK_D 1
-#endif
-#ifndef ML_NPAIRS_CHECK_E
-#define ML_NPAIRS_CHECK_E 1
-#endif
 #define PAIR_KEY(a, b) (0x8000000000000000ULL | ((u64)(uint32_t)(a) << 32) | (u64)(uint32_t)(b))
 #define TOK_HASH_B 0x100000001b3ULL
 
@@ -136,7 +127,8 @@ __global__ void __launch_bounds__(256) k_compact_long(const LongEntry* ent, i64 
 //     so the words rewritten by merge m (the "affected log" segment of m) are a superset of the
 //     words that contain any pair created by m.  Candidates for (p, q) = CSR postings of its slot
 //     + the segments of the merges that produced p or q since the last rebuild.
-// Stale and duplicate candidates are filtered by a per-word stamp and by re-scanning the word.
+// Duplicate candidates are filtered by a per-word stamp (grid mode) or a shared-memory claim set (leader
+// mode); stale ones cost a look at the word and change nothing (the rewrite finds no site).
 //
 // Two execution modes, chosen uniformly by all CTAs after a grid barrier:
 //   grid mode   every CTA takes part (argmax -> grid sync -> rewrite -> grid sync)
@@ -147,7 +139,6 @@ struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
 #define ML_TOP_N 512
 
 #define ML_MAX_RANGES 12
-#define ML_LEADER_ACT_MAX 32768
 #ifndef ML_LEADER_ITEMS_MAX
 #define ML_LEADER_ITEMS_MAX 1024
 #endif
@@ -199,17 +190,6 @@ __device__ __forceinline__ void grid_barrier(const MergeParams& M) {
     __syncthreads();
 }
 
-__device__ __forceinline__ i64 pair_find(const MergeParams& M, u64 key) {
-    u64 mask = (u64)M.pcap - 1;
-    u64 slot = mix64(key) & mask;
-    for (i64 probes = 0; probes < M.pcap; probes++) {
-        u64 k = __ldcg(&M.pkey[slot]);
-        if (k == key) return (i64)slot;
-        if (k == 0) return -1;
-        slot = (slot + 1) & mask;
-    }
-    return -1;
-}
 // expect_new: the key is very likely absent (it contains a token created by the current merge), so the probe
 // starts with the CAS instead of a load: one L2 round trip less on the critical path of every merge.
 // created_ctr: shared-memory counter of new pairs (leader mode), else the global MS_NPAIRS is bumped.
@@ -419,12 +399,6 @@ __device__ void rebuild_index(const MergeParams& M, i64* sh_scan, i64 m_now) {
 
 // Leader mode keeps the counts of the top-list pairs mirrored in shared memory (the leader is the only
 // writer while it runs), so the per-merge argmax needs no global gather at all.
-#ifndef ML_NEW_COMMIT
-#define ML_NEW_COMMIT 1
-#endif
-#ifndef ML_USE_MIRROR
-#define ML_USE_MIRROR 1
-#endif
 // Counts are kept as two 32-bit halves: shared memory has native 32-bit atomic adds, while a 64-bit add is a
 // compare-and-swap loop (~145 cycles uncontended, far worse when every rewrite site hits the same entry).
 struct LeaderMirror { uint32_t lo[ML_TOP_N], hi[ML_TOP_N]; uint8_t pending[ML_TOP_N]; int32_t mkey[2 * ML_TOP_N]; int16_t mval[2 * ML_TOP_N]; };
@@ -806,38 +780,6 @@ __device__ void commit_merge(const MergeParams& M, i64 m, int32_t a, int32_t b, 
         }
     }
 }
-// the same, executed by ONE WARP (leader mode: overlaps with the rewrite done by the other warps)
-__device__ void commit_merge_warp(const MergeParams& M, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 alog_start) {
-    const int lane = threadIdx.x & 31;
-    if (lane == 0) {
-        M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c;
-        M.seg_start[m] = (int32_t)alog_start;
-        M.merge_next[m] = is_new ? -1 : M.tok_first[c];
-    }
-    if (is_new) {
-        i64 oa = M.tok_off[a], ob = M.tok_off[b], oc = M.tok_off[c];
-        i64 la = M.tok_off[a + 1] - oa, lb = M.tok_off[b + 1] - ob;
-        if (oc + la + lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
-            if (lane == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL);
-        } else {
-            for (i64 k = lane; k < la; k += 32) M.tok_bytes[oc + k] = M.tok_bytes[oa + k];
-            for (i64 k = lane; k < lb; k += 32) M.tok_bytes[oc + la + k] = M.tok_bytes[ob + k];
-            __syncwarp();
-            if (lane == 0) {
-                u64 H = M.tok_hash[a] * M.tok_pow[b] + M.tok_hash[b];
-                M.tok_off[c + 1] = oc + la + lb;
-                M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
-                M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], la, M.tok_pre[b]);
-                M.tok_first[c] = -1;
-                __threadfence();
-                u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
-                while (M.tset[slot] != 0) slot = (slot + 1) & mask;
-                atomicExch(&M.tset[slot], (H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1));
-                M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + la + lb;
-            }
-        }
-    }
-}
 // leader-mode commit by one warp; MI comes from lookup_merged, oc = current end of the token byte pool
 __device__ void commit_merge_leader(const MergeParams& M, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 alog_start,
                                     const MergedInfo& MI, i64 oc) {
@@ -871,7 +813,6 @@ __device__ __forceinline__ void close_merge(const MergeParams& M, i64 m, int32_t
 }
 
 // ---- leader mode: CTA 0 runs merges alone, block barriers only ---------------------------------
-struct ClaimedWord { i64 off; i64 f; int32_t w; int32_t n; };
 
 // best entry of the top list, computed by ONE block (every block gets the same answer when all call it)
 __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh_cnt) {
@@ -1259,7 +1200,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         const i64 top_n = M.state[MS_TOP_N];
         const bool top_ovf = M.state[MS_TOP_OVF] != 0;
         if (m >= M.num_merges || M.state[MS_ERROR] || M.state[MS_DONE]) break;
-        if (ML_NPAIRS_CHECK_E && M.state[MS_NPAIRS] * 4 > M.pcap * 3) { if (gtid == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); break; }
+        if (M.state[MS_NPAIRS] * 4 > M.pcap * 3) { if (gtid == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); break; }
 
         // ---- (re)build the top list when it cannot prove the maximum any more
         if (T2 == 0 || (T2 > 0 && top_ovf)) {
