@@ -1087,7 +1087,6 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         if (C.npairs_new + C.nnew) atomicAdd((u64*)&M.state[MS_NPAIRS], (u64)(C.npairs_new + C.nnew));
 #if ML_TIMING
         M.state[20] += t_arg; M.state[21] += t_rng; M.state[23] += t_rw; M.state[24] += t_close;
-        M.state[22] += sh_tacc[2]; M.state[27] += sh_tacc[3]; M.state[28] += sh_tacc[4]; M.state[12] += sh_tacc[0]; M.state[13] += sh_tacc[1];
 #endif
         M.state[25] += s_act; M.state[26] += s_items;
         M.state[MS_LEADER_MERGES] += n_done;
@@ -1237,6 +1236,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         //      (same data, same answer); the barrier only keeps the rewrite (which changes the counts)
         //      from starting before every CTA has read them.
         Best best;
+        ML_CLOCK(g0);
         if (T2 > 0) {
             best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
             grid_barrier(M);
@@ -1256,8 +1256,10 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             }
         }
         const int32_t a = best.a, b = best.b;
+        ML_CLOCK(g1);
         if (threadIdx.x == 0) { build_ranges(M, best.slot, a, b, &R); sh_c = lookup_merged(M, a, b, n_tok); }
         __syncthreads();
+        ML_CLOCK(g2);
         if (R.n < 0 || alog_n + R.total > M.alog_cap) {
             // fold the affected log into the CSR index first, then look the candidates up again
             grid_barrier(M);
@@ -1271,7 +1273,23 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         if (blockIdx.x == 0) commit_merge(M, m, a, b, c, is_new, alog_n);
         const int32_t stamp = (int32_t)(m + 1);
         const i64 T2u = T2 > 0 ? T2 : 0;
-        if (a != b && R.total * 32 <= gstride * 4) {
+        if (a != b && R.total * 8 <= gstride) {
+            // up to one candidate per 8-lane group in a single pass: the stamp exchange and the word header loads of
+            // a candidate are issued together (one DRAM round trip instead of two), four words per warp in flight
+            const i64 gg = gtid >> 3;
+            const int lane = threadIdx.x & 31, gl = lane & 7;
+            int32_t w = -1;
+            i64 off = 0, f = 0; int n = 0;
+            int32_t old = stamp;
+            if (gg < R.total) {
+                w = range_item(R, gg);
+                if (gl == 0) old = atomicExch(&M.wstamp[w], stamp);
+                off = M.woff[w]; n = M.wlen[w]; f = M.wcnt[w];
+            }
+            old = __shfl_sync(0xffffffffu, old, lane & 24);       // all 32 lanes: groups beyond the list carry old == stamp
+            if (old == stamp) w = -1;
+            rewrite_words_g8(M, w, off, n, f, a, b, c, T, T2u, nullptr, is_new);
+        } else if (a != b && R.total * 32 <= gstride * 4) {
             const i64 gw = gtid >> 5, nw = gstride >> 5;
             for (i64 it = gw; it < R.total; it += nw) {
                 int32_t w = range_item(R, it);
@@ -1288,7 +1306,12 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr, is_new);
             }
         }
+        ML_CLOCK(g3);
         grid_barrier(M);
+        ML_CLOCK(g4);
+#if ML_TIMING
+        if (gtid == 0) { M.state[12] += g1 - g0; M.state[13] += g2 - g1; M.state[22] += g3 - g2; M.state[27] += g4 - g3; M.state[28] += R.total; }
+#endif
         // every CTA writes the same values: no further barrier needed before the next iteration
         if (threadIdx.x == 0) { close_merge(M, m, c); if (T2 < 0) M.state[MS_T2] = 0; }
         if (gtid == 0) M.state[MS_GRID_MERGES]++;
