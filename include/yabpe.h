@@ -166,6 +166,9 @@ typedef struct {
     int32_t* merge_new;         /* device, num_merges: resulting id                               */
     int64_t* state;             /* device int64[32], zeroed except [MS_NTOK] = n_base             */
     int64_t num_merges; int64_t min_frequency;
+    int64_t rebuild_every;      /* merges between pair->words index rebuilds; 0 = only when the log is full.
+                                 * Candidates of a pair are its postings at the last rebuild plus every word rewritten
+                                 * when one of its tokens was created: a superset that grows stale between rebuilds */
 } yabpe_merge_args;
 
 int yabpe_merge_loop(const yabpe_merge_args* m, void* stream);

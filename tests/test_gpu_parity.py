@@ -198,6 +198,24 @@ def test_train_medium_corpus_vs_oracle_and_deterministic(yabpe, tmp_path):
     assert got1[0] == want[0]
 
 
+def test_train_with_frequent_index_rebuilds(yabpe, tmp_path, monkeypatch):
+    """The pair -> words index is rebuilt every `rebuild_every` merges (engine.rebuild_period); force a tiny period so
+    that dozens of rebuilds (and leader exits for them) happen, and a zero period (rebuild only when the log is full)."""
+    data = common.synth_tinystories(2_000_000, seed=5)
+    p = tmp_path / "r.txt"
+    p.write_bytes(data)
+    want = oracle.train_bpe(p, 1800, ["<|endoftext|>"], fast=True)
+    for period in ("37", "0"):
+        monkeypatch.setenv("YABPE_REBUILD_EVERY", period)
+        tr = yabpe.BBPETrainer(yabpe.BBPETrainerConfig(vocab_size=1800, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
+                                                       special_tokens=["<|endoftext|>"]))
+        model = tr.train([p])
+        assert model.merges == want[1], period
+        assert {v: k for k, v in model.vocab.items()} == want[0], period
+        if period == "37":
+            assert tr.last_stats.index_rebuilds >= 30
+
+
 def test_train_edge_cases(yabpe, tmp_path):
     p = tmp_path / "e.txt"
     p.write_bytes(b"")

@@ -167,6 +167,7 @@ struct MergeParams {
     // outputs
     int32_t* merges; int32_t* merge_new; i64* state;
     i64 num_merges; i64 min_freq;
+    i64 rebuild_every;                           // merges between index rebuilds (0: only when the affected-word log is full)
 };
 
 // Grid-wide barrier on two words of the state array (arrival counter + generation).  The kernel is
@@ -829,6 +830,7 @@ __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh
 
 #define LR_TOP 1      // leader stopped: top list exhausted / overflowed
 #define LR_OTHER 2    // leader stopped: the next merge needs the whole grid (or nothing is left to do)
+#define LR_REBUILD 3  // leader stopped: time to fold the affected-word log into the CSR index (fewer stale candidates)
 
 
 // ---- batch selection -------------------------------------------------------------------------------
@@ -914,6 +916,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
     int reason = LR_OTHER;
     int cached = 0;                      // entries of the top list whose count is mirrored in shared memory
     const i64 npairs0 = __ldcg(&M.state[MS_NPAIRS]);
+    const i64 last_rebuild_m = __ldcg(&M.state[MS_LAST_REBUILD_M]);
     if (threadIdx.x == 0) {
         C.act_n = (int)__ldcg(&M.state[MS_ACT_N]); C.alog_n = (int)__ldcg(&M.state[MS_ALOG_N]);
         C.error = (int)__ldcg(&M.state[MS_ERROR]);
@@ -932,6 +935,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         const int alog_n = C.alog_n;
         if (C.error) break;
         if (C.top_ovf || C.top_n > ML_TOP_N) { reason = LR_TOP; break; }
+        if (M.rebuild_every > 0 && m - last_rebuild_m >= M.rebuild_every) { reason = LR_REBUILD; break; }
         if ((npairs0 + C.npairs_new + C.nnew) * 4 > M.pcap * 3) { if (threadIdx.x == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); break; }
         // ---- A: best pair of the top list
         const int tn = C.top_n;
@@ -1226,10 +1230,11 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             n_tok = (int32_t)M.state[MS_NTOK];
             alog_n = M.state[MS_ALOG_N];
             const i64 reason = M.state[MS_LEADER_REASON];
-            if (m == m0 && reason != LR_TOP) { backoff = backoff < 64 ? backoff * 2 : 64; skip = backoff; } else backoff = 1;
+            if (m == m0 && reason == LR_OTHER) { backoff = backoff < 64 ? backoff * 2 : 64; skip = backoff; } else backoff = 1;
             if (m >= M.num_merges || M.state[MS_ERROR]) break;
             grid_barrier(M);                                    // everyone has re-read the state
             if (reason == LR_TOP) continue;                 // top list exhausted: rebuild it first
+            if (reason == LR_REBUILD) { rebuild_index(M, sh_scan, m); continue; }
         }
 
         // ---- one merge in grid mode.  With a valid top list every CTA finds the best pair on its own

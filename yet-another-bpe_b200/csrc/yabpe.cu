@@ -294,7 +294,7 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     ARG_CHECK(m->alog_cap >= 2 * m->n_words + ML_LEADER_ITEMS_MAX);
     M.partial = (Best*)m->partial; M.bsum = (i64*)m->bsum;
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
-    M.num_merges = m->num_merges; M.min_freq = m->min_frequency;
+    M.num_merges = m->num_merges; M.min_freq = m->min_frequency; M.rebuild_every = m->rebuild_every;
 
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, 0));
