@@ -160,6 +160,7 @@ typedef struct {
     int32_t* seg_start; int32_t* seg_end;        /* device, num_merges each                       */
     int32_t* merge_next;        /* device, num_merges                                             */
     int32_t* tok_first;         /* device, max_tokens                                             */
+    void* tok_head;             /* device, max_tokens * 16 bytes (16-byte aligned scratch)        */
     void* partial;              /* device, 24 bytes per CTA (>= 1024 entries)                     */
     int64_t* bsum;              /* device, one per CTA (>= 1024 entries)                          */
     int32_t* merges;            /* device, 2 * num_merges: (left id, right id) per merge          */

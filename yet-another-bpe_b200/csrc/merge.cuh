@@ -163,6 +163,7 @@ struct MergeParams {
     int32_t* seg_start; int32_t* seg_end;      // per merge
     int32_t* merge_next;                        // per merge: previous merge (since rebuild) with the same product token
     int32_t* tok_first;                         // per token: latest merge since the last rebuild producing it, or -1
+    int4* tok_head;                             // per token: {that merge, its segment start, end, the previous such merge}: one load instead of a chain
     Best* partial; i64* bsum;
     // outputs
     int32_t* merges; int32_t* merge_new; i64* state;
@@ -345,7 +346,7 @@ __device__ void rebuild_index(const MergeParams& M, i64* sh_scan, i64 m_now) {
     i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     for (i64 i = gtid; i < M.pcap; i += gstride) M.icnt[i] = 0;
     // forget the affected-log segments: the CSR built below covers everything
-    for (i64 mm = M.state[MS_LAST_REBUILD_M] + gtid; mm < m_now; mm += gstride) M.tok_first[M.merge_new[mm]] = -1;
+    for (i64 mm = M.state[MS_LAST_REBUILD_M] + gtid; mm < m_now; mm += gstride) { M.tok_first[M.merge_new[mm]] = -1; M.tok_head[M.merge_new[mm]].x = -1; }
     grid_barrier(M);
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
         int32_t w = M.sym_word[i];
@@ -704,12 +705,19 @@ struct Ranges { const int32_t* base[ML_MAX_RANGES]; int len[ML_MAX_RANGES]; int 
 
 __device__ void build_ranges(const MergeParams& M, int32_t slot, int32_t a, int32_t b, Ranges* R) {
     int n = 0; i64 total = 0;
-    uint32_t p0 = M.ioff[slot], p1 = M.ioff[slot + 1];
+    // the four loads below are independent: one round trip in the common case (each token made by <= 1 merge since the rebuild)
+    const uint32_t p0 = M.ioff[slot], p1 = M.ioff[slot + 1];
+    const int4 ha = M.tok_head[a], hb = M.tok_head[b];
     if (p1 > p0) { R->base[n] = M.ipost + p0; R->len[n] = (int)(p1 - p0); total += p1 - p0; n++; }
     for (int side = 0; side < 2; side++) {
-        int32_t t = side == 0 ? a : b;
         if (side == 1 && b == a) break;
-        for (int32_t mm = M.tok_first[t]; mm >= 0; mm = M.merge_next[mm]) {
+        const int4 h = side == 0 ? ha : hb;
+        if (h.x < 0) continue;
+        if (h.z > h.y) {
+            if (n >= ML_MAX_RANGES) { R->n = -1; R->total = total; return; }
+            R->base[n] = M.alog_word + h.y; R->len[n] = h.z - h.y; total += h.z - h.y; n++;
+        }
+        for (int32_t mm = h.w; mm >= 0; mm = M.merge_next[mm]) {
             int ln = M.seg_end[mm] - M.seg_start[mm];
             if (ln <= 0) continue;
             if (n >= ML_MAX_RANGES) { R->n = -1; R->total = total; return; }
@@ -771,7 +779,7 @@ __device__ void commit_merge(const MergeParams& M, i64 m, int32_t a, int32_t b, 
                 M.tok_off[c + 1] = oc + la + lb;
                 M.tok_hash[c] = H; M.tok_pow[c] = M.tok_pow[a] * M.tok_pow[b];
                 M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], la, M.tok_pre[b]);
-                M.tok_first[c] = -1;
+                M.tok_first[c] = -1; M.tok_head[c].x = -1;
                 __threadfence();
                 u64 mask = (u64)M.tset_cap - 1, slot = mix64(H) & mask;
                 while (M.tset[slot] != 0) slot = (slot + 1) & mask;
@@ -801,15 +809,17 @@ __device__ void commit_merge_leader(const MergeParams& M, i64 m, int32_t a, int3
         M.tok_off[c + 1] = oc + MI.la + MI.lb;
         M.tok_hash[c] = MI.H; M.tok_pow[c] = MI.P;
         M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], MI.la, M.tok_pre[b]);
-        M.tok_first[c] = -1;
+        M.tok_first[c] = -1; M.tok_head[c].x = -1;
         *(volatile u64*)&M.tset[MI.tslot] = (MI.H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1);
         M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + MI.la + MI.lb;
     }
 }
 // after the rewrite of merge m finished: close its segment and link it to its product token
 __device__ __forceinline__ void close_merge(const MergeParams& M, i64 m, int32_t c) {
-    M.seg_end[m] = (int32_t)__ldcg(&M.state[MS_ALOG_N]);
+    const int32_t e = (int32_t)__ldcg(&M.state[MS_ALOG_N]);
+    M.seg_end[m] = e;
     M.tok_first[c] = (int32_t)m;
+    M.tok_head[c] = make_int4((int32_t)m, M.seg_start[m], e, M.merge_next[m]);
     M.state[MS_NMERGES] = m + 1;
 }
 
@@ -1069,7 +1079,11 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         ML_TACC(4, qb);
         ML_CLOCK(c3);
         // ---- D: close the merge; thresholds of the pairs it created
-        if (threadIdx.x == 0) { M.seg_end[m] = C.alog_n; M.tok_first[c] = (int32_t)m; }
+        if (threadIdx.x == 0) {
+            const int32_t prev = is_new ? -1 : M.tok_first[c];        // == merge_next[m] written by the commit warp
+            M.seg_end[m] = C.alog_n; M.tok_first[c] = (int32_t)m;
+            M.tok_head[c] = make_int4((int32_t)m, alog_n, C.alog_n, prev);
+        }
         if (threadIdx.x == 32) { const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, __ldcg(&M.pcnt[best.slot])); }
         if (is_new) leader_new_pairs(M, &C, T, T2);
         __syncthreads();
@@ -1177,7 +1191,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             if (s >= 0) { atomicAdd((u64*)&M.pcnt[s], (u64)M.wcnt[w]); M.wslot[i] = (int32_t)s; }
         }
     }
-    for (i64 t = gtid; t < M.max_tokens; t += gstride) M.tok_first[t] = -1;
+    for (i64 t = gtid; t < M.max_tokens; t += gstride) { M.tok_first[t] = -1; M.tok_head[t] = make_int4(-1, 0, 0, -1); }
     for (i64 t = gtid; t < M.state[MS_NTOK]; t += gstride) M.tok_pre[t] = tok_prefix_of_bytes(M.tok_bytes + M.tok_off[t], M.tok_off[t + 1] - M.tok_off[t]);
     grid_barrier(M);
     {

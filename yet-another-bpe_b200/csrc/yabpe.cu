@@ -290,7 +290,8 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = m->ipost; M.inact = m->inact; M.intop = m->intop; M.act = m->act;
     M.top_slot = m->top_slot; M.top_key = (u64*)m->top_key; M.hist = m->hist;
     M.alog_word = m->alog_word; M.alog_cap = m->alog_cap; M.seg_start = m->seg_start; M.seg_end = m->seg_end;
-    M.merge_next = m->merge_next; M.tok_first = m->tok_first;
+    M.merge_next = m->merge_next; M.tok_first = m->tok_first; M.tok_head = (int4*)m->tok_head;
+    ARG_CHECK(((uintptr_t)m->tok_head & 15) == 0);
     ARG_CHECK(m->alog_cap >= 2 * m->n_words + ML_LEADER_ITEMS_MAX);
     M.partial = (Best*)m->partial; M.bsum = (i64*)m->bsum;
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;

@@ -69,7 +69,7 @@ class MergeArgs(C.Structure):
         ("ioff", C.c_void_p), ("icnt", C.c_void_p), ("ipost", C.c_void_p), ("inact", C.c_void_p), ("intop", C.c_void_p), ("top_slot", C.c_void_p), ("top_key", C.c_void_p), ("hist", C.c_void_p),
         ("act", C.c_void_p),
         ("alog_word", C.c_void_p), ("alog_cap", C.c_int64), ("seg_start", C.c_void_p), ("seg_end", C.c_void_p),
-        ("merge_next", C.c_void_p), ("tok_first", C.c_void_p),
+        ("merge_next", C.c_void_p), ("tok_first", C.c_void_p), ("tok_head", C.c_void_p),
         ("partial", C.c_void_p), ("bsum", C.c_void_p),
         ("merges", C.c_void_p), ("merge_new", C.c_void_p), ("state", C.c_void_p),
         ("num_merges", C.c_int64), ("min_frequency", C.c_int64), ("rebuild_every", C.c_int64),

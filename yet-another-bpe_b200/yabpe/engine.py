@@ -283,6 +283,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         nm1 = max(num_merges, 1)
         seg_start, seg_end, merge_next = z(nm1, torch.int32), z(nm1, torch.int32), z(nm1, torch.int32)
         tok_first = z(max_tokens, torch.int32)
+        tok_head = z(4 * max_tokens + 4, torch.int32)
         partial, bsum = z(1024 * 3, torch.int64), z(1024, torch.int64)
         merges, merge_new = z(2 * max(num_merges, 1), torch.int32), z(max(num_merges, 1), torch.int32)
         state_np = np.zeros(32, dtype=np.int64)
@@ -301,7 +302,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.top_slot = top_slot.data_ptr(); m.top_key = top_key.data_ptr(); m.hist = hist.data_ptr()
         m.alog_word = alog_word.data_ptr(); m.alog_cap = alog_cap
         m.seg_start = seg_start.data_ptr(); m.seg_end = seg_end.data_ptr()
-        m.merge_next = merge_next.data_ptr(); m.tok_first = tok_first.data_ptr()
+        m.merge_next = merge_next.data_ptr(); m.tok_first = tok_first.data_ptr(); m.tok_head = tok_head.data_ptr()
         m.partial = partial.data_ptr(); m.bsum = bsum.data_ptr()
         m.merges = merges.data_ptr(); m.merge_new = merge_new.data_ptr(); m.state = state.data_ptr()
         m.num_merges = num_merges; m.min_frequency = min_frequency
