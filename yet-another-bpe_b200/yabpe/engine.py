@@ -245,7 +245,9 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
     max_tokens = n_base + num_merges + 2
     for attempt in range(6):
         if pcap is None:
-            pcap = _pow2_at_least(min(max(4 * words.n_syms, 1 << 16), 1 << 26))
+            # distinct pairs stay well below the symbol count (0.07-0.2 x on the bench corpora); the kernel reports a
+            # table that fills beyond 3/4 and the loop below retries with a four times larger one
+            pcap = _pow2_at_least(min(max(words.n_syms, 1 << 16), 1 << 26))
         if pool_cap is None:
             pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
         alog_cap = max(2 * words.n_words, 1 << 16) + 4096
