@@ -211,7 +211,8 @@ def train_device_sharded(trainer, text_dev, n: int, name: str = "<shard>"):
                                     threshold_rebuilds=int(mr.state[_ffi.MS_TREBUILDS]), n_pairs=int(mr.state[_ffi.MS_NPAIRS]),
                                     leader_merges=int(mr.state[_ffi.MS_LEADER_MERGES]), grid_merges=int(mr.state[_ffi.MS_GRID_MERGES]))
     vocab = {b: i for i, b in enumerate(mr.tokens)}
-    merges = [(mr.tokens[int(a)], mr.tokens[int(b)]) for a, b in mr.merges]
+    toks = mr.tokens
+    merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]
     return trainer._finish(vocab, merges)
 
 

@@ -329,7 +329,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
             mn = merge_new[:nm].cpu().numpy()
             used = int(st[_ffi.MS_POOL_USED]) if ntok > n_base else int(tok_off[n_base])
             pool = d_tok_bytes[:max(used, 1)].cpu().numpy().tobytes()
-            offs = d_tok_off[:ntok + 1].cpu().numpy()
+            offs = d_tok_off[:ntok + 1].cpu().tolist()
             tokens = [pool[offs[i]:offs[i + 1]] for i in range(ntok)]
             return MergeResult(merges=mg, merge_new=mn, tokens=tokens, state=st)
         if err & _ffi.ME_INTERNAL:

@@ -212,7 +212,8 @@ class BBPETrainer:
             self.timing.update(specials_ms=ev[0].elapsed_time(ev[1]), pretok_tiles_ms=ev[1].elapsed_time(ev[2]),
                                long_tokens_ms=ev[2].elapsed_time(ev[3]), compact_ms=e0.elapsed_time(e1))
         vocab = {b: i for i, b in enumerate(mr.tokens)}
-        merges = [(mr.tokens[int(a)], mr.tokens[int(b)]) for a, b in mr.merges]
+        toks = mr.tokens
+        merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]       # .tolist(): plain ints, not numpy scalars
         return self._finish(vocab, merges)
 
     def save(self, output_dir: str | Path) -> None:
