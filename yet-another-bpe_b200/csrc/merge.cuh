@@ -23,6 +23,14 @@
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
 #endif
+#ifndef ML_TRACE
+#define ML_TRACE 0            // > 0: thread 0 of CTA 0 writes a clock trace of leader merges [ML_TRACE, ML_TRACE + 8) to M.partial
+#endif
+#if ML_TRACE
+#define ML_TR(k) do { if (threadIdx.x == 0 && m >= ML_TRACE && m < ML_TRACE + 8) ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + (k)] = clock64(); } while (0)
+#else
+#define ML_TR(k)
+#endif
 #if ML_TIMING
 #define ML_CLOCK(v) long long v = clock64()
 #define ML_T0(v) long long v = clock64()
@@ -942,6 +950,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
     __syncthreads();
     for (int iter = 0; iter < ML_LEADER_BATCH && m < M.num_merges; iter++) {
         ML_CLOCK(c0);
+        ML_TR(0);
         const int alog_n = C.alog_n;
         if (C.error) break;
         if (C.top_ovf || C.top_n > ML_TOP_N) { reason = LR_TOP; break; }
@@ -1024,6 +1033,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         if (best.slot < 0 || best.cnt < T2) { reason = LR_TOP; break; }
         if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
         ML_CLOCK(c1);
+        ML_TR(1);
         // ---- B: candidate ranges + merged token
         if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); C.cur_slot = best.slot; }
         if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok, &MI);
@@ -1032,6 +1042,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
         if (R.n < 0 || R.total > ML_LEADER_ITEMS_MAX || alog_n + R.total > M.alog_cap) break;
         ML_CLOCK(c2);
+        ML_TR(2);
         const int32_t a = best.a, b = best.b, c = sh_c;
         const bool is_new = c == n_tok;
         // ---- C: commit (last warp) || claim + rewrite (one 8-lane group per candidate item)
@@ -1050,8 +1061,13 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 take = __shfl_sync(0xffffffffu, take, lane & 24);
                 if (!take) w_cur = -1;
             }
+            ML_TR(3);
             uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
             if (w_cur >= 0) { off_cur = (uint32_t)M.woff[w_cur]; n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur]; }
+#if ML_TRACE
+            if (n_cur < 0) M.state[MS_SCRATCH] = off_cur + f_cur;
+            ML_TR(4);
+#endif
             for (int base = 0; base + warp * 4 < total; base += ngroups) {     // warps without a candidate go straight to the barrier
                 ML_T0(q);
                 const int it2 = base + it0 + 2 * ngroups;
@@ -1064,8 +1080,10 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
                 if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
                 ML_TACC(0, q);
+                if (base == 0) ML_TR(5);
                 if (a != b) rewrite_words_g8(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
                 else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new);
+                if (base == 0) ML_TR(6);
                 ML_TACC(2, q);
 #if ML_TIMING
                 if (threadIdx.x == 0) sh_tacc[3] += 1;
@@ -1075,9 +1093,11 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         }
         if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }
         ML_T0(qb);
+        ML_TR(7);
         __syncthreads();
         ML_TACC(4, qb);
         ML_CLOCK(c3);
+        ML_TR(8);
         // ---- D: close the merge; thresholds of the pairs it created
         if (threadIdx.x == 0) {
             const int32_t prev = is_new ? -1 : M.tok_first[c];        // == merge_next[m] written by the commit warp
@@ -1088,6 +1108,10 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         if (is_new) leader_new_pairs(M, &C, T, T2);
         __syncthreads();
         ML_CLOCK(c4);
+        ML_TR(9);
+#if ML_TRACE
+        if (threadIdx.x == 0 && m >= ML_TRACE && m < ML_TRACE + 8) { ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + 10] = R.total; ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + 11] = C.alog_n - alog_n; ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + 12] = C.nnew; }
+#endif
 #if ML_TIMING
         t_arg += c1 - c0; t_rng += c2 - c1; t_rw += c3 - c2; t_close += c4 - c3;
 #endif

@@ -319,6 +319,12 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         if timing is not None:
             t1 = torch.cuda.Event(enable_timing=True); t1.record()
         st = state.cpu().numpy()
+        import os as _os
+        if _os.environ.get('YABPE_TRACE'):
+            tr = bsum[512:512 + 8 * 24].cpu().numpy().reshape(8, 24)
+            for row in tr:
+                base = row[0]
+                print('[trace]', [int(x - base) for x in row[:10]], 'items', int(row[10]), 'rewritten', int(row[11]), 'new pairs', int(row[12]), flush=True)
         if timing is not None:
             timing["merge_loop_ms"] = t0.elapsed_time(t1)
         err = int(st[_ffi.MS_ERROR])
