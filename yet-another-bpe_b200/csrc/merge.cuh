@@ -83,45 +83,63 @@ struct WordTable {
     i64* counters;       // [0] n_words, [1] n_syms
 };
 
+// Word ids and symbol offsets are handed out with ONE pair of atomics per warp (ballot + prefix sums): millions of
+// unique pre-tokens would otherwise serialise on the two counters (5 ms for the 5 M words of the OWT-shaped GB).
 __global__ void __launch_bounds__(256) k_compact_short(const ulonglong2* keys, const i64* counts, i64 cap, WordTable W) {
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
-        ulonglong2 kv = keys[i];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (i64 base = (i64)blockIdx.x * blockDim.x; base < cap; base += stride) {     // warp-uniform trip count
+        const i64 i = base + threadIdx.x;
+        ulonglong2 kv; kv.x = 0; kv.y = 0;
+        if (i < cap) kv = keys[i];
+        const bool occ = kv.y != 0;
+        const int len = occ ? (int)(kv.x >> 56) : 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, occ);
         int32_t wid = -1;
-        if (kv.y != 0) {
-            int len = (int)(kv.x >> 56);
-            wid = (int32_t)atomicAdd((u64*)&W.counters[0], 1ULL);
-            i64 off = (i64)atomicAdd((u64*)&W.counters[1], (u64)len);
-            W.woff[wid] = off; W.wlen[wid] = len; W.wcnt[wid] = counts[i];
-            for (int k = 0; k < len; k++) {
-                int b = k < 7 ? (int)((kv.x >> (8 * k)) & 0xff) : (int)((kv.y >> (8 * (k - 7))) & 0xff);
-                W.wsym[off + k] = b; W.sym_word[off + k] = wid;
+        if (m) {
+            int inc = len;                                                          // inclusive prefix sum of the lengths
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            i64 wid0 = 0, off0 = 0;
+            if (lane == 0) { wid0 = (i64)atomicAdd((u64*)&W.counters[0], (u64)__popc(m)); off0 = (i64)atomicAdd((u64*)&W.counters[1], (u64)total); }
+            wid0 = __shfl_sync(0xffffffffu, wid0, 0); off0 = __shfl_sync(0xffffffffu, off0, 0);
+            if (occ) {
+                wid = (int32_t)(wid0 + __popc(m & ((1u << lane) - 1u)));
+                const i64 off = off0 + inc - len;
+                W.woff[wid] = off; W.wlen[wid] = len; W.wcnt[wid] = counts[i];
+                for (int k = 0; k < len; k++) {
+                    int b = k < 7 ? (int)((kv.x >> (8 * k)) & 0xff) : (int)((kv.y >> (8 * (k - 7))) & 0xff);
+                    W.wsym[off + k] = b; W.sym_word[off + k] = wid;
+                }
             }
         }
-        if (W.sword) W.sword[i] = wid;
+        if (W.sword && i < cap) W.sword[i] = wid;
     }
 }
 
+// long pre-tokens: every warp scans 32 entries at a time and copies the occupied ones with all its lanes
 __global__ void __launch_bounds__(256) k_compact_long(const LongEntry* ent, i64 cap, const uint8_t* text, WordTable W) {
-    __shared__ i64 sh_off; __shared__ int32_t sh_wid;
-    for (i64 i = blockIdx.x; i < cap; i += gridDim.x) {
-        LongEntry e = ent[i];
-        bool occ = e.h >= 2;
-        if (threadIdx.x == 0) {
-            sh_wid = -1;
-            if (occ) {
-                sh_wid = (int32_t)atomicAdd((u64*)&W.counters[0], 1ULL);
-                sh_off = (i64)atomicAdd((u64*)&W.counters[1], (u64)e.len);
-                W.woff[sh_wid] = sh_off; W.wlen[sh_wid] = (int32_t)e.len; W.wcnt[sh_wid] = e.count;
-            }
-            if (W.lword) W.lword[i] = sh_wid;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (i64 base = (i64)blockIdx.x * blockDim.x; base < cap; base += stride) {
+        const i64 i = base + threadIdx.x;
+        LongEntry e; e.h = 0; e.pos = 0; e.len = 0; e.count = 0;
+        if (i < cap) e = ent[i];
+        const bool occ = e.h >= 2;
+        uint32_t m = __ballot_sync(0xffffffffu, occ);
+        int32_t wid = -1;
+        while (m) {
+            const int src = __ffs(m) - 1; m &= m - 1;
+            const i64 len = __shfl_sync(0xffffffffu, e.len, src), pos = __shfl_sync(0xffffffffu, e.pos, src);
+            const i64 cnt = __shfl_sync(0xffffffffu, e.count, src);
+            i64 w0 = 0, off0 = 0;
+            if (lane == 0) { w0 = (i64)atomicAdd((u64*)&W.counters[0], 1ULL); off0 = (i64)atomicAdd((u64*)&W.counters[1], (u64)len); }
+            w0 = __shfl_sync(0xffffffffu, w0, 0); off0 = __shfl_sync(0xffffffffu, off0, 0);
+            if (lane == 0) { W.woff[w0] = off0; W.wlen[w0] = (int32_t)len; W.wcnt[w0] = cnt; }
+            for (i64 k = lane; k < len; k += 32) { W.wsym[off0 + k] = text[pos + k]; W.sym_word[off0 + k] = (int32_t)w0; }
+            if (lane == src) wid = (int32_t)w0;
         }
-        __syncthreads();
-        if (occ) {
-            i64 off = sh_off; int32_t wid = sh_wid;
-            for (i64 k = threadIdx.x; k < e.len; k += blockDim.x) { W.wsym[off + k] = text[e.pos + k]; W.sym_word[off + k] = wid; }
-        }
-        __syncthreads();
+        if (W.lword && i < cap) W.lword[i] = wid;
     }
 }
 

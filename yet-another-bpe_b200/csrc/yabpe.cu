@@ -323,15 +323,28 @@ __global__ void __launch_bounds__(256) k_encode_words_short(EncodeModel E, int32
         wlen[w] = encode_word_thread(E, wsym + woff[w], n);
     }
 }
+// Words longer than ENC_LONG_WORD symbols are rare: every block scans 256 word lengths at a time (coalesced) and only
+// enters the block-cooperative encoder for the ones it finds (a serial scan of millions of lengths per block cost
+// more than the encoding itself).
 __global__ void __launch_bounds__(256) k_encode_words_long(EncodeModel E, int32_t* wsym, int32_t* scratch, const i64* woff,
                                                             const int32_t* wlen_in, int32_t* wlen_out, i64 n_words) {
     __shared__ int sh_i[2 + 8]; __shared__ u64 sh_u;
-    for (i64 w = blockIdx.x; w < n_words; w += gridDim.x) {
-        int n = wlen_in[w];
-        if (n <= ENC_LONG_WORD) continue;
-        int r = encode_word_block(E, wsym + woff[w], scratch + woff[w], n, sh_i, &sh_u);
+    __shared__ int sh_long[256]; __shared__ int sh_nlong;
+    for (i64 base = (i64)blockIdx.x * 256; base < n_words; base += (i64)gridDim.x * 256) {
+        const i64 w = base + threadIdx.x;
+        const int n = w < n_words ? wlen_in[w] : 0;
+        if (threadIdx.x == 0) sh_nlong = 0;
         __syncthreads();
-        if (threadIdx.x == 0) wlen_out[w] = r;
+        if (n > ENC_LONG_WORD) sh_long[atomicAdd(&sh_nlong, 1)] = (int)threadIdx.x;
+        __syncthreads();
+        const int nl = sh_nlong;
+        for (int k = 0; k < nl; k++) {
+            const i64 wk = base + sh_long[k];
+            int r = encode_word_block(E, wsym + woff[wk], scratch + woff[wk], wlen_in[wk], sh_i, &sh_u);
+            __syncthreads();
+            if (threadIdx.x == 0) wlen_out[wk] = r;
+            __syncthreads();
+        }
         __syncthreads();
     }
 }
