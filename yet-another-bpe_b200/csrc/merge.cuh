@@ -27,9 +27,12 @@
 #define ML_TRACE 0            // > 0: thread 0 of CTA 0 writes a clock trace of leader merges [ML_TRACE, ML_TRACE + 8) to M.partial
 #endif
 #if ML_TRACE
+__device__ long long* g_trace_row = nullptr;
+#define ML_TRG(k) do { if (threadIdx.x == 0 && g_trace_row) g_trace_row[(k)] = clock64(); } while (0)
 #define ML_TR(k) do { if (threadIdx.x == 0 && m >= ML_TRACE && m < ML_TRACE + 8) ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + (k)] = clock64(); } while (0)
 #else
 #define ML_TR(k)
+#define ML_TRG(k)
 #endif
 #if ML_TIMING
 #define ML_CLOCK(v) long long v = clock64()
@@ -278,6 +281,12 @@ __device__ __forceinline__ Best shfl_best(const Best& v, int o) {
     Best r;
     r.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o); r.slot = __shfl_xor_sync(0xffffffffu, v.slot, o);
     r.a = __shfl_xor_sync(0xffffffffu, v.a, o); r.b = __shfl_xor_sync(0xffffffffu, v.b, o); r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ Best shfl_best_from(const Best& v, int src) {
+    Best r;
+    r.cnt = __shfl_sync(0xffffffffu, v.cnt, src); r.slot = __shfl_sync(0xffffffffu, v.slot, src);
+    r.a = __shfl_sync(0xffffffffu, v.a, src); r.b = __shfl_sync(0xffffffffu, v.b, src); r.pad = __shfl_sync(0xffffffffu, v.pad, src);
     return r;
 }
 __device__ Best block_best(const MergeParams& M, Best v, Best* sh) {
@@ -695,6 +704,7 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
         if (gl == 0) xm1 = carry_prev;
         carry_prev = __shfl_sync(0xffffffffu, x0, 7, 8);
         __syncwarp();
+        if (base == 0) ML_TRG(13);
         const bool valid = j < n;
         const bool sel0 = valid && x0 == a && x1 == b;
         const bool rem0 = valid && xm1 == a && x0 == b;
@@ -703,6 +713,7 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
         const unsigned keepmask = (__ballot_sync(0xffffffffu, keep) >> gshift) & 0xffu;
         any |= ((__ballot_sync(0xffffffffu, sel0) >> gshift) & 0xffu) != 0;
         if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, ps0, f, lm);
+        if (base == 0) ML_TRG(14);
         int32_t nslot = ps0; bool has_pair = false;
         if (keep) {
             const int jn = sel0 ? j + 2 : j + 1;
@@ -714,6 +725,7 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
             }
         }
         __syncwarp();
+        if (base == 0) ML_TRG(15);
         if (keep) {
             const int ni = out + __popc(keepmask & ((1u << gl) - 1));
             if (ni != j || sel0) s[ni] = sel0 ? c : x0;           // untouched prefix of the word: nothing to store
@@ -1030,6 +1042,27 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
             if (ncand == 1) best = sh_cand[0];
             else if (ncand <= 32) {                     // ties: byte-wise comparison, every warp redundantly (no barrier)
                 Best t = lane < ncand ? sh_cand[lane] : Best{0, -1, 0, 0, 0};
+                // fast path: lexicographic maximum of (prefix of a, prefix of b) with four redux.sync rounds.  Different
+                // prefixes order the tokens; equal prefixes decide only when the tokens themselves are equal.
+                {
+                    bool alive = lane < ncand;
+                    const u64 pa = alive ? C.tpa[t.pad] : 0ULL, pb = alive ? C.tpb[t.pad] : 0ULL;
+                    uint32_t wv = (uint32_t)(pa >> 32), mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+                    wv = (uint32_t)pa; mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+                    const uint32_t amax = __reduce_max_sync(0xffffffffu, alive ? (uint32_t)t.a : 0u);
+                    const uint32_t amin = __reduce_min_sync(0xffffffffu, alive ? (uint32_t)t.a : 0xffffffffu);
+                    if (amax == amin) {                                  // every survivor has the SAME left token: the right one decides
+                        wv = (uint32_t)(pb >> 32); mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+                        wv = (uint32_t)pb; mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+                        const uint32_t am = __ballot_sync(0xffffffffu, alive);
+                        if (__popc(am) == 1) {
+                            const int src = __ffs(am) - 1;
+                            t = shfl_best_from(t, src);
+                            best = t;
+                        }
+                    }
+                }
+                if (best.slot < 0) {
                 for (int o = 16; o > 0; o >>= 1) {
                     Best u = shfl_best(t, o);
                     u.pad = __shfl_xor_sync(0xffffffffu, t.pad, o);
@@ -1043,6 +1076,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                     if (gt) t = u;
                 }
                 best = t;
+                }
             } else {
                 __syncthreads();
                 best = block_best(M, (mine.slot >= 0 && mine.cnt == mx) ? mine : Best{0, -1, 0, 0, 0}, sh_best);
@@ -1099,6 +1133,9 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
                 if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
                 ML_TACC(0, q);
                 if (base == 0) ML_TR(5);
+#if ML_TRACE
+                if (threadIdx.x == 0) g_trace_row = (base == 0 && m >= ML_TRACE && m < ML_TRACE + 8) ? &((long long*)M.bsum)[512 + (m - ML_TRACE) * 24] : nullptr;
+#endif
                 if (a != b) rewrite_words_g8(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
                 else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new);
                 if (base == 0) ML_TR(6);

@@ -324,7 +324,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
             tr = bsum[512:512 + 8 * 24].cpu().numpy().reshape(8, 24)
             for row in tr:
                 base = row[0]
-                print('[trace]', [int(x - base) for x in row[:10]], 'items', int(row[10]), 'rewritten', int(row[11]), 'new pairs', int(row[12]), flush=True)
+                print('[trace]', [int(x - base) for x in row[:10]], 'g8', [int(x - base) for x in row[13:16]], 'items', int(row[10]), 'rewritten', int(row[11]), 'new pairs', int(row[12]), flush=True)
         if timing is not None:
             timing["merge_loop_ms"] = t0.elapsed_time(t1)
         err = int(st[_ffi.MS_ERROR])
