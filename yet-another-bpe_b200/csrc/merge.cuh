@@ -469,8 +469,10 @@ struct LeaderCtx {
     LeaderMirror LM;
     int32_t tslot[ML_TOP_N]; u64 tkey[ML_TOP_N];
     u64 tpa[ML_TOP_N], tpb[ML_TOP_N];            // 8-byte prefixes of the two tokens of every entry (tie-break without global loads)
+    u64 tha[ML_TOP_N], thb[ML_TOP_N], tpwb[ML_TOP_N];   // hash(a), hash(b), base^len(b): the merged token's hash without a round trip
     int32_t dedupe[ML_DEDUPE_N];                 // word + 1: candidate words already taken by the current merge (0 = free)
     int32_t newp[ML_NEWP_N];                     // slots of the pairs created by the current merge (spill: M.newp)
+    u64 newp_key[ML_NEWP_N];                     // and their keys (tokens known without waiting for the table)
     int top_n, top_ovf, act_n, alog_n, npairs_new, error, nnew;
     int32_t cur_slot;                            // pair-table slot of the pair being merged
 };
@@ -523,7 +525,7 @@ __device__ __forceinline__ int32_t pair_add(const MergeParams& M, int32_t x, int
             const u64 k = atomicCAS(&M.pkey[slot], 0ULL, key);
             if (k == 0) {
                 const int idx = atomicAdd(&lc->nnew, 1);
-                if (idx < ML_NEWP_N) lc->newp[idx] = (int32_t)slot; else M.newp[idx - ML_NEWP_N] = (int32_t)slot;
+                if (idx < ML_NEWP_N) { lc->newp[idx] = (int32_t)slot; lc->newp_key[idx] = key; } else M.newp[idx - ML_NEWP_N] = (int32_t)slot;
                 break;
             }
             if (k == key) break;
@@ -564,8 +566,11 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
     const int n = lc->nnew;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int32_t s = i < ML_NEWP_N ? lc->newp[i] : M.newp[i - ML_NEWP_N];
+        const u64 key = i < ML_NEWP_N ? lc->newp_key[i] : __ldcg(&M.pkey[s]);
+        const int32_t ka = (int32_t)((key >> 32) & 0x7fffffff), kb = (int32_t)(key & 0xffffffffu);
+        // one round trip: the count and (speculatively, most new pairs stay below T2) the token data of a top-list entry
         const i64 cnt = __ldcg(&M.pcnt[s]);
-        const u64 key = __ldcg(&M.pkey[s]);
+        const u64 pre_a = M.tok_pre[ka], pre_b = M.tok_pre[kb], h_a = M.tok_hash[ka], h_b = M.tok_hash[kb], pw_b = M.tok_pow[kb];
         if (cnt < T) continue;
         const uint32_t bit = 1u << (s & 31);
         atomicOr(&M.inact[s >> 5], bit);
@@ -576,7 +581,7 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
                 atomicOr(&M.intop[s >> 5], bit);
                 M.top_slot[idx] = s; M.top_key[idx] = key;
                 lc->tslot[idx] = s; lc->tkey[idx] = key; mirror_set(&lc->LM, idx, cnt);
-                lc->tpa[idx] = M.tok_pre[(int32_t)((key >> 32) & 0x7fffffff)]; lc->tpb[idx] = M.tok_pre[(int32_t)(key & 0xffffffffu)];
+                lc->tpa[idx] = pre_a; lc->tpb[idx] = pre_b; lc->tha[idx] = h_a; lc->thb[idx] = h_b; lc->tpwb[idx] = pw_b;
                 mirror_insert(&lc->LM, s, idx);
             } else lc->top_ovf = 1;
         }
@@ -796,6 +801,34 @@ __device__ int32_t lookup_merged(const MergeParams& M, int32_t a, int32_t b, int
     }
 }
 
+// leader mode: the hash of the merged bytes comes from the top-list entry (shared memory), so the token-set probe and
+// the loads the commit needs (offsets, base^len(a)) are ONE round trip instead of two
+__device__ int32_t lookup_merged_leader(const MergeParams& M, const LeaderCtx& C, int idx, int32_t a, int32_t b, int32_t n_tok, MergedInfo* info) {
+    const u64 H = C.tha[idx] * C.tpwb[idx] + C.thb[idx];
+    const u64 mask = (u64)M.tset_cap - 1;
+    u64 slot = mix64(H) & mask;
+    u64 e = *(volatile u64*)&M.tset[slot];
+    const i64 oa = M.tok_off[a], oa1 = M.tok_off[a + 1], ob = M.tok_off[b], ob1 = M.tok_off[b + 1];
+    const u64 pa_ = M.tok_pow[a];
+    const i64 la = oa1 - oa, lb = ob1 - ob;
+    info->H = H; info->P = pa_ * C.tpwb[idx]; info->oa = oa; info->ob = ob; info->la = la; info->lb = lb;
+    for (;;) {
+        if (e == 0) { info->tslot = (i64)slot; return n_tok; }
+        int32_t id = (int32_t)(e & 0xffffffffu) - 1;
+        if ((e >> 32) == (H >> 32) && id < n_tok && M.tok_hash[id] == H && M.tok_off[id + 1] - M.tok_off[id] == la + lb) {
+            const uint8_t* pc = M.tok_bytes + M.tok_off[id];
+            const uint8_t* pa = M.tok_bytes + oa;
+            const uint8_t* pb = M.tok_bytes + ob;
+            bool eq = true;
+            for (i64 k = 0; k < la && eq; k++) eq = pc[k] == pa[k];
+            for (i64 k = 0; k < lb && eq; k++) eq = pc[la + k] == pb[k];
+            if (eq) return id;
+        }
+        slot = (slot + 1) & mask;
+        e = *(volatile u64*)&M.tset[slot];
+    }
+}
+
 // record merge m and (when the bytes are new) create token c; executed by ONE block
 __device__ void commit_merge(const MergeParams& M, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 alog_start) {
     if (threadIdx.x == 0) {
@@ -934,11 +967,10 @@ __device__ __forceinline__ i64 warp_max_i64(i64 v) {
 //   C  the last warp records the merge / creates the token while every other 8-lane group takes ONE candidate
 //      item, claims its word in a shared-memory set (no global stamp), loads the word and rewrites it
 //   D  thread 0 closes the merge's affected-log segment (plain stores; all counters are in shared memory)
-__device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin, const i64 T2) {
+__device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i64 T, i64 Tmin, const i64 T2) {
     __shared__ Ranges R;
     __shared__ int32_t sh_c;
     __shared__ MergedInfo MI;
-    __shared__ LeaderCtx C;
     __shared__ i64 sh_wmax[ML_THREADS / 32];    // stage A: per-warp maximum count
 #if ML_BATCH_STATS
     __shared__ u64 sh_selkeys[32 * ML_SEL];
@@ -995,7 +1027,9 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
             if ((int)threadIdx.x >= cached && C.LM.pending[threadIdx.x]) {   // entry without a mirrored count yet
                 mirror_set(&C.LM, threadIdx.x, __ldcg(&M.pcnt[sl]));
                 mirror_insert(&C.LM, sl, threadIdx.x);
-                C.tpa[threadIdx.x] = M.tok_pre[(int32_t)((k >> 32) & 0x7fffffff)]; C.tpb[threadIdx.x] = M.tok_pre[(int32_t)(k & 0xffffffffu)];
+                const int32_t ka = (int32_t)((k >> 32) & 0x7fffffff), kb = (int32_t)(k & 0xffffffffu);
+                C.tpa[threadIdx.x] = M.tok_pre[ka]; C.tpb[threadIdx.x] = M.tok_pre[kb];
+                C.tha[threadIdx.x] = M.tok_hash[ka]; C.thb[threadIdx.x] = M.tok_hash[kb]; C.tpwb[threadIdx.x] = M.tok_pow[kb];
             }
             const i64 cnt = mirror_get(&C.LM, threadIdx.x);
             if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
@@ -1080,6 +1114,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
             } else {
                 __syncthreads();
                 best = block_best(M, (mine.slot >= 0 && mine.cnt == mx) ? mine : Best{0, -1, 0, 0, 0}, sh_best);
+                if (best.slot >= 0) best.pad = mirror_find(&C.LM, best.slot);      // block_best does not carry the list index
             }
         }
         if (best.slot < 0 || best.cnt < T2) { reason = LR_TOP; break; }
@@ -1088,7 +1123,7 @@ __device__ void leader_loop(const MergeParams& M, Best* sh_best, i64 T, i64 Tmin
         ML_TR(1);
         // ---- B: candidate ranges + merged token
         if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R); C.cur_slot = best.slot; }
-        if (threadIdx.x == 32) sh_c = lookup_merged(M, best.a, best.b, n_tok, &MI);
+        if (threadIdx.x == 32) sh_c = lookup_merged_leader(M, C, best.pad, best.a, best.b, n_tok, &MI);
         for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
         if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
@@ -1252,6 +1287,9 @@ __device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* s
     return true;
 }
 
+extern __shared__ __align__(16) unsigned char ml_dyn_smem[];      // LeaderCtx (used by CTA 0 in leader mode)
+#define ML_DYN_SMEM_BYTES ((int)sizeof(LeaderCtx))
+
 __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     __shared__ Best sh_best[ML_THREADS / 32];
     __shared__ i64 sh_scan[1 + ML_THREADS / 32];
@@ -1311,7 +1349,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             const i64 m0 = m;
             grid_barrier(M);                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
-                leader_loop(M, sh_best, T, Tmin, T2);
+                leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
             } else {

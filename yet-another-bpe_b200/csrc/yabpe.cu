@@ -297,14 +297,19 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
     M.num_merges = m->num_merges; M.min_freq = m->min_frequency; M.rebuild_every = m->rebuild_every;
 
+    static bool ml_attr_set = false;
+    if (!ml_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_DYN_SMEM_BYTES));
+        ml_attr_set = true;
+    }
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, ML_DYN_SMEM_BYTES));
     ARG_CHECK(per_sm >= 1);
     per_sm = 1;
     int grid = num_sms() * per_sm;
     if (grid > 1024) grid = 1024;
     void* args[] = {&M};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(grid), dim3(ML_THREADS), args, 0, st)); LAUNCHED();
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(grid), dim3(ML_THREADS), args, ML_DYN_SMEM_BYTES, st)); LAUNCHED();
     return YABPE_OK;
 }
 
