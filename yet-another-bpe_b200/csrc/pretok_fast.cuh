@@ -1,4 +1,4 @@
-// pretok_fast.cuh -- warp-autonomous pre-tokenise + count kernel (trainer mode, interior text).
+// pretok_fast.cuh -- warp-autonomous pre-tokenise + count kernel (trainer and encode mode, interior text).
 //
 // Same contract as k_pretok_count (pretok.cuh): replaces /root/reference/src/yet_another_bpe/
 // trainer.py:146-170 (regex.findall of the GPT-2 pattern) + trainer.py:221-225 (word_freq).
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     __syncthreads();
 
     u64 my_us = 0, my_ul = 0, my_ub = 0;
-    uint32_t my_tok = 0, my_miss = 0;              // warp-uniform
+    uint32_t my_tok = 0, my_miss = 0, n_special = 0;   // warp-uniform
     int lqn = 0;
     uint32_t phase0 = 0, phase1 = 0;
     const i64 stepA = (i64)gridDim.x * PW_WARPS * PW_CH, endA = c_hi * PW_CH;
@@ -202,6 +202,11 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             const int k = base + lane;
             int s = 0, len = 0;
             if (k < total) { s = W.tokpos[k]; len = (int)W.tokpos[k + 1] - s; }      // sentinel 0xFFFF: len > 14
+            if (P.mode == 1 && P.n_sp > 0) {             // encode: a recognised special is a separator, not a word
+                const bool is_sp = k < total && ((W.recw[buf][(s >> 5) + 4] >> (s & 31)) & 1u);
+                if (is_sp) len = 0;                      // neither short nor long below (length 0 is ignored by the long queue)
+                n_special += __popc(__ballot_sync(0xffffffffu, is_sp));
+            }
             uint32_t kx = 0, ky = 0, kz = 0, kw = 0, h = 0;
             bool miss = false;
             const bool is_short = (unsigned)(len - 1) < (unsigned)PT_SHORT_MAX;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             }
             my_miss += __popc(__ballot_sync(0xffffffffu, miss));
             // long (15 bytes .. one chunk) and over-long pre-tokens
-            const bool is_long = k < total && !is_short;
+            const bool is_long = k < total && !is_short && len > 0;
             const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
             if (lm) {
                 if (is_long) {
@@ -282,10 +287,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         my_ul += __shfl_xor_sync(0xffffffffu, my_ul, o); my_ub += __shfl_xor_sync(0xffffffffu, my_ub, o);
     }
     if (lane == 0) {
-        if (my_tok) atomicAdd((u64*)&P.stats[ST_NTOK], (u64)my_tok);
+        if (my_tok > n_special) atomicAdd((u64*)&P.stats[ST_NTOK], (u64)(my_tok - n_special));
         if (my_us) atomicAdd((u64*)&P.stats[ST_UNIQ_SHORT], my_us);
         if (my_ul) atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], my_ul);
         if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
-        if (my_tok > my_miss) atomicAdd((u64*)&P.stats[ST_CACHE_HIT], (u64)(my_tok - my_miss));
+        if (my_tok > my_miss + n_special) atomicAdd((u64*)&P.stats[ST_CACHE_HIT], (u64)(my_tok - my_miss - n_special));
     }
 }

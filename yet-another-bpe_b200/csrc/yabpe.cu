@@ -171,11 +171,11 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pretok_count, PT_THREADS, PT_CACHE_BYTES));
         if (per_sm < 1) per_sm = 1;
-        // Trainer mode, interior text: the warp-autonomous kernel; it leaves the chunks that touch a hard cut,
+        // Interior text: the warp-autonomous kernel; it leaves the chunks that touch a hard cut,
         // the ends of the text or the edge of the owned range in P.work for the generic kernel (list mode).
         // Dense cuts (tiny reference chunk sizes) or a missing work list: the generic kernel does everything.
         const i64 c_lo = P.own_lo / PW_CH, c_hi = (P.own_hi - 1) / PW_CH + 1;
-        const bool warp_path = a->mode == 0 && !(stages & 8) && P.work && P.work_cap >= 4 * (i64)P.n_cuts + 16 &&
+        const bool warp_path = !(stages & 8) && P.work && P.work_cap >= 4 * (i64)P.n_cuts + 16 &&
                                c_hi - c_lo >= 4 && 8 * (i64)P.n_cuts < c_hi - c_lo;
         if (warp_path) {
             i64 grid_w = (c_hi - c_lo + PW_WARPS - 1) / PW_WARPS;
