@@ -189,6 +189,12 @@ typedef struct {
 
 int yabpe_encode_words(const yabpe_encode_model* e, const yabpe_word_table* w, int64_t n_words, void* stream);
 
+/* Between yabpe_encode_words and yabpe_encode_ids: turns the encoded symbols into vocabulary ids in place and
+ * overwrites the occurrence count of every table slot (short_counts[], long_entries[].count) with the lookup
+ * record of its word (first id slot << 24 | number of ids).  Needs w->sword / w->lword.  Call exactly once. */
+int yabpe_encode_finalize(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
+                          int64_t n_words, void* stream);
+
 typedef struct {
     int64_t* tile_count;        /* device, n_tiles + 1                                            */
     int32_t* out_ids; int64_t out_cap;

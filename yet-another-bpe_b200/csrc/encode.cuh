@@ -153,7 +153,7 @@ template <bool WRITE>
 __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, EncodeModel E, EncodeOut O) {
     __shared__ TileSmem S;
     __shared__ i64 sh_min; __shared__ u64 sh_acc; __shared__ i64 sh[4];
-    __shared__ int sh_ovf_k; __shared__ int sh_ovf_w;
+    __shared__ int sh_ovf_k; __shared__ i64 sh_ovf_w;      // sh_ovf_w: lookup record (first id slot << 24 | id count) or -1
     __shared__ i64 sh_base;
     init_tile_smem(S);
     const int tid = threadIdx.x;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
                 u64 h = block_long_hash(P.text, gpos, e - gpos, &sh_acc);
                 int created;
                 i64 slot = block_long_upsert(P.lent, P.lcap, P.text, h, gpos, e - gpos, 0, true, &created, sh);
-                if (tid == 0) { sh_ovf_k = k; sh_ovf_w = slot >= 0 ? O.lword[slot] : -1; }
+                if (tid == 0) { sh_ovf_k = k; sh_ovf_w = slot >= 0 ? P.lent[slot].count : -1; }
             }
             __syncthreads();
         }
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
         i64 running = 0;       // ids emitted by earlier rounds of this tile
         for (int kbase = 0; kbase < ntok; kbase += PT_THREADS) {
             int k = kbase + tid;
-            int cnt = 0; int32_t wid = -1; int32_t spid = -1;
+            int cnt = 0; i64 info = -1; int32_t spid = -1;       // info: lookup record written by k_encode_finalize
             int s = 0; i64 gpos = 0; bool live = false;
             if (k < ntok) {
                 s = S.tokpos[k]; gpos = g0 + s;
@@ -205,23 +205,22 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
                     spid = sp >= 0 ? E.sp_ids[sp] : -1;
                     cnt = spid >= 0 ? 1 : 0;
                 } else if (k == sh_ovf_k) {
-                    wid = sh_ovf_w;
-                    cnt = wid >= 0 ? O.wlen[wid] : 0;
+                    info = sh_ovf_w;
+                    cnt = info >= 0 ? (int)(info & 0xffffff) : 0;
                 } else {
                     int len = (int)S.tokpos[k + 1] - s;
                     if (len <= PT_SHORT_MAX) {
                         u64 k0, k1;
                         pack_short_key(txt, s, len, &k0, &k1);
-                        i64 slot = short_find(P.skeys, P.scap, k0, k1);
-                        wid = slot >= 0 ? O.sword[slot] : -1;
+                        info = short_find_info(P.skeys, P.scounts, P.scap, k0, k1);      // key and record in one round trip
                     } else {
                         u64 h = 0;
                         for (int j = 0; j < len; j++) h += long_hash_term(txt[s + j], j);
                         i64 slot = long_find(P.lent, P.lcap, P.text, long_hash_fix(h), gpos, len);
-                        wid = slot >= 0 ? O.lword[slot] : -1;
+                        info = slot >= 0 ? P.lent[slot].count : -1;
                     }
-                    cnt = wid >= 0 ? O.wlen[wid] : 0;
-                    if (wid < 0) P.stats[ST_TABLE_FULL] = 2;     // cannot happen: every token was inserted in step 1
+                    cnt = info >= 0 ? (int)(info & 0xffffff) : 0;
+                    if (info < 0) P.stats[ST_TABLE_FULL] = 2;    // cannot happen: every token was inserted in step 1
                 }
             }
             int total;
@@ -234,15 +233,38 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
                     if (lo < P.n_cuts && P.cuts[lo] == gpos) O.doc_off[lo + 1] = dst;
                 }
                 if (spid >= 0) { if (dst < O.out_cap) O.out_ids[dst] = spid; }
-                else if (wid >= 0) {
-                    const int32_t* src = O.wsym + O.woff[wid];
-                    for (int j = 0; j < cnt; j++) if (dst + j < O.out_cap) O.out_ids[dst + j] = E.sym_out[src[j]];
+                else if (info >= 0) {
+                    const int32_t* src = O.wsym + (info >> 24);           // already vocabulary ids (k_encode_finalize)
+                    for (int j = 0; j < cnt; j++) if (dst + j < O.out_cap) O.out_ids[dst + j] = src[j];
                 }
             }
             running += total;
         }
         if (!WRITE && tid == 0) O.tile_count[tile] = running;
         __syncthreads();
+    }
+}
+
+// After the unique words are encoded: (1) symbols -> vocabulary ids in place, (2) every table slot gets the lookup
+// record of its word (first id slot << 24 | id count) where the occurrence count used to be (not needed any more), so
+// that the two tile passes go from a token to its ids with ONE probe instead of slot -> word -> length / offset.
+__global__ void __launch_bounds__(256) k_encode_finalize_ids(EncodeModel E, int32_t* wsym, const i64* woff, const int32_t* wlen, i64 n_words) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        int32_t* s = wsym + woff[w];
+        const int n = wlen[w];
+        for (int j = 0; j < n; j++) s[j] = E.sym_out[s[j]];
+    }
+}
+__global__ void __launch_bounds__(256) k_encode_finalize_slots(i64* scounts, i64 scap, const int32_t* sword, LongEntry* lent, i64 lcap,
+                                                               const int32_t* lword, const i64* woff, const int32_t* wlen) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < scap + lcap; i += stride) {
+        const bool is_short = i < scap;
+        const int32_t wid = is_short ? sword[i] : lword[i - scap];
+        if (wid < 0) continue;
+        const i64 info = (woff[wid] << 24) | (i64)wlen[wid];
+        if (is_short) scounts[i] = info; else lent[i - scap].count = info;
     }
 }
 

@@ -285,6 +285,20 @@ __device__ __forceinline__ i64 short_find(const ulonglong2* keys, i64 cap, u64 k
     return -1;
 }
 
+// lookup of the per-slot record (encode passes after k_encode_finalize): key and record are loaded together
+__device__ __forceinline__ i64 short_find_info(const ulonglong2* keys, const i64* infos, i64 cap, u64 k0, u64 k1) {
+    u64 mask = (u64)cap - 1;
+    u64 slot = short_hash(k0, k1) & mask;
+    for (int probe = 0; probe < 8192; probe++) {
+        const ulonglong2 kv = keys[slot];
+        const i64 info = infos[slot];
+        if (kv.x == k0 && kv.y == k1) return info;
+        if (kv.x == 0) return -1;
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
+
 __device__ __forceinline__ u64 long_hash_fix(u64 h) { return h < 2 ? h + 2 : h; }
 
 __device__ bool text_equal(const uint8_t* text, i64 a, i64 b, i64 len) {

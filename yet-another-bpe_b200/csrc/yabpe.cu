@@ -367,6 +367,20 @@ extern "C" int yabpe_encode_words(const yabpe_encode_model* e, const yabpe_word_
     return YABPE_OK;
 }
 
+extern "C" int yabpe_encode_finalize(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
+                                     int64_t n_words, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(a && e && w && n_words >= 0 && w->sword && w->lword);
+    ARG_CHECK(a->short_cap > 0 && a->long_cap > 0);
+    if (n_words == 0) return YABPE_OK;
+    EncodeModel E = make_model(e);
+    k_encode_finalize_ids<<<num_sms() * 8, 256, 0, st>>>(E, w->wsym, (const i64*)w->woff, w->wlen, n_words); LAUNCHED();
+    k_encode_finalize_slots<<<num_sms() * 8, 256, 0, st>>>((i64*)a->short_counts, a->short_cap, w->sword, (LongEntry*)a->long_entries,
+                                                          a->long_cap, w->lword, (const i64*)w->woff, w->wlen); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
 extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
                                 const yabpe_encode_out* o, int32_t pass, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

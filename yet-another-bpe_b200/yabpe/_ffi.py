@@ -24,7 +24,7 @@ INT64_MAX = (1 << 63) - 1
 EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
-    "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof",
+    "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize",
 ]
 
 
@@ -117,6 +117,8 @@ def load() -> C.CDLL:
     L.yabpe_merge_loop.argtypes = [C.POINTER(MergeArgs), C.c_void_p]
     L.yabpe_encode_words.restype = C.c_int
     L.yabpe_encode_words.argtypes = [C.POINTER(EncodeModel), C.POINTER(WordTable), C.c_int64, C.c_void_p]
+    L.yabpe_encode_finalize.restype = C.c_int
+    L.yabpe_encode_finalize.argtypes = [C.POINTER(PretokArgs), C.POINTER(EncodeModel), C.POINTER(WordTable), C.c_int64, C.c_void_p]
     L.yabpe_encode_ids.restype = C.c_int
     L.yabpe_encode_ids.argtypes = [C.POINTER(PretokArgs), C.POINTER(EncodeModel), C.POINTER(WordTable),
                                    C.POINTER(EncodeOut), C.c_int32, C.c_void_p]

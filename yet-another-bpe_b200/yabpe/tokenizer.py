@@ -133,6 +133,7 @@ class BBPETokenizer:
         words = engine.compact_words(torch, res, st, with_maps=True)
         stream = _ffi.stream_ptr(torch)
         _ffi.check(L.yabpe_encode_words(C.byref(e), C.byref(words.table), words.n_words, stream))
+        _ffi.check(L.yabpe_encode_finalize(C.byref(res.args), C.byref(e), C.byref(words.table), words.n_words, stream))
         mark()
         lo, hi = own if own is not None else (0, n)
         n_tiles = int(L.yabpe_num_tiles(lo, hi))
