@@ -88,8 +88,11 @@ typedef struct {
     int64_t own_lo, own_hi;     /* only pre-tokens starting in [own_lo, own_hi) are counted       */
     uint32_t* cand_bits;        /* device, (n + 63) / 32 words, zeroed; may be NULL when n_sp = 0 */
     uint32_t* rec_bits;         /* device, same size, zeroed: recognised special starts (output)  */
-    void* short_keys;           /* device, short_cap * 16 bytes, zeroed                           */
-    int64_t* short_counts;      /* device, short_cap, zeroed                                      */
+    void* short_keys;           /* device, zeroed.  short_counts != NULL: short_cap * 16 bytes of keys;      */
+                                /*   short_counts == NULL: 32-byte aligned, short_cap * 32 bytes, per slot      */
+                                /*   {key word 0, key word 1, count, reserved} (key and count in one sector:    */
+                                /*   for tables far larger than the L2)                                        */
+    int64_t* short_counts;      /* device, short_cap, zeroed -- or NULL for the interleaved layout */
     int64_t short_cap;          /* power of two                                                   */
     void* long_entries;         /* device, long_cap * 32 bytes, zeroed                            */
     int64_t long_cap;           /* power of two                                                   */
@@ -190,7 +193,7 @@ typedef struct {
 int yabpe_encode_words(const yabpe_encode_model* e, const yabpe_word_table* w, int64_t n_words, void* stream);
 
 /* Between yabpe_encode_words and yabpe_encode_ids: turns the encoded symbols into vocabulary ids in place and
- * overwrites the occurrence count of every table slot (short_counts[], long_entries[].count) with the lookup
+ * overwrites the occurrence count of every table slot (short table and long_entries[].count) with the lookup
  * record of its word (first id slot << 24 | number of ids).  Needs w->sword / w->lword.  Call exactly once. */
 int yabpe_encode_finalize(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
                           int64_t n_words, void* stream);

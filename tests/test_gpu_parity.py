@@ -198,6 +198,28 @@ def test_train_medium_corpus_vs_oracle_and_deterministic(yabpe, tmp_path):
     assert got1[0] == want[0]
 
 
+@pytest.mark.parametrize("layout", ["interleaved", "split"])
+def test_short_table_layouts(yabpe, tmp_path, monkeypatch, layout):
+    """The pre-token table has two layouts (32-byte {key, count} slots for DRAM-sized tables, separate key / count
+    arrays for small hot ones, chosen by capacity): every consumer -- counting, compaction, training, the multi-GPU
+    re-insert kernel's table, encode lookups -- must give the same results with either."""
+    monkeypatch.setenv("YABPE_SHORT_LAYOUT", layout)
+    rng = random.Random(7)
+    text = "".join(rng.choice(ALPHABET + [" the", " of", "ing", "\n"]) for _ in range(150_000)).encode("utf-8")
+    for sp, mode in (([], "train"), (["<|endoftext|>"], "train"), (["<|endoftext|>"], "encode")):
+        assert _device_counts(text, sp, mode=mode) == _oracle_counts(text, sp, mode=mode), (sp, mode)
+    data = common.synth_owt(1_000_000, seed=3)
+    p = tmp_path / "l.txt"
+    p.write_bytes(data)
+    assert yabpe.train_bpe(p, 1200, ["<|endoftext|>"]) == oracle.train_bpe(p, 1200, ["<|endoftext|>"], fast=True)
+    v, m = common.gpt2_vocab_and_merges()
+    t = yabpe.Tokenizer(v, m, ["<|endoftext|>"])
+    o = oracle.Tokenizer(v, m, ["<|endoftext|>"])
+    s = data[:300_000].decode("utf-8", errors="ignore")
+    assert t.encode(s) == o.encode(s)
+    assert t.encode_batch([s[:1000], "", s[1000:5000]]) == [o.encode(s[:1000]), [], o.encode(s[1000:5000])]
+
+
 def test_train_with_frequent_index_rebuilds(yabpe, tmp_path, monkeypatch):
     """The pair -> words index is rebuilt every `rebuild_every` merges (engine.rebuild_period); force a tiny period so
     that dozens of rebuilds (and leader exits for them) happen, and a zero period (rebuild only when the log is full)."""

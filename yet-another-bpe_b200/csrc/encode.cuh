@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
                     if (len <= PT_SHORT_MAX) {
                         u64 k0, k1;
                         pack_short_key(txt, s, len, &k0, &k1);
-                        info = short_find_info(P.skeys, P.scounts, P.scap, k0, k1);      // key and record in one round trip
+                        info = short_find_info(P.st, k0, k1);      // key and record in one round trip
                     } else {
                         u64 h = 0;
                         for (int j = 0; j < len; j++) h += long_hash_term(txt[s + j], j);
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_encode_finalize_ids(EncodeModel E, int3
         for (int j = 0; j < n; j++) s[j] = E.sym_out[s[j]];
     }
 }
-__global__ void __launch_bounds__(256) k_encode_finalize_slots(i64* scounts, i64 scap, const int32_t* sword, LongEntry* lent, i64 lcap,
+__global__ void __launch_bounds__(256) k_encode_finalize_slots(ShortTab st, i64 scap, const int32_t* sword, LongEntry* lent, i64 lcap,
                                                                const int32_t* lword, const i64* woff, const int32_t* wlen) {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < scap + lcap; i += stride) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) k_encode_finalize_slots(i64* scounts, i64
         const int32_t wid = is_short ? sword[i] : lword[i - scap];
         if (wid < 0) continue;
         const i64 info = (woff[wid] << 24) | (i64)wlen[wid];
-        if (is_short) scounts[i] = info; else lent[i - scap].count = info;
+        if (is_short) *st.cnt((u64)i) = info; else lent[i - scap].count = info;
     }
 }
 

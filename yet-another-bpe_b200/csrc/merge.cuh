@@ -88,13 +88,14 @@ struct WordTable {
 
 // Word ids and symbol offsets are handed out with ONE pair of atomics per warp (ballot + prefix sums): millions of
 // unique pre-tokens would otherwise serialise on the two counters (5 ms for the 5 M words of the OWT-shaped GB).
-__global__ void __launch_bounds__(256) k_compact_short(const ulonglong2* keys, const i64* counts, i64 cap, WordTable W) {
+__global__ void __launch_bounds__(256) k_compact_short(const ShortTab ST, i64 cap, WordTable W) {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     for (i64 base = (i64)blockIdx.x * blockDim.x; base < cap; base += stride) {     // warp-uniform trip count
         const i64 i = base + threadIdx.x;
         ulonglong2 kv; kv.x = 0; kv.y = 0;
-        if (i < cap) kv = keys[i];
+        i64 occ_count = 0;
+        if (i < cap) { kv = *(const ulonglong2*)ST.key((u64)i); occ_count = *ST.cnt((u64)i); }
         const bool occ = kv.y != 0;
         const int len = occ ? (int)(kv.x >> 56) : 0;
         const uint32_t m = __ballot_sync(0xffffffffu, occ);
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) k_compact_short(const ulonglong2* keys, c
             if (occ) {
                 wid = (int32_t)(wid0 + __popc(m & ((1u << lane) - 1u)));
                 const i64 off = off0 + inc - len;
-                W.woff[wid] = off; W.wlen[wid] = len; W.wcnt[wid] = counts[i];
+                W.woff[wid] = off; W.wlen[wid] = len; W.wcnt[wid] = occ_count;
                 for (int k = 0; k < len; k++) {
                     int b = k < 7 ? (int)((kv.x >> (8 * k)) & 0xff) : (int)((kv.y >> (8 * (k - 7))) & 0xff);
                     W.wsym[off + k] = b; W.sym_word[off + k] = wid;

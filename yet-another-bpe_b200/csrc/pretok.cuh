@@ -42,6 +42,16 @@
 #define ST_CACHE_HIT 10    // warp kernel: pre-tokens counted in the shared-memory cache (diagnostic)
 
 struct LongEntry { u64 h; i64 pos; i64 len; i64 count; };
+// Short table.  Two layouts behind one accessor pair:
+//   interleaved (32-byte slots {k0, k1, count, -}): a probe and the count update that follows it touch ONE DRAM sector --
+//               for tables far larger than the L2 (millions of unique pre-tokens)
+//   split       (16-byte keys, 8-byte counts in separate arrays): the key lines stay read-only, so probes of hot words
+//               do not queue behind the count atomics of the same sector -- for small, heavily contended tables
+struct ShortTab {
+    char* kb; char* cb; int ks, cs; i64 cap;
+    __device__ __forceinline__ u64* key(u64 slot) const { return (u64*)(kb + slot * (u64)ks); }
+    __device__ __forceinline__ i64* cnt(u64 slot) const { return (i64*)(cb + slot * (u64)cs); }
+};
 
 struct PretokParams {
     const uint8_t* text; i64 n;
@@ -49,7 +59,7 @@ struct PretokParams {
     int mode; int n_sp;
     i64 own_lo, own_hi;
     uint32_t* cand; uint32_t* rec;
-    ulonglong2* skeys; i64* scounts; i64 scap;
+    ShortTab st; i64 scap;
     LongEntry* lent; i64 lcap;
     i64* ovf_pos; i64 ovf_cap;
     i64* stats;
@@ -225,27 +235,27 @@ __device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) {
 }
 
 // returns slot (>=0) and adds `add` to its count; *created = 1 when this call created the entry
-__device__ __forceinline__ i64 short_insert_h(ulonglong2* keys, i64* counts, i64 cap, u64 h, u64 k0, u64 k1, i64 add, int* created) {
-    u64 mask = (u64)cap - 1;
+__device__ __forceinline__ i64 short_insert_h(const ShortTab& T, u64 h, u64 k0, u64 k1, i64 add, int* created) {
+    u64 mask = (u64)T.cap - 1;
     u64 slot = h & mask;
     *created = 0;
 #pragma unroll 1
     for (int probe = 0; probe < 8192; probe++) {
-        u64* kp = (u64*)&keys[slot];
+        u64* kp = T.key(slot);
         u64 c0 = *(volatile u64*)kp;
         if (c0 == 0) { c0 = atomicCAS(kp, 0ULL, k0); if (c0 == 0) c0 = k0; }
         if (c0 == k0) {
             u64 c1 = *(volatile u64*)(kp + 1);
             if (c1 == 0) { c1 = atomicCAS(kp + 1, 0ULL, k1); if (c1 == 0) { c1 = k1; *created = 1; } }
-            if (c1 == k1) { atomicAdd((u64*)&counts[slot], (u64)add); return (i64)slot; }
+            if (c1 == k1) { atomicAdd((u64*)T.cnt(slot), (u64)add); return (i64)slot; }
         }
         slot = (slot + 1) & mask;
     }
     return -1;
 }
 
-__device__ __forceinline__ i64 short_insert(ulonglong2* keys, i64* counts, i64 cap, u64 k0, u64 k1, i64 add, int* created) {
-    return short_insert_h(keys, counts, cap, short_hash(k0, k1), k0, k1, add, created);
+__device__ __forceinline__ i64 short_insert(const ShortTab& T, u64 k0, u64 k1, i64 add, int* created) {
+    return short_insert_h(T, short_hash(k0, k1), k0, k1, add, created);
 }
 
 // Per-CTA pre-aggregation cache in shared memory: hot pre-tokens (Zipf head) are counted with
@@ -273,11 +283,11 @@ __device__ __forceinline__ bool cache_add(u64* ck0, u64* ck1, uint32_t* cc, u64 
 }
 
 // read-only lookup (encode passes); -1 when absent
-__device__ __forceinline__ i64 short_find(const ulonglong2* keys, i64 cap, u64 k0, u64 k1) {
-    u64 mask = (u64)cap - 1;
+__device__ __forceinline__ i64 short_find(const ShortTab& T, u64 k0, u64 k1) {
+    u64 mask = (u64)T.cap - 1;
     u64 slot = short_hash(k0, k1) & mask;
     for (int probe = 0; probe < 8192; probe++) {
-        ulonglong2 kv = keys[slot];
+        const ulonglong2 kv = *(const ulonglong2*)T.key(slot);
         if (kv.x == k0 && kv.y == k1) return (i64)slot;
         if (kv.x == 0) return -1;
         slot = (slot + 1) & mask;
@@ -285,13 +295,13 @@ __device__ __forceinline__ i64 short_find(const ulonglong2* keys, i64 cap, u64 k
     return -1;
 }
 
-// lookup of the per-slot record (encode passes after k_encode_finalize): key and record are loaded together
-__device__ __forceinline__ i64 short_find_info(const ulonglong2* keys, const i64* infos, i64 cap, u64 k0, u64 k1) {
-    u64 mask = (u64)cap - 1;
+// lookup of the per-slot record (encode passes after k_encode_finalize): key and record sit in the same sector
+__device__ __forceinline__ i64 short_find_info(const ShortTab& T, u64 k0, u64 k1) {
+    u64 mask = (u64)T.cap - 1;
     u64 slot = short_hash(k0, k1) & mask;
     for (int probe = 0; probe < 8192; probe++) {
-        const ulonglong2 kv = keys[slot];
-        const i64 info = infos[slot];
+        const ulonglong2 kv = *(const ulonglong2*)T.key(slot);
+        const i64 info = *T.cnt(slot);
         if (kv.x == k0 && kv.y == k1) return info;
         if (kv.x == 0) return -1;
         slot = (slot + 1) & mask;
@@ -935,7 +945,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS) k_pretok_count(Pret
                         for (int i = 0; i < PT_MAXMISS; i++) if (i == nmiss) { mk0[i] = k0; mk1[i] = k1; mh[i] = h; }
                         nmiss++;
                     } else {
-                        if (short_insert_h(P.skeys, P.scounts, P.scap, h, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                        if (short_insert_h(P.st, h, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
                         if (created) { my_us++; my_ub += len; }
                     }
                 }
@@ -950,14 +960,14 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS) k_pretok_count(Pret
             ulonglong2 kv[PT_MAXMISS];
             const u64 smask_ = (u64)P.scap - 1;
 #pragma unroll
-            for (int i = 0; i < PT_MAXMISS; i++) if (i < nmiss) kv[i] = __ldcg(&P.skeys[mh[i] & smask_]);
+            for (int i = 0; i < PT_MAXMISS; i++) if (i < nmiss) kv[i] = __ldcg((const ulonglong2*)P.st.key(mh[i] & smask_));
 #pragma unroll
             for (int i = 0; i < PT_MAXMISS; i++) {
                 if (i >= nmiss) continue;
-                if (kv[i].x == mk0[i] && kv[i].y == mk1[i]) atomicAdd((u64*)&P.scounts[mh[i] & smask_], 1ULL);
+                if (kv[i].x == mk0[i] && kv[i].y == mk1[i]) atomicAdd((u64*)P.st.cnt(mh[i] & smask_), 1ULL);
                 else {
                     int created;
-                    if (short_insert_h(P.skeys, P.scounts, P.scap, mh[i], mk0[i], mk1[i], 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                    if (short_insert_h(P.st, mh[i], mk0[i], mk1[i], 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
                     if (created) { my_us++; my_ub += (u64)(mk0[i] >> 56); }
                 }
             }
@@ -971,7 +981,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS) k_pretok_count(Pret
         if (k1 == 0) continue;
         u64 k0 = ck0[i];
         int created;
-        if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, (i64)cc[i], &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+        if (short_insert(P.st, k0, k1, (i64)cc[i], &created) < 0) P.stats[ST_TABLE_FULL] = 1;
         if (created) { my_us++; my_ub += (u64)(k0 >> 56); }
     }
     // block-level reduction of the statistics

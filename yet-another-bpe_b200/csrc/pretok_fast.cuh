@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     auto consume = [&]() {
         if (pend) {
             const u64 k0 = (u64)pkx | ((u64)pky << 32), k1 = (u64)pkz | ((u64)pkw << 32);
-            if (pkv.x == k0 && pkv.y == k1) atomicAdd((u64*)&P.scounts[pslot], 1ULL);
+            if (pkv.x == k0 && pkv.y == k1) atomicAdd((u64*)P.st.cnt(pslot), 1ULL);
             else {
                 int created;
-                if (short_insert_h(P.skeys, P.scounts, P.scap, pslot, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                if (short_insert_h(P.st, pslot, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
                 if (created) { my_us++; my_ub += pky >> 24; }
             }
             pend = false;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             if (miss) {
                 pend = true; pkx = kx; pky = ky; pkz = kz; pkw = kw;
                 pslot = (uint32_t)(h & smask);
-                pkv = __ldcg(&P.skeys[pslot]);
+                pkv = __ldcg((const ulonglong2*)P.st.key(pslot));
             }
             my_miss += __popc(__ballot_sync(0xffffffffu, miss));
             // long (15 bytes .. one chunk) and over-long pre-tokens
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         const uint4 a = ckeys[i];
         const u64 k0 = (u64)a.x | ((u64)a.y << 32), k1 = (u64)a.z | ((u64)a.w << 32);
         int created;
-        if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, (i64)cn, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+        if (short_insert(P.st, k0, k1, (i64)cn, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
         if (created) { my_us++; my_ub += k0 >> 56; }
     }
     for (int o = 16; o > 0; o >>= 1) {

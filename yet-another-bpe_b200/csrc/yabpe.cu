@@ -99,7 +99,10 @@ static int make_params(const yabpe_pretok_args* a, PretokParams* P) {
     P->mode = a->mode; P->n_sp = a->n_sp;
     P->own_lo = a->own_lo; P->own_hi = a->own_hi;
     P->cand = a->cand_bits; P->rec = a->rec_bits;
-    P->skeys = (ulonglong2*)a->short_keys; P->scounts = (i64*)a->short_counts; P->scap = a->short_cap;
+    P->scap = a->short_cap;
+    P->st.kb = (char*)a->short_keys; P->st.cap = a->short_cap;
+    if (a->short_counts) { P->st.ks = 16; P->st.cb = (char*)a->short_counts; P->st.cs = 8; ARG_CHECK(((uintptr_t)a->short_keys & 15) == 0); }
+    else { P->st.ks = 32; P->st.cb = (char*)a->short_keys + 16; P->st.cs = 32; ARG_CHECK(((uintptr_t)a->short_keys & 31) == 0); }
     P->lent = (LongEntry*)a->long_entries; P->lcap = a->long_cap;
     P->ovf_pos = (i64*)a->ovf_pos; P->ovf_cap = a->ovf_cap;
     P->stats = (i64*)a->stats;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(256) k_insert_words(PretokParams P, const i64*
             u64 lo = 0, hi = 0;
             for (int k = 0; k < len; k++) { u64 b = P.text[pos + k]; if (k < 8) lo |= b << (8 * k); else hi |= b << (8 * (k - 8)); }
             const u64 k0 = (lo & 0x00FFFFFFFFFFFFFFULL) | ((u64)len << 56), k1 = (lo >> 56) | (hi << 8) | (1ULL << 56);
-            if (short_insert(P.skeys, P.scounts, P.scap, k0, k1, c, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+            if (short_insert(P.st, k0, k1, c, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
             if (created) { my_us++; my_ub += len; }
         } else if (len <= 256) {
             u64 h = 0;
@@ -268,7 +271,8 @@ extern "C" int yabpe_compact_words(const yabpe_pretok_args* a, const yabpe_word_
     ARG_CHECK(a && w && w->wsym && w->sym_word && w->woff && w->wlen && w->wcnt && w->counters);
     WordTable W = make_words(w);
     int grid = num_sms() * 8;
-    k_compact_short<<<grid, 256, 0, st>>>((const ulonglong2*)a->short_keys, (const i64*)a->short_counts, a->short_cap, W); LAUNCHED();
+    PretokParams PC; { int rc0 = make_params(a, &PC); if (rc0) return rc0; }
+    k_compact_short<<<grid, 256, 0, st>>>(PC.st, a->short_cap, W); LAUNCHED();
     k_compact_long<<<grid, 256, 0, st>>>((const LongEntry*)a->long_entries, a->long_cap, a->text, W); LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;
@@ -375,7 +379,8 @@ extern "C" int yabpe_encode_finalize(const yabpe_pretok_args* a, const yabpe_enc
     if (n_words == 0) return YABPE_OK;
     EncodeModel E = make_model(e);
     k_encode_finalize_ids<<<num_sms() * 8, 256, 0, st>>>(E, w->wsym, (const i64*)w->woff, w->wlen, n_words); LAUNCHED();
-    k_encode_finalize_slots<<<num_sms() * 8, 256, 0, st>>>((i64*)a->short_counts, a->short_cap, w->sword, (LongEntry*)a->long_entries,
+    PretokParams PF; { int rc0 = make_params(a, &PF); if (rc0) return rc0; }
+    k_encode_finalize_slots<<<num_sms() * 8, 256, 0, st>>>(PF.st, a->short_cap, w->sword, (LongEntry*)a->long_entries,
                                                           a->long_cap, w->lword, (const i64*)w->woff, w->wlen); LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;

@@ -77,8 +77,9 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
     L = _ffi.load()
     dev = text_dev.device
+    cold_hint = False
     if short_cap is None or long_cap is None:
-        est_s, est_l = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode)
+        est_s, est_l, cold_hint = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode)
         short_cap = short_cap or est_s
         long_cap = long_cap or est_l
     n_cuts = 0 if cuts is None else int(len(cuts))
@@ -87,8 +88,13 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     words32 = (n + 63) // 32 + 1
     cand = torch.zeros(words32, dtype=torch.int32, device=dev) if specials else None
     rec = torch.zeros(words32, dtype=torch.int32, device=dev) if specials else None
-    skeys = torch.zeros(short_cap * 2, dtype=torch.int64, device=dev)
-    scounts = torch.zeros(short_cap, dtype=torch.int64, device=dev)
+    # small tables (hot, L2-resident): keys and counts apart, probes never queue behind count atomics;
+    # large tables (DRAM-resident): 32-byte slots {key, count, -}, one sector per probe + update
+    import os
+    layout = os.environ.get("YABPE_SHORT_LAYOUT")              # tests force either layout on small inputs
+    interleaved = layout == "interleaved" if layout else cold_hint
+    skeys = torch.zeros(short_cap * (4 if interleaved else 2), dtype=torch.int64, device=dev)
+    scounts = None if interleaved else torch.zeros(short_cap, dtype=torch.int64, device=dev)
     lent = torch.zeros(long_cap * 4, dtype=torch.int64, device=dev)
     ovf_cap = n // 992 + 16         # at most one over-long pre-token per 992-byte chunk of the warp kernel
     ovf = torch.empty(ovf_cap, dtype=torch.int64, device=dev)
@@ -104,7 +110,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     a.own_lo, a.own_hi = own if own is not None else (0, n)
     a.cand_bits = cand.data_ptr() if specials else None
     a.rec_bits = rec.data_ptr() if specials else None
-    a.short_keys = skeys.data_ptr(); a.short_counts = scounts.data_ptr(); a.short_cap = short_cap
+    a.short_keys = skeys.data_ptr(); a.short_counts = None if interleaved else scounts.data_ptr(); a.short_cap = short_cap
     a.long_entries = lent.data_ptr(); a.long_cap = long_cap
     a.ovf_pos = ovf.data_ptr(); a.ovf_cap = ovf_cap
     a.stats = stats.data_ptr()
@@ -130,12 +136,15 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
 _SAMPLE_BYTES = 16 << 20
 
 
-def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple[int, int]:
+def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple[int, int, bool]:
     """Hash-table capacities.  Small inputs: proportional to n.  Large inputs: count the unique
     pre-tokens of a 16 MB prefix and extrapolate (Heaps' law, exponent 0.75), so that a 2 GB corpus
-    with 10^5 word types does not zero and scan GB-sized tables.  Overflow is detected and retried."""
+    with 10^5 word types does not zero and scan GB-sized tables.  Overflow is detected and retried.
+    The third value picks the short-table layout: interleaved {key, count} slots when the sample says the table
+    will be large and cold (more than 5 % of the sample's pre-tokens are first occurrences), split arrays for a
+    small table that every SM hammers (see ShortTab in pretok.cuh)."""
     if n <= 4 * _SAMPLE_BYTES:
-        return (_pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26)), _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24)))
+        return (_pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26)), _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24)), False)
     m = _SAMPLE_BYTES
     while m > 0 and (int(text_dev[m].item()) & 0xC0) == 0x80:
         m -= 1
@@ -148,7 +157,8 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple
     ul = max(int(st[_ffi.ST_UNIQ_LONG]), 1 << 6) * scale
     if st[_ffi.ST_TABLE_FULL] != 0:
         us, ul = 1 << 24, 1 << 22
-    return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))))
+    cold = int(st[_ffi.ST_UNIQ_SHORT]) > 0.05 * max(int(st[_ffi.ST_NTOK]), 1)
+    return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))), cold)
 
 
 def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None,
