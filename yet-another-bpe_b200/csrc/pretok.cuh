@@ -235,23 +235,38 @@ __device__ __forceinline__ u64 short_hash(u64 k0, u64 k1) {
 }
 
 // returns slot (>=0) and adds `add` to its count; *created = 1 when this call created the entry
-__device__ __forceinline__ i64 short_insert_h(const ShortTab& T, u64 h, u64 k0, u64 k1, i64 add, int* created) {
+// 16-byte compare-and-swap (atom.cas.b128, sm_90+): a slot is claimed with ONE atomic instead of a word-by-word protocol
+__device__ __forceinline__ ulonglong2 atom_cas128(void* p, u64 c0, u64 c1, u64 v0, u64 v1) {
+    ulonglong2 old;
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+                 "atom.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old.x), "=l"(old.y) : "l"(c0), "l"(c1), "l"(v0), "l"(v1), "l"(p) : "memory");
+    return old;
+}
+
+// `seen` = what a previous 16-byte load of the first slot returned (saves the first read), or {~0, ~0} for "not read yet"
+__device__ __forceinline__ i64 short_insert_seen(const ShortTab& T, u64 h, u64 k0, u64 k1, i64 add, int* created, ulonglong2 seen) {
     u64 mask = (u64)T.cap - 1;
     u64 slot = h & mask;
     *created = 0;
 #pragma unroll 1
     for (int probe = 0; probe < 8192; probe++) {
-        u64* kp = T.key(slot);
-        u64 c0 = *(volatile u64*)kp;
-        if (c0 == 0) { c0 = atomicCAS(kp, 0ULL, k0); if (c0 == 0) c0 = k0; }
-        if (c0 == k0) {
-            u64 c1 = *(volatile u64*)(kp + 1);
-            if (c1 == 0) { c1 = atomicCAS(kp + 1, 0ULL, k1); if (c1 == 0) { c1 = k1; *created = 1; } }
-            if (c1 == k1) { atomicAdd((u64*)T.cnt(slot), (u64)add); return (i64)slot; }
+        ulonglong2 kv = seen;
+        if (kv.x == ~0ULL) kv = __ldcg((const ulonglong2*)T.key(slot));
+        seen.x = ~0ULL;
+        if (kv.x == 0 && kv.y == 0) {
+            kv = atom_cas128(T.key(slot), 0ULL, 0ULL, k0, k1);
+            if (kv.x == 0 && kv.y == 0) { *created = 1; atomicAdd((u64*)T.cnt(slot), (u64)add); return (i64)slot; }
         }
+        if (kv.x == k0 && kv.y == k1) { atomicAdd((u64*)T.cnt(slot), (u64)add); return (i64)slot; }
+        if ((kv.x == 0) != (kv.y == 0)) continue;          // half a key (both words are non-zero in every key): a torn read, look again
         slot = (slot + 1) & mask;
     }
     return -1;
+}
+__device__ __forceinline__ i64 short_insert_h(const ShortTab& T, u64 h, u64 k0, u64 k1, i64 add, int* created) {
+    ulonglong2 none; none.x = ~0ULL; none.y = ~0ULL;
+    return short_insert_seen(T, h, k0, k1, add, created, none);
 }
 
 __device__ __forceinline__ i64 short_insert(const ShortTab& T, u64 k0, u64 k1, i64 add, int* created) {

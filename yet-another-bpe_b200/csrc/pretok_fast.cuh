@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             if (pkv.x == k0 && pkv.y == k1) atomicAdd((u64*)P.st.cnt(pslot), 1ULL);
             else {
                 int created;
-                if (short_insert_h(P.st, pslot, k0, k1, 1, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+                if (short_insert_seen(P.st, pslot, k0, k1, 1, &created, pkv) < 0) P.stats[ST_TABLE_FULL] = 1;     // pkv: the probe already read this slot
                 if (created) { my_us++; my_ub += pky >> 24; }
             }
             pend = false;
