@@ -41,7 +41,10 @@ WORKLOADS = {
     "gpt2-encode-1g": ("owt", 1_000_000_000, 50_257, 20260103),
 }
 SPECIALS = ["<|endoftext|>"]
-NCU_TRAFFIC_RATIO = 1.24          # (dram__bytes_read + dram__bytes_write) / corpus bytes of k_pretok_warp, profiles/r1_ncu_pretok_warp_*.txt
+# (dram__bytes_read + dram__bytes_write) / corpus bytes of k_pretok_warp from the committed ncu --set full captures
+# (profiles/r1_ncu_pretok_warp_details.txt, profiles/r1_ncu_pretok_warp_owt.txt): the OWT-shaped corpus has 50x the unique
+# pre-tokens, so its count-table traffic dwarfs the text itself
+NCU_TRAFFIC_RATIO = {"tinystories": 1.24, "owt": 7.0}
 METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
 UNIT = "MB/s"
 
@@ -351,7 +354,7 @@ def main() -> None:
     if tile_ms:
         achieved = n / (tile_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_pretok_warp (+ k_pretok_count on the boundary chunks)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": int(n * NCU_TRAFFIC_RATIO), "peak_source": peak_kind,
+                    "frac": round(achieved / peak, 4), "traffic": int(n * NCU_TRAFFIC_RATIO[kind]), "peak_source": peak_kind,
                     "traffic_source": "dram bytes per algorithmic byte from the committed ncu --set full capture (profiles/), scaled to this launch",
                     "algorithmic_bytes_per_launch": n, "ms_per_launch": round(tile_ms, 3)}
 
