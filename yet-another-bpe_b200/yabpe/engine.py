@@ -208,10 +208,6 @@ def compact_words(torch, res: PretokResult, st: np.ndarray, with_maps: bool) -> 
     w.counters = counters.data_ptr()
     if n_words > 0:
         _ffi.check(L.yabpe_compact_words(C.byref(res.args), C.byref(w), _ffi.stream_ptr(torch)))
-    import os
-    if os.environ.get("YABPE_DEBUG_SYNC"):
-        torch.cuda.synchronize()
-        print(f"[yabpe debug] compact ok: n_words={n_words} n_syms={n_syms} counters={counters.tolist()}", flush=True)
     return WordArrays(table=w, n_words=n_words, n_syms=n_syms,
                       keep=[wsym, sym_word, woff, wlen, wcnt, sword, lword, counters],
                       wsym=wsym, woff=woff, wlen=wlen, wcnt=wcnt)
@@ -321,16 +317,12 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.rebuild_every = rebuild_period(words.n_syms)
         if timing is not None:
             t0 = torch.cuda.Event(enable_timing=True); t0.record()
-        import os
-        if os.environ.get("YABPE_DEBUG_SYNC"):
-            torch.cuda.synchronize()
-            print("[yabpe debug] before merge loop: ok", flush=True)
         _ffi.check(L.yabpe_merge_loop(C.byref(m), _ffi.stream_ptr(torch)))
         if timing is not None:
             t1 = torch.cuda.Event(enable_timing=True); t1.record()
         st = state.cpu().numpy()
         import os as _os
-        if _os.environ.get('YABPE_TRACE'):
+        if _os.environ.get('YABPE_TRACE'):           # only meaningful with a -DML_TRACE=<merge> build (tools/trace_merge.sh)
             tr = bsum[512:512 + 8 * 24].cpu().numpy().reshape(8, 24)
             for row in tr:
                 base = row[0]
