@@ -99,6 +99,8 @@ typedef struct {
     int64_t* ovf_pos;           /* device scratch for over-long pre-token starts                  */
     int64_t ovf_cap;
     int64_t* stats;             /* device int64[16]; caller zeroes it and sets [ERR_POS]=INT64_MAX */
+    const void* hot_keys;       /* device, yabpe_hot_cache_entries() * 16 bytes from yabpe_select_hot, or NULL: */
+                                /*   keys the warp kernel pre-loads into its shared-memory cache                 */
     int64_t* work;              /* device scratch, 3 * work_cap int64 (boundary work items), or NULL */
     int64_t work_cap;           /*   >= 4 * n_cuts + 16 enables the warp kernel in trainer mode   */
 } yabpe_pretok_args;
@@ -209,6 +211,12 @@ typedef struct {
 int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
                      const yabpe_encode_out* o, int32_t pass, void* stream);
 int64_t yabpe_num_tiles(int64_t own_lo, int64_t own_hi);
+
+/* Hot set for the warp kernel's shared-memory cache: from the tables of a counted SAMPLE of the corpus (`sample`, after
+ * yabpe_pretok_count on e.g. its first 16 MB) pick, for every cache index, the most frequent key that maps to it.
+ * hot_keys: yabpe_hot_cache_entries() * 16 bytes; scratch: yabpe_hot_cache_entries() * 8 bytes.  Result-neutral. */
+int32_t yabpe_hot_cache_entries(void);
+int yabpe_select_hot(const yabpe_pretok_args* sample, void* hot_keys, void* scratch, void* stream);
 
 /* kernels launched by this library since load (the bench's `gpu_launches`) */
 int64_t yabpe_launch_count(void);

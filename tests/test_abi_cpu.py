@@ -33,7 +33,7 @@ def lib():
 
 def test_every_declared_function_is_exported(lib):
     header = (ROOT / "include" / "yabpe.h").read_text()
-    declared = set(re.findall(r"^(?:const char\*|int|int64_t)\s+(yabpe_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:const char\*|int|int32_t|int64_t)\s+(yabpe_\w+)\s*\(", header, flags=re.M))
     assert len(declared) >= 12
     from yabpe import _ffi
     assert declared == set(_ffi.EXPORTS)

@@ -98,7 +98,12 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     asm volatile("" : "+l"(Wp));
     WarpSmem& W = *Wp;
 
-    for (int i = threadIdx.x; i < PW_NC; i += PW_THREADS) { ckeys[i] = make_uint4(0, 0, 0, 0); ccnt[i] = 0; }
+    // The cache starts from the hot set of the sizing sample when there is one (k_hot_select: for every cache index the
+    // most frequent sample key that maps to it) -- claimed with count 0; the remaining slots are claimed first come.
+    for (int i = threadIdx.x; i < PW_NC; i += PW_THREADS) {
+        const uint4 hk = P.hot_keys ? P.hot_keys[i] : make_uint4(0, 0, 0, 0);
+        ckeys[i] = hk; ccnt[i] = hk.w ? 0x80000000u : 0u;
+    }
     if (threadIdx.x < 16) {
         uint32_t m[4];
         for (int j = 0; j < 4; j++) {
@@ -292,5 +297,22 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         if (my_ul) atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], my_ul);
         if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
         if (my_tok > my_miss + n_special) atomicAdd((u64*)&P.stats[ST_CACHE_HIT], (u64)(my_tok - my_miss - n_special));
+    }
+}
+
+// ---- hot set for the cache, from the table of the sizing sample ---------------------------------------------------
+// pass 1: best[ci] = max over sample keys with cache index ci of (count << 24 | low slot bits); pass 2: the winner's key
+__global__ void __launch_bounds__(256) k_hot_select(const ShortTab ST, u64* best, uint4* hot_keys, int pass) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < ST.cap; i += stride) {
+        const ulonglong2 kv = *(const ulonglong2*)ST.key((u64)i);
+        if (kv.y == 0) continue;
+        const i64 cnt = *ST.cnt((u64)i);
+        if (cnt < 2) continue;                                   // a word seen once in the sample is not worth a slot
+        const uint32_t kx = (uint32_t)kv.x, ky = (uint32_t)(kv.x >> 32), kz = (uint32_t)kv.y, kw = (uint32_t)(kv.y >> 32);
+        const uint32_t ci = short_hash_w(kx, ky, kz, kw) >> (32 - PW_NC_LOG2);
+        const u64 tag = ((u64)cnt << 24) | ((u64)i & 0xffffffULL);
+        if (pass == 0) atomicMax(&best[ci], tag);
+        else if (best[ci] == tag) hot_keys[ci] = make_uint4(kx, ky, kz, kw);
     }
 }

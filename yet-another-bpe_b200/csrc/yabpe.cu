@@ -107,8 +107,26 @@ static int make_params(const yabpe_pretok_args* a, PretokParams* P) {
     P->ovf_pos = (i64*)a->ovf_pos; P->ovf_cap = a->ovf_cap;
     P->stats = (i64*)a->stats;
     P->work = (i64*)a->work; P->work_cap = a->work ? a->work_cap : 0; P->list_mode = 0;
+    P->hot_keys = (const uint4*)a->hot_keys;
     P->tile_base = a->own_lo / PT_TILE;
     P->n_tiles = a->own_hi > a->own_lo ? (a->own_hi - 1) / PT_TILE - P->tile_base + 1 : 0;
+    return YABPE_OK;
+}
+
+extern "C" int32_t yabpe_hot_cache_entries(void) { return PW_NC; }
+
+// hot_keys: PW_NC * 16 bytes, scratch: PW_NC uint64 (both device, zeroed by this call)
+extern "C" int yabpe_select_hot(const yabpe_pretok_args* sample, void* hot_keys, void* scratch, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokParams P;
+    int rc = make_params(sample, &P);
+    if (rc) return rc;
+    ARG_CHECK(hot_keys && scratch && ((uintptr_t)hot_keys & 15) == 0);
+    CUDA_TRY(cudaMemsetAsync(hot_keys, 0, (size_t)PW_NC * 16, st));
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)PW_NC * 8, st));
+    k_hot_select<<<num_sms() * 8, 256, 0, st>>>(P.st, (u64*)scratch, (uint4*)hot_keys, 0); LAUNCHED();
+    k_hot_select<<<num_sms() * 8, 256, 0, st>>>(P.st, (u64*)scratch, (uint4*)hot_keys, 1); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
     return YABPE_OK;
 }
 

@@ -24,7 +24,8 @@ INT64_MAX = (1 << 63) - 1
 EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
-    "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize",
+    "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize", "yabpe_hot_cache_entries",
+    "yabpe_select_hot",
 ]
 
 
@@ -47,7 +48,7 @@ class PretokArgs(C.Structure):
         ("long_entries", C.c_void_p), ("long_cap", C.c_int64),
         ("ovf_pos", C.c_void_p), ("ovf_cap", C.c_int64),
         ("stats", C.c_void_p),
-        ("work", C.c_void_p), ("work_cap", C.c_int64),
+        ("hot_keys", C.c_void_p), ("work", C.c_void_p), ("work_cap", C.c_int64),
     ]
 
 
@@ -125,6 +126,9 @@ def load() -> C.CDLL:
     L.yabpe_num_tiles.restype = C.c_int64
     L.yabpe_num_tiles.argtypes = [C.c_int64, C.c_int64]
     L.yabpe_launch_count.restype = C.c_int64
+    L.yabpe_hot_cache_entries.restype = C.c_int32
+    L.yabpe_select_hot.restype = C.c_int
+    L.yabpe_select_hot.argtypes = [C.POINTER(PretokArgs), C.c_void_p, C.c_void_p, C.c_void_p]
     L.yabpe_sizeof.restype = C.c_int64
     L.yabpe_sizeof.argtypes = [C.c_int32]
     for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut)):

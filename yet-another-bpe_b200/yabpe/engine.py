@@ -77,9 +77,9 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
     L = _ffi.load()
     dev = text_dev.device
-    cold_hint = False
+    cold_hint, hot = False, None
     if short_cap is None or long_cap is None:
-        est_s, est_l, cold_hint = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode)
+        est_s, est_l, cold_hint, hot = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode)
         short_cap = short_cap or est_s
         long_cap = long_cap or est_l
     n_cuts = 0 if cuts is None else int(len(cuts))
@@ -115,7 +115,8 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     a.ovf_pos = ovf.data_ptr(); a.ovf_cap = ovf_cap
     a.stats = stats.data_ptr()
     a.work = work.data_ptr(); a.work_cap = work_cap
-    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work], stats=stats,
+    a.hot_keys = hot.data_ptr() if hot is not None else None
+    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work, hot], stats=stats,
                        short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n)
     if n > 0:
         extra = 8 if generic_only else 0        # stages bit 3: generic tile kernel only (A/B parity tests)
@@ -136,15 +137,16 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
 _SAMPLE_BYTES = 16 << 20
 
 
-def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple[int, int, bool]:
+def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode):
     """Hash-table capacities.  Small inputs: proportional to n.  Large inputs: count the unique
     pre-tokens of a 16 MB prefix and extrapolate (Heaps' law, exponent 0.75), so that a 2 GB corpus
     with 10^5 word types does not zero and scan GB-sized tables.  Overflow is detected and retried.
     The third value picks the short-table layout: interleaved {key, count} slots when the sample says the table
     will be large and cold (more than 5 % of the sample's pre-tokens are first occurrences), split arrays for a
-    small table that every SM hammers (see ShortTab in pretok.cuh)."""
+    small table that every SM hammers (see ShortTab in pretok.cuh).
+    Fourth value: the hot set of the sample for the warp kernel's shared-memory cache (device tensor or None)."""
     if n <= 4 * _SAMPLE_BYTES:
-        return (_pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26)), _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24)), False)
+        return (_pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26)), _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24)), False, None)
     m = _SAMPLE_BYTES
     while m > 0 and (int(text_dev[m].item()) & 0xC0) == 0x80:
         m -= 1
@@ -158,7 +160,13 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode) -> tuple
     if st[_ffi.ST_TABLE_FULL] != 0:
         us, ul = 1 << 24, 1 << 22
     cold = int(st[_ffi.ST_UNIQ_SHORT]) > 0.05 * max(int(st[_ffi.ST_NTOK]), 1)
-    return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))), cold)
+    L = _ffi.load()
+    nc = int(L.yabpe_hot_cache_entries())
+    hot = torch.empty(2 * nc, dtype=torch.int64, device=text_dev.device)
+    scratch = torch.empty(nc, dtype=torch.int64, device=text_dev.device)
+    _ffi.check(L.yabpe_select_hot(C.byref(res.args), hot.data_ptr(), scratch.data_ptr(), _ffi.stream_ptr(torch)))
+    hot._yabpe_keep = (res, scratch)              # the sample tables must outlive the (stream-ordered) selection
+    return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))), cold, hot)
 
 
 def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None,
