@@ -158,7 +158,7 @@ typedef struct {
     int32_t* ipost;             /* device, n_syms                                                 */
     uint32_t* inact;            /* device, (pcap + 31) / 32                                       */
     uint32_t* intop;            /* device, (pcap + 31) / 32, zeroed                               */
-    int32_t* top_slot; uint64_t* top_key;        /* device, 512 entries each                      */
+    int32_t* top_slot; uint64_t* top_key;        /* device, 1024 entries each                     */
     int32_t* hist;              /* device, 1024 ints                                              */
     int32_t* act;               /* device, pcap                                                   */
     int32_t* alog_word; int64_t alog_cap;        /* affected-word log, >= 2 * n_words + 4096      */

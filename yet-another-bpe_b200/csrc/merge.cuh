@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(256) k_compact_long(const LongEntry* ent, i64 
 //               other CTAs wait at one grid barrier; used while the active set and the
 //               affected word lists are small (the common case after the first few hundred merges)
 struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
-#define ML_TOP_N 512
+#ifndef ML_TOP_LOG2
+#define ML_TOP_LOG2 9
+#endif
+#define ML_TOP_N (1 << ML_TOP_LOG2)          // entries of the top list: one per thread in the argmax (<= ML_THREADS)
 
 #define ML_MAX_RANGES 12
 #ifndef ML_LEADER_ITEMS_MAX
@@ -444,7 +447,7 @@ __device__ __forceinline__ i64 mirror_get(const LeaderMirror* lm, int idx) { ret
 __device__ __forceinline__ void mirror_set(LeaderMirror* lm, int idx, i64 v) { lm->lo[idx] = (uint32_t)(u64)v; lm->hi[idx] = (uint32_t)((u64)v >> 32); lm->pending[idx] = 0; }
 
 __device__ __forceinline__ int mirror_find(const LeaderMirror* lm, int32_t slot) {
-    uint32_t h = ((uint32_t)slot * 2654435761u) >> 22;          // 10 bits (2 * ML_TOP_N = 1024 entries)
+    uint32_t h = ((uint32_t)slot * 2654435761u) >> (31 - ML_TOP_LOG2);          // 2 * ML_TOP_N entries
     for (;;) {
         const int32_t k = lm->mkey[h];
         if (k == slot + 1) return lm->mval[h];
@@ -453,7 +456,7 @@ __device__ __forceinline__ int mirror_find(const LeaderMirror* lm, int32_t slot)
     }
 }
 __device__ __forceinline__ void mirror_insert(LeaderMirror* lm, int32_t slot, int idx) {
-    uint32_t h = ((uint32_t)slot * 2654435761u) >> 22;
+    uint32_t h = ((uint32_t)slot * 2654435761u) >> (31 - ML_TOP_LOG2);
     for (;;) {
         const int32_t old = atomicCAS(&lm->mkey[h], 0, slot + 1);
         if (old == 0) { lm->mval[h] = (int16_t)idx; return; }
