@@ -682,11 +682,14 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
     if (any && lane == 0) { M.wlen[w] = out; alog_append(M, w, lm); }
 }
 
-// four words per warp, one per 8-lane group (words are short: ~6 symbols on average).  Group-local
-// version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes must call it together.
-__device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
+// 32 / G words per warp, one per G-lane group (G = 8: words are ~6 symbols on average; G = 4: twice as many candidates per
+// pass once the words have shrunk).  Group-local version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes
+// must call it together.
+template <int G>
+__device__ void rewrite_words_g(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
                                  int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew) {
-    const int lane = threadIdx.x & 31, gl = lane & 7, gshift = lane & 24;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), gshift = lane & ~(G - 1);
+    constexpr unsigned GM = (1u << G) - 1u;
     int32_t* s = M.wsym + (w >= 0 ? off : 0);
     int32_t* ws = M.wslot + (w >= 0 ? off : 0);
     if (w < 0) n = 0;
@@ -695,23 +698,23 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
     int32_t carry_prev = -1;
     // the symbols of chunk k+1 are loaded before the atomics of chunk k are issued (software pipelining: a word
     // longer than 8 symbols would otherwise pay the L2 round trips of every chunk one after the other);
-    // chunk k only stores to positions < 8(k+1), chunk k+1 only loads positions >= 8(k+1)
+    // chunk k only stores to positions < G(k+1), chunk k+1 only loads positions >= G(k+1)
     int32_t nx0 = -1, nx1 = -1, nx2 = -1, nx3 = -1, nps0 = 0;
     if (gl < n) nx0 = s[gl];
     if (gl + 1 < n) { nx1 = s[gl + 1]; nps0 = ws[gl]; }
     if (gl + 2 < n) nx2 = s[gl + 2];
     if (gl + 3 < n) nx3 = s[gl + 3];
-    for (int base = 0; __any_sync(0xffffffffu, base < n); base += 8) {
+    for (int base = 0; __any_sync(0xffffffffu, base < n); base += G) {
         const int j = base + gl;
         const int32_t x0 = nx0, x1 = nx1, x2 = nx2, x3 = nx3, ps0 = nps0;
         nx0 = -1; nx1 = -1; nx2 = -1; nx3 = -1; nps0 = 0;
-        if (j + 8 < n) nx0 = s[j + 8];
-        if (j + 9 < n) { nx1 = s[j + 9]; nps0 = ws[j + 8]; }
-        if (j + 10 < n) nx2 = s[j + 10];
-        if (j + 11 < n) nx3 = s[j + 11];
-        int32_t xm1 = __shfl_up_sync(0xffffffffu, x0, 1, 8);
+        if (j + G < n) nx0 = s[j + G];
+        if (j + G + 1 < n) { nx1 = s[j + G + 1]; nps0 = ws[j + G]; }
+        if (j + G + 2 < n) nx2 = s[j + G + 2];
+        if (j + G + 3 < n) nx3 = s[j + G + 3];
+        int32_t xm1 = __shfl_up_sync(0xffffffffu, x0, 1, G);
         if (gl == 0) xm1 = carry_prev;
-        carry_prev = __shfl_sync(0xffffffffu, x0, 7, 8);
+        carry_prev = __shfl_sync(0xffffffffu, x0, G - 1, G);
         __syncwarp();
         if (base == 0) ML_TRG(13);
         const bool valid = j < n;
@@ -719,8 +722,8 @@ __device__ void rewrite_words_g8(const MergeParams& M, int32_t w, i64 off, int n
         const bool rem0 = valid && xm1 == a && x0 == b;
         const bool sel1 = x1 == a && x2 == b;
         const bool keep = valid && !rem0;
-        const unsigned keepmask = (__ballot_sync(0xffffffffu, keep) >> gshift) & 0xffu;
-        any |= ((__ballot_sync(0xffffffffu, sel0) >> gshift) & 0xffu) != 0;
+        const unsigned keepmask = (__ballot_sync(0xffffffffu, keep) >> gshift) & GM;
+        any |= ((__ballot_sync(0xffffffffu, sel0) >> gshift) & GM) != 0;
         if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, ps0, f, lm);
         if (base == 0) ML_TRG(14);
         int32_t nslot = ps0; bool has_pair = false;
@@ -957,6 +960,42 @@ __device__ __forceinline__ void select_top(u64 key, u64* sh_keys /* [32][ML_SEL]
     }
 }
 
+// Stage C of the leader: every G-lane group of the first nwarps-1 warps takes candidates it0, it0 + ngroups, ...
+// Software pipeline over the passes of a group: the candidate of pass p+2 and the word header of pass p+1 are loaded
+// while pass p is rewritten, so only the first pass pays those round trips in full (the word arrays of a large corpus
+// do not fit the L2: every round trip is a DRAM access).
+template <int G>
+__device__ __forceinline__ void leader_rewrite(const MergeParams& M, LeaderCtx& C, const Ranges& R, int warp, int lane, int nwarps,
+                                               int32_t a, int32_t b, int32_t c, i64 T, i64 T2, bool is_new) {
+    constexpr int GPW = 32 / G;                      // groups per warp
+    const int ngroups = (nwarps - 1) * GPW, gl = lane & (G - 1), lead = lane & ~(G - 1);
+    const int total = (int)R.total;
+    const int it0 = warp * GPW + lane / G;
+    int32_t w_cur = it0 < total ? range_item(R, it0) : -1;
+    int32_t w_nx = it0 + ngroups < total ? range_item(R, it0 + ngroups) : -1;
+    {
+        int take = (w_cur >= 0 && gl == 0) ? (dedupe_claim(&C, w_cur) ? 1 : 0) : 0;
+        take = __shfl_sync(0xffffffffu, take, lead);
+        if (!take) w_cur = -1;
+    }
+    uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
+    if (w_cur >= 0) { off_cur = (uint32_t)M.woff[w_cur]; n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur]; }
+    for (int base = 0; base + warp * GPW < total; base += ngroups) {     // warps without a candidate go straight to the barrier
+        const int it2 = base + it0 + 2 * ngroups;
+        const int32_t w_nx2 = it2 < total ? range_item(R, it2) : -1;
+        {
+            int take = (w_nx >= 0 && gl == 0) ? (dedupe_claim(&C, w_nx) ? 1 : 0) : 0;
+            take = __shfl_sync(0xffffffffu, take, lead);
+            if (!take) w_nx = -1;
+        }
+        uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
+        if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
+        if (a != b) rewrite_words_g<G>(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
+        else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new);
+        w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = w_nx2;
+    }
+}
+
 // warp-wide maximum of non-negative 64-bit values with two redux.sync (32-bit) instead of ten shuffles
 __device__ __forceinline__ i64 warp_max_i64(i64 v) {
     const uint32_t hi = (uint32_t)((u64)v >> 32), lo = (uint32_t)(u64)v;
@@ -1139,51 +1178,9 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         // ---- C: commit (last warp) || claim + rewrite (one 8-lane group per candidate item)
         if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
         else {
-            const int ngroups = (nwarps - 1) * 4, gl = lane & 7;
-            const int total = (int)R.total;
-            // Software pipeline over the passes of this group: the candidate of pass p+2 and the word header of pass
-            // p+1 are loaded while pass p is rewritten, so only the first pass pays those round trips in full
-            // (the word arrays of a large corpus do not fit the L2: every round trip is a DRAM access).
-            const int it0 = warp * 4 + (lane >> 3);
-            int32_t w_cur = it0 < total ? range_item(R, it0) : -1;
-            int32_t w_nx = it0 + ngroups < total ? range_item(R, it0 + ngroups) : -1;
-            {
-                int take = (w_cur >= 0 && gl == 0) ? (dedupe_claim(&C, w_cur) ? 1 : 0) : 0;
-                take = __shfl_sync(0xffffffffu, take, lane & 24);
-                if (!take) w_cur = -1;
-            }
-            ML_TR(3);
-            uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
-            if (w_cur >= 0) { off_cur = (uint32_t)M.woff[w_cur]; n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur]; }
-#if ML_TRACE
-            if (n_cur < 0) M.state[MS_SCRATCH] = off_cur + f_cur;
-            ML_TR(4);
-#endif
-            for (int base = 0; base + warp * 4 < total; base += ngroups) {     // warps without a candidate go straight to the barrier
-                ML_T0(q);
-                const int it2 = base + it0 + 2 * ngroups;
-                const int32_t w_nx2 = it2 < total ? range_item(R, it2) : -1;
-                {
-                    int take = (w_nx >= 0 && gl == 0) ? (dedupe_claim(&C, w_nx) ? 1 : 0) : 0;
-                    take = __shfl_sync(0xffffffffu, take, lane & 24);
-                    if (!take) w_nx = -1;
-                }
-                uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
-                if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
-                ML_TACC(0, q);
-                if (base == 0) ML_TR(5);
-#if ML_TRACE
-                if (threadIdx.x == 0) g_trace_row = (base == 0 && m >= ML_TRACE && m < ML_TRACE + 8) ? &((long long*)M.bsum)[512 + (m - ML_TRACE) * 24] : nullptr;
-#endif
-                if (a != b) rewrite_words_g8(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
-                else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new);
-                if (base == 0) ML_TR(6);
-                ML_TACC(2, q);
-#if ML_TIMING
-                if (threadIdx.x == 0) sh_tacc[3] += 1;
-#endif
-                w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = w_nx2;
-            }
+            // 8-lane groups (124 candidates per pass) while that is one pass, 4-lane groups (248 per pass) beyond
+            if (a != b && R.total > (nwarps - 1) * 4) leader_rewrite<4>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
+            else leader_rewrite<8>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
         }
         if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }
         ML_T0(qb);
@@ -1428,7 +1425,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             }
             old = __shfl_sync(0xffffffffu, old, lane & 24);       // all 32 lanes: groups beyond the list carry old == stamp
             if (old == stamp) w = -1;
-            rewrite_words_g8(M, w, off, n, f, a, b, c, T, T2u, nullptr, is_new);
+            rewrite_words_g<8>(M, w, off, n, f, a, b, c, T, T2u, nullptr, is_new);
         } else if (a != b && R.total * 32 <= gstride * 4) {
             const i64 gw = gtid >> 5, nw = gstride >> 5;
             for (i64 it = gw; it < R.total; it += nw) {
