@@ -1179,7 +1179,8 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
         else {
             // 8-lane groups (124 candidates per pass) while that is one pass, 4-lane groups (248 per pass) beyond
-            if (a != b && R.total > (nwarps - 1) * 4) leader_rewrite<4>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
+            if (a != b && R.total > (nwarps - 1) * 8) leader_rewrite<2>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
+            else if (a != b && R.total > (nwarps - 1) * 4) leader_rewrite<4>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
             else leader_rewrite<8>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
         }
         if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }
