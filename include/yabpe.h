@@ -111,6 +111,12 @@ typedef struct {
  *          which it reads on the device -- no host round trip. */
 int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream);
 
+/* Pre-token starts in text order: bit p of start_bits (device, (n + 31) / 32 words) is set iff a pre-token starts
+ * at byte p.  Replaces the ORDER of the list trainer.py:200-214 (_preprocess_corpus) returns -- the counting path
+ * only keeps the multiset.  Call after yabpe_pretok_count on the same args (it reads rec_bits, the recognised
+ * specials, and relies on that call's strict UTF-8 check). */
+int yabpe_token_starts(const yabpe_pretok_args* a, uint32_t* start_bits, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Word table.  Replaces the dict[tuple[bytes,...], int] built at trainer.py:221-225 by flat
  * arrays: one int32 symbol slot per byte of every unique pre-token.

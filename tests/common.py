@@ -87,6 +87,23 @@ def load_pretok_cases() -> list[dict]:
     return json.loads((GOLDEN / "pretokenize_cases.json").read_text())
 
 
+def load_class_api_cases() -> dict:
+    """tests/golden/class_api_cases.json (tools/make_golden.py make_class_api): reference outputs of
+    _preprocess_corpus, _merge_loop(sequences), save() and from_file()."""
+    d = json.loads((GOLDEN / "class_api_cases.json").read_text())
+    for c in d["preprocess"]:
+        c["files"] = [base64.b64decode(x) for x in c["files_b64"]]
+        c["want"] = [bytes.fromhex(x) for x in c["sequences"]]
+    for c in d["merge_loop"]:
+        c["seqs"] = [bytes.fromhex(x) for x in c["sequences"]]
+        c["want_vocab"] = [bytes.fromhex(x) for x in c["vocab"]]
+        c["want_merges"] = [(bytes.fromhex(a), bytes.fromhex(b)) for a, b in c["merges"]]
+    for c in d["persist"]:
+        c["input"] = (ROOT / c["input_file"]).read_bytes() if "input_file" in c else base64.b64decode(c["input_b64"])
+        c["files"] = {k: base64.b64decode(v) for k, v in c["files_b64"].items()}
+    return d
+
+
 def load_encode_cases() -> tuple[dict, list[dict]]:
     d = json.loads((GOLDEN / "encode_cases.json").read_text())
     models = {}

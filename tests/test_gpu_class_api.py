@@ -1,0 +1,135 @@
+"""SURVEY 8(f) rows 1-2 on the GPU: BBPETrainer._preprocess_corpus / _merge_loop(sequences) (the private entry
+points tests/test_trainer.py of the reference calls) and a save() -> from_file() -> encode round trip, against the
+reference's outputs (tests/golden/class_api_cases.json) and the CPU oracle."""
+from __future__ import annotations
+
+import random
+from collections import Counter
+
+import pytest
+
+import common
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def yabpe():
+    import yabpe as y
+    from yabpe import _ffi
+    _ffi.require_cuda()
+    return y
+
+
+def _write(tmp_path, blobs, tag):
+    paths = []
+    for i, b in enumerate(blobs):
+        p = tmp_path / f"{tag}_{i}.txt"
+        p.write_bytes(b)
+        paths.append(p)
+    return paths
+
+
+def _cfg(yabpe, **kw):
+    kw.setdefault("max_workers", 1)
+    return yabpe.BBPETrainerConfig(**kw)
+
+
+# ------------------------------------------------------------------------------- _preprocess_corpus
+def test_preprocess_corpus_golden(yabpe, tmp_path):
+    for k, c in enumerate(common.load_class_api_cases()["preprocess"]):
+        tr = yabpe.BBPETrainer(_cfg(yabpe, chunk_size_bytes=c["chunk_size"], special_tokens=c["specials"]))
+        seqs = tr._preprocess_corpus(_write(tmp_path, c["files"], f"g{k}"))
+        assert all(isinstance(s, list) for s in seqs)
+        assert [bytes(s) for s in seqs] == c["want"], (c["specials"], c["chunk_size"])
+
+
+def test_preprocess_corpus_order_vs_oracle(yabpe, tmp_path):
+    """Text order of the start bitmap (generic per-byte rule) against the oracle's sequential scan, and its multiset
+    against the counting kernels (warp + tile) on the same text: three implementations, one answer."""
+    from yabpe.trainer import pretoken_counts
+    rng = random.Random(77)
+    alphabet = list("ab Z'sdmtlvre19!<|>\n\t \r") + ["é", "中", " ", "　", "\U0001f643", "'ll", "don't",
+                                                     "<|endoftext|>", "<|e|>", " the", "x" * 40]
+    for sp, cs in (([], 1 << 30), (["<|endoftext|>"], 1 << 30), (["<|e|>", "<|endoftext|>"], 4099), (["\nb", "ab", "a"], 513)):
+        text = "".join(rng.choice(alphabet) for _ in range(120_000)).encode("utf-8")
+        tr = yabpe.BBPETrainer(_cfg(yabpe, chunk_size_bytes=cs, special_tokens=sp))
+        got = [bytes(s) for s in tr._preprocess_corpus(_write(tmp_path, [text], "o"))]
+        assert b"".join(got) == text
+        assert got == oracle.pretokenize(text, sp, "train", cs), (sp, cs)
+        counts = pretoken_counts(text, sp, chunk_size_bytes=cs)
+        counts.pop("__n_pretokens__")
+        assert counts == dict(Counter(got)), (sp, cs)
+    for name in ("corpus.en", "tinystories_sample.txt", "german.txt"):
+        data = (common.FIXTURES / name).read_bytes()
+        tr = yabpe.BBPETrainer(_cfg(yabpe, chunk_size_bytes=1024, special_tokens=["<|endoftext|>"]))
+        got = [bytes(s) for s in tr._preprocess_corpus([common.FIXTURES / name])]
+        assert got == oracle.pretokenize(data, ["<|endoftext|>"], "train", 1024), name
+    # MB-long pre-tokens and 4-byte code points at the end of the text
+    data = b"q" * 1_300_000 + b" tail " + "中".encode() * 3000 + b"\n\n" + "\U0001f643".encode()
+    tr = yabpe.BBPETrainer(_cfg(yabpe, special_tokens=[]))
+    assert [bytes(s) for s in tr._preprocess_corpus(_write(tmp_path, [data], "l"))] == oracle.pretokenize(data, [], "train", 8 << 20)
+
+
+def test_preprocess_corpus_edge_cases(yabpe, tmp_path):
+    tr = yabpe.BBPETrainer(_cfg(yabpe))
+    empty, one = _write(tmp_path, [b"", b"Hello world!"], "e")
+    assert tr._preprocess_corpus([empty]) == []
+    assert tr._preprocess_corpus([empty, one, empty]) == [list(b"Hello"), list(b" world"), list(b"!")]
+    assert tr._preprocess_corpus([str(one)]) == [list(b"Hello"), list(b" world"), list(b"!")]
+    with pytest.raises(FileNotFoundError):
+        tr._preprocess_corpus([tmp_path / "missing.txt"])
+    bad = _write(tmp_path, [b"ok \xe4\xb8 broken"], "b")[0]
+    with pytest.raises(ValueError, match="invalid UTF-8 at position 3"):
+        tr._preprocess_corpus([bad])
+
+
+# ------------------------------------------------------------------------------- _merge_loop(sequences)
+def test_merge_loop_sequences_golden(yabpe):
+    for c in common.load_class_api_cases()["merge_loop"]:
+        tr = yabpe.BBPETrainer(_cfg(yabpe, **c["config"]))
+        vocab, merges = tr._merge_loop([list(s) for s in c["seqs"]])
+        assert list(vocab.keys()) == c["want_vocab"] and list(vocab.values()) == list(range(len(vocab))), c["config"]
+        assert merges == c["want_merges"], c["config"]
+        assert all(isinstance(a, bytes) and isinstance(b, bytes) for a, b in merges)
+
+
+def test_merge_loop_sequences_vs_oracle_and_train(yabpe, tmp_path):
+    """_merge_loop(_preprocess_corpus(files)) is train(files) (trainer.py:75-90), also with min_frequency > 1."""
+    data = (common.FIXTURES / "tinystories_sample.txt").read_bytes()[:200_000]
+    path = _write(tmp_path, [data], "t")[0]
+    for vs, mf, sp in ((700, 1, ["<|endoftext|>"]), (2000, 7, ["<|endoftext|>", "the"])):
+        cfg = _cfg(yabpe, vocab_size=vs, min_frequency=mf, chunk_size_bytes=50_000, special_tokens=sp)
+        tr = yabpe.BBPETrainer(cfg)
+        vocab, merges = tr._merge_loop(tr._preprocess_corpus([path]))
+        model = yabpe.BBPETrainer(cfg).train([path])
+        assert (vocab, merges) == (model.vocab, model.merges)
+        want_vocab, want_merges = oracle.train_bpe(path, vs, sp, min_frequency=mf, chunk_size_bytes=50_000)
+        assert merges == want_merges and {v: k for k, v in vocab.items()} == want_vocab
+        if mf > 1:
+            assert len(merges) < vs - len(tr._init_base_vocab())          # stopped by the frequency floor
+    # long words (> 256 symbols) and single-symbol words through the sequence entry point
+    rng = random.Random(5)
+    seqs = [bytes(rng.choice(b"ab") for _ in range(rng.choice((1, 2, 3, 300, 700)))) for _ in range(400)]
+    ot = oracle.Trainer([])
+    for w, f in Counter(seqs).items():
+        ot.feed_word(w, f)
+    want_vocab, want_merges = ot.run(300, 2)
+    vocab, merges = yabpe.BBPETrainer(_cfg(yabpe, vocab_size=300, min_frequency=2, special_tokens=[]))._merge_loop([list(s) for s in seqs])
+    assert merges == want_merges and {v: k for k, v in vocab.items()} == want_vocab
+
+
+# ------------------------------------------------------------------------------- save -> from_file -> encode
+def test_persisted_model_round_trip(yabpe, tmp_path):
+    for i, c in enumerate(common.load_class_api_cases()["persist"]):
+        path = _write(tmp_path, [c["input"]], f"p{i}")[0]
+        tr = yabpe.BBPETrainer(_cfg(yabpe, vocab_size=c["vocab_size"], min_frequency=1, chunk_size_bytes=1 << 30,
+                                    special_tokens=c["specials"]))
+        tr.train([path])
+        tr.save(tmp_path / f"model{i}")
+        for name, want in c["files"].items():                              # trained on the GPU, written like the reference
+            assert (tmp_path / f"model{i}" / name).read_bytes() == want, name
+        tok = yabpe.BBPETokenizer.from_file(tmp_path / f"model{i}")
+        for e in c["encodes"]:
+            assert tok.encode(e["text"]) == e["ids"], e["text"]

@@ -221,8 +221,83 @@ def make_encode() -> None:
     print("encode cases:", len(cases))
 
 
+def make_class_api() -> None:
+    """the private trainer entry points the reference's own tests call
+    (tests/test_trainer.py:27-42,214,245) and the on-disk format (trainer.py:94-117, tokenizer.py:106-150)."""
+    rng = random.Random(20260105)
+    out: dict = dict(preprocess=[], merge_loop=[], persist=[])
+
+    def cfg(**kw):
+        kw.setdefault("max_workers", 1)
+        return BBPETrainerConfig(**kw)
+
+    # -- _preprocess_corpus: per-occurrence byte lists, files and text in order
+    corpus = (FIX / "corpus.en").read_bytes()
+    pp = [
+        ([rand_text(rng, 1500).encode()], ["<|endoftext|>"], 1 << 30),
+        ([rand_text(rng, 1500).encode()], ["<|e|>", "<|endoftext|>"], 97),
+        ([rand_text(rng, 1200).encode(), b"", rand_text(rng, 700).encode()], [" <", "<|e|>"], 256),
+        ([adversarial_text(rng, 1).encode()], ["<|endoftext|>"], 1024),
+        ([corpus[:20000]], [], 4096),
+        (["hello hello world<|endoftext|>".encode(), "h\u00e9llo w\u00f6rld \u4e2d\u6587 don't\r\n\r\n  x ".encode()], ["<|endoftext|>"], 8),
+    ]
+    for files, sp, cs in pp:
+        with tempfile.TemporaryDirectory() as td:
+            paths = []
+            for i, d in enumerate(files):
+                q = Path(td) / f"f{i}.txt"
+                q.write_bytes(d)
+                paths.append(q)
+            seqs = BBPETrainer(cfg(chunk_size_bytes=cs, special_tokens=sp))._preprocess_corpus(paths)
+        out["preprocess"].append(dict(files_b64=[b64(d) for d in files], specials=sp, chunk_size=cs,
+                                      sequences=[hx(bytes(x)) for x in seqs]))
+
+    # -- _merge_loop(sequences)
+    def run_ml(seqs, **kw):
+        vocab, merges = BBPETrainer(cfg(**kw))._merge_loop([list(x) for x in seqs])
+        inv = {v: k for k, v in vocab.items()}
+        out["merge_loop"].append(dict(sequences=[hx(bytes(x)) for x in seqs], config=kw,
+                                      vocab=[hx(inv[i]) for i in range(len(inv))], merges=[[hx(a), hx(b)] for a, b in merges]))
+
+    run_ml([], vocab_size=300, min_frequency=1)
+    run_ml([b"Hello", b"Hello"], vocab_size=265, min_frequency=1)
+    run_ml([b"AB"] * 100 + [b"CD"] * 50 + [b"EF"] * 10, vocab_size=270, min_frequency=1)
+    run_ml([b"AB", b"CD", b"EF", b"GH", b"IJ"] * 10, vocab_size=262, min_frequency=1)
+    run_ml([b"AB"] * 10 + [b"CD"] * 5 + [b"EF"] * 4 + [b"GH"], vocab_size=300, min_frequency=5)
+    run_ml([], vocab_size=300, min_frequency=1, special_tokens=["[PAD]", "[UNK]", "[BOS]", "[EOS]", "[MASK]"])
+    words = [bytes(rng.choice(b"abc\xc3\xa9 ") for _ in range(rng.randint(1, 9))) for _ in range(60)]
+    run_ml([rng.choice(words) for _ in range(3000)], vocab_size=330, min_frequency=1, special_tokens=["<|endoftext|>"])
+    run_ml([rng.choice(words) for _ in range(3000)], vocab_size=400, min_frequency=25, special_tokens=[])
+    run_ml([b"a" * 300, b"a" * 7, b"aaab" * 90, b"b"] * 3, vocab_size=290, min_frequency=2, special_tokens=["a"])
+
+    # -- save() / from_file(): literal files and what the (lossy) loader gets back
+    texts = ["Hello, how are you?", " the cat\r\nsat  on\n\nthe mat<|endoftext|> caf\u00e9 \u4e2d\u6587 don't", ""]
+    for data, vs, sp in [(corpus, 420, ["<|endoftext|>"]),
+                         (("a b\r\nc\rd \u00e9\u00e9 \u0085x\u2028y  z\t\tq " * 40).encode(), 300, ["<|endoftext|>", "[PAD]"])]:
+        with tempfile.TemporaryDirectory() as td:
+            q = Path(td) / "in.txt"
+            q.write_bytes(data)
+            tr = BBPETrainer(cfg(vocab_size=vs, min_frequency=1, chunk_size_bytes=1 << 30, special_tokens=sp))
+            model = tr.train([q])
+            tr.save(Path(td) / "model")
+            files = {n: b64((Path(td) / "model" / n).read_bytes()) for n in ("vocab.json", "merges.txt", "special_tokens.json")}
+            tok = BBPETokenizer.from_file(Path(td) / "model")
+            loaded_vocab = sorted(((hx(k), v) for k, v in tok._vocab.items()), key=lambda kv: kv[1])
+            loaded_merges = [[hx(a), hx(b)] for a, b in tok._merges]
+            inv = {v: k for k, v in model.vocab.items()}
+            out["persist"].append(dict(
+                **(dict(input_file="tests/fixtures_gpt2/corpus.en") if data is corpus else dict(input_b64=b64(data))),
+                vocab_size=vs, specials=sp, files_b64=files,
+                trained_vocab=[hx(inv[i]) for i in range(len(inv))], trained_merges=[[hx(a), hx(b)] for a, b in model.merges],
+                loaded_vocab=loaded_vocab, loaded_merges=loaded_merges, loaded_specials=list(tok._special_tokens),
+                encodes=[dict(text=t, ids=tok.encode(t)) for t in texts]))
+    (GOLD / "class_api_cases.json").write_text(json.dumps(out, ensure_ascii=True, indent=0))
+    print("class api cases:", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
     make_pretok()
     make_train()
     make_encode()
+    make_class_api()

@@ -167,6 +167,36 @@ static int run_specials(const yabpe_pretok_args* a, const PretokParams& P, cudaS
     return YABPE_OK;
 }
 
+// ---- pre-token starts in text order (the list trainer.py:200-214 returns, as a bitmap) ----
+// One thread per byte, the generic start rule over global memory (common.cuh is_token_start: an implementation
+// independent of the SWAR scan in k_pretok_warp and of the tile scan in k_pretok_count), one ballot per warp.
+__global__ void __launch_bounds__(256) k_token_starts(PretokParams P, uint32_t* bits) {
+    GlobalText G{P.text, P.n, P.cuts, P.n_cuts, P.n_sp > 0 ? P.rec : nullptr, -1, P.mode};
+    const i64 n_round = (P.n + 31) & ~(i64)31;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        const bool st = p < P.n && is_token_start(G, p);
+        const unsigned m = __ballot_sync(0xffffffffu, st);
+        if ((threadIdx.x & 31) == 0) bits[p >> 5] = m;
+    }
+}
+
+extern "C" int yabpe_token_starts(const yabpe_pretok_args* a, uint32_t* start_bits, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokParams P;
+    int rc = make_params(a, &P);
+    if (rc) return rc;
+    ARG_CHECK(start_bits != nullptr);
+    rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
+    if (rc) return rc;
+    if (P.n <= 0) return YABPE_OK;
+    i64 grid = (P.n + 255) / 256;
+    if (grid > (i64)num_sms() * 16) grid = (i64)num_sms() * 16;
+    k_token_starts<<<(int)grid, 256, 0, st>>>(P, start_bits); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
 extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PretokParams P;

@@ -183,6 +183,15 @@ def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None,
     raise _ffi.YabpeError("pre-token hash tables kept overflowing")
 
 
+def token_starts(torch, res: PretokResult) -> np.ndarray:
+    """Byte offsets of every pre-token start of the text `res` was counted on, ascending (yabpe_token_starts)."""
+    n = int(res.args.n)
+    bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=res.text.device)
+    _ffi.check(_ffi.load().yabpe_token_starts(C.byref(res.args), bits.data_ptr(), _ffi.stream_ptr(torch)))
+    words = bits.cpu().numpy().view(np.uint8)
+    return np.flatnonzero(np.unpackbits(words, bitorder="little")[:n]).astype(np.int64)
+
+
 @dataclass
 class WordArrays:
     table: _ffi.WordTable

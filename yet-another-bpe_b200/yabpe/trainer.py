@@ -216,6 +216,59 @@ class BBPETrainer:
         merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]       # .tolist(): plain ints, not numpy scalars
         return self._finish(vocab, merges)
 
+    def _preprocess_corpus(self, files: Sequence[str | Path]) -> list[list[int]]:
+        """Every pre-token occurrence as a list of byte values, files and text in order (trainer.py:200-214;
+        tests/test_trainer.py:27-42).  The training path never materialises this list (it only needs the multiset);
+        here the device marks the pre-token starts (yabpe_token_starts) and the host slices the bytes."""
+        torch = _ffi.require_cuda()
+        cfg = self.config
+        specials = [s.encode("utf-8") for s in cfg.special_tokens]
+        out: list[list[int]] = []
+        for f in files:
+            p = Path(f) if isinstance(f, str) else f
+            if not p.exists():
+                raise FileNotFoundError(f"File not found: {p}")           # trainer.py:204-205
+            blob = np.fromfile(p, dtype=np.uint8)
+            n = int(blob.size)
+            if n == 0:
+                continue
+            cuts = [c for c in chunk_cuts(blob, cfg.chunk_size_bytes) if 0 < c < n]
+            text_dev, _ = engine.to_device_text(torch, blob)
+            res, st = engine.pretok_count_checked(torch, text_dev, n, np.asarray(cuts, dtype=np.int64) if cuts else None,
+                                                  specials, mode=0)
+            err = int(st[_ffi.ST_ERR_POS])
+            if err != _ffi.INT64_MAX:                                     # trainer.py:157-160
+                raise ValueError(f"File {p} contains invalid UTF-8 at position {err}.")
+            starts = engine.token_starts(torch, res).tolist()
+            raw = blob.tobytes()
+            out.extend(list(raw[s:e]) for s, e in zip(starts, starts[1:] + [n]))
+        return out
+
+    def _merge_loop(self, sequences: Sequence[Sequence[int]]) -> tuple[dict[bytes, int], list[tuple[bytes, bytes]]]:
+        """The merge loop on a caller-supplied list of byte-value sequences, one per pre-token occurrence
+        (trainer.py:216-302; tests/test_trainer.py:214,245).  The occurrences are de-duplicated on the device
+        (yabpe_insert_words: the word_freq dict of trainer.py:221-225), then k_merge_loop runs as in train()."""
+        torch = _ffi.require_cuda()
+        from . import distributed as D
+        cfg = self.config
+        base_vocab = self._init_base_vocab()
+        num_merges = max(0, cfg.vocab_size - len(base_vocab))            # trainer.py:238
+        seqs = [bytes(bytearray(s)) for s in sequences if len(s)]         # ValueError for values outside 0..255
+        if not seqs or num_merges == 0:
+            self._vocab, self._merges = base_vocab, []
+            return base_vocab, []
+        lens = torch.tensor([len(s) for s in seqs], dtype=torch.int32, device="cuda")
+        data = torch.from_numpy(np.frombuffer(b"".join(seqs), dtype=np.uint8).copy()).cuda()
+        packed = D.reduce_packed_cuda(D.Packed(lens, torch.ones(len(seqs), dtype=torch.int64, device="cuda"), data))
+        words = D.words_from_packed(torch, packed)
+        mr = engine.merge_loop(torch, words, list(base_vocab.keys()), num_merges, int(cfg.min_frequency),
+                               restore=lambda: D.words_restore(torch, words, packed))
+        toks = mr.tokens
+        vocab = {b: i for i, b in enumerate(toks)}
+        merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]
+        self._vocab, self._merges = vocab, merges
+        return vocab, merges
+
     def save(self, output_dir: str | Path) -> None:
         """Same on-disk format as trainer.py:94-117 (latin-1 keys, "a b" merge lines)."""
         if not self._vocab:
