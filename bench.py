@@ -226,6 +226,21 @@ def run_encode(args) -> None:
                 "achieved": round(alg / (stage[dom] / 1e3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(alg / (stage[dom] / 1e3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": stage[dom]}
+    # the way back (tokenizer.py:323-349 decode): ids -> bytes on the device; every byte must be the input's
+    decode = None
+    if n_ids:
+        ids_keep = ids.clone()
+        out = tok.decode_device(ids_keep)
+        torch.cuda.synchronize()
+        d0 = torch.cuda.Event(enable_timing=True); d1 = torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            out = tok.decode_device(ids_keep)
+        d1.record(); torch.cuda.synchronize()
+        dms = d0.elapsed_time(d1) / args.steps
+        decode = {"ms": round(dms, 3), "GB/s (4 B per id in + bytes out)": round((4 * n_ids + int(out.numel())) / (dms / 1e3) / 1e9, 1),
+                  "round_trip_equal": bool(out.numel() == n and torch.equal(out, text_dev[:n]))}
+        del ids_keep, out
     e2e = None
     if not args.skip_e2e:
         host = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -268,7 +283,7 @@ def run_encode(args) -> None:
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": f"synthetic ({kind}-shaped, torch generator, seed {seed})",
             "config": {"workload": args.workload, "total_bytes": int(total_bytes), "bytes_per_gpu": n, "vocab_size": len(vocab), "merges": len(merges),
                        "special_tokens": SPECIALS, "ids": int(total_ids), "l2": "inputs (>= 125 MB per GPU) larger than the 126 MB L2"},
-            "stage_ms": stage, "unique_words": timings[-1].get("unique_words"),
+            "stage_ms": stage, "unique_words": timings[-1].get("unique_words"), "decode": decode,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary()}))
     if world > 1:
         dist.destroy_process_group()

@@ -218,6 +218,25 @@ int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_model* e, co
                      const yabpe_encode_out* o, int32_t pass, void* stream);
 int64_t yabpe_num_tiles(int64_t own_lo, int64_t own_hi);
 
+/* ---------------------------------------------------------------------------------------------
+ * Decode.  Replaces the byte gather of tokenizer.py:323-349 (b"".join(vocab_inv[i] for i in ids if i in vocab_inv));
+ * the UTF-8 decode of the result (strict, else errors="replace") stays with the caller.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const int32_t* ids; int64_t n_ids;   /* device                                                          */
+    const int64_t* tok_off;     /* device, vocab_cap + 1: bytes of id i = tok_bytes[tok_off[i] .. tok_off[i+1]);     */
+                                /*   an id that is not in the vocabulary has an empty range                          */
+    const uint8_t* tok_bytes;   /* device                                                                            */
+    int32_t vocab_cap; int32_t _pad;     /* ids outside [0, vocab_cap) are skipped                                   */
+    int64_t* block_count;       /* device, yabpe_decode_blocks(n_ids) + 1                                            */
+    uint8_t* out; int64_t out_cap;       /* device (pass 1)                                                          */
+} yabpe_decode_args;
+
+/* pass 0: byte counts per block + exclusive scan (total bytes in block_count[yabpe_decode_blocks(n_ids)]);
+ * pass 1: write the bytes (out must hold that total). */
+int yabpe_decode_ids(const yabpe_decode_args* d, int32_t pass, void* stream);
+int64_t yabpe_decode_blocks(int64_t n_ids);
+
 /* Hot set for the warp kernel's shared-memory cache: from the tables of a counted SAMPLE of the corpus (`sample`, after
  * yabpe_pretok_count on e.g. its first 16 MB) pick, for every cache index, the most frequent key that maps to it.
  * hot_keys: yabpe_hot_cache_entries() * 16 bytes; scratch: yabpe_hot_cache_entries() * 8 bytes.  Result-neutral. */

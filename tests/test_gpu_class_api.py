@@ -133,3 +133,59 @@ def test_persisted_model_round_trip(yabpe, tmp_path):
         tok = yabpe.BBPETokenizer.from_file(tmp_path / f"model{i}")
         for e in c["encodes"]:
             assert tok.encode(e["text"]) == e["ids"], e["text"]
+
+
+# ------------------------------------------------------------------------------- decode on the device
+def test_decode_device_vs_host_gather(yabpe):
+    """yabpe_decode_ids against b"".join(vocab_inv[i] for i in ids if i in vocab_inv) (tokenizer.py:335-339):
+    unknown / negative / out-of-range ids are skipped, ids without bytes (gaps in the vocabulary) too."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(11)
+    vocab, merges = common.gpt2_vocab_and_merges()
+    tok = yabpe.Tokenizer(vocab, merges, ["<|endoftext|>"]).inner
+    gappy = {i: b for i, b in vocab.items() if i % 7 != 3}                 # ids 3, 10, 17, ... are not in the vocabulary
+    gappy[60000] = b"x" * 300                                              # a long token beyond a gap
+    tok2 = yabpe.Tokenizer(gappy, [], None).inner
+    for t, inv in ((tok, vocab), (tok2, gappy)):
+        for n in (1, 2047, 2048, 2049, 300_000):
+            ids = rng.integers(-3, 60_010, size=n).astype(np.int32)
+            ids[rng.integers(0, n, size=max(1, n // 50))] = 60000
+            got = t.decode_device(torch.from_numpy(ids).cuda()).cpu().numpy().tobytes()
+            assert got == b"".join(inv[i] for i in ids.tolist() if i in inv), n
+    assert tok.decode_device(torch.empty(0, dtype=torch.int32, device="cuda")).numel() == 0
+    # nothing to write at all
+    assert tok2.decode_device(torch.full((5000,), 3, dtype=torch.int32, device="cuda")).numel() == 0
+
+
+def test_decode_long_lists_take_the_device_path(yabpe, monkeypatch):
+    from yabpe import tokenizer as T
+    vocab, merges = common.gpt2_vocab_and_merges()
+    tok = yabpe.Tokenizer(vocab, merges, ["<|endoftext|>"])
+    text = ("The quick brown fox — naïve café 中文 \U0001f643 don't stop.\r\n\r\n<|endoftext|>" * 3000)
+    ids = tok.encode(text)
+    assert len(ids) >= T._DECODE_DEVICE_MIN
+    calls = []
+    orig = T.BBPETokenizer.decode_device
+    monkeypatch.setattr(T.BBPETokenizer, "decode_device", lambda self, *a, **k: (calls.append(1), orig(self, *a, **k))[1])
+    assert tok.decode(ids) == text and calls
+    # truncated inside a multi-byte character: strict decode fails, the whole buffer is re-decoded with replacement
+    cut = ids[: len(ids) - 7] + [{b: i for i, b in vocab.items()}[b"\xe4"]]
+    host = b"".join(vocab[i] for i in cut)
+    assert tok.decode(cut) == host.decode("utf-8", errors="replace")
+    assert tok.decode(ids[:50]) == b"".join(vocab[i] for i in ids[:50]).decode("utf-8", errors="replace")
+    assert tok.decode([]) == ""
+
+
+def test_encode_decode_round_trip_on_device(yabpe):
+    """Size-independent property at 64 MB: decode(encode(text)) is the text, byte for byte, without leaving the device."""
+    import sys
+    import torch
+    sys.path.insert(0, str(common.ROOT / "tools"))
+    from synth_gpu import synth_corpus_device
+    vocab, merges = common.gpt2_vocab_and_merges()
+    tok = yabpe.Tokenizer(vocab, merges, ["<|endoftext|>"]).inner
+    text_dev, n = synth_corpus_device(torch, 64 << 20, "owt", 20260103)
+    ids, _ = tok.encode_device(text_dev, n)
+    out = tok.decode_device(ids.clone())
+    assert out.numel() == n and torch.equal(out, text_dev[:n])

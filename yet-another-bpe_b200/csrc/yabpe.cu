@@ -6,6 +6,7 @@
 #include "../../include/yabpe.h"
 #include "encode.cuh"
 #include "pretok_fast.cuh"
+#include "decode.cuh"
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
@@ -46,6 +47,7 @@ extern "C" int64_t yabpe_sizeof(int32_t which) {
         case 2: return (int64_t)sizeof(yabpe_merge_args);
         case 3: return (int64_t)sizeof(yabpe_encode_model);
         case 4: return (int64_t)sizeof(yabpe_encode_out);
+        case 5: return (int64_t)sizeof(yabpe_decode_args);
         default: return -1;
     }
 }
@@ -456,6 +458,31 @@ extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_m
     } else {
         ARG_CHECK(o->out_ids || o->out_cap == 0);
         k_encode_tiles<true><<<grid, PT_THREADS, 0, st>>>(P, E, O); LAUNCHED();
+    }
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
+// ---- decode: ids -> bytes ----
+extern "C" int64_t yabpe_decode_blocks(int64_t n_ids) { return n_ids > 0 ? (n_ids + DC_IDS - 1) / DC_IDS : 0; }
+
+extern "C" int yabpe_decode_ids(const yabpe_decode_args* d, int32_t pass, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(d && d->n_ids >= 0 && d->block_count && d->vocab_cap >= 0);
+    if (d->n_ids == 0) return YABPE_OK;
+    ARG_CHECK(d->ids && d->tok_off && d->tok_bytes);
+    DecodeParams D;
+    D.ids = d->ids; D.n_ids = d->n_ids; D.tok_off = (const i64*)d->tok_off; D.tok_bytes = d->tok_bytes;
+    D.vocab_cap = d->vocab_cap; D.block_count = (i64*)d->block_count; D.out = d->out; D.out_cap = d->out_cap;
+    const i64 n_blocks = yabpe_decode_blocks(d->n_ids);
+    i64 grid = (i64)num_sms() * 8;
+    if (grid > n_blocks) grid = n_blocks;
+    if (pass == 0) {
+        k_decode_ids<false><<<(int)grid, DC_THREADS, 0, st>>>(D); LAUNCHED();
+        k_scan_tiles<<<1, 1024, 0, st>>>(D.block_count, n_blocks); LAUNCHED();
+    } else {
+        ARG_CHECK(d->out || d->out_cap == 0);
+        k_decode_ids<true><<<(int)grid, DC_THREADS, 0, st>>>(D); LAUNCHED();
     }
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;

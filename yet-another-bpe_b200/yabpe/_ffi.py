@@ -25,7 +25,7 @@ EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
     "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize", "yabpe_hot_cache_entries",
-    "yabpe_select_hot", "yabpe_token_starts",
+    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks",
 ]
 
 
@@ -89,6 +89,12 @@ class EncodeOut(C.Structure):
     _fields_ = [("tile_count", C.c_void_p), ("out_ids", C.c_void_p), ("out_cap", C.c_int64), ("doc_off", C.c_void_p)]
 
 
+class DecodeArgs(C.Structure):
+    _fields_ = [("ids", C.c_void_p), ("n_ids", C.c_int64), ("tok_off", C.c_void_p), ("tok_bytes", C.c_void_p),
+                ("vocab_cap", C.c_int32), ("_pad", C.c_int32), ("block_count", C.c_void_p),
+                ("out", C.c_void_p), ("out_cap", C.c_int64)]
+
+
 _lib: C.CDLL | None = None
 _device_ready: set[int] = set()
 
@@ -131,9 +137,13 @@ def load() -> C.CDLL:
     L.yabpe_select_hot.argtypes = [C.POINTER(PretokArgs), C.c_void_p, C.c_void_p, C.c_void_p]
     L.yabpe_token_starts.restype = C.c_int
     L.yabpe_token_starts.argtypes = [C.POINTER(PretokArgs), C.c_void_p, C.c_void_p]
+    L.yabpe_decode_ids.restype = C.c_int
+    L.yabpe_decode_ids.argtypes = [C.POINTER(DecodeArgs), C.c_int32, C.c_void_p]
+    L.yabpe_decode_blocks.restype = C.c_int64
+    L.yabpe_decode_blocks.argtypes = [C.c_int64]
     L.yabpe_sizeof.restype = C.c_int64
     L.yabpe_sizeof.argtypes = [C.c_int32]
-    for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut)):
+    for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut, DecodeArgs)):
         if L.yabpe_sizeof(which) != C.sizeof(st):
             raise YabpeUnavailable(f"{st.__name__}: ctypes layout ({C.sizeof(st)} B) != libyabpe.so ({L.yabpe_sizeof(which)} B); rebuild")
     if L.yabpe_abi_version() != ABI_VERSION:

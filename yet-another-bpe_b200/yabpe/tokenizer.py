@@ -18,6 +18,8 @@ from . import _ffi, engine
 
 _ITER_BATCH_BYTES = 4 << 20
 _ITER_BATCH_ITEMS = 1 << 16
+_DECODE_DEVICE_MIN = 1 << 16       # ids; shorter lists are gathered on the host
+_DECODE_DEVICE_MAX_ID = 1 << 24    # offsets are a dense array over the id range
 
 
 class BBPETokenizer:
@@ -231,12 +233,64 @@ class BBPETokenizer:
             for ids in self.encode_batch(batch):
                 yield from ids
 
+    def _device_vocab(self, torch):
+        """Vocabulary bytes as (offsets int64 [cap + 1], pool uint8) on the device; ids without bytes get an empty range."""
+        dev = torch.cuda.current_device()
+        dv = getattr(self, "_dev_vocab", None)
+        if dv is None or dv[0] != dev:
+            inv = self._vocab_inv
+            cap = max((i for i in inv if isinstance(i, int) and 0 <= i < (1 << 31) - 1), default=-1) + 1
+            lens = np.zeros(cap + 1, dtype=np.int64)
+            for i, b in inv.items():
+                if 0 <= i < cap:
+                    lens[i + 1] = len(b)
+            off = np.cumsum(lens)
+            pool = np.frombuffer(b"".join(inv[i] for i in range(cap) if i in inv) + b"\0" * 16, dtype=np.uint8).copy()
+            dv = (dev, cap, torch.from_numpy(off).cuda(), torch.from_numpy(pool).cuda())
+            self._dev_vocab = dv
+        return dv[1], dv[2], dv[3]
+
+    def decode_device(self, ids_dev, n_ids: int | None = None):
+        """Bytes of the ids in an int32 device tensor, as a uint8 device tensor (yabpe_decode_ids: ids that are not in
+        the vocabulary are skipped, tokenizer.py:335-339).  One host sync (the byte count)."""
+        torch = _ffi.require_cuda()
+        L = _ffi.load()
+        n_ids = int(ids_dev.numel()) if n_ids is None else int(n_ids)
+        if n_ids == 0:
+            return torch.empty(0, dtype=torch.uint8, device="cuda")
+        assert ids_dev.dtype == torch.int32 and ids_dev.is_cuda and ids_dev.is_contiguous()
+        cap, off, pool = self._device_vocab(torch)
+        n_blocks = int(L.yabpe_decode_blocks(n_ids))
+        counts = torch.empty(n_blocks + 1, dtype=torch.int64, device="cuda")
+        d = _ffi.DecodeArgs()
+        d.ids, d.n_ids, d.tok_off, d.tok_bytes, d.vocab_cap = ids_dev.data_ptr(), n_ids, off.data_ptr(), pool.data_ptr(), cap
+        d.block_count, d.out, d.out_cap = counts.data_ptr(), None, 0
+        stream = _ffi.stream_ptr(torch)
+        _ffi.check(L.yabpe_decode_ids(C.byref(d), 0, stream))
+        total = int(counts[n_blocks].item())
+        out = torch.empty(max(total, 1), dtype=torch.uint8, device="cuda")
+        d.out, d.out_cap = out.data_ptr(), total
+        _ffi.check(L.yabpe_decode_ids(C.byref(d), 1, stream))
+        return out[:total]
+
     def decode(self, ids: Sequence[int]) -> str:
-        """tokenizer.py:323-349: unknown ids skipped; strict UTF-8, else errors='replace'."""
+        """tokenizer.py:323-349: unknown ids skipped; strict UTF-8, else errors='replace'.  The byte gather runs on
+        the device from _DECODE_DEVICE_MIN ids up (below that a kernel launch costs more than the join)."""
         if not len(ids):
             return ""
-        inv = self._vocab_inv
-        buf = b"".join(inv[i] for i in ids if i in inv)
+        buf = None
+        if len(ids) >= _DECODE_DEVICE_MIN and max(self._vocab_inv, default=0) < _DECODE_DEVICE_MAX_ID:
+            try:
+                arr = np.asarray(ids, dtype=np.int64)
+            except (OverflowError, TypeError, ValueError):
+                arr = None
+            if arr is not None and arr.ndim == 1:
+                torch = _ffi.require_cuda()
+                arr = np.where((arr >= 0) & (arr < (1 << 31) - 1), arr, -1).astype(np.int32)
+                buf = self.decode_device(torch.from_numpy(arr).cuda()).cpu().numpy().tobytes()
+        if buf is None:
+            inv = self._vocab_inv
+            buf = b"".join(inv[i] for i in ids if i in inv)
         try:
             return buf.decode("utf-8")
         except UnicodeDecodeError:
