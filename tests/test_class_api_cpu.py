@@ -63,3 +63,14 @@ def test_save_before_training_raises(tmp_path):
     import yabpe
     with pytest.raises(ValueError, match="not been trained"):
         yabpe.BBPETrainer().save(tmp_path / "x")
+
+
+def test_cli_arguments_and_missing_input(tmp_path, capsys):
+    """scripts/train_bpe.py: the reference script's defaults, and its FileNotFoundError before any device work."""
+    import pytest
+    from yabpe.scripts import train_bpe
+    with pytest.raises(SystemExit) as e:
+        train_bpe.main(["--help"])
+    assert e.value.code == 0 and "--vocab-size" in capsys.readouterr().out
+    with pytest.raises(FileNotFoundError, match="Data file not found"):
+        train_bpe.main(["--input", str(tmp_path / "nope.txt")])

@@ -189,3 +189,16 @@ def test_encode_decode_round_trip_on_device(yabpe):
     ids, _ = tok.encode_device(text_dev, n)
     out = tok.decode_device(ids.clone())
     assert out.numel() == n and torch.equal(out, text_dev[:n])
+
+
+def test_cli_trains_and_saves(yabpe, tmp_path, capsys):
+    from yabpe.scripts import train_bpe
+    out = tmp_path / "model"
+    assert train_bpe.main(["--input", str(common.FIXTURES / "corpus.en"), "--output", str(out), "--vocab-size", "400",
+                           "--min-frequency", "2"]) == 0
+    assert "Number of merges: 143" in capsys.readouterr().out
+    tok = yabpe.BBPETokenizer.from_file(out)
+    assert tok.vocab_size == 400 and tok.special_tokens == ["<|endoftext|>"]
+    want_vocab, want_merges = oracle.train_bpe(common.FIXTURES / "corpus.en", 400, ["<|endoftext|>"], min_frequency=2,
+                                               chunk_size_bytes=20 << 20)
+    assert len(want_merges) == 143 and tok.decode(tok.encode("the cat sat")) == "the cat sat"
