@@ -155,3 +155,39 @@ def test_encode_matches_reference():
     for _ in range(500):
         s = "".join(rng.choice("ab ") for _ in range(rng.randint(0, 12)))
         assert orc.encode(s) == ref.encode(s), s
+
+
+def test_class_api_surface_matches_reference():
+    """Every public name, config default and call signature a user of the reference relies on exists, unchanged,
+    in the replacement classes -- plus the private entry points the reference's tests call."""
+    import dataclasses
+    import inspect
+    sys.path.insert(0, str(REF / "src"))
+    import yet_another_bpe.tokenizer as rt
+    import yet_another_bpe.trainer as rr
+    import yabpe.tokenizer as ot
+    import yabpe.trainer as otr
+
+    ref_cfg = {f.name: (f.default if f.default is not dataclasses.MISSING else f.default_factory())
+               for f in dataclasses.fields(rr.BBPETrainerConfig)}
+    our_cfg = {f.name: (f.default if f.default is not dataclasses.MISSING else f.default_factory())
+               for f in dataclasses.fields(otr.BBPETrainerConfig)}
+    assert our_cfg == ref_cfg
+
+    def public(cls):
+        return {n for n, v in inspect.getmembers(cls) if not n.startswith("_") and (callable(v) or isinstance(v, property))}
+
+    def params(fn):
+        return [p for p in inspect.signature(fn).parameters if p != "self"]
+
+    for ref_cls, our_cls, private in ((rr.BBPETrainer, otr.BBPETrainer, ["_preprocess_corpus", "_merge_loop", "_init_base_vocab"]),
+                                      (rt.BBPETokenizer, ot.BBPETokenizer, []),
+                                      (rr.BBPEModel, otr.BBPEModel, [])):
+        missing = public(ref_cls) - public(our_cls)
+        assert not missing, (ref_cls.__name__, missing)
+        for name in sorted(public(ref_cls)) + private + ["__init__"]:
+            r, o = getattr(ref_cls, name), getattr(our_cls, name)
+            if isinstance(r, property):
+                assert isinstance(o, property), name
+                continue
+            assert params(o)[: len(params(r))] == params(r), (ref_cls.__name__, name, params(r), params(o))
