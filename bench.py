@@ -46,6 +46,7 @@ SPECIALS = ["<|endoftext|>"]
 # pre-tokens, so its count-table traffic dwarfs the text itself
 NCU_TRAFFIC_RATIO = {"tinystories": 1.24, "owt": 7.0}
 METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
+ENCODE_METRIC = "GPT-2 encode throughput (pretokenize + BPE by rank + ids in text order)"
 UNIT = "MB/s"
 
 
@@ -141,6 +142,30 @@ def run_reference(args) -> None:
     if sample is None:
         gen = common.synth_tinystories if kind == "tinystories" else common.synth_owt
         sample = gen(sample_bytes, seed=seed)
+    if args.workload.startswith("gpt2-encode"):
+        # BASELINE.json configs[3]: the reference's encode (tokenizer.py:152-308) as the C port, GPT-2 vocabulary
+        from oracle import oracle
+        gv, gm = common.gpt2_vocab_and_merges()
+        otok = oracle.Tokenizer(gv, gm, SPECIALS)
+        text = sample.decode("utf-8")
+        for _ in range(args.warmup):
+            otok.encode(text[: 1 << 20])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n_ids = len(otok.encode(text))
+        t = time.perf_counter() - t0
+        mbps = len(sample) * args.steps / t / 1e6
+        print(json.dumps({
+            "impl": "reference", "metric": ENCODE_METRIC, "value": round(mbps, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * t / args.steps, 2), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": args.workload, "vocab_size": len(gv), "merges": len(gm), "special_tokens": SPECIALS,
+                       "note": "reference is pure Python (not on the GPU box); timed: C port of tokenizer.py, one core"},
+            "cpu_baseline": {"value": round(mbps, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{len(sample)} bytes of the {kind}-shaped generator (seed {seed}), {n_ids} ids per step"},
+            "e2e": {"value": round(mbps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
     for _ in range(args.warmup):
         cpu_port_run(sample[: 1 << 20], vocab)
     t = 0.0
@@ -248,12 +273,18 @@ def run_encode(args) -> None:
         ids_h = torch.empty(n_ids, dtype=torch.int32).pin_memory()          # pinned landing buffer for the ids
 
         def e2e_step():
+            if args.encode_e2e == "pipelined":    # the host-buffer API: pieces cut after specials, copies overlap the encode
+                return int(tok.encode_pinned(host, out=ids_h, piece_bytes=args.piece_mb << 20).numel())
             dev2, n2 = engine.to_device_text(torch, host, non_blocking=True)
             ids2, _ = tok.encode_device(dev2, n2, reuse_output=True)
             ids_h[: ids2.numel()].copy_(ids2, non_blocking=True)
             return int(ids2.numel())
 
+        ids_ref = ids.clone()                     # device-resident result of the timed region (the reuse buffer is overwritten below)
         e2e_step()                                # warm-up: allocator blocks for the text copy
+        torch.cuda.synchronize()
+        assert torch.equal(ids_h[:n_ids].cuda(), ids_ref), "end-to-end ids differ from the device-resident run"
+        del ids_ref
         reps = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
@@ -265,7 +296,8 @@ def run_encode(args) -> None:
         if world > 1:
             tm = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(tm, op=dist.ReduceOp.MAX); dt = float(tm.item())
         e2e = {"value": round(total_bytes / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(total_bytes),
-               "d2h_bytes_per_step": int(4 * total_ids), "ms_per_step": round(dt * 1e3, 2)}
+               "d2h_bytes_per_step": int(4 * total_ids), "ms_per_step": round(dt * 1e3, 2),
+               "mode": args.encode_e2e + (f" ({args.piece_mb} MiB pieces, H2D / encode / D2H on three streams)" if args.encode_e2e == "pipelined" else "")}
     cpu = None
     if not args.skip_cpu and rank == 0 and world == 1:
         from oracle import oracle
@@ -278,7 +310,7 @@ def run_encode(args) -> None:
                "sample": f"first {len(sample)} bytes of the same text, {len(want)} ids, {dt:.1f} s; C port of tokenizer.py (one core, as the reference)"}
     if rank == 0:
         print(json.dumps({
-            "metric": "GPT-2 encode throughput (pretokenize + BPE by rank + ids in text order)", "value": round(value, 2), "unit": UNIT,
+            "metric": ENCODE_METRIC, "value": round(value, 2), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": f"synthetic ({kind}-shaped, torch generator, seed {seed})",
             "config": {"workload": args.workload, "total_bytes": int(total_bytes), "bytes_per_gpu": n, "vocab_size": len(vocab), "merges": len(merges),
@@ -300,6 +332,8 @@ def main() -> None:
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--encode-mb", type=int, default=256)
+    ap.add_argument("--encode-e2e", default="pipelined", choices=["pipelined", "serial"])
+    ap.add_argument("--piece-mb", type=int, default=128)
     args = ap.parse_args()
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("YABPE_BENCH_WATCHDOG_S", "600")), exit=True)   # never hang a GPU box

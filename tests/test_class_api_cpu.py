@@ -74,3 +74,37 @@ def test_cli_arguments_and_missing_input(tmp_path, capsys):
     assert e.value.code == 0 and "--vocab-size" in capsys.readouterr().out
     with pytest.raises(FileNotFoundError, match="Data file not found"):
         train_bpe.main(["--input", str(tmp_path / "nope.txt")])
+
+
+def test_encode_pinned_piece_cuts_are_exact():
+    """BBPETokenizer._piece_ends (host logic of encode_pinned): pieces end right after a special token, so the
+    concatenation of the oracle's per-piece ids equals its ids for the whole text; specials that could overlap
+    (several, or one with a border) keep the text in one piece."""
+    import numpy as np
+    import yabpe
+    vocab, merges = oracle.train_bpe_bytes(common.synth_tinystories(60_000, seed=3), 400, ["<|endoftext|>"])
+    text = common.synth_tinystories(300_000, seed=5) + b"<|endoftext|><|endoftext|>tail without a separator " * 3
+    host = np.frombuffer(text, dtype=np.uint8)
+    inv = {v: k for k, v in vocab.items()}
+    tok = yabpe.BBPETokenizer(vocab=inv, merges=merges, special_tokens=["<|endoftext|>"])
+    otok = oracle.Tokenizer(vocab, merges, ["<|endoftext|>"])
+    want = otok.encode(text.decode("utf-8"))
+    for piece in (1_000, 4_096, 50_000, 250_000, 1 << 20):
+        ends = tok._piece_ends(host, len(text), piece)
+        assert ends[-1] == len(text) and ends == sorted(set(ends))
+        if piece < len(text) // 2:
+            assert len(ends) > 1
+        got, lo = [], 0
+        for e in ends:
+            if e != len(text):
+                assert text[:e].endswith(b"<|endoftext|>")
+            got += otok.encode(text[lo:e].decode("utf-8"))
+            lo = e
+        assert got == want, piece
+    # no special in the text at all / two specials / a special with a border: one piece
+    plain = np.frombuffer(b"abc def " * 4000, dtype=np.uint8)
+    assert tok._piece_ends(plain, plain.size, 1000) == [plain.size]
+    two = yabpe.BBPETokenizer(vocab=inv, merges=merges, special_tokens=["<|endoftext|>", "<|pad|>"])
+    assert two._piece_ends(host, len(text), 1000) == [len(text)]
+    bordered = yabpe.BBPETokenizer(vocab=inv, merges=merges, special_tokens=["|x|"])
+    assert bordered._piece_ends(np.frombuffer(b"a|x|x|b " * 999, dtype=np.uint8), 7992, 100) == [7992]

@@ -316,6 +316,28 @@ def test_encode_synthetic_and_long_words(yabpe):
     assert t.encode(long_text) == o.encode(long_text)
 
 
+def test_encode_pinned_streams_pieces_exactly(yabpe):
+    """encode_pinned (host bytes in, host ids out, pieces pipelined over three streams) == encode of the whole text,
+    for piece sizes from a few documents to everything, pinned or pageable input, given or grown output buffer."""
+    import torch
+    v, m = common.gpt2_vocab_and_merges()
+    t = yabpe.Tokenizer(v, m, ["<|endoftext|>"]).inner
+    o = oracle.Tokenizer(v, m, ["<|endoftext|>"])
+    raw = common.synth_owt(3_000_000, seed=11) + b"<|endoftext|><|endoftext|> tail"
+    want = o.encode(raw.decode("utf-8"))
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    pinned = host.pin_memory()
+    for piece in (20_000, 300_000, 1_000_000, 1 << 30):
+        assert t.encode_pinned(pinned, piece_bytes=piece).tolist() == want, piece
+    out = torch.empty(len(want) + 5, dtype=torch.int32).pin_memory()
+    got = t.encode_pinned(pinned, out=out, piece_bytes=250_000)
+    assert got.data_ptr() == out.data_ptr() and got.tolist() == want
+    small = torch.empty(1000, dtype=torch.int32).pin_memory()          # too small: a larger buffer is allocated
+    assert t.encode_pinned(host, out=small, piece_bytes=250_000).tolist() == want
+    assert t.encode_pinned(torch.empty(0, dtype=torch.uint8)).numel() == 0
+    assert t.encode(raw.decode("utf-8")) == want                        # the plain path is untouched by the streams
+
+
 def test_encode_roundtrip_property_large(yabpe):
     """Size-independent property at a larger size: decode(encode(x)) == x, ids are valid."""
     v, m = common.gpt2_vocab_and_merges()

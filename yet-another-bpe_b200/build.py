@@ -12,8 +12,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "csrc" / "yabpe.cu"
 OUT = HERE / "yabpe" / "libyabpe.so"
-DEPS = [HERE / "csrc" / n for n in ("yabpe.cu", "common.cuh", "pretok.cuh", "merge.cuh", "encode.cuh",
-                                    "unicode_tables.inc")] + [HERE.parent / "include" / "yabpe.h"]
+DEPS = sorted((HERE / "csrc").glob("*.cu*")) + [HERE / "csrc" / "unicode_tables.inc", HERE.parent / "include" / "yabpe.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

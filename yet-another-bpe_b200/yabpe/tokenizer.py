@@ -176,6 +176,110 @@ class BBPETokenizer:
         self._keep = (res, words, tile_count)
         return ids[:total], doc_off
 
+    # -- host buffers in, host buffers out ------------------------------------------------------
+    def _piece_ends(self, host_np: np.ndarray, n: int, piece_bytes: int) -> list[int]:
+        """Ends of the pieces `encode_pinned` streams: every interior end lies right after an occurrence of the
+        special token, so that encode(text) == concat(encode(piece)) (tokenizer.py:171-189: the parts between
+        specials are independent texts).  Exact only when occurrences cannot overlap each other -- one special
+        token without a border (no proper prefix that is also a suffix); otherwise the text stays one piece."""
+        if n <= piece_bytes or len(self._sp_bytes) != 1:
+            return [n]
+        sp = self._sp_bytes[0]
+        if any(sp[:k] == sp[-k:] for k in range(1, len(sp))):
+            return [n]
+        ends: list[int] = []
+        lo = 0
+        while n - lo > piece_bytes + piece_bytes // 2:
+            target, window, at = lo + piece_bytes, 1 << 16, -1
+            while at < 0 and window <= 2 * piece_bytes:
+                a = max(lo, target - window)
+                at = host_np[a:target].tobytes().rfind(sp)
+                if at >= 0:
+                    at += a
+                elif a == lo:
+                    break
+                window *= 4
+            if at < 0:                            # no special inside this piece: look forward instead
+                at = host_np[target:n].tobytes().find(sp)
+                if at < 0:
+                    break
+                at += target
+            lo = at + len(sp)
+            if lo >= n:
+                break
+            ends.append(lo)
+        ends.append(n)
+        return ends
+
+    def encode_pinned(self, host, out=None, piece_bytes: int = 128 << 20):
+        """ids of the UTF-8 bytes in `host` (1-D uint8 torch tensor, ideally pinned) as an int32 host tensor.
+
+        The text is streamed through the device in pieces cut after special tokens (`_piece_ends`): the
+        host->device copy of piece i+1 and the device->host copy of the ids of piece i-1 run on their own
+        streams while piece i is encoded, so a large buffer costs about max(copy in, encode, copy out)
+        instead of their sum.  `out` (pinned int32, optional) receives the ids when it is large enough; the
+        returned tensor is a view of it.  Same ids as `encode` of the whole text."""
+        torch = _ffi.require_cuda()
+        n = int(host.numel())
+        if n == 0:
+            return torch.empty(0, dtype=torch.int32)
+        assert host.dtype == torch.uint8 and host.dim() == 1 and not host.is_cuda
+        ends = self._piece_ends(host.numpy(), n, int(piece_bytes))
+        starts = [0] + ends[:-1]
+        cap = max(((e - s + 15) // 16) * 16 + 64 for s, e in zip(starts, ends))
+        cur = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_in.wait_stream(cur)
+        bufs = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(min(2, len(ends)))]
+        free_ev = [None] * len(bufs)               # the encode of the piece that used the buffer last
+        in_ev: list = [None] * len(ends)
+
+        def copy_in(i: int) -> None:
+            b, ln = bufs[i % len(bufs)], ends[i] - starts[i]
+            with torch.cuda.stream(s_in):
+                if free_ev[i % len(bufs)] is not None:
+                    s_in.wait_event(free_ev[i % len(bufs)])
+                b[:ln].copy_(host[starts[i]:ends[i]], non_blocking=True)
+                b[ln:((ln + 15) // 16) * 16 + 64].zero_()
+                in_ev[i] = torch.cuda.Event()
+                in_ev[i].record(s_in)
+
+        def ensure_out(need: int, done: int, used: int):
+            """A pinned landing buffer for `need` ids; the `used` ids already copied are carried over."""
+            nonlocal out
+            if out is not None and out.numel() >= need:
+                return
+            est = int(need * (n / done) * 1.05) + 4096        # ids per byte so far, scaled to the whole text
+            new = torch.empty(max(est, need), dtype=torch.int32).pin_memory()
+            if used:
+                s_out.synchronize()
+                new[:used].copy_(out[:used])
+            out = new
+
+        if out is not None:
+            assert out.dtype == torch.int32 and out.dim() == 1 and not out.is_cuda
+        pos = 0
+        copy_in(0)
+        for i in range(len(ends)):
+            if i + 1 < len(ends):
+                copy_in(i + 1)
+            cur.wait_event(in_ev[i])
+            ln = ends[i] - starts[i]
+            ids, _ = self.encode_device(bufs[i % len(bufs)][:((ln + 15) // 16) * 16 + 64], ln)
+            done = torch.cuda.Event()
+            done.record(cur)
+            free_ev[i % len(bufs)] = done
+            k = int(ids.numel())
+            ensure_out(pos + k, ends[i], pos)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                out[pos:pos + k].copy_(ids, non_blocking=True)
+            ids.record_stream(s_out)
+            pos += k
+        s_out.synchronize()
+        cur.wait_stream(s_in)
+        return out[:pos]
+
     # -- reference API --------------------------------------------------------------------------
     def encode(self, text: str) -> list[int]:
         if not text:
