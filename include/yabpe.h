@@ -243,6 +243,12 @@ int64_t yabpe_decode_blocks(int64_t n_ids);
 int32_t yabpe_hot_cache_entries(void);
 int yabpe_select_hot(const yabpe_pretok_args* sample, void* hot_keys, void* scratch, void* stream);
 
+/* Store n_words (<= 4096) int64 device words into MAPPED pinned host memory (cudaHostAlloc / torch pin_memory under
+ * unified addressing) from a kernel: stream-ordered like a copy, but it does not wait for the copy engines, which
+ * BBPETokenizer.encode_pinned keeps busy with bulk transfers.  The host reads them after an event on `stream`.
+ * (Replaces the `.item()` / `.cpu()` reads of table statistics; no reference counterpart.) */
+int yabpe_publish(void* host_mapped_dst, const void* device_src, int32_t n_words, void* stream);
+
 /* kernels launched by this library since load (the bench's `gpu_launches`) */
 int64_t yabpe_launch_count(void);
 

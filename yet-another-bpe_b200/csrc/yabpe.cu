@@ -463,6 +463,22 @@ extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_m
     return YABPE_OK;
 }
 
+// ---- counters to the host without a copy engine ----
+// A few 64-bit words, stored by one warp straight into MAPPED pinned host memory.  A cudaMemcpy of the same words would
+// queue behind whatever bulk transfer occupies the device-to-host copy engine (encode_pinned streams GBs of ids while
+// the next piece needs its table statistics); a store from an SM does not.
+__global__ void k_publish(volatile i64* host_dst, const i64* src, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += 32) host_dst[i] = src[i];
+    __threadfence_system();
+}
+
+extern "C" int yabpe_publish(void* host_mapped_dst, const void* device_src, int32_t n_words, void* stream) {
+    ARG_CHECK(host_mapped_dst && device_src && n_words > 0 && n_words <= 4096);
+    k_publish<<<1, 32, 0, (cudaStream_t)stream>>>((volatile i64*)host_mapped_dst, (const i64*)device_src, n_words); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
 // ---- decode: ids -> bytes ----
 extern "C" int64_t yabpe_decode_blocks(int64_t n_ids) { return n_ids > 0 ? (n_ids + DC_IDS - 1) / DC_IDS : 0; }
 

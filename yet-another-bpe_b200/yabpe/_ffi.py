@@ -25,7 +25,7 @@ EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
     "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize", "yabpe_hot_cache_entries",
-    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks",
+    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks", "yabpe_publish",
 ]
 
 
@@ -141,6 +141,8 @@ def load() -> C.CDLL:
     L.yabpe_decode_ids.argtypes = [C.POINTER(DecodeArgs), C.c_int32, C.c_void_p]
     L.yabpe_decode_blocks.restype = C.c_int64
     L.yabpe_decode_blocks.argtypes = [C.c_int64]
+    L.yabpe_publish.restype = C.c_int
+    L.yabpe_publish.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.yabpe_sizeof.restype = C.c_int64
     L.yabpe_sizeof.argtypes = [C.c_int32]
     for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut, DecodeArgs)):

@@ -56,6 +56,25 @@ def to_device_text(torch, host: np.ndarray | "torch.Tensor", non_blocking: bool 
     return dev, n
 
 
+class Mailbox:
+    """Pinned host words that a kernel writes directly (yabpe_publish, mapped memory under unified addressing).
+    Reading a few device counters this way is stream-ordered like `.cpu()` but does not use a copy engine, so it is
+    not held up by bulk transfers running on other streams (BBPETokenizer.encode_pinned)."""
+
+    def __init__(self, torch, n_words: int = 64) -> None:
+        self.torch = torch
+        self.buf = torch.zeros(n_words, dtype=torch.int64).pin_memory()
+        self.event = torch.cuda.Event()
+
+    def read(self, src, n_words: int) -> np.ndarray:
+        """The first `n_words` int64 words of the device tensor `src`, once the current stream has reached this point."""
+        assert src.dtype == self.torch.int64 and src.is_cuda and n_words <= self.buf.numel()
+        _ffi.check(_ffi.load().yabpe_publish(self.buf.data_ptr(), src.data_ptr(), n_words, _ffi.stream_ptr(self.torch)))
+        self.event.record()
+        self.event.synchronize()
+        return self.buf[:n_words].numpy().copy()
+
+
 @dataclass
 class PretokResult:
     args: _ffi.PretokArgs
@@ -65,21 +84,35 @@ class PretokResult:
     long_cap: int = 0
     text: "object" = None
     n: int = 0
+    mailbox: "Mailbox | None" = None
+    cold: bool = False                           # short-table layout chosen (interleaved slots)
+    hot: "object" = None                         # hot set handed to the warp kernel's cache
 
     def stats_host(self) -> np.ndarray:
+        if self.mailbox is not None:
+            return self.mailbox.read(self.stats, 16)
         return self.stats.cpu().numpy()
+
+    def sizing(self) -> tuple:
+        """(short_cap, long_cap, cold, hot): lets the next, similar text skip the sizing sample."""
+        return (self.short_cap, self.long_cap, self.cold, self.hot)
 
 
 def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: list[bytes], mode: int,
                  own: tuple[int, int] | None = None, short_cap: int | None = None,
                  long_cap: int | None = None, stage_events: list | None = None,
-                 generic_only: bool = False) -> PretokResult:
-    """Launch special resolution + the tile kernel + the long-token kernel (all async)."""
+                 generic_only: bool = False, mailbox: Mailbox | None = None, sizing: tuple | None = None) -> PretokResult:
+    """Launch special resolution + the tile kernel + the long-token kernel (all async).
+    `sizing` = PretokResult.sizing() of an earlier, similar text: its layout and hot set are reused and its capacities
+    are the default, so no sizing sample is counted.  `mailbox`: statistics reach the host through yabpe_publish."""
     L = _ffi.load()
     dev = text_dev.device
     cold_hint, hot = False, None
-    if short_cap is None or long_cap is None:
-        est_s, est_l, cold_hint, hot = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode)
+    if sizing is not None:
+        short_cap, long_cap = short_cap or sizing[0], long_cap or sizing[1]
+        cold_hint, hot = sizing[2], sizing[3]
+    elif short_cap is None or long_cap is None:
+        est_s, est_l, cold_hint, hot = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode, mailbox)
         short_cap = short_cap or est_s
         long_cap = long_cap or est_l
     n_cuts = 0 if cuts is None else int(len(cuts))
@@ -100,9 +133,13 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     ovf = torch.empty(ovf_cap, dtype=torch.int64, device=dev)
     work_cap = 4 * n_cuts + 64
     work = torch.empty(3 * work_cap, dtype=torch.int64, device=dev)
-    stats_np = np.zeros(16, dtype=np.int64)
-    stats_np[_ffi.ST_ERR_POS] = _ffi.INT64_MAX
-    stats = torch.from_numpy(stats_np).to(dev)
+    if mailbox is not None:                      # no host->device copy either: it would queue behind a bulk upload
+        stats = torch.zeros(16, dtype=torch.int64, device=dev)
+        stats[_ffi.ST_ERR_POS:_ffi.ST_ERR_POS + 1].fill_(_ffi.INT64_MAX)
+    else:
+        stats_np = np.zeros(16, dtype=np.int64)
+        stats_np[_ffi.ST_ERR_POS] = _ffi.INT64_MAX
+        stats = torch.from_numpy(stats_np).to(dev)
     a = _ffi.PretokArgs()
     a.text = text_dev.data_ptr(); a.n = n
     a.cuts = cuts_t.data_ptr() if n_cuts else None; a.n_cuts = n_cuts; a.mode = mode
@@ -117,7 +154,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     a.work = work.data_ptr(); a.work_cap = work_cap
     a.hot_keys = hot.data_ptr() if hot is not None else None
     res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work, hot], stats=stats,
-                       short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n)
+                       short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n, mailbox=mailbox, cold=interleaved, hot=hot)
     if n > 0:
         extra = 8 if generic_only else 0        # stages bit 3: generic tile kernel only (A/B parity tests)
         a.stages = extra
@@ -137,7 +174,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
 _SAMPLE_BYTES = 16 << 20
 
 
-def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode):
+def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode, mailbox: Mailbox | None = None):
     """Hash-table capacities.  Small inputs: proportional to n.  Large inputs: count the unique
     pre-tokens of a 16 MB prefix and extrapolate (Heaps' law, exponent 0.75), so that a 2 GB corpus
     with 10^5 word types does not zero and scan GB-sized tables.  Overflow is detected and retried.
@@ -148,11 +185,16 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode):
     if n <= 4 * _SAMPLE_BYTES:
         return (_pow2_at_least(min(max(n // 4, 1 << 12), 1 << 26)), _pow2_at_least(min(max(n // 32, 1 << 8), 1 << 24)), False, None)
     m = _SAMPLE_BYTES
-    while m > 0 and (int(text_dev[m].item()) & 0xC0) == 0x80:
-        m -= 1
+    if mailbox is not None:                      # the four bytes at the sample's end in one mailbox read
+        tail = mailbox.read(text_dev[m - 8:m + 8].view(torch.int64), 2).view(np.uint8)
+        while m > _SAMPLE_BYTES - 4 and (int(tail[8 + m - _SAMPLE_BYTES]) & 0xC0) == 0x80:
+            m -= 1
+    else:
+        while m > 0 and (int(text_dev[m].item()) & 0xC0) == 0x80:
+            m -= 1
     sub_cuts = None if cuts is None else np.asarray([c for c in cuts if 0 < c < m], dtype=np.int64)
     res = pretok_count(torch, text_dev, m, sub_cuts if sub_cuts is not None and len(sub_cuts) else None, specials, mode,
-                       short_cap=1 << 22, long_cap=1 << 20)     # the prefix as a text of its own: an estimate only
+                       short_cap=1 << 22, long_cap=1 << 20, mailbox=mailbox)     # the prefix as a text of its own: an estimate only
     st = res.stats_host()
     scale = (n / m) ** 0.75
     us = max(int(st[_ffi.ST_UNIQ_SHORT]), 1 << 10) * scale
@@ -170,11 +212,13 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode):
 
 
 def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None,
-                         generic_only: bool = False) -> tuple[PretokResult, np.ndarray]:
+                         generic_only: bool = False, mailbox: Mailbox | None = None,
+                         sizing: tuple | None = None) -> tuple[PretokResult, np.ndarray]:
     """pretok_count + one host sync; grows the tables and retries when they overflow."""
     short_cap = long_cap = None
     for _ in range(8):
-        res = pretok_count(torch, text_dev, n, cuts, specials, mode, own, short_cap, long_cap, generic_only=generic_only)
+        res = pretok_count(torch, text_dev, n, cuts, specials, mode, own, short_cap, long_cap, generic_only=generic_only,
+                           mailbox=mailbox, sizing=sizing)
         st = res.stats_host()
         if st[_ffi.ST_TABLE_FULL] == 0:
             return res, st

@@ -110,12 +110,14 @@ class BBPETokenizer:
         return self._dev[1]
 
     def encode_device(self, text_dev, n: int, cuts: np.ndarray | None = None, own: tuple[int, int] | None = None,
-                      reuse_output: bool = False):
+                      reuse_output: bool = False, mailbox: "engine.Mailbox | None" = None, sizing: tuple | None = None):
         """Encode `n` bytes resident on the device; `cuts` = interior document boundaries.
         Returns (ids tensor int32 on device, doc_off tensor int64 or None).  One host sync
         (table sizes) + one (id count).  reuse_output=True writes the ids into a buffer kept by the
         tokenizer (sized from the previous call, grown on demand): no allocation and no host sync between
-        the two tile passes; the returned view is valid until the next call."""
+        the two tile passes; the returned view is valid until the next call.
+        `mailbox` / `sizing` (encode_pinned): counters reach the host through yabpe_publish instead of copies, and
+        the table sizing of an earlier piece (`self.last_sizing`) replaces the sizing sample."""
         torch = _ffi.require_cuda()
         L = _ffi.load()
         if n == 0:
@@ -130,7 +132,9 @@ class BBPETokenizer:
                 ev = torch.cuda.Event(enable_timing=True); ev.record(); evs.append(ev)
 
         mark()
-        res, st = engine.pretok_count_checked(torch, text_dev, n, cuts, self._sp_bytes, mode=1, own=own)
+        res, st = engine.pretok_count_checked(torch, text_dev, n, cuts, self._sp_bytes, mode=1, own=own,
+                                              mailbox=mailbox, sizing=sizing)
+        self.last_sizing = res.sizing()
         mark()
         words = engine.compact_words(torch, res, st, with_maps=True)
         stream = _ffi.stream_ptr(torch)
@@ -162,7 +166,7 @@ class BBPETokenizer:
             self._ids_buf = buf
             ids = buf
         else:
-            total = int(tile_count[n_tiles].item())
+            total = int(mailbox.read(tile_count[n_tiles:], 1)[0]) if mailbox is not None else int(tile_count[n_tiles].item())
             ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
             o.out_ids = ids.data_ptr(); o.out_cap = total
             _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
@@ -189,7 +193,7 @@ class BBPETokenizer:
             return [n]
         ends: list[int] = []
         lo = 0
-        while n - lo > piece_bytes + piece_bytes // 2:
+        while n - lo > piece_bytes + piece_bytes // 8:      # a short last piece is fine: its ids are the un-overlapped tail
             target, window, at = lo + piece_bytes, 1 << 16, -1
             while at < 0 and window <= 2 * piece_bytes:
                 a = max(lo, target - window)
@@ -259,13 +263,17 @@ class BBPETokenizer:
         if out is not None:
             assert out.dtype == torch.int32 and out.dim() == 1 and not out.is_cuda
         pos = 0
+        mailbox = engine.Mailbox(torch)            # counters bypass the copy engines the bulk transfers occupy
+        sizing = None                              # table sizes, layout and hot set of the first piece serve the others
         copy_in(0)
         for i in range(len(ends)):
             if i + 1 < len(ends):
                 copy_in(i + 1)
             cur.wait_event(in_ev[i])
             ln = ends[i] - starts[i]
-            ids, _ = self.encode_device(bufs[i % len(bufs)][:((ln + 15) // 16) * 16 + 64], ln)
+            ids, _ = self.encode_device(bufs[i % len(bufs)][:((ln + 15) // 16) * 16 + 64], ln, mailbox=mailbox, sizing=sizing)
+            if sizing is None and len(ends) > 1 and ends[1] - starts[1] <= 2 * ln:
+                sizing = self.last_sizing
             done = torch.cuda.Event()
             done.record(cur)
             free_ev[i % len(bufs)] = done
