@@ -45,6 +45,9 @@ SPECIALS = ["<|endoftext|>"]
 # (profiles/r1_ncu_pretok_warp_details.txt, profiles/r1_ncu_pretok_warp_owt.txt): the OWT-shaped corpus has 50x the unique
 # pre-tokens, so its count-table traffic dwarfs the text itself
 NCU_TRAFFIC_RATIO = {"tinystories": 1.24, "owt": 7.0}
+# the same for the encode tile passes (profiles/r1_ncu_encode_tiles.txt: 256 MB of OWT-shaped text, 3.0 M unique words): DRAM bytes per
+# TEXT byte -- the table probes (one 32-byte sector per token for the key + lookup record, another for its ids) dominate
+NCU_ENCODE_TRAFFIC_PER_TEXT_BYTE = {"count_pass_ms": 4.42, "write_pass_ms": 11.24}
 METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
 ENCODE_METRIC = "GPT-2 encode throughput (pretokenize + BPE by rank + ids in text order)"
 UNIT = "MB/s"
@@ -249,8 +252,10 @@ def run_encode(args) -> None:
     roofline = {"bound": "hbm", "kernel": {"pretok_count_ms": "k_pretok_count (mode 1)", "count_pass_ms": "k_encode_tiles<false>",
                                             "write_pass_ms": "k_encode_tiles<true>", "words_ms": "k_encode_words"}[dom],
                 "achieved": round(alg / (stage[dom] / 1e3) / 1e9, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(alg / (stage[dom] / 1e3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_kind,
-                "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": stage[dom]}
+                "frac": round(alg / (stage[dom] / 1e3) / 1e9 / peak, 4),
+                "traffic": int(n * NCU_ENCODE_TRAFFIC_PER_TEXT_BYTE[dom]) if dom in NCU_ENCODE_TRAFFIC_PER_TEXT_BYTE else None,
+                "traffic_source": "dram bytes per text byte from the committed ncu --set full capture (profiles/r1_ncu_encode_tiles.txt), scaled to this launch",
+                "peak_source": peak_kind, "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": stage[dom]}
     # the way back (tokenizer.py:323-349 decode): ids -> bytes on the device; every byte must be the input's
     decode = None
     if n_ids:

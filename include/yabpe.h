@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YABPE_ABI_VERSION 2
+#define YABPE_ABI_VERSION 3
 
 #define YABPE_OK 0
 #define YABPE_ERR_CUDA (-1)

@@ -450,7 +450,16 @@ extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_m
     if (P.n_tiles == 0) return YABPE_OK;
     rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
     if (rc) return rc;
-    int grid = num_sms() * 4;
+    // persistent grid: as many CTAs per SM as registers and the ~36 KB tile area allow (5 on sm_100a; the passes are
+    // bound by the latency of the table probes, so every resident warp counts)
+    static int per_sm[2] = {0, 0};
+    if (per_sm[pass != 0] == 0) {
+        int nb = 0;
+        CUDA_TRY(pass == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_encode_tiles<false>, PT_THREADS, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_encode_tiles<true>, PT_THREADS, 0));
+        per_sm[pass != 0] = nb < 1 ? 1 : nb;
+    }
+    int grid = num_sms() * per_sm[pass != 0];
     if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
     if (pass == 0) {
         k_encode_tiles<false><<<grid, PT_THREADS, 0, st>>>(P, E, O); LAUNCHED();

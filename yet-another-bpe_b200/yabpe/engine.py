@@ -320,7 +320,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         alog_cap = max(2 * words.n_words, 1 << 16) + 4096
         tset_cap = _pow2_at_least(4 * max_tokens)
         # base tokens on the host
-        tok_bytes = np.zeros(pool_cap, dtype=np.uint8)
+        tok_bytes = np.zeros(sum(len(b) for b in base_tokens) + 16, dtype=np.uint8)      # only the used prefix is uploaded
         tok_off = np.zeros(max_tokens + 1, dtype=np.int64)
         th = np.zeros(max_tokens, dtype=np.uint64)
         tp = np.zeros(max_tokens, dtype=np.uint64)
@@ -337,7 +337,9 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
                 slot = (slot + 1) & (tset_cap - 1)
             tset[slot] = (h & 0xFFFFFFFF00000000) | (i + 1)
         t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
-        d_tok_bytes, d_tok_off, d_th, d_tp, d_tset = t(tok_bytes), t(tok_off), t(th.view(np.int64)), t(tp.view(np.int64)), t(tset.view(np.int64))
+        d_tok_bytes = torch.zeros(pool_cap, dtype=torch.uint8, device=dev)
+        d_tok_bytes[:len(tok_bytes)].copy_(torch.from_numpy(tok_bytes))
+        d_tok_off, d_th, d_tp, d_tset = t(tok_off), t(th.view(np.int64)), t(tp.view(np.int64)), t(tset.view(np.int64))
         z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
         wstamp = z(words.n_words + 1, torch.int32)
         wslot = z(words.n_syms + 8, torch.int32)
