@@ -157,7 +157,10 @@ def test_train_corpus_en_matches_reference_fixture(yabpe):
     assert set(vocab.values()) == {bytes([i]) for i in range(256)} | {b"<|endoftext|>"} | {a + b for a, b in ref}
 
 
-def test_train_golden_cases(yabpe, tmp_path):
+@pytest.mark.parametrize("streamed", [False, True])
+def test_train_golden_cases(yabpe, tmp_path, streamed):
+    """streamed=True forces train(files) through the pinned-staging upload (pieces of 1 000 bytes, so every file spans
+    several pieces and chunk cuts fall anywhere inside them); the default path reads small files whole."""
     for c in common.load_train_cases():
         paths = []
         for i, blob in enumerate(c["inputs"]):
@@ -166,7 +169,10 @@ def test_train_golden_cases(yabpe, tmp_path):
             paths.append(p)
         cfg = yabpe.BBPETrainerConfig(vocab_size=c["vocab_size"], min_frequency=c["min_frequency"], max_workers=1,
                                       chunk_size_bytes=c["chunk_size"], special_tokens=c["specials"])
-        model = yabpe.BBPETrainer(cfg).train(paths)
+        tr = yabpe.BBPETrainer(cfg)
+        if streamed:
+            tr.stream_min_bytes, tr.stream_piece_bytes = 0, 1000
+        model = tr.train(paths)
         assert model.merges == c["merges_b"], c["name"]
         assert {v: k for k, v in model.vocab.items()} == c["vocab_b"], c["name"]
 
@@ -192,7 +198,11 @@ def test_train_medium_corpus_vs_oracle_and_deterministic(yabpe, tmp_path):
     p.write_bytes(data)
     want = oracle.train_bpe(p, 2500, ["<|endoftext|>"], fast=True)
     got1 = yabpe.train_bpe(p, 2500, ["<|endoftext|>"])
-    got2 = yabpe.train_bpe(p, 2500, ["<|endoftext|>"])
+    tr = yabpe.BBPETrainer(yabpe.BBPETrainerConfig(vocab_size=2500, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
+                                                   special_tokens=["<|endoftext|>"]))
+    tr.stream_min_bytes, tr.stream_piece_bytes = 0, 5_000_001          # second run: the streamed upload (5 pieces)
+    m2 = tr.train([p])
+    got2 = ({v: k for k, v in m2.vocab.items()}, m2.merges)
     assert got1[1] == got2[1]
     assert got1[1] == want[1]
     assert got1[0] == want[0]

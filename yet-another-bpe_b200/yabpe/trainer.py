@@ -121,6 +121,8 @@ class BBPETrainer:
         self._merges: list[tuple[bytes, bytes]] = []
         self.last_stats = TrainStats()
         self.profile = False            # True: record CUDA-event stage durations into self.timing
+        self.stream_min_bytes = 64 << 20          # train(files): inputs this large are streamed through pinned staging
+        self.stream_piece_bytes = 32 << 20
         self.timing: dict[str, float] = {}
 
     # -- reference API ---------------------------------------------------------------------
@@ -128,12 +130,58 @@ class BBPETrainer:
         if not files:
             raise ValueError("At least one file must be provided")       # trainer.py:72-73
         paths = [Path(f) if isinstance(f, str) else f for f in files]
-        blobs: list[np.ndarray] = []
         for p in paths:
             if not p.exists():
                 raise FileNotFoundError(f"File not found: {p}")           # trainer.py:204-205
-            blobs.append(np.fromfile(p, dtype=np.uint8))
+        sizes = [p.stat().st_size for p in paths]
+        if sum(sizes) >= self.stream_min_bytes:
+            return self._train_streamed_files(paths, sizes)
+        blobs = [np.fromfile(p, dtype=np.uint8) for p in paths]
         return self.train_from_buffers(blobs, [str(p) for p in paths])
+
+    def _train_streamed_files(self, paths: list[Path], sizes: list[int]) -> BBPEModel:
+        """Large inputs: the files are read piece by piece straight into two pinned staging buffers and copied to their
+        place in the device text on a copy stream, so reading piece k+1 overlaps the upload of piece k and the corpus
+        never exists as a pageable host array (np.fromfile + a pageable copy costs a second pass over the bytes).
+        Chunk cuts (P1) are then taken from the bytes around each cut on the device, per file."""
+        torch = _ffi.require_cuda()
+        total = sum(sizes)
+        if total == 0:
+            return self._finish(self._init_base_vocab(), [])              # trainer.py:81-85
+        text_dev = torch.empty(((total + 15) // 16) * 16 + 64, dtype=torch.uint8, device="cuda")
+        text_dev[total:].zero_()
+        piece = max(int(self.stream_piece_bytes), 1)
+        stage = [torch.empty(piece, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        in_flight: list = [None, None]
+        cur, copy = torch.cuda.current_stream(), torch.cuda.Stream()
+        copy.wait_stream(cur)
+        off, k = 0, 0
+        for p, size in zip(paths, sizes):
+            done = 0
+            with open(p, "rb", buffering=0) as f:
+                while done < size:
+                    buf = stage[k % 2]
+                    if in_flight[k % 2] is not None:
+                        in_flight[k % 2].synchronize()                    # its previous upload has left the buffer
+                    got = f.readinto(memoryview(buf.numpy())[:min(piece, size - done)])
+                    if not got:
+                        raise OSError(f"{p} shrank while it was read ({done} of {size} bytes)")
+                    with torch.cuda.stream(copy):
+                        text_dev[off + done:off + done + got].copy_(buf[:got], non_blocking=True)
+                        in_flight[k % 2] = torch.cuda.Event()
+                        in_flight[k % 2].record(copy)
+                    done += got
+                    k += 1
+            off += size
+        cur.wait_stream(copy)
+        file_starts, cuts, off = [], [], 0
+        for size in sizes:
+            file_starts.append(off)
+            if size:
+                cuts += [off + c for c in device_chunk_cuts(text_dev[off:off + size], size, int(self.config.chunk_size_bytes))]
+                cuts.append(off + size)                                   # a file end is a hard boundary too
+            off += size
+        return self._train_on_device(torch, text_dev, total, cuts, file_starts, [str(p) for p in paths])
 
     def train_from_buffers(self, blobs: Sequence[np.ndarray], names: Sequence[str] | None = None) -> BBPEModel:
         """Train from host byte buffers, one per file (pinned memory makes the H2D copy fastest)."""
