@@ -298,10 +298,17 @@ def run_encode(args) -> None:
         barrier()
         dt = (time.perf_counter() - t0) / reps
         assert got == n_ids
+        t0 = time.perf_counter()                  # the bare copies on this box (one after the other), for reading the number above
+        text_dev[:n].copy_(host, non_blocking=True); torch.cuda.synchronize()
+        h2d_only_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        ids_h[:n_ids].copy_(ids[:n_ids], non_blocking=True); torch.cuda.synchronize()
+        d2h_only_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
             tm = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(tm, op=dist.ReduceOp.MAX); dt = float(tm.item())
         e2e = {"value": round(total_bytes / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(total_bytes),
                "d2h_bytes_per_step": int(4 * total_ids), "ms_per_step": round(dt * 1e3, 2),
+               "h2d_only_ms": round(h2d_only_ms, 2), "d2h_only_ms": round(d2h_only_ms, 2),
                "mode": args.encode_e2e + (f" ({args.piece_mb} MiB pieces, H2D / encode / D2H on three streams)" if args.encode_e2e == "pipelined" else "")}
     cpu = None
     if not args.skip_cpu and rank == 0 and world == 1:
@@ -426,7 +433,7 @@ def main() -> None:
         host = torch.empty(n, dtype=torch.uint8).pin_memory()
         host.copy_(text_dev[:n])
         host_np = host.numpy()
-        reps = max(1, min(args.steps, 2))
+        reps = max(1, min(args.steps, 3))
 
         def e2e_step():
             tr2 = yabpe.BBPETrainer(cfg)
@@ -436,12 +443,20 @@ def main() -> None:
             return tr2.train_from_buffers([host_np])
 
         e2e_step()                                # warm-up: the caching allocator gets its 2 GB text block and table blocks
+        e2e_step()
         barrier()
+        rep_ms = []
         t0 = time.perf_counter()
         for _ in range(reps):
+            t1 = time.perf_counter()
             m2 = e2e_step()
+            rep_ms.append(round((time.perf_counter() - t1) * 1e3, 2))     # train_from_buffers returns host objects: the step is complete
         barrier()
         dt = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()                  # the bare upload on this box, for reading the number above (PCIe differs between boxes)
+        text_dev[:n].copy_(host)
+        torch.cuda.synchronize()
+        h2d_only_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
             tmax = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -449,7 +464,7 @@ def main() -> None:
         if rank == 0:
             d2h = sum(len(a) + len(b) for a, b in m2.merges) + sum(len(k) for k in m2.vocab)
             e2e = {"value": round(total_bytes / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(total_bytes),
-                   "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 2)}
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 2), "ms_per_rep": rep_ms, "h2d_only_ms": round(h2d_only_ms, 2)}
             assert m2.merges == model.merges
         del host, host_np
 
