@@ -64,13 +64,51 @@ def measured_peak_gbs() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons during the timed region: NVML (pynvml, ~20 samples per 100 ms) when it loads, else one
+    `nvidia-smi` query after the other (each takes longer than a short timed region, so few samples)."""
 
     def __init__(self, index: int = 0):
         self.rows: list[list[str]] = []
         self._stop = threading.Event()
-        self._thread = threading.Thread(target=self._run, daemon=True)
         self.index = index
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = self._cuda_device_handle(pynvml, index)
+            pynvml.nvmlDeviceGetClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+        self._thread = threading.Thread(target=self._run_nvml if self._nvml else self._run, daemon=True)
+
+    @staticmethod
+    def _cuda_device_handle(pynvml, index: int):
+        """NVML handle of CUDA device `index` (by UUID: CUDA_VISIBLE_DEVICES may renumber the devices)."""
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(index)
+
+    def _run_nvml(self):
+        nv, h = self._nvml, self._handle
+        bits = [(nv.nvmlClocksThrottleReasonHwSlowdown, 2), (nv.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
+                (nv.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (nv.nvmlClocksThrottleReasonSwPowerCap, 5)]
+        while not self._stop.is_set():
+            try:
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                       "Not Active", "Not Active", "Not Active", "Not Active"]
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, col in bits:
+                    if mask & bit:
+                        row[col] = "Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -103,7 +141,7 @@ class ClockSampler:
                 if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": self.source}
 
 
 def _trim_utf8(b: bytes) -> bytes:
