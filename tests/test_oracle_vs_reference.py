@@ -191,3 +191,31 @@ def test_class_api_surface_matches_reference():
                 assert isinstance(o, property), name
                 continue
             assert params(o)[: len(params(r))] == params(r), (ref_cls.__name__, name, params(r), params(o))
+
+
+def test_piece_cuts_of_encode_pinned_hold_for_the_live_reference():
+    """encode_pinned streams the text in pieces that end right after a special token and concatenates the ids
+    (yabpe/tokenizer.py:_piece_ends).  The claim behind it -- the reference's encode(text) equals the concatenation of its
+    encode(piece) -- is checked against the reference's own BBPETokenizer, on fuzz text dense in specials and in the F3
+    corner cases (special after a space, after punctuation, back to back, before a contraction)."""
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "yet-another-bpe_b200"))
+    import yabpe
+    BBPETrainer, BBPETrainerConfig, BBPETokenizer = _ref()
+    vocab, merges = oracle.train_bpe_bytes(("the cat sat on the mat, don't you think? " * 300).encode(), 330, ["<|endoftext|>"])
+    inv = {b: i for i, b in vocab.items()}
+    ref_tok = BBPETokenizer(vocab=inv, merges=merges, special_tokens=["<|endoftext|>"])
+    ours = yabpe.BBPETokenizer(vocab=inv, merges=merges, special_tokens=["<|endoftext|>"])
+    rng = random.Random(11)
+    for _ in range(40):
+        text = "".join(_rs(rng, rng.randint(0, 40)) + rng.choice(["<|endoftext|>", " <|endoftext|>", "!<|endoftext|>'s", "<|endoftext|><|endoftext|>"])
+                       for _ in range(rng.randint(3, 30))) + _rs(rng, rng.randint(0, 30))
+        raw = text.encode("utf-8")
+        want = ref_tok.encode(text)
+        for piece in (16, 64, 300):
+            ends = ours._piece_ends(np.frombuffer(raw, dtype=np.uint8), len(raw), piece)
+            got, lo = [], 0
+            for e in ends:
+                got += ref_tok.encode(raw[lo:e].decode("utf-8"))
+                lo = e
+            assert got == want, (text, piece, ends)
