@@ -201,7 +201,8 @@ def run_reference(args) -> None:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * t / args.steps, 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
             "config": {"workload": args.workload, "vocab_size": len(gv), "merges": len(gm), "special_tokens": SPECIALS,
-                       "note": "reference is pure Python (not on the GPU box); timed: C port of tokenizer.py, one core"},
+                       "note": "reference is pure Python (not on the GPU box); timed: C port of tokenizer.py, one core -- the Python reference "
+                               "itself measured 2.1-2.5 MB/s in the authoring container (BASELINE.md section 2)"},
             "cpu_baseline": {"value": round(mbps, 3), "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{len(sample)} bytes of the {kind}-shaped generator (seed {seed}), {n_ids} ids per step"},
             "e2e": {"value": round(mbps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,7 +221,8 @@ def run_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * t / args.steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
         "config": {"workload": args.workload, "vocab_size": vocab, "special_tokens": SPECIALS,
-                   "note": "reference is pure Python (not on the GPU box); timed: C port of trainer.py, linear max() scan"},
+                   "note": "reference is pure Python (not on the GPU box); timed: C port of trainer.py, linear max() scan -- the Python "
+                           "reference itself measured 2.8-3.0 MB/s on this stage in the authoring container (BASELINE.md section 2)"},
         "cpu_baseline": {"value": round(mbps, 3), "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{len(sample)} bytes of the {kind}-shaped generator (numpy, seed {seed}), "
                                    f"vocab {vocab}, {nm} merges; reference uses max_workers=1 (threads are GIL-bound)"},
