@@ -116,3 +116,25 @@ def test_special_packing_and_base_vocab():
     base = tr._init_base_vocab()
     # 256 bytes, then specials unless their bytes are already a key (duplicate special, 1-byte special): trainer.py:119-134
     assert len(base) == 257 and base[b"<|endoftext|>"] == 256 and base[b"a"] == 97
+
+
+def test_device_chunk_cuts_equal_host_chunk_cuts_per_file():
+    """The streamed upload of train(files) takes the reference chunk cuts from the bytes on the device, file by file
+    (trainer.py:_train_streamed_files); the rule only indexes a tensor, so it is checked here on CPU tensors against
+    the host rule for several files laid end to end."""
+    import torch
+    from yabpe.trainer import chunk_cuts, device_chunk_cuts
+    rng = np.random.default_rng(5)
+    alphabet = ["a", " ", "é", "中", "\U0001f643", "\n"]
+    files = ["".join(rng.choice(alphabet, size=int(k))).encode("utf-8") for k in (0, 1, 37, 400, 2, 1500)]
+    blob = np.frombuffer(b"".join(files), dtype=np.uint8)
+    dev = torch.from_numpy(blob.copy())
+    for cs in (1, 3, 4, 7, 64, 97, 1 << 20):
+        off, got, want = 0, [], []
+        for f in files:
+            n = len(f)
+            if n:
+                got += [off + c for c in device_chunk_cuts(dev[off:off + n], n, cs)] + [off + n]
+                want += [off + c for c in chunk_cuts(np.frombuffer(f, dtype=np.uint8), cs)]
+            off += n
+        assert got == want, cs
