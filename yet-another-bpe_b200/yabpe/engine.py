@@ -46,7 +46,10 @@ def pack_specials(specials: list[bytes]) -> tuple[np.ndarray, np.ndarray]:
 def to_device_text(torch, host: np.ndarray | "torch.Tensor", non_blocking: bool = False):
     """Copy `host` bytes into a padded device buffer (capacity round_up(n,16)+64, tail zeroed)."""
     if isinstance(host, np.ndarray):
-        host = torch.from_numpy(host)
+        import warnings
+        with warnings.catch_warnings():           # a read-only view (np.frombuffer of bytes) is only ever read here
+            warnings.simplefilter("ignore", UserWarning)
+            host = torch.from_numpy(host)
     n = int(host.numel())
     cap = ((n + 15) // 16) * 16 + 64
     dev = torch.empty(cap, dtype=torch.uint8, device="cuda")
