@@ -104,6 +104,20 @@ def load_class_api_cases() -> dict:
     return d
 
 
+def load_prefix_special_cases() -> dict:
+    """tests/golden/prefix_specials_cases.json (tools/make_golden.py make_prefix_specials): prefix-related special tokens
+    right before chunk cuts, file ends and document ends -- reference outputs of findall / split, train() and encode()."""
+    d = json.loads((GOLDEN / "prefix_specials_cases.json").read_text())
+    for c in d["train"]:
+        c["inputs"] = [base64.b64decode(x) for x in c["inputs_b64"]]
+        c["merges_b"] = [(bytes.fromhex(a), bytes.fromhex(b)) for a, b in c["merges"]]
+        c["vocab_b"] = {i: bytes.fromhex(v) for i, v in enumerate(c["vocab"])}
+    m = d["encode_model"]
+    d["encode_model"] = ({i: bytes.fromhex(v) for i, v in enumerate(m["vocab"])},
+                         [(bytes.fromhex(a), bytes.fromhex(b)) for a, b in m["merges"]])
+    return d
+
+
 def load_encode_cases() -> tuple[dict, list[dict]]:
     d = json.loads((GOLDEN / "encode_cases.json").read_text())
     models = {}

@@ -90,6 +90,39 @@ def test_pretok_counts_fuzz_and_adversarial(yabpe):
         assert _device_counts(text, sp, mode="encode") == _oracle_counts(text, sp, mode="encode"), sp
 
 
+def test_prefix_related_specials_at_hard_boundaries(yabpe, tmp_path):
+    """every re-match of a recognised special must stop at the same hard boundary as its recognition did
+    ('<|eot|>' + CUT + 'x' is not '<|eot|>x').  Reference-generated vectors; documents batched through cuts."""
+    from yabpe.trainer import pretoken_counts
+    d = common.load_prefix_special_cases()
+    for c in d["pretok"]:
+        blobs = [x.encode("utf-8") for x in c["docs"]]
+        want = Counter(t.encode("utf-8") for toks in c["tokens"] for t in toks
+                       if not (c["mode"] == "encode" and t in c["specials"]))
+        cuts = np.cumsum([len(b) for b in blobs])[:-1].tolist()
+        for generic in (False, True):
+            got = pretoken_counts(b"".join(blobs), c["specials"], mode=c["mode"], cuts=cuts, generic_only=generic)
+            got.pop("__n_pretokens__")
+            assert got == dict(want), (c["mode"], c["specials"], c["docs"], generic)
+    for c in d["train"]:
+        paths = []
+        for i, blob in enumerate(c["inputs"]):
+            p = tmp_path / f"pf_{i}.txt"
+            p.write_bytes(blob)
+            paths.append(p)
+        cfg = yabpe.BBPETrainerConfig(vocab_size=c["vocab_size"], min_frequency=c["min_frequency"], max_workers=1,
+                                      chunk_size_bytes=c["chunk_size"], special_tokens=c["specials"])
+        model = yabpe.BBPETrainer(cfg).train(paths)
+        assert model.merges == c["merges_b"], (c["specials"], c["chunk_size"])
+        assert {v: k for k, v in model.vocab.items()} == c["vocab_b"]
+    v, m = d["encode_model"]
+    for c in d["encode_docs"]:
+        t = yabpe.Tokenizer(v, m, c["specials"])
+        assert t.encode_batch(c["docs"]) == c["ids"], c["docs"]
+        assert list(t.encode_iterable(c["docs"])) == [i for ids in c["ids"] for i in ids]
+        assert [t.encode(x) for x in c["docs"]] == c["ids"]
+
+
 def test_pretok_fast_path_large_fuzz(yabpe):
     """Interior tiles take the register-resident fast path: hammer it with every event kind at every alignment."""
     rng = random.Random(321)

@@ -44,6 +44,26 @@ def test_train_golden(fast):
         assert vocab == c["vocab_b"], c["name"]
 
 
+def test_prefix_related_specials_at_hard_boundaries():
+    """A special is never matched across a chunk cut / file end / document end, even when a longer special that
+    starts with it would fit across the boundary (reference-generated, tools/make_golden.py make_prefix_specials)."""
+    d = common.load_prefix_special_cases()
+    for c in d["pretok"]:
+        for doc, want in zip(c["docs"], c["tokens"]):
+            assert oracle.pretokenize(doc.encode("utf-8"), c["specials"], c["mode"]) == [t.encode("utf-8") for t in want], (c, doc)
+    for c in d["train"]:
+        tr = oracle.Trainer(c["specials"])
+        for blob in c["inputs"]:
+            tr.feed_bytes(blob, c["chunk_size"])
+        vocab, merges = tr.run(c["vocab_size"], c["min_frequency"], False)
+        assert merges == c["merges_b"] and vocab == c["vocab_b"], (c["specials"], c["chunk_size"])
+    v, m = d["encode_model"]
+    for c in d["encode_docs"]:
+        t = oracle.Tokenizer(v, m, c["specials"])
+        assert [t.encode(x) for x in c["docs"]] == c["ids"]
+        assert list(t.encode_iterable(c["docs"])) == [i for ids in c["ids"] for i in ids]
+
+
 def test_pretokenize_golden():
     for c in common.load_pretok_cases():
         got = oracle.pretokenize(c["text"].encode("utf-8"), c["specials"], c["mode"])

@@ -295,9 +295,60 @@ def make_class_api() -> None:
     print("class api cases:", {k: len(v) for k, v in out.items()})
 
 
+def make_prefix_specials() -> None:
+    """Prefix-related special tokens next to hard boundaries (chunk cuts, file ends, document ends): the
+    reference never matches a special across a boundary (trainer.py:146-170 scans each chunk as its own text;
+    tests/adapters.py:30-34 encodes each item on its own), so '<|eot|>' + CUT + 'x...' must stay '<|eot|>'
+    even when '<|eot|>x' is a special of higher priority."""
+    out: dict = dict(pretok=[], train=[], encode_docs=[])
+    g = regex.compile(GPT2)
+    # -- pre-tokenisation of independent texts (documents / chunks), both modes
+    doc_sets = [
+        ["ab\n<|eot|>", "xyz <|eot|>x <|eot|>", "x<|eot|>", "x"],
+        ["<|eot|>", "x<|eot|>x", "<|eot|>"],
+        ["hello <|eot|>", "x <|eot|>xx<|eot|>", "xx"],
+        ["a\n<|e", "ot|>x b\n<|eot|>", "xb"],
+    ]
+    for sp in (["<|eot|>x", "<|eot|>"], ["<|eot|>", "<|eot|>x"], ["<|eot|>", "<|eot|>x", "<|eot|>xx"]):
+        for docs in doc_sets:
+            pat = "|".join(regex.escape(t) for t in sp) + "|" + GPT2
+            out["pretok"].append(dict(mode="train", specials=sp, docs=docs,
+                                      tokens=[[t for t in regex.findall(pat, d) if t] for d in docs]))
+            srt = sorted(sp, key=len, reverse=True)
+            spat = regex.compile("(" + "|".join(regex.escape(t) for t in srt) + ")")
+            per_doc = []
+            for d in docs:
+                toks = []
+                for part in spat.split(d):
+                    if part:
+                        toks += [part] if part in sp else g.findall(part)
+                per_doc.append(toks)
+            out["pretok"].append(dict(mode="encode", specials=sp, docs=docs, tokens=per_doc))
+    # -- training: the special ends exactly at a chunk cut (chunk_size 16) / at a file end
+    blocks = ["aaaaaaaa\n<|eot|>", "xyz hello x worl", "d\nabc de\n<|eot|>", "x<|eot|>x  tail\n"]
+    assert all(len(b) == 16 for b in blocks)
+    body = "".join(blocks) * 6
+    for sp in (["<|eot|>x", "<|eot|>"], ["<|eot|>", "<|eot|>x"]):
+        for files, cs in (([body.encode()], 16), ([body.encode()], 1 << 30),
+                          ([b"hello hello\n<|eot|>", b"xyz hello x<|eot|>", b"x<|eot|>x hello"], 1 << 30)):
+            vocab, merges = train_ref(files, 300, sp, 1, cs)
+            out["train"].append(dict(inputs_b64=[b64(f) for f in files], vocab_size=300, specials=sp, min_frequency=1,
+                                     chunk_size=cs, merges=[[hx(a), hx(b)] for a, b in merges],
+                                     vocab=[hx(vocab[i]) for i in range(len(vocab))]))
+    # -- encode of independent documents (encode_iterable / encode_batch): ids per document
+    sp = ["<|eot|>", "<|eot|>x"]
+    vocab, merges = train_ref([(body * 3).encode()], 290, sp, 1, 1 << 30)
+    tok = BBPETokenizer(vocab={v: k for k, v in vocab.items()}, merges=merges, special_tokens=sp)
+    for docs in doc_sets + [["<|eot|>x", "x<|eot|>", "x", "", "<|eot|>"]]:
+        out["encode_docs"].append(dict(specials=sp, docs=docs, ids=[tok.encode(d) for d in docs]))
+    out["encode_model"] = dict(vocab=[hx(vocab[i]) for i in range(len(vocab))], merges=[[hx(a), hx(b)] for a, b in merges])
+    (GOLD / "prefix_specials_cases.json").write_text(json.dumps(out, ensure_ascii=True, indent=0))
+    print("prefix-special cases:", {k: len(v) for k, v in out.items() if isinstance(v, list)})
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    make_pretok()
-    make_train()
-    make_encode()
-    make_class_api()
+    only = sys.argv[1:]
+    for fn in (make_pretok, make_train, make_encode, make_class_api, make_prefix_specials):
+        if not only or fn.__name__ in only:
+            fn()

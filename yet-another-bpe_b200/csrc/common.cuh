@@ -120,6 +120,15 @@ __device__ __forceinline__ int special_match(const uint8_t* text, i64 i, i64 lim
     return -1;
 }
 
+// first hard boundary > i (chunk cut, file / document end, or n): a special never straddles one, so EVERY
+// match or re-match of a special at i uses this as its limit -- recognition and the later length look-ups must agree
+// even when one special is a prefix of another ('<|eot|>' + cut + 'x' is not '<|eot|>x')
+__device__ __forceinline__ i64 hard_end_after(const i64* cuts, int n_cuts, i64 n, i64 i) {
+    int lo = 0, hi = n_cuts;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cuts[mid] <= i) lo = mid + 1; else hi = mid; }
+    return lo < n_cuts ? cuts[lo] : n;
+}
+
 // ---------------------------------------------------------------------------------
 // Generic accessor over global memory.  Fences:
 //   cuts[]     sorted hard boundaries (FL + FR at each cut); 0 and n are implicit
@@ -150,7 +159,7 @@ struct GlobalText {
         i64 lo = p - c_sp.max_len + 1; if (lo < 0) lo = 0;
         for (i64 q = p; q >= lo; q--) {
             if (rec_bit(q)) {
-                int s = special_match(text, q, n);
+                int s = special_match(text, q, hard_end_after(cuts, n_cuts, n, q));
                 int m = s >= 0 ? c_sp.offs[s + 1] - c_sp.offs[s] : 0;
                 if (q + m > p) { *len_out = m; return q; }
                 return -1;   // recognised specials never overlap: the nearest one decides

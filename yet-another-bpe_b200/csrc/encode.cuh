@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
             }
             if (live) {
                 if (P.n_sp > 0 && ((S.recw[(s >> 5) + 4] >> (s & 31)) & 1)) {   // recognised special: its id, or dropped (tokenizer.py:177-181)
-                    int sp = special_match(P.text, gpos, P.n);
+                    int sp = special_match(P.text, gpos, logical_end_after(P, gpos));
                     spid = sp >= 0 ? E.sp_ids[sp] : -1;
                     cnt = spid >= 0 ? 1 : 0;
                 } else if (k == sh_ovf_k) {

@@ -98,10 +98,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // K1a: special-token candidates -> bitmap
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ i64 logical_end_after(const PretokParams& P, i64 i) {
-    // first hard boundary > i (chunk cut or n): specials never straddle a cut
-    int lo = 0, hi = P.n_cuts;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] <= i) lo = mid + 1; else hi = mid; }
-    return lo < P.n_cuts ? P.cuts[lo] : P.n;
+    return hard_end_after(P.cuts, P.n_cuts, P.n, i);
 }
 
 __global__ void __launch_bounds__(256) k_special_candidates(PretokParams P, i64 lo, i64 hi) {
@@ -485,7 +482,7 @@ __device__ void tile_scan_generic(const PretokParams& P, TileSmem& S, i64 tile, 
                 int bit = __ffs(w) - 1; w &= w - 1;
                 i64 q = (wi << 5) + bit;
                 if (q < lo || q >= hi) continue;
-                int s = special_match(P.text, q, P.n);
+                int s = special_match(P.text, q, logical_end_after(P, q));
                 if (s < 0) continue;
                 int m = c_sp.offs[s + 1] - c_sp.offs[s];
                 for (int k = 0; k <= m; k++) {
@@ -734,7 +731,7 @@ __device__ __forceinline__ uint32_t segment_scan(const PretokParams& P, const ui
                     const int q = x0 + 32 * j + bit;                 // window offset
                     int m;
                     if (c_sp.n == 1) m = c_sp.offs[1];
-                    else { int sp = special_match(P.text, g0 + q, P.n); m = sp >= 0 ? c_sp.offs[sp + 1] - c_sp.offs[sp] : 1; }
+                    else { int sp = special_match(P.text, g0 + q, logical_end_after(P, g0 + q)); m = sp >= 0 ? c_sp.offs[sp + 1] - c_sp.offs[sp] : 1; }
                     const int e = q + m;
                     if (e < x0 - 3 || q > x0 + 32) continue;
                     const int lo = (q > x0 ? q : x0) - x0, hi = (e < x0 + 32 ? e : x0 + 32) - x0;

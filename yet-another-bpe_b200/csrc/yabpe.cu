@@ -27,15 +27,22 @@ static long long g_launches = 0;
 
 #define LAUNCHED() (g_launches++)
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+// Per-device state.  Function attributes (dynamic shared-memory opt-in), the SM count and occupancy results belong to
+// ONE device: a process that switches devices (the Python layer supports it) must not reuse what it learnt on the first.
+#define YABPE_MAX_DEVICES 64
+struct DevInfo { int num_sms; bool pretok_attr, merge_attr; int enc_per_sm[2]; };
+static DevInfo g_dev[YABPE_MAX_DEVICES];
+static DevInfo& dev_info() {
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= YABPE_MAX_DEVICES) dev = YABPE_MAX_DEVICES - 1;      // state shared beyond 64 devices: still correct, re-queried lazily
+    DevInfo& D = g_dev[dev];
+    if (!D.num_sms) {
+        cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (D.num_sms <= 0) D.num_sms = 148;
     }
-    return g_num_sms;
+    return D;
 }
+static int num_sms() { return dev_info().num_sms; }
 
 extern "C" const char* yabpe_last_error(void) { return g_err; }
 extern "C" int yabpe_abi_version(void) { return YABPE_ABI_VERSION; }
@@ -215,11 +222,11 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
         if (rc) return rc;
     }
     if (P.n_tiles > 0 && (stages & 2)) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        DevInfo& DI = dev_info();
+        if (!DI.pretok_attr) {
             CUDA_TRY(cudaFuncSetAttribute(k_pretok_count, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_CACHE_BYTES));
             CUDA_TRY(cudaFuncSetAttribute(k_pretok_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
-            attr_set = true;
+            DI.pretok_attr = true;
         }
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pretok_count, PT_THREADS, PT_CACHE_BYTES));
@@ -351,10 +358,10 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
     M.num_merges = m->num_merges; M.min_freq = m->min_frequency; M.rebuild_every = m->rebuild_every;
 
-    static bool ml_attr_set = false;
-    if (!ml_attr_set) {
+    DevInfo& DI = dev_info();
+    if (!DI.merge_attr) {
         CUDA_TRY(cudaFuncSetAttribute(k_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_DYN_SMEM_BYTES));
-        ml_attr_set = true;
+        DI.merge_attr = true;
     }
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, ML_DYN_SMEM_BYTES));
@@ -452,7 +459,7 @@ extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_m
     if (rc) return rc;
     // persistent grid: as many CTAs per SM as registers and the ~36 KB tile area allow (5 on sm_100a; the passes are
     // bound by the latency of the table probes, so every resident warp counts)
-    static int per_sm[2] = {0, 0};
+    int* per_sm = dev_info().enc_per_sm;
     if (per_sm[pass != 0] == 0) {
         int nb = 0;
         CUDA_TRY(pass == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_encode_tiles<false>, PT_THREADS, 0)

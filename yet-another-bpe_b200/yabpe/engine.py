@@ -192,8 +192,9 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode, mailbox:
         tail = mailbox.read(text_dev[m - 8:m + 8].view(torch.int64), 2).view(np.uint8)
         while m > _SAMPLE_BYTES - 4 and (int(tail[8 + m - _SAMPLE_BYTES]) & 0xC0) == 0x80:
             m -= 1
-    else:
-        while m > 0 and (int(text_dev[m].item()) & 0xC0) == 0x80:
+    else:                                        # one 8-byte read; a code point has at most 3 continuation bytes, so the
+        tail = text_dev[m - 4:m + 4].cpu().numpy()       # walk is bounded even on input that is not UTF-8 (the kernel reports it)
+        while m > _SAMPLE_BYTES - 4 and (int(tail[4 + m - _SAMPLE_BYTES]) & 0xC0) == 0x80:
             m -= 1
     sub_cuts = None if cuts is None else np.asarray([c for c in cuts if 0 < c < m], dtype=np.int64)
     res = pretok_count(torch, text_dev, m, sub_cuts if sub_cuts is not None and len(sub_cuts) else None, specials, mode,
