@@ -1,26 +1,34 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the BPE training hot path on B200 (contract: see the task statement).
 
-A "step" is one full `train_bpe` (pre-tokenise + count + word table + merge loop) over one batch
-of synthetic text.  Default workload (N=1): BASELINE.json configs[1] -- TinyStories-shaped
-synthetic corpus, 2e9 bytes, vocab 10 000, special token <|endoftext|>.
+A "step" is one full `train_bpe` (pre-tokenise + count + word table + merge loop) over one batch of synthetic text.
+Default workload: BASELINE.json configs[2], the configuration its metric is quoted on -- OpenWebText-shaped
+synthetic corpus, 11e9 bytes, vocab 32 000, special token <|endoftext|> (`--workload tinystories-2g-v10k` is
+configs[1], `--workload gpt2-encode-1g` configs[3]).
 
   value        corpus MB / s, inputs already resident in HBM when the timed region starts
-  e2e          the same through the host-buffer API (pinned host bytes -> H2D -> train -> D2H of
-               merges / vocab), copies inside the timed region
-  roofline     dominant HBM kernel (k_pretok_warp): corpus bytes / its CUDA-event duration vs the
-               measured HBM copy peak in MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle port (oracle/bpe_oracle.c, reference algorithm) on a bounded sample
-  --impl reference   the same oracle port on the host cores (the reference is pure Python and is
-               not present on the GPU box; the port follows trainer.py line by line)
+  e2e          the same through the host-buffer API (pinned host bytes -> H2D -> train -> D2H of merges / vocab),
+               copies inside the timed region
+  roofline     dominant HBM kernel (k_pretok_warp): corpus bytes / its CUDA-event duration vs the measured HBM copy
+               peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle port (oracle/bpe_oracle.c: the reference algorithm, linear max() scan) on a bounded sample
+  same_sample  the GPU arm on the IDENTICAL sample bytes: {gpu_ms, cpu_ms, merges_equal} -- a like-for-like ratio and
+               parity at the bench configuration; `reference_sample` does the same against the UNMODIFIED Python
+               reference (baseline/_ref, installed by __graft_entry__.build()) on a smaller sample
+  N > 1        STRONG scaling: the same corpus, sharded by byte range (yabpe/sharding.py), `digest` of (vocab, merges)
+               identical at every N; the merge loop is sequential, so `amdahl` states the ceiling
+  --impl reference   the reference's own CPU implementation on the host cores: the Python reference from baseline/_ref
+               when present (kind "reference"), else the C port (kind "port"); each step a bounded sample
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -32,25 +40,25 @@ for p in (ROOT, ROOT / "yet-another-bpe_b200", ROOT / "tools"):
 
 WORKLOADS = {
     # name: (kind, bytes, vocab, seed)
-    "tinystories-2g-v10k": ("tinystories", 2_000_000_000, 10_000, 20260101),
-    "owt-11g-v32k": ("owt", 11_000_000_000, 32_000, 20260102),
+    "owt-11g-v32k": ("owt", 11_000_000_000, 32_000, 20260102),              # BASELINE.json configs[2] (default)
+    "tinystories-2g-v10k": ("tinystories", 2_000_000_000, 10_000, 20260101),  # configs[1]
     "tinystories-256m-v10k": ("tinystories", 256_000_000, 10_000, 20260101),
     "owt-1g-v32k": ("owt", 1_000_000_000, 32_000, 20260102),
-    # BASELINE.json configs[3]: GPT-2 50257-vocab encode of 1e9 bytes of OWT-shaped text, sharded by document
-    # (strong scaling: every rank encodes 1e9 / world bytes); a different metric (encode MB/s), selected explicitly
+    # configs[3]: GPT-2 50257-vocab encode of 1e9 bytes of OWT-shaped text, sharded by document (strong scaling);
+    # a different metric (encode MB/s), selected explicitly
     "gpt2-encode-1g": ("owt", 1_000_000_000, 50_257, 20260103),
 }
+DEFAULT_WORKLOAD = "owt-11g-v32k"
 SPECIALS = ["<|endoftext|>"]
-# (dram__bytes_read + dram__bytes_write) / corpus bytes of k_pretok_warp from the committed ncu --set full captures
-# (profiles/r1_ncu_pretok_warp_details.txt, profiles/r1_ncu_pretok_warp_owt.txt): the OWT-shaped corpus has 50x the unique
-# pre-tokens, so its count-table traffic dwarfs the text itself
+# (dram__bytes_read + dram__bytes_write) / corpus bytes of the pre-tokenise + count kernel from the committed
+# ncu --set full captures (profiles/): the OWT-shaped corpus has 50x the unique pre-tokens, so its count-table traffic
+# is what the kernel moves besides the text itself
 NCU_TRAFFIC_RATIO = {"tinystories": 1.24, "owt": 7.0}
-# the same for the encode tile passes (profiles/r1_ncu_encode_tiles.txt: 256 MB of OWT-shaped text, 3.0 M unique words): DRAM bytes per
-# TEXT byte -- the table probes (one 32-byte sector per token for the key + lookup record, another for its ids) dominate
 NCU_ENCODE_TRAFFIC_PER_TEXT_BYTE = {"count_pass_ms": 4.42, "write_pass_ms": 11.24}
 METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
 ENCODE_METRIC = "GPT-2 encode throughput (pretokenize + BPE by rank + ids in text order)"
 UNIT = "MB/s"
+REF_DIR = ROOT / "baseline" / "_ref"
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -152,93 +160,198 @@ def _trim_utf8(b: bytes) -> bytes:
     return b
 
 
-def cpu_port_run(sample: bytes, vocab: int) -> tuple[float, int]:
-    """One timed run of the oracle port on `sample`; returns (seconds, merges)."""
+def model_digest(vocab: dict, merges: list) -> str:
+    """sha256 over the ordered merges and the (bytes -> id) vocabulary: equal digests <=> equal models."""
+    h = hashlib.sha256()
+    for a, b in merges:
+        h.update(len(a).to_bytes(4, "little")); h.update(a); h.update(len(b).to_bytes(4, "little")); h.update(b)
+    for k, v in sorted(vocab.items(), key=lambda kv: kv[1]):
+        h.update(int(v).to_bytes(4, "little")); h.update(len(k).to_bytes(4, "little")); h.update(k)
+    return h.hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------------------------- CPU arms
+def cpu_port_run(sample: bytes, vocab: int, fast: bool = False):
+    """One timed run of the oracle port on `sample`; returns (seconds, vocab, merges)."""
     from oracle import oracle
     t0 = time.perf_counter()
-    _, merges = oracle.train_bpe_bytes(sample, vocab, SPECIALS, fast=False)
-    return time.perf_counter() - t0, len(merges)
+    v, merges = oracle.train_bpe_bytes(sample, vocab, SPECIALS, fast=fast)
+    return time.perf_counter() - t0, v, merges
+
+
+def reference_module():
+    """The unmodified reference's adapter functions from baseline/_ref (a plain copy / pip --target install of
+    /root/reference made by __graft_entry__.build(); it travels to the GPU box with the snapshot), or None."""
+    if not (REF_DIR / "yet_another_bpe" / "trainer.py").exists():
+        return None
+    if str(REF_DIR) not in sys.path:
+        sys.path.insert(0, str(REF_DIR))
+    try:
+        import importlib
+        mod = importlib.import_module("yet_another_bpe")
+        from yet_another_bpe.tokenizer import BBPETokenizer       # noqa: F401
+        from yet_another_bpe.trainer import BBPETrainer, BBPETrainerConfig  # noqa: F401
+        return mod
+    except Exception:
+        return None
+
+
+def reference_train(sample: bytes, vocab: int):
+    """tests/adapters.py:66-99 `run_train_bpe` on `sample`, through the reference's own classes; (seconds, vocab, merges)."""
+    from yet_another_bpe.trainer import BBPETrainer, BBPETrainerConfig
+    with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as f:
+        f.write(sample)
+        path = f.name
+    try:
+        t0 = time.perf_counter()
+        cfg = BBPETrainerConfig(vocab_size=vocab, min_frequency=1, max_workers=1, chunk_size_bytes=1024 * 1024 * 1024,
+                                seed=42, special_tokens=SPECIALS)
+        model = BBPETrainer(cfg).train([Path(path)])
+        vocab_inv = {v: k for k, v in model.vocab.items()}
+        dt = time.perf_counter() - t0
+    finally:
+        os.unlink(path)
+    return dt, vocab_inv, model.merges
+
+
+def reference_tokenizer(vocab: dict, merges: list):
+    """tests/adapters.py:37-63 `get_tokenizer`."""
+    from yet_another_bpe.tokenizer import BBPETokenizer
+    return BBPETokenizer(vocab={v: k for k, v in vocab.items()}, merges=merges, special_tokens=SPECIALS)
+
+
+def host_sample(kind: str, seed: int, nbytes: int) -> bytes:
+    """The first `nbytes` of the workload's corpus: from the GPU generator when a device is present (identical to what
+    the GPU arm trains on), else the numpy generator of the same shape."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from synth_gpu import synth_corpus_device
+            dev_text, dn = synth_corpus_device(torch, nbytes, kind, seed, piece_bytes=min(max(nbytes, 1 << 20), 256 << 20))
+            out = _trim_utf8(dev_text[:dn].cpu().numpy().tobytes())
+            del dev_text
+            torch.cuda.empty_cache()
+            return out
+    except Exception:
+        pass
+    sys.path.insert(0, str(ROOT / "tests"))
+    import common
+    gen = common.synth_tinystories if kind == "tinystories" else common.synth_owt
+    return _trim_utf8(gen(nbytes, seed=seed))
 
 
 def run_reference(args) -> None:
-    """--impl reference: the CPU port of the reference algorithm on the host cores (rank 0 only)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU implementation on the host cores (rank 0 only; one core: the adapter sets
+    max_workers=1 and the thread pool is GIL-bound)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     kind, nbytes, vocab, seed = WORKLOADS[args.workload]
     sys.path.insert(0, str(ROOT / "tests"))
     import common
-    sample_bytes = args.cpu_sample_mb << 20
-    sample = None
-    try:                                      # same generator as the GPU arm when a device is present
-        import torch
-        if torch.cuda.is_available():
-            from synth_gpu import synth_corpus_device
-            dev_text, dn = synth_corpus_device(torch, sample_bytes, kind, seed, piece_bytes=min(sample_bytes, 256 << 20))
-            sample = _trim_utf8(dev_text[:dn].cpu().numpy().tobytes())
-            del dev_text
-            torch.cuda.empty_cache()
-    except Exception:
-        sample = None
-    if sample is None:
-        gen = common.synth_tinystories if kind == "tinystories" else common.synth_owt
-        sample = gen(sample_bytes, seed=seed)
-    if args.workload.startswith("gpt2-encode"):
-        # BASELINE.json configs[3]: the reference's encode (tokenizer.py:152-308) as the C port, GPT-2 vocabulary
-        from oracle import oracle
+    ref = reference_module()
+    which = "reference" if ref is not None else "port"
+    # every step is a bounded sample: the whole run has to end within a few minutes
+    budget = min(30.0, max(4.0, 200.0 / max(args.steps, 1)))
+    encode = args.workload.startswith("gpt2-encode")
+    if encode:
         gv, gm = common.gpt2_vocab_and_merges()
-        otok = oracle.Tokenizer(gv, gm, SPECIALS)
+        if ref is not None:
+            tok = reference_tokenizer(gv, gm)
+            enc = lambda s: tok.encode(s)                                  # noqa: E731
+            rate = 1.2e6                                                   # bytes / s, measured (BASELINE.md section 2)
+        else:
+            from oracle import oracle
+            otok = oracle.Tokenizer(gv, gm, SPECIALS)
+            enc = lambda s: otok.encode(s)                                 # noqa: E731
+            rate = 15e6
+        probe = host_sample(kind, seed, 1 << 18).decode("utf-8")
+        t0 = time.perf_counter(); enc(probe); rate = len(probe.encode()) / max(time.perf_counter() - t0, 1e-3)
+        nsample = int(min(max(rate * budget, 1 << 18), 256 << 20))
+        sample = host_sample(kind, seed, nsample)
         text = sample.decode("utf-8")
         for _ in range(args.warmup):
-            otok.encode(text[: 1 << 20])
+            enc(text[: 1 << 16])
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            n_ids = len(otok.encode(text))
+            n_ids = len(enc(text))
         t = time.perf_counter() - t0
         mbps = len(sample) * args.steps / t / 1e6
+        cpu = {"value": round(mbps, 4), "unit": UNIT, "cores": 1, "kind": which,
+               "sample": f"{len(sample)} bytes of the {kind}-shaped generator (seed {seed}), {n_ids} ids per step; "
+                         f"{'tokenizer.py BBPETokenizer.encode from baseline/_ref' if ref is not None else 'C port of tokenizer.py'}, one core"}
         print(json.dumps({
-            "impl": "reference", "metric": ENCODE_METRIC, "value": round(mbps, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "impl": "reference", "metric": ENCODE_METRIC, "value": round(mbps, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * t / args.steps, 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
             "config": {"workload": args.workload, "vocab_size": len(gv), "merges": len(gm), "special_tokens": SPECIALS,
-                       "note": "reference is pure Python (not on the GPU box); timed: C port of tokenizer.py, one core -- the Python reference "
-                               "itself measured 2.1-2.5 MB/s in the authoring container (BASELINE.md section 2)"},
-            "cpu_baseline": {"value": round(mbps, 3), "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{len(sample)} bytes of the {kind}-shaped generator (seed {seed}), {n_ids} ids per step"},
-            "e2e": {"value": round(mbps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "sample_bytes": len(sample)},
+            "cpu_baseline": cpu, "e2e": {"value": round(mbps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
+
+    port_note = None
+    if ref is not None:
+        probe = host_sample(kind, seed, 16 << 10)
+        t16, _, _ = reference_train(probe, vocab)
+        nsample = int(min(max((16 << 10) * (budget / max(t16, 1e-3)) ** (1 / 1.5), 16 << 10), 512 << 10))
+        run = lambda s: reference_train(s, vocab)                          # noqa: E731
+        small = host_sample(kind, seed, 8 << 10)
+    else:
+        t1, _, _ = cpu_port_run(host_sample(kind, seed, 256 << 10), vocab)
+        nsample = int(min(max((256 << 10) * (budget / max(t1, 1e-3)) ** (1 / 1.3), 256 << 10), 64 << 20))
+        run = lambda s: cpu_port_run(s, vocab)                             # noqa: E731
+        small = host_sample(kind, seed, 64 << 10)
+    sample = host_sample(kind, seed, nsample)
     for _ in range(args.warmup):
-        cpu_port_run(sample[: 1 << 20], vocab)
-    t = 0.0
-    nm = 0
+        run(small)                                                         # warm-up: imports, regex compile, allocator
+    t, nm, merges = 0.0, 0, None
     for _ in range(args.steps):
-        dt, nm = cpu_port_run(sample, vocab)
+        dt, _, merges = run(sample)
         t += dt
+        nm = len(merges)
     mbps = len(sample) * args.steps / t / 1e6
+    if ref is not None:                                                    # the C port on the same bytes, for scale
+        pt, _, pm = cpu_port_run(sample, vocab)
+        port_note = {"port_s_same_sample": round(pt, 3), "port_merges_equal_reference": pm == merges}
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(mbps, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": round(mbps, 5), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * t / args.steps, 2),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
-        "config": {"workload": args.workload, "vocab_size": vocab, "special_tokens": SPECIALS,
-                   "note": "reference is pure Python (not on the GPU box); timed: C port of trainer.py, linear max() scan -- the Python "
-                           "reference itself measured 2.8-3.0 MB/s on this stage in the authoring container (BASELINE.md section 2)"},
-        "cpu_baseline": {"value": round(mbps, 3), "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{len(sample)} bytes of the {kind}-shaped generator (numpy, seed {seed}), "
-                                   f"vocab {vocab}, {nm} merges; reference uses max_workers=1 (threads are GIL-bound)"},
-        "e2e": {"value": round(mbps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+        "config": {"workload": args.workload, "vocab_size": vocab, "special_tokens": SPECIALS, "sample_bytes": len(sample),
+                   "note": "a bounded SAMPLE of the workload per step (the reference cannot hold more: 35 B of RSS per corpus byte and an "
+                           "O(live pairs) max() per merge, BASELINE.md section 2); MB/s at this size is dominated by the merge loop -- "
+                           "compare like for like with the `same_sample` / `reference_sample` objects of the GPU arm's line"},
+        "cpu_baseline": {"value": round(mbps, 5), "unit": UNIT, "cores": 1, "kind": which,
+                         "sample": f"first {len(sample)} bytes of the {kind}-shaped corpus (seed {seed}), vocab {vocab}, {nm} merges per step; "
+                                   + ("run_train_bpe of the unmodified Python reference (baseline/_ref), max_workers=1" if ref is not None
+                                      else "C port of trainer.py (oracle/, linear max() scan)")},
+        "e2e": {"value": round(mbps, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if port_note:
+        line["port"] = port_note
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------- encode arm
+def ids_digest(torch, ids, offset: int):
+    """(count, sum, position-weighted sum) of an id shard whose first id has global index `offset` (int64 wrap-around):
+    the per-rank triples add up to the same totals however the text is sharded."""
+    if ids.numel() == 0:
+        return torch.zeros(3, dtype=torch.int64, device="cuda")
+    v = ids.to(torch.int64)
+    pos = (torch.arange(ids.numel(), device=ids.device, dtype=torch.int64) + offset) % 65521 + 1
+    return torch.stack([torch.tensor(ids.numel(), device=ids.device, dtype=torch.int64), v.sum(), (v * pos).sum()])
+
+
 def run_encode(args) -> None:
-    """--workload gpt2-encode-1g: batched encode with the GPT-2 vocabulary / merges (tests/fixtures_gpt2)."""
+    """--workload gpt2-encode-1g: batched encode with the GPT-2 vocabulary / merges (tests/fixtures_gpt2), document-sharded."""
     import numpy as np
     import torch
     import yabpe
     from synth_gpu import synth_corpus_device
     from yabpe import _ffi, engine
+    from yabpe import distributed as D
     sys.path.insert(0, str(ROOT / "tests"))
     import common
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,8 +362,17 @@ def run_encode(args) -> None:
     kind, nbytes, vocab_n, seed = WORKLOADS[args.workload]
     vocab, merges = common.gpt2_vocab_and_merges()
     tok = yabpe.Tokenizer(vocab, merges, SPECIALS).inner
-    shard = nbytes // world                                  # documents are independent: shard by document, no exchange
-    text_dev, n = synth_corpus_device(torch, shard, kind, seed + rank, lex_seed=seed)
+    # ONE text for every N (strong scaling): each rank keeps the documents of its byte range (cut right after a special token)
+    full_dev, n_full = synth_corpus_device(torch, nbytes, kind, seed)
+    lo, hi = D.document_shard(tok, lambda a, b: full_dev[a:b].cpu().numpy().tobytes(), n_full, rank, world)
+    n = hi - lo
+    if world > 1:
+        text_dev = torch.zeros(((n + 15) // 16) * 16 + 64, dtype=torch.uint8, device="cuda")
+        text_dev[:n] = full_dev[lo:hi]
+    else:
+        text_dev = full_dev
+    del full_dev
+    torch.cuda.empty_cache()
     torch.cuda.synchronize()
 
     def barrier():
@@ -277,9 +399,16 @@ def run_encode(args) -> None:
     launches = _ffi.launch_count() - launches0
     n_ids = int(ids.numel())
     tot = torch.tensor([float(n), float(n_ids), ms_total], device="cuda", dtype=torch.float64)
+    id_off = 0
     if world > 1:
         mx = tot.clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         ms_total = float(mx[2].item())
+        counts = [None] * world
+        dist.all_gather_object(counts, n_ids)
+        id_off = sum(counts[:rank])
+    dg = ids_digest(torch, ids, id_off)
+    if world > 1:
+        dist.all_reduce(dg)
     total_bytes, total_ids = float(tot[0].item()), float(tot[1].item())
     ms_step = ms_total / args.steps
     value = total_bytes / (ms_step / 1e3) / 1e6
@@ -289,7 +418,7 @@ def run_encode(args) -> None:
     hbm_stages = {k: v for k, v in stage.items() if k != "words_ms"}      # k_encode_words is latency-bound work on the UNIQUE words
     dom = max(hbm_stages, key=hbm_stages.get)
     alg = {"pretok_count_ms": n, "count_pass_ms": n, "write_pass_ms": n + 4 * n_ids}[dom]
-    roofline = {"bound": "hbm", "kernel": {"pretok_count_ms": "k_pretok_count (mode 1)", "count_pass_ms": "k_encode_tiles<false>",
+    roofline = {"bound": "hbm", "kernel": {"pretok_count_ms": "k_pretok_warp (mode 1)", "count_pass_ms": "k_encode_tiles<false>",
                                             "write_pass_ms": "k_encode_tiles<true>", "words_ms": "k_encode_words"}[dom],
                 "achieved": round(alg / (stage[dom] / 1e3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(alg / (stage[dom] / 1e3) / 1e9 / peak, 4),
@@ -350,37 +479,47 @@ def run_encode(args) -> None:
                "d2h_bytes_per_step": int(4 * total_ids), "ms_per_step": round(dt * 1e3, 2),
                "h2d_only_ms": round(h2d_only_ms, 2), "d2h_only_ms": round(d2h_only_ms, 2),
                "mode": args.encode_e2e + (f" ({args.piece_mb} MiB pieces, H2D / encode / D2H on three streams)" if args.encode_e2e == "pipelined" else "")}
-    cpu = None
-    if not args.skip_cpu and rank == 0 and world == 1:
+    cpu = same = None
+    if not args.skip_cpu and rank == 0:
         from oracle import oracle
-        sample = _trim_utf8(text_dev[: min(n, args.cpu_sample_mb << 20)].cpu().numpy().tobytes())
+        sample = _trim_utf8(text_dev[: min(n, (args.cpu_sample_mb or 48) << 20)].cpu().numpy().tobytes())
         otok = oracle.Tokenizer(vocab, merges, SPECIALS)
         t0 = time.perf_counter()
         want = otok.encode(sample.decode("utf-8"))
         dt = time.perf_counter() - t0
         cpu = {"value": round(len(sample) / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first {len(sample)} bytes of the same text, {len(want)} ids, {dt:.1f} s; C port of tokenizer.py (one core, as the reference)"}
+        sd, sn = engine.to_device_text(torch, np.frombuffer(sample, dtype=np.uint8))
+        tok.encode_device(sd, sn)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        got_ids, _ = tok.encode_device(sd, sn)
+        torch.cuda.synchronize(); gdt = time.perf_counter() - t0
+        same = {"bytes": len(sample), "gpu_ms": round(gdt * 1e3, 2), "cpu_ms": round(dt * 1e3, 1),
+                "ids_equal": got_ids.cpu().tolist() == want}
     if rank == 0:
         print(json.dumps({
             "metric": ENCODE_METRIC, "value": round(value, 2), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": f"synthetic ({kind}-shaped, torch generator, seed {seed})",
             "config": {"workload": args.workload, "total_bytes": int(total_bytes), "bytes_per_gpu": n, "vocab_size": len(vocab), "merges": len(merges),
-                       "special_tokens": SPECIALS, "ids": int(total_ids), "l2": "inputs (>= 125 MB per GPU) larger than the 126 MB L2"},
+                       "special_tokens": SPECIALS, "ids": int(total_ids), "l2": "inputs (>= 125 MB per GPU) larger than the 126 MB L2",
+                       "sharding": "documents: every rank encodes the byte range of ONE text that ends right after a special token"},
+            "digest": [int(x) for x in dg.tolist()],
             "stage_ms": stage, "unique_words": timings[-1].get("unique_words"), "decode": decode,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary()}))
+            "roofline": roofline, "cpu_baseline": cpu, "same_sample": same, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary()}))
     if world > 1:
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------- train arm
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tinystories-2g-v10k", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-mb", type=int, default=48)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-mb", type=float, default=0, help="bytes of the corpus the CPU port is timed on (default: by workload)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--encode-mb", type=int, default=256)
@@ -388,11 +527,12 @@ def main() -> None:
     ap.add_argument("--piece-mb", type=int, default=128)
     args = ap.parse_args()
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("YABPE_BENCH_WATCHDOG_S", "600")), exit=True)   # never hang a GPU box
+    faulthandler.dump_traceback_later(int(os.environ.get("YABPE_BENCH_WATCHDOG_S", "900")), exit=True)   # never hang a GPU box
     if args.impl == "reference":
         run_reference(args)
         return
     if args.workload.startswith("gpt2-encode"):
+        args.cpu_sample_mb = int(args.cpu_sample_mb)
         run_encode(args)
         return
 
@@ -400,8 +540,9 @@ def main() -> None:
     import torch
     import yabpe
     from synth_gpu import synth_corpus_device
-    from yabpe import _ffi, engine
-    from yabpe.distributed import train_device_sharded
+    from yabpe import _ffi, engine, sharding
+    from yabpe import distributed as D
+    from yabpe.trainer import device_chunk_cuts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -411,11 +552,41 @@ def main() -> None:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, nbytes, vocab, seed = WORKLOADS[args.workload]
-    text_dev, n = synth_corpus_device(torch, nbytes, kind, seed + rank, lex_seed=seed)     # one corpus: shared lexicon, own text
-    torch.cuda.synchronize()
-
     cfg = yabpe.BBPETrainerConfig(vocab_size=vocab, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
                                   special_tokens=SPECIALS)
+    # ONE corpus whatever N is (strong scaling).  N > 1: every rank generates it, plans the same byte-range shards from the
+    # bytes around the ideal edges and keeps its own window [edge_r, edge_{r+1} + halo)
+    text_dev, n_total = synth_corpus_device(torch, nbytes, kind, seed)
+    torch.cuda.synchronize()
+    sharded_parity = None
+    if world > 1:
+        read = lambda a, b: text_dev[a:b].cpu().numpy().tobytes()          # noqa: E731
+        hard = device_chunk_cuts(text_dev, n_total, int(cfg.chunk_size_bytes))
+        edges = sharding.plan_shards(read, n_total, world, [s.encode() for s in SPECIALS], hard)
+        start, own_len, n_local = sharding.shard_window(edges, rank, n_total)
+        # untimed self-check on a slice of the same corpus: sharded training == the oracle (rank 0 compares)
+        chk_n = min(n_total, 8 << 20)
+        while chk_n > 0 and (int(text_dev[chk_n].item()) & 0xC0) == 0x80:
+            chk_n -= 1
+        chk_edges = sharding.plan_shards(read, chk_n, world, [s.encode() for s in SPECIALS], [])
+        cs, co, cn = sharding.shard_window(chk_edges, rank, chk_n)
+        chk_dev = torch.zeros(((cn + 15) // 16) * 16 + 64, dtype=torch.uint8, device="cuda")
+        chk_dev[:cn] = text_dev[cs:cs + cn]
+        chk_cfg = yabpe.BBPETrainerConfig(vocab_size=2000, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30, special_tokens=SPECIALS)
+        chk_model = D.train_range_sharded(yabpe.BBPETrainer(chk_cfg), chk_dev, cs, co, cn, [])
+        if rank == 0:
+            from oracle import oracle
+            ov, om = oracle.train_bpe_bytes(text_dev[:chk_n].cpu().numpy().tobytes(), 2000, SPECIALS, fast=True)
+            sharded_parity = {"bytes": chk_n, "vocab": 2000, "edges": chk_edges,
+                              "equal_oracle": bool(chk_model.merges == om and {v: k for k, v in chk_model.vocab.items()} == ov)}
+        del chk_dev
+        local_dev = torch.zeros(((n_local + 15) // 16) * 16 + 64, dtype=torch.uint8, device="cuda")
+        local_dev[:n_local] = text_dev[start:start + n_local]
+        del text_dev
+        torch.cuda.empty_cache()
+    else:
+        hard, edges, start, own_len, n_local, local_dev = [], [0, n_total], 0, n_total, n_total, text_dev
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -426,9 +597,9 @@ def main() -> None:
         tr = yabpe.BBPETrainer(cfg)
         tr.profile = profile
         if world > 1:
-            model = train_device_sharded(tr, text_dev, n)
+            model = D.train_range_sharded(tr, local_dev, start, own_len, n_local, hard)
         else:
-            model = tr.train_device(text_dev, n)
+            model = tr.train_device(local_dev, n_local)
         return tr, model
 
     for _ in range(args.warmup):
@@ -446,43 +617,45 @@ def main() -> None:
         barrier()
         ms_total = ev0.elapsed_time(ev1)
     launches = _ffi.launch_count() - launches0
+    tile_ms = float(np.mean([t["pretok_tiles_ms"] for t in timings if "pretok_tiles_ms" in t])) if timings and "pretok_tiles_ms" in timings[0] else 0.0
+    pre_ms = float(np.mean([sum(t.get(k, 0.0) for k in ("specials_ms", "pretok_tiles_ms", "long_tokens_ms")) for t in timings])) if timings else 0.0
     if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_total, tile_ms, pre_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total, tile_ms_max, pre_ms_max = (float(x) for x in t.tolist())
+    else:
+        tile_ms_max, pre_ms_max = tile_ms, pre_ms
     ms_step = ms_total / args.steps
-    total_bytes = n * world
-    value = total_bytes / (ms_step / 1e3) / 1e6
+    value = n_total / (ms_step / 1e3) / 1e6
     stats = tr.last_stats
 
-    # roofline of the dominant kernel: algorithmic bytes = corpus bytes read once per launch
+    # roofline of the dominant HBM kernel: algorithmic bytes = the shard's bytes, read once per launch (this rank's launch)
     peak, peak_kind = measured_peak_gbs()
-    tile_ms = float(np.mean([t["pretok_tiles_ms"] for t in timings if "pretok_tiles_ms" in t])) if timings and "pretok_tiles_ms" in timings[0] else None
     merge_ms = float(np.mean([t["merge_loop_ms"] for t in timings if "merge_loop_ms" in t])) if timings and "merge_loop_ms" in timings[0] else None
     roofline = None
     if tile_ms:
-        achieved = n / (tile_ms / 1e3) / 1e9
+        achieved = n_local / (tile_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_pretok_warp (+ k_pretok_count on the boundary chunks)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": int(n * NCU_TRAFFIC_RATIO[kind]), "peak_source": peak_kind,
+                    "frac": round(achieved / peak, 4), "traffic": int(n_local * NCU_TRAFFIC_RATIO[kind]), "peak_source": peak_kind,
                     "traffic_source": "dram bytes per algorithmic byte from the committed ncu --set full capture (profiles/), scaled to this launch",
-                    "algorithmic_bytes_per_launch": n, "ms_per_launch": round(tile_ms, 3)}
+                    "algorithmic_bytes_per_launch": n_local, "ms_per_launch": round(tile_ms, 3)}
 
-    # e2e: pinned host bytes -> H2D -> train -> D2H results (every rank copies its own shard)
+    # e2e: pinned host bytes -> H2D -> train -> D2H results (every rank uploads its own shard of the corpus)
     e2e = None
     if not args.skip_e2e:
-        host = torch.empty(n, dtype=torch.uint8).pin_memory()
-        host.copy_(text_dev[:n])
+        host = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+        host.copy_(local_dev[:n_local])
         host_np = host.numpy()
         reps = max(1, min(args.steps, 3))
 
         def e2e_step():
             tr2 = yabpe.BBPETrainer(cfg)
             if world > 1:
-                dev2, n2 = engine.to_device_text(torch, host, non_blocking=True)
-                return train_device_sharded(tr2, dev2, n2)
+                dev2, _ = engine.to_device_text(torch, host, non_blocking=True)
+                return D.train_range_sharded(tr2, dev2, start, own_len, n_local, hard)
             return tr2.train_from_buffers([host_np])
 
-        e2e_step()                                # warm-up: the caching allocator gets its 2 GB text block and table blocks
+        e2e_step()                                # warm-up: the caching allocator gets its text block and table blocks
         e2e_step()
         barrier()
         rep_ms = []
@@ -490,11 +663,11 @@ def main() -> None:
         for _ in range(reps):
             t1 = time.perf_counter()
             m2 = e2e_step()
-            rep_ms.append(round((time.perf_counter() - t1) * 1e3, 2))     # train_from_buffers returns host objects: the step is complete
+            rep_ms.append(round((time.perf_counter() - t1) * 1e3, 2))     # the model comes back as host objects: the step is complete
         barrier()
         dt = (time.perf_counter() - t0) / reps
         t0 = time.perf_counter()                  # the bare upload on this box, for reading the number above (PCIe differs between boxes)
-        text_dev[:n].copy_(host)
+        local_dev[:n_local].copy_(host)
         torch.cuda.synchronize()
         h2d_only_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
@@ -503,7 +676,7 @@ def main() -> None:
             dt = float(tmax.item())
         if rank == 0:
             d2h = sum(len(a) + len(b) for a, b in m2.merges) + sum(len(k) for k in m2.vocab)
-            e2e = {"value": round(total_bytes / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(total_bytes),
+            e2e = {"value": round(n_total / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(n_total),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 2), "ms_per_rep": rep_ms, "h2d_only_ms": round(h2d_only_ms, 2)}
             assert m2.merges == model.merges
         del host, host_np
@@ -512,10 +685,10 @@ def main() -> None:
     encode = None
     if args.encode_mb > 0 and rank == 0:
         tok = yabpe.BBPETokenizer(vocab=model.vocab, merges=model.merges, special_tokens=SPECIALS)
-        en = min(n, args.encode_mb << 20)
-        while en > 0 and (int(text_dev[en].item()) & 0xC0) == 0x80:
+        en = min(n_local, args.encode_mb << 20)
+        while en > 0 and (int(local_dev[en].item()) & 0xC0) == 0x80:
             en -= 1
-        sl = text_dev[:((en + 15) // 16) * 16 + 64].clone()
+        sl = local_dev[:((en + 15) // 16) * 16 + 64].clone()
         sl[en:].zero_()
         tok.encode_device(sl, en)
         torch.cuda.synchronize()
@@ -524,38 +697,66 @@ def main() -> None:
         ids, _ = tok.encode_device(sl, en)
         b.record(); torch.cuda.synchronize()
         encode = {"MBps": round(en / (a.elapsed_time(b) / 1e3) / 1e6, 2), "bytes": en, "ids": int(ids.numel())}
+        del sl, ids
 
-    cpu = None
+    # CPU arms on bounded samples of the SAME corpus, and the GPU arm on the identical bytes (rank 0, N = 1 only)
+    cpu = same = ref_same = None
     if not args.skip_cpu and rank == 0 and world == 1:
-        sample = text_dev[: args.cpu_sample_mb << 20].cpu().numpy().tobytes()
-        while sample and (sample[-1] & 0xC0) == 0x80:
-            sample = sample[:-1]
-        if sample and sample[-1] >= 0xC0:
-            sample = sample[:-1]
-        dt, nm = cpu_port_run(sample, vocab)
+        sample_mb = args.cpu_sample_mb or (2 if vocab > 16_000 else 48)      # the port's max() scan is O(live pairs) per merge
+        sample = _trim_utf8(local_dev[: int(sample_mb * (1 << 20))].cpu().numpy().tobytes())
+        dt, pv, pm = cpu_port_run(sample, vocab)
+        ft, _, fm = cpu_port_run(sample, vocab, fast=True)
         cpu = {"value": round(len(sample) / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"first {len(sample)} bytes of the same corpus, vocab {vocab}, {nm} merges, {dt:.1f} s; "
+               "sample": f"first {len(sample)} bytes of the same corpus, vocab {vocab}, {len(pm)} merges, {dt:.1f} s; "
                          f"C port of trainer.py (linear max() scan); host has {os.cpu_count()} cores, the reference uses 1"}
 
+        def gpu_on(sample_bytes: bytes):
+            sd, sn = engine.to_device_text(torch, np.frombuffer(sample_bytes, dtype=np.uint8))
+            yabpe.BBPETrainer(cfg).train_device(sd, sn)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            mdl = yabpe.BBPETrainer(cfg).train_device(sd, sn)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) * 1e3, mdl
+
+        gms, gm = gpu_on(sample)
+        same = {"bytes": len(sample), "vocab": vocab, "gpu_ms": round(gms, 2), "cpu_ms": round(dt * 1e3, 1), "cpu_kind": "port",
+                "cpu_heap_variant_ms": round(ft * 1e3, 1), "ratio": round(dt * 1e3 / gms, 1),
+                "merges_equal": bool(gm.merges == pm and gm.merges == fm and {v: k for k, v in gm.vocab.items()} == pv)}
+        if reference_module() is not None:
+            rs = _trim_utf8(sample[: 64 << 10])
+            rt, rv, rm = reference_train(rs, vocab)
+            gms2, gm2 = gpu_on(rs)
+            ref_same = {"bytes": len(rs), "vocab": vocab, "gpu_ms": round(gms2, 2), "cpu_ms": round(rt * 1e3, 1), "cpu_kind": "reference",
+                        "ratio": round(rt * 1e3 / gms2, 1), "merges": len(rm),
+                        "merges_equal": bool(gm2.merges == rm and {v: k for k, v in gm2.vocab.items()} == rv)}
+
     if rank == 0:
+        stage_ms = {k: round(float(np.mean([t[k] for t in timings])), 3) for k in (timings[0] if timings else {}) if k.endswith("_ms")}
+        serial_ms = (merge_ms or 0.0) + stage_ms.get("compact_ms", 0.0)
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/int64", "data": f"synthetic ({kind}-shaped, torch generator, lexicon seed {seed}, text seed {seed}+rank)",
-            "config": {"workload": args.workload, "corpus_bytes_per_gpu": n, "vocab_size": vocab, "special_tokens": SPECIALS,
-                       "l2": "inputs (>= 256 MB) larger than the 126 MB L2", "n_pretokens": stats.n_pretokens,
-                       "unique_words": stats.n_words, "merges": stats.n_merges},
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 2), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8/int64", "data": f"synthetic ({kind}-shaped, torch generator, seed {seed}; the same corpus at every N)",
+            "config": {"workload": args.workload, "corpus_bytes": n_total, "bytes_per_gpu": n_local, "vocab_size": vocab, "special_tokens": SPECIALS,
+                       "l2": "inputs (>= 256 MB per GPU) larger than the 126 MB L2", "n_pretokens": stats.n_pretokens,
+                       "unique_words": stats.n_words, "merges": stats.n_merges,
+                       "sharding": "byte ranges of one corpus at safe edges (yabpe/sharding.py), NCCL all-to-all of hash-partitioned unique words" if world > 1 else "none"},
+            "digest": model_digest(model.vocab, model.merges),
             "train_wall_s": round(ms_step / 1e3, 4),
             "merges_per_s": round(stats.n_merges / (merge_ms / 1e3), 1) if merge_ms else None,
             "us_per_merge": round(1e3 * merge_ms / max(stats.n_merges, 1), 2) if merge_ms else None,
-            "pretokenize_GBps": round(n / (tile_ms / 1e3) / 1e9, 2) if tile_ms else None,
-            "stage_ms": {k: round(float(np.mean([t[k] for t in timings])), 3) for k in (timings[0] if timings else {}) if k.endswith("_ms")},
+            "pretokenize_GBps": round(n_total / (tile_ms_max / 1e3) / 1e9, 2) if tile_ms_max else None,
+            "pretokenize_count_stage_ms": round(pre_ms_max, 3),
+            "stage_ms": stage_ms,
+            "amdahl": {"serial_ms": round(serial_ms, 2), "note": "merge loop + word table on rank 0 (inherently sequential, SURVEY 8e): "
+                       "the ceiling of the step's 1 -> N speed-up is step / serial",
+                       "max_speedup": round(ms_step / serial_ms, 3) if serial_ms else None},
             "leader_cycles[argmax,ranges,claim+commit,rewrite,close,sum_act,sum_items,sum_words]": timings[-1].get("leader_cycles") if timings else None,
             "merge_loop": {"index_rebuilds": stats.index_rebuilds, "threshold_rebuilds": stats.threshold_rebuilds,
                            "pairs_created": stats.n_pairs, "leader_mode_merges": stats.leader_merges,
                            "grid_mode_merges": stats.grid_merges},
-            "encode": encode,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "encode": encode, "sharded_parity": sharded_parity,
+            "roofline": roofline, "cpu_baseline": cpu, "same_sample": same, "reference_sample": ref_same, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
         print(json.dumps(line))

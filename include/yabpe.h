@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YABPE_ABI_VERSION 3
+#define YABPE_ABI_VERSION 4
 
 #define YABPE_OK 0
 #define YABPE_ERR_CUDA (-1)
@@ -141,6 +141,25 @@ int yabpe_compact_words(const yabpe_pretok_args* a, const yabpe_word_table* w, v
 int yabpe_insert_words(const yabpe_pretok_args* a, const int64_t* offs, const int32_t* lens, const int64_t* counts,
                        int64_t n_words, int32_t has_long, void* stream);
 
+/* Multi-GPU exchange, sending side: partition the unique words of `w` (straight after yabpe_compact_words, symbols are
+ * still single bytes) by hash(bytes) mod n_ranks and pack them per destination rank for the NCCL all-to-all.
+ *   pass 0: dest[i] = destination of word i; totals[d] = (bytes << 26 | words) sent to rank d (totals zeroed by the caller)
+ *   pass 1: out_lens / out_cnts / out_data filled, destination d's words contiguous from word base_w[d] / byte base_b[d]
+ *           (base_* = exclusive prefix sums of the unpacked totals, device); cursor = n_ranks zeroed uint64 scratch
+ * Equal byte strings get equal destinations on every rank, so each rank can merge its partition on its own
+ * (yabpe_insert_words) -- together they rebuild trainer.py:221-225's word_freq of the whole corpus. */
+typedef struct {
+    yabpe_word_table words; int64_t n_words;
+    int32_t n_ranks; int32_t _pad;
+    uint8_t* dest;              /* device, n_words                                                 */
+    uint64_t* totals;           /* device, n_ranks                                                 */
+    const int64_t* base_w; const int64_t* base_b;   /* device, n_ranks each (pass 1)               */
+    uint64_t* cursor;           /* device, n_ranks, zeroed (pass 1)                                */
+    int32_t* out_lens; int64_t* out_cnts; uint8_t* out_data;   /* device (pass 1)                  */
+} yabpe_partition_args;
+
+int yabpe_partition_words(const yabpe_partition_args* p, int32_t pass, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Merge loop.  Replaces trainer.py:216-302 (_merge_loop): pair histogram, best-pair selection
  * max(count, (left_bytes, right_bytes)), left-to-right rewrite, incremental deltas.  One
@@ -253,7 +272,7 @@ int yabpe_publish(void* host_mapped_dst, const void* device_src, int32_t n_words
 int64_t yabpe_launch_count(void);
 
 /* sizeof() of the argument structs as compiled (0 pretok_args, 1 word_table, 2 merge_args, 3 encode_model,
- * 4 encode_out): lets a binding check its own struct layout against the library it loaded. */
+ * 4 encode_out, 5 decode_args, 6 partition_args): lets a binding check its own struct layout against the library it loaded. */
 int64_t yabpe_sizeof(int32_t which);
 
 #ifdef __cplusplus

@@ -1,4 +1,5 @@
-"""2-GPU parity: pre-tokenise/count sharded over ranks + NCCL all-to-all == single-GPU multi-file training."""
+"""2-GPU parity: pre-tokenise/count sharded over ranks (byte ranges of one corpus, and files per rank) + NCCL
+all-to-all == the oracle and == single-GPU training.  bench.py runs the same worker at N = 2 (`--self-check`)."""
 from __future__ import annotations
 
 import socket
@@ -23,4 +24,4 @@ def test_sharded_training_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "dist_gpu_worker.py")],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert "DIST_OK" in res.stdout
+    assert "DIST_OK" in res.stdout and res.stdout.count("RANGE_OK") == 2 and "ENCODE_OK" in res.stdout

@@ -7,6 +7,7 @@
 #include "encode.cuh"
 #include "pretok_fast.cuh"
 #include "decode.cuh"
+#include "exchange.cuh"
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
@@ -55,6 +56,7 @@ extern "C" int64_t yabpe_sizeof(int32_t which) {
         case 3: return (int64_t)sizeof(yabpe_encode_model);
         case 4: return (int64_t)sizeof(yabpe_encode_out);
         case 5: return (int64_t)sizeof(yabpe_decode_args);
+        case 6: return (int64_t)sizeof(yabpe_partition_args);
         default: return -1;
     }
 }
@@ -312,6 +314,28 @@ extern "C" int yabpe_insert_words(const yabpe_pretok_args* a, const int64_t* off
     if (n_words == 0) return YABPE_OK;
     k_insert_words<<<num_sms() * 8, 256, 0, st>>>(P, (const i64*)offs, lens, (const i64*)counts, n_words); LAUNCHED();
     if (has_long) { k_insert_words_long<<<num_sms() * 2, 256, 0, st>>>(P, (const i64*)offs, lens, (const i64*)counts, n_words); LAUNCHED(); }
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
+extern "C" int yabpe_partition_words(const yabpe_partition_args* p, int32_t pass, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(p && p->n_words >= 0 && p->n_ranks >= 1 && p->n_ranks <= PX_MAX_RANKS);
+    if (p->n_words == 0) return YABPE_OK;
+    ARG_CHECK(p->words.wsym && p->words.woff && p->words.wlen && p->words.wcnt && p->dest && p->totals);
+    ARG_CHECK(p->n_words < (1LL << PX_WORD_BITS));
+    PartParams P;
+    P.wsym = p->words.wsym; P.woff = (const i64*)p->words.woff; P.wlen = p->words.wlen; P.wcnt = (const i64*)p->words.wcnt;
+    P.n_words = p->n_words; P.G = p->n_ranks; P.dest = p->dest; P.totals = (u64*)p->totals;
+    P.base_w = (const i64*)p->base_w; P.base_b = (const i64*)p->base_b; P.cursor = (u64*)p->cursor;
+    P.out_lens = p->out_lens; P.out_cnts = (i64*)p->out_cnts; P.out_data = p->out_data;
+    i64 grid = (p->n_words + 255) / 256;
+    if (grid > (i64)num_sms() * 8) grid = (i64)num_sms() * 8;
+    if (pass == 0) { k_partition_words<0><<<(int)grid, 256, 0, st>>>(P); LAUNCHED(); }
+    else {
+        ARG_CHECK(p->base_w && p->base_b && p->cursor && p->out_lens && p->out_cnts && p->out_data);
+        k_partition_words<1><<<(int)grid, 256, 0, st>>>(P); LAUNCHED();
+    }
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;
 }

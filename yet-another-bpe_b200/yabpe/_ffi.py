@@ -11,7 +11,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libyabpe.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # stats / state slots (include/yabpe.h)
 ST_NTOK, ST_UNIQ_SHORT, ST_UNIQ_LONG, ST_UNIQ_BYTES, ST_ERR_POS, ST_TABLE_FULL, ST_OVF_N = 0, 1, 2, 3, 4, 5, 6
@@ -25,7 +25,7 @@ EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
     "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize", "yabpe_hot_cache_entries",
-    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks", "yabpe_publish",
+    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks", "yabpe_publish", "yabpe_partition_words",
 ]
 
 
@@ -95,6 +95,12 @@ class DecodeArgs(C.Structure):
                 ("out", C.c_void_p), ("out_cap", C.c_int64)]
 
 
+class PartitionArgs(C.Structure):
+    _fields_ = [("words", WordTable), ("n_words", C.c_int64), ("n_ranks", C.c_int32), ("_pad", C.c_int32),
+                ("dest", C.c_void_p), ("totals", C.c_void_p), ("base_w", C.c_void_p), ("base_b", C.c_void_p),
+                ("cursor", C.c_void_p), ("out_lens", C.c_void_p), ("out_cnts", C.c_void_p), ("out_data", C.c_void_p)]
+
+
 _lib: C.CDLL | None = None
 _device_ready: set[int] = set()
 
@@ -143,9 +149,11 @@ def load() -> C.CDLL:
     L.yabpe_decode_blocks.argtypes = [C.c_int64]
     L.yabpe_publish.restype = C.c_int
     L.yabpe_publish.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.yabpe_partition_words.restype = C.c_int
+    L.yabpe_partition_words.argtypes = [C.POINTER(PartitionArgs), C.c_int32, C.c_void_p]
     L.yabpe_sizeof.restype = C.c_int64
     L.yabpe_sizeof.argtypes = [C.c_int32]
-    for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut, DecodeArgs)):
+    for which, st in enumerate((PretokArgs, WordTable, MergeArgs, EncodeModel, EncodeOut, DecodeArgs, PartitionArgs)):
         if L.yabpe_sizeof(which) != C.sizeof(st):
             raise YabpeUnavailable(f"{st.__name__}: ctypes layout ({C.sizeof(st)} B) != libyabpe.so ({L.yabpe_sizeof(which)} B); rebuild")
     if L.yabpe_abi_version() != ABI_VERSION:
