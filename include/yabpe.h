@@ -45,7 +45,7 @@ extern "C" {
 #define YABPE_ST_SLOW_N 9      /* boundary work items the warp kernel left to the generic kernel */
 #define YABPE_ST_CACHE_HIT 10  /* pre-tokens counted in shared memory by the warp kernel   */
 
-/* indices into the int64[32] merge-loop state array */
+/* indices into the int64[64] merge-loop state array */
 #define YABPE_MS_NMERGES 0
 #define YABPE_MS_NTOK 1
 #define YABPE_MS_ERROR 2       /* bit 0: pair table full, bit 1: token pool full, bit 2: internal */
@@ -195,11 +195,13 @@ typedef struct {
     int64_t* bsum;              /* device, one per CTA (>= 1024 entries)                          */
     int32_t* merges;            /* device, 2 * num_merges: (left id, right id) per merge          */
     int32_t* merge_new;         /* device, num_merges: resulting id                               */
-    int64_t* state;             /* device int64[32], zeroed except [MS_NTOK] = n_base             */
+    int64_t* state;             /* device int64[64], zeroed except [MS_NTOK] = n_base             */
     int64_t num_merges; int64_t min_frequency;
     int64_t rebuild_every;      /* merges between pair->words index rebuilds; 0 = only when the log is full.
                                  * Candidates of a pair are its postings at the last rebuild plus every word rewritten
                                  * when one of its tokens was created: a superset that grows stale between rebuilds */
+    int64_t helper_min_syms;    /* leader mode: idle CTAs prefetch the next merges' words into the L2 when n_syms exceeds this
+                                 * (0 = default, 8 Mi slots: smaller word arrays stay L2-resident anyway; < 0 = always).  Result-neutral */
 } yabpe_merge_args;
 
 int yabpe_merge_loop(const yabpe_merge_args* m, void* stream);

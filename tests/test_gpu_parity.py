@@ -281,6 +281,24 @@ def test_train_with_frequent_index_rebuilds(yabpe, tmp_path, monkeypatch):
             assert tr.last_stats.index_rebuilds >= 30
 
 
+def test_train_with_prefetch_helpers_and_tie_regime(yabpe, tmp_path, monkeypatch):
+    """(1) The leader's prefetch helpers (idle CTAs pulling the next merges' words into the L2) only run on word arrays
+    beyond the L2 size; YABPE_HELPER_MIN_SYMS=-1 forces them on a small corpus -- results must not move.
+    (2) A small corpus trained to exhaustion spends most merges in the massive-tie regime (thousands of pairs share the
+    maximum count, the top list stays disabled between retries): every merge there is decided by the byte-wise tie-break."""
+    monkeypatch.setenv("YABPE_HELPER_MIN_SYMS", "-1")
+    data = common.synth_owt(3_000_000, seed=11)
+    p = tmp_path / "h.txt"
+    p.write_bytes(data)
+    assert yabpe.train_bpe(p, 3000, ["<|endoftext|>"]) == oracle.train_bpe(p, 3000, ["<|endoftext|>"], fast=True)
+    monkeypatch.delenv("YABPE_HELPER_MIN_SYMS")
+    small = common.synth_owt(200_000, seed=12)
+    p.write_bytes(small)
+    got = yabpe.train_bpe(p, 32000, ["<|endoftext|>"])
+    want = oracle.train_bpe(p, 32000, ["<|endoftext|>"], fast=True)
+    assert len(want[1]) > 10000 and got == want
+
+
 def test_train_edge_cases(yabpe, tmp_path):
     p = tmp_path / "e.txt"
     p.write_bytes(b"")

@@ -71,6 +71,10 @@ __device__ long long* g_trace_row = nullptr;
 #define MS_TOP_REBUILDS 28
 #define MS_BAR_COUNT 29
 #define MS_BAR_GEN 30
+#define MS_TIE_CNT 32        // count at which the top list overflowed (more than ML_TOP_N pairs tie for the maximum)
+#define MS_TIE_LEFT 33       // merges left before the next attempt to rebuild the top list in that regime
+#define MS_TOP_N_LIVE 34     // leader mode: current length of the top list (read by the prefetch helpers)
+#define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
 #define ME_TOK_POOL_FULL 2
@@ -202,6 +206,7 @@ struct MergeParams {
     int32_t* merges; int32_t* merge_new; i64* state;
     i64 num_merges; i64 min_freq;
     i64 rebuild_every;                           // merges between index rebuilds (0: only when the affected-word log is full)
+    i64 helper_min_syms;                         // prefetch helpers run when the word arrays have more symbol slots than this
 };
 
 // Grid-wide barrier on two words of the state array (arrival counter + generation).  The kernel is
@@ -1048,6 +1053,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         sh_ncand = 0; C.cur_slot = -1;
     }
     __syncthreads();
+    if (threadIdx.x == 0) *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;
     {
         const int tn0 = C.top_n < ML_TOP_N ? C.top_n : ML_TOP_N;
         if ((int)threadIdx.x < tn0) { C.tslot[threadIdx.x] = M.top_slot[threadIdx.x]; C.tkey[threadIdx.x] = M.top_key[threadIdx.x]; C.LM.pending[threadIdx.x] = 1; }
@@ -1195,6 +1201,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             const int32_t prev = is_new ? -1 : M.tok_first[c];        // == merge_next[m] written by the commit warp
             M.seg_end[m] = C.alog_n; M.tok_first[c] = (int32_t)m;
             M.tok_head[c] = make_int4((int32_t)m, alog_n, C.alog_n, prev);
+            *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;        // for the prefetch helpers
         }
         if (threadIdx.x == 32) { const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, __ldcg(&M.pcnt[best.slot])); }
         if (is_new) leader_new_pairs(M, &C, T, T2);
@@ -1283,10 +1290,69 @@ __device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* s
         i64 n_old = M.state[MS_TOP_N]; if (n_old > ML_TOP_N) n_old = ML_TOP_N;
         for (i64 i = gtid; i < n_old; i += gstride) { int32_t sl = M.top_slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
         grid_barrier(M);
-        if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_T2] = -1; }
+        if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_T2] = -1; M.state[MS_TIE_CNT] = hi; M.state[MS_TIE_LEFT] = 64; }
     } else if (gtid == 0) M.state[MS_T2] = T2;
     grid_barrier(M);
     return true;
+}
+
+// ---- prefetch helpers (leader mode) ---------------------------------------------------------------------------------
+// While CTA 0 runs merges alone, the word arrays of a large corpus (GBs) miss the L2, so every dependent step of a merge
+// (postings -> word header -> symbols) is a DRAM round trip.  The pair that will be merged NEXT is almost always among the
+// few largest of the top list, which lives in global memory: a helper CTA (otherwise idle at the grid barrier) keeps
+// finding the ML_SEL largest entries, walks their candidate lists exactly as the leader will, and pulls the lines the
+// leader is going to touch into the L2 (prefetch.global.L2).  Helpers only read (through the L2: ld.cg) and prefetch;
+// whatever they see -- stale list entries, half-updated words -- can only make a prefetch useless, never change a result.
+#ifndef ML_HELPERS
+#define ML_HELPERS 2
+#endif
+#ifndef ML_HELPER_MIN_SYMS
+#define ML_HELPER_MIN_SYMS (8 << 20)      // word arrays below ~100 MB stay in the L2 anyway (126 MB): nothing to prefetch
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __noinline__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_keys, Ranges* R) {
+    __shared__ int sh_stop;
+    for (int round = 0;; round++) {
+        if (threadIdx.x == 0) sh_stop = *(volatile i64*)&M.state[MS_LEADER_GEN] != gen;
+        __syncthreads();
+        if (sh_stop) break;
+        i64 tn = __ldcg(&M.state[MS_TOP_N_LIVE]);
+        if (tn > ML_TOP_N) tn = ML_TOP_N;
+        u64 key = 0;
+        if ((i64)threadIdx.x < tn) {
+            const i64 cnt = __ldcg(&M.pcnt[__ldcg(&M.top_slot[threadIdx.x])]);
+            if (cnt > 0) key = ((u64)cnt << 9) | (u64)(511 - (int)threadIdx.x);
+        }
+        u64 topk[ML_SEL];
+        select_top(key, sh_keys, topk);                  // one block barrier inside
+        for (int r = hidx; r < ML_SEL; r += ML_HELPERS) {
+            __syncthreads();
+            if (topk[r] == 0) continue;                  // block-uniform
+            const int idx = 511 - (int)(topk[r] & 511);
+            if (threadIdx.x == 0) {
+                const int32_t slot = __ldcg(&M.top_slot[idx]);
+                const u64 k = __ldcg(&M.top_key[idx]);
+                build_ranges(M, slot, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), R);
+            }
+            __syncthreads();
+            if (R->n < 0) continue;
+            const i64 total = R->total < 2 * ML_LEADER_ITEMS_MAX ? R->total : 2 * ML_LEADER_ITEMS_MAX;
+            for (i64 it = threadIdx.x; it < total; it += blockDim.x) {
+                i64 j = it; int32_t w = -1;
+                for (int q = 0; q < R->n; q++) { if (j < R->len[q]) { w = __ldcg(&R->base[q][j]); break; } j -= R->len[q]; }
+                if (w < 0 || w >= M.n_words) continue;
+                prefetch_l2(&M.wcnt[w]);
+                const i64 off = __ldcg(&M.woff[w]);
+                const int n = __ldcg(&M.wlen[w]);
+                if (off < 0 || off >= M.n_syms) continue;
+                prefetch_l2(&M.wsym[off]); prefetch_l2(&M.wslot[off]);
+                if (n > 8) { prefetch_l2(&M.wsym[off + (n < 64 ? n : 64) - 1]); prefetch_l2(&M.wslot[off + (n < 64 ? n : 64) - 1]); }
+            }
+        }
+        __syncthreads();
+        __nanosleep(500);
+    }
 }
 
 extern __shared__ __align__(16) unsigned char ml_dyn_smem[];      // LeaderCtx (used by CTA 0 in leader mode)
@@ -1296,7 +1362,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     __shared__ Best sh_best[ML_THREADS / 32];
     __shared__ i64 sh_scan[1 + ML_THREADS / 32];
     __shared__ i64 sh_cnt[ML_THREADS / 32];
-    __shared__ int sh_hist[1024];
+    __shared__ __align__(16) int sh_hist[1024];
     __shared__ int32_t sh_c;
     __shared__ Ranges R;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
@@ -1333,6 +1399,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         const i64 act_n = M.state[MS_ACT_N];
         const i64 gen = M.state[MS_LEADER_GEN];
         i64 T2 = M.state[MS_T2];
+        const i64 tie_cnt = M.state[MS_TIE_CNT], tie_left = M.state[MS_TIE_LEFT];
         const i64 top_n = M.state[MS_TOP_N];
         const bool top_ovf = M.state[MS_TOP_OVF] != 0;
         if (m >= M.num_merges || M.state[MS_ERROR] || M.state[MS_DONE]) break;
@@ -1354,6 +1421,8 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
+            } else if ((int)blockIdx.x <= ML_HELPERS && M.n_syms > M.helper_min_syms) {
+                helper_loop(M, gen, (int)blockIdx.x - 1, (u64*)sh_hist, &R);        // sh_hist (4 KB) is free while the leader runs
             } else {
                 if (threadIdx.x == 0) while (*(volatile i64*)&M.state[MS_LEADER_GEN] == gen) __nanosleep(2000);
                 __syncthreads();
@@ -1451,7 +1520,12 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         if (gtid == 0) { M.state[12] += g1 - g0; M.state[13] += g2 - g1; M.state[22] += g3 - g2; M.state[27] += g4 - g3; M.state[28] += R.total; }
 #endif
         // every CTA writes the same values: no further barrier needed before the next iteration
-        if (threadIdx.x == 0) { close_merge(M, m, c); if (T2 < 0) M.state[MS_T2] = 0; }
+        // Massive ties (T2 < 0: every merge scans the active set): rebuilding the top list after EVERY merge only to see it
+        // overflow again cost ten grid barriers per merge; try again when the maximum count has moved or after 64 merges.
+        if (threadIdx.x == 0) {
+            close_merge(M, m, c);
+            if (T2 < 0) { if (best.cnt != tie_cnt || tie_left <= 1) M.state[MS_T2] = 0; else M.state[MS_TIE_LEFT] = tie_left - 1; }
+        }
         if (gtid == 0) M.state[MS_GRID_MERGES]++;
         __syncthreads();
     }

@@ -7,6 +7,7 @@ compute runs in libyabpe.so.  Shared by the trainer (trainer.py) and the tokeniz
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -361,7 +362,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         tok_head = z(4 * max_tokens + 4, torch.int32)
         partial, bsum = z(1024 * 3, torch.int64), z(1024, torch.int64)
         merges, merge_new = z(2 * max(num_merges, 1), torch.int32), z(max(num_merges, 1), torch.int32)
-        state_np = np.zeros(32, dtype=np.int64)
+        state_np = np.zeros(64, dtype=np.int64)
         state_np[_ffi.MS_NTOK] = n_base
         state = t(state_np)
         m = _ffi.MergeArgs()
@@ -382,6 +383,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.merges = merges.data_ptr(); m.merge_new = merge_new.data_ptr(); m.state = state.data_ptr()
         m.num_merges = num_merges; m.min_frequency = min_frequency
         m.rebuild_every = rebuild_period(words.n_syms)
+        m.helper_min_syms = int(os.environ.get("YABPE_HELPER_MIN_SYMS", "0"))     # tests force the prefetch helpers on small inputs (-1)
         if timing is not None:
             t0 = torch.cuda.Event(enable_timing=True); t0.record()
         _ffi.check(L.yabpe_merge_loop(C.byref(m), _ffi.stream_ptr(torch)))
