@@ -84,7 +84,10 @@ typedef struct {
     int32_t n_sp;
     int32_t stages;             /* 0 = all; else bit 0: special resolution, bit 1: tile kernel,   */
                                 /*   bit 2: over-long pre-tokens (lets a caller time each stage), */
-                                /*   bit 3: generic tile kernel only (no warp kernel; for tests)  */
+                                /*   bit 3: generic tile kernel only (no warp kernel; for tests), */
+                                /*   bit 4: own_lo is a text start (0 or one of `cuts`): the special-token  */
+                                /*   passes cover [own_lo, n) only -- piece-wise counting into ONE table set */
+                                /*   while the text is still being uploaded (caller zeroes stats[6], [9])   */
     int64_t own_lo, own_hi;     /* only pre-tokens starting in [own_lo, own_hi) are counted       */
     uint32_t* cand_bits;        /* device, (n + 63) / 32 words, zeroed; may be NULL when n_sp = 0 */
     uint32_t* rec_bits;         /* device, same size, zeroed: recognised special starts (output)  */
@@ -202,6 +205,7 @@ typedef struct {
                                  * when one of its tokens was created: a superset that grows stale between rebuilds */
     int64_t helper_min_syms;    /* leader mode: idle CTAs prefetch the next merges' words into the L2 when n_syms exceeds this
                                  * (0 = default, 8 Mi slots: smaller word arrays stay L2-resident anyway; < 0 = always).  Result-neutral */
+    int64_t helper_mode;        /* 0 = no helpers, 1 = CTAs 1..2, 2 = the CTAs on the SMs next to the leader's                      */
 } yabpe_merge_args;
 
 int yabpe_merge_loop(const yabpe_merge_args* m, void* stream);

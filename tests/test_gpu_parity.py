@@ -290,13 +290,44 @@ def test_train_with_prefetch_helpers_and_tie_regime(yabpe, tmp_path, monkeypatch
     data = common.synth_owt(3_000_000, seed=11)
     p = tmp_path / "h.txt"
     p.write_bytes(data)
-    assert yabpe.train_bpe(p, 3000, ["<|endoftext|>"]) == oracle.train_bpe(p, 3000, ["<|endoftext|>"], fast=True)
+    want = oracle.train_bpe(p, 3000, ["<|endoftext|>"], fast=True)
+    for mode in ("1", "2"):
+        monkeypatch.setenv("YABPE_HELPER_MODE", mode)
+        assert yabpe.train_bpe(p, 3000, ["<|endoftext|>"]) == want, mode
     monkeypatch.delenv("YABPE_HELPER_MIN_SYMS")
+    monkeypatch.delenv("YABPE_HELPER_MODE")
     small = common.synth_owt(200_000, seed=12)
     p.write_bytes(small)
     got = yabpe.train_bpe(p, 32000, ["<|endoftext|>"])
     want = oracle.train_bpe(p, 32000, ["<|endoftext|>"], fast=True)
     assert len(want[1]) > 10000 and got == want
+
+
+def test_train_counted_while_uploaded(yabpe, tmp_path):
+    """train_from_buffers on large host buffers counts piece k while piece k + 1 is still being uploaded (pieces cut at the
+    safe edges of yabpe/sharding.py, all into one table set): forced here with 1 MiB pieces on two buffers, reference chunk
+    cuts inside pieces, a 30 000-byte pre-token across a piece edge and back-to-back specials."""
+    blobs = [common.synth_owt(9_000_000, seed=21) + b" " + b"z" * 30000 + b"\n" + common.synth_tinystories(2_000_000, seed=22),
+             (b"a<|endoftext|><|endoftext|>b !<|endoftext|>\n" * 3000) + common.synth_adversarial(1_500_000, seed=23)]
+    for chunk in (1 << 30, 2_000_003):
+        cfg = yabpe.BBPETrainerConfig(vocab_size=1800, min_frequency=1, max_workers=1, chunk_size_bytes=chunk,
+                                      special_tokens=["<|endoftext|>"])
+        tr = yabpe.BBPETrainer(cfg)
+        tr.pipeline_min_bytes, tr.pipeline_piece_bytes = 0, 1 << 20
+        model = tr.train_from_buffers([np.frombuffer(b, dtype=np.uint8) for b in blobs])
+        o = oracle.Trainer(["<|endoftext|>"])
+        for b in blobs:
+            o.feed_bytes(b, chunk)
+        vocab, merges = o.run(1800, 1, True)
+        assert model.merges == merges, chunk
+        assert {v: k for k, v in model.vocab.items()} == vocab, chunk
+        assert tr.last_stats.n_pretokens == o.num_pretokens
+    # invalid UTF-8 is still reported with its file and offset
+    bad = bytearray(common.synth_owt(3_000_000, seed=24)); bad[2_500_000] = 0xFF
+    tr = yabpe.BBPETrainer(cfg)
+    tr.pipeline_min_bytes, tr.pipeline_piece_bytes = 0, 1 << 20
+    with pytest.raises(ValueError, match="invalid UTF-8 at position 2500000"):
+        tr.train_from_buffers([np.frombuffer(bytes(bad), dtype=np.uint8)], ["bad.txt"])
 
 
 def test_train_edge_cases(yabpe, tmp_path):

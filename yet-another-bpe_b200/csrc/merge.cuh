@@ -74,6 +74,7 @@ __device__ long long* g_trace_row = nullptr;
 #define MS_TIE_CNT 32        // count at which the top list overflowed (more than ML_TOP_N pairs tie for the maximum)
 #define MS_TIE_LEFT 33       // merges left before the next attempt to rebuild the top list in that regime
 #define MS_TOP_N_LIVE 34     // leader mode: current length of the top list (read by the prefetch helpers)
+#define MS_LEADER_SMID 35    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
 #define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
@@ -207,6 +208,7 @@ struct MergeParams {
     i64 num_merges; i64 min_freq;
     i64 rebuild_every;                           // merges between index rebuilds (0: only when the affected-word log is full)
     i64 helper_min_syms;                         // prefetch helpers run when the word arrays have more symbol slots than this
+    i64 helper_mode;                             // 0 off, 1 CTAs 1..ML_HELPERS, 2 the CTAs on the SMs next to the leader's (smid ^ 1, ^ 2)
 };
 
 // Grid-wide barrier on two words of the state array (arrival counter + generation).  The kernel is
@@ -510,8 +512,7 @@ __device__ __forceinline__ bool dedupe_claim(LeaderCtx* lc, int32_t w) {
 
 __device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t slot, i64 f, LeaderCtx* lc) {
     atomicAdd((u64*)&M.pcnt[slot], (u64)(-f));     // the slot of every adjacency is cached in wslot: no probe
-    // the merged pair itself is decremented by EVERY site: its mirrored count is re-read once after the rewrite instead
-    if (lc && slot != lc->cur_slot) mirror_add(lc, slot, -f);
+    mirror_add(lc, slot, -f);                      // (never the merged pair itself: its count is set to 0 once per merge)
 }
 // "Top list": every pair with count >= T2, kept in global memory (at most ML_TOP_N entries) and
 // maintained by pair_add in both modes.  Scanning the whole active set every merge is bound by the
@@ -603,7 +604,10 @@ __device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, Lea
 }
 
 // one thread rewrites one word in place (left->right, non-overlapping) and applies the deltas
-__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew) {
+// `cur` = table slot of the pair being merged.  Every site would decrement that ONE counter (thousands of atomics on a single
+// address in a heavy merge: they serialise in the L2); the merge removes every occurrence of the pair (trainer.py:268-285:
+// its count ends at 0 and the key is deleted), so nobody decrements it and its count is stored as 0 once per merge.
+__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew, int32_t cur) {
     const i64 off = M.woff[w];
     int32_t* s = M.wsym + off;
     int32_t* ws = M.wslot + off;
@@ -616,13 +620,13 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
         int32_t x = s[j];
         if (j + 1 < n && x == a && s[j + 1] == b) {
             const int32_t sl_ab = ws[j];
-            if (o > 0) { pair_sub(M, ws[j - 1], f, lm); ws[o - 1] = pair_add(M, prev_new, c, f, T, T2, lm, xnew); }
-            pair_sub(M, sl_ab, f, lm);
+            if (o > 0) { if (ws[j - 1] != cur) pair_sub(M, ws[j - 1], f, lm); ws[o - 1] = pair_add(M, prev_new, c, f, T, T2, lm, xnew); }
+            (void)sl_ab;
             s[o++] = c; prev_new = c; prev_changed = true; any = true; j += 2;
         } else {
             if (o > 0) {
                 const int32_t sl_old = ws[j - 1];
-                if (prev_changed) { pair_sub(M, sl_old, f, lm); ws[o - 1] = pair_add(M, prev_new, x, f, T, T2, lm, xnew); }
+                if (prev_changed) { if (sl_old != cur) pair_sub(M, sl_old, f, lm); ws[o - 1] = pair_add(M, prev_new, x, f, T, T2, lm, xnew); }
                 else ws[o - 1] = sl_old;
             }
             s[o++] = x; prev_new = x; prev_changed = false; j += 1;
@@ -663,7 +667,7 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
         const unsigned keepmask = __ballot_sync(0xffffffffu, keep);
         any |= __any_sync(0xffffffffu, sel0);
         // old pair (j, j+1) disappears when either side is part of a site
-        if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, ps0, f, lm);
+        if (valid && j + 1 < n && !sel0 && (rem0 || sel1)) pair_sub(M, ps0, f, lm);      // sel0: the merged pair itself (see rewrite_word_thread)
         // new pair starting at kept position j
         int32_t nslot = ps0; bool has_pair = false;
         if (keep) {
@@ -729,7 +733,7 @@ __device__ void rewrite_words_g(const MergeParams& M, int32_t w, i64 off, int n,
         const bool keep = valid && !rem0;
         const unsigned keepmask = (__ballot_sync(0xffffffffu, keep) >> gshift) & GM;
         any |= ((__ballot_sync(0xffffffffu, sel0) >> gshift) & GM) != 0;
-        if (valid && j + 1 < n && (sel0 || rem0 || sel1)) pair_sub(M, ps0, f, lm);
+        if (valid && j + 1 < n && !sel0 && (rem0 || sel1)) pair_sub(M, ps0, f, lm);      // sel0: the merged pair itself (see rewrite_word_thread)
         if (base == 0) ML_TRG(14);
         int32_t nslot = ps0; bool has_pair = false;
         if (keep) {
@@ -996,7 +1000,7 @@ __device__ __forceinline__ void leader_rewrite(const MergeParams& M, LeaderCtx& 
         uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
         if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
         if (a != b) rewrite_words_g<G>(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
-        else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new);
+        else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new, C.cur_slot);
         w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = w_nx2;
     }
 }
@@ -1203,7 +1207,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             M.tok_head[c] = make_int4((int32_t)m, alog_n, C.alog_n, prev);
             *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;        // for the prefetch helpers
         }
-        if (threadIdx.x == 32) { const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, __ldcg(&M.pcnt[best.slot])); }
+        if (threadIdx.x == 32) { M.pcnt[best.slot] = 0; const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, 0); }
         if (is_new) leader_new_pairs(M, &C, T, T2);
         __syncthreads();
         ML_CLOCK(c4);
@@ -1311,7 +1315,7 @@ __device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* s
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __noinline__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_keys, Ranges* R) {
+__device__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_keys, Ranges* R) {
     __shared__ int sh_stop;
     for (int round = 0;; round++) {
         if (threadIdx.x == 0) sh_stop = *(volatile i64*)&M.state[MS_LEADER_GEN] != gen;
@@ -1376,6 +1380,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             if (s >= 0) { atomicAdd((u64*)&M.pcnt[s], (u64)M.wcnt[w]); M.wslot[i] = (int32_t)s; }
         }
     }
+    if (gtid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); M.state[MS_LEADER_SMID] = smid; }
     for (i64 t = gtid; t < M.max_tokens; t += gstride) { M.tok_first[t] = -1; M.tok_head[t] = make_int4(-1, 0, 0, -1); }
     for (i64 t = gtid; t < M.state[MS_NTOK]; t += gstride) M.tok_pre[t] = tok_prefix_of_bytes(M.tok_bytes + M.tok_off[t], M.tok_off[t + 1] - M.tok_off[t]);
     grid_barrier(M);
@@ -1389,6 +1394,17 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     const i64 Tmin = M.min_freq > 1 ? M.min_freq : 1;
     i64 T = M.state[MS_MAXCNT] / 2; if (T < Tmin) T = Tmin;
     rebuild_active(M, T);
+
+    // prefetch helpers of the leader mode (result-neutral): which CTAs, if any
+    int helper_idx = -1;
+    if (M.helper_mode != 0 && M.n_syms > M.helper_min_syms && blockIdx.x != 0) {
+        if (M.helper_mode == 1) { if ((int)blockIdx.x <= ML_HELPERS) helper_idx = (int)blockIdx.x - 1; }
+        else {
+            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const unsigned lead = (unsigned)M.state[MS_LEADER_SMID];
+            if (smid == (lead ^ 1u)) helper_idx = 0; else if (smid == (lead ^ 2u)) helper_idx = 1;
+        }
+    }
 
     int skip = 0, backoff = 1;
     for (;;) {
@@ -1421,8 +1437,8 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
-            } else if ((int)blockIdx.x <= ML_HELPERS && M.n_syms > M.helper_min_syms) {
-                helper_loop(M, gen, (int)blockIdx.x - 1, (u64*)sh_hist, &R);        // sh_hist (4 KB) is free while the leader runs
+            } else if (helper_idx >= 0) {
+                helper_loop(M, gen, helper_idx, (u64*)sh_hist, &R);        // sh_hist (4 KB) is free while the leader runs
             } else {
                 if (threadIdx.x == 0) while (*(volatile i64*)&M.state[MS_LEADER_GEN] == gen) __nanosleep(2000);
                 __syncthreads();
@@ -1477,7 +1493,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         }
         const int32_t c = sh_c;
         const bool is_new = c == n_tok;
-        if (blockIdx.x == 0) commit_merge(M, m, a, b, c, is_new, alog_n);
+        if (blockIdx.x == 0) { commit_merge(M, m, a, b, c, is_new, alog_n); if (threadIdx.x == 0) M.pcnt[best.slot] = 0; }
         const int32_t stamp = (int32_t)(m + 1);
         const i64 T2u = T2 > 0 ? T2 : 0;
         if (a != b && R.total * 8 <= gstride) {
@@ -1510,7 +1526,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             for (i64 it = gtid; it < R.total; it += gstride) {
                 int32_t w = range_item(R, it);
                 if (atomicExch(&M.wstamp[w], stamp) == stamp) continue;
-                rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr, is_new);
+                rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr, is_new, best.slot);
             }
         }
         ML_CLOCK(g3);

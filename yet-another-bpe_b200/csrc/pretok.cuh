@@ -158,9 +158,9 @@ __device__ bool any_bit(const uint32_t* bm, i64 lo, i64 hi) {   // any set bit i
 // every warp iteration.  Each warp therefore first gathers candidate positions into its own shared-memory list
 // (ballot + prefix) and runs the slow path 32 candidates at a time with all lanes busy.
 __device__ __forceinline__ int resolve_candidate(const PretokParams& P, i64 q, i64 ctx_lo, int D) {
-    // chain head?  no candidate in [q-D, q)
-    if (D > 0 && any_bit(P.cand, q - D, q - 1)) return 0;      // resolved by the walk of its chain's head
-    (void)ctx_lo;
+    // chain head?  no candidate in [q-D, q) -- nor before ctx_lo, a text start the caller vouches for (a hard cut: specials
+    // never straddle one, so nothing to its left can reach q)
+    if (D > 0 && any_bit(P.cand, q - D > ctx_lo ? q - D : ctx_lo, q - 1)) return 0;      // resolved by the walk of its chain's head
     GlobalText G{P.text, P.n, P.cuts, P.n_cuts, nullptr, -1, P.mode};
     int n_rec = 0;
     i64 e = -1, cur = q;

@@ -165,15 +165,16 @@ __global__ void __launch_bounds__(256) k_long_tokens_dyn(PretokParams P) {
     }
 }
 
-static int run_specials(const yabpe_pretok_args* a, const PretokParams& P, cudaStream_t st) {
+static int run_specials(const yabpe_pretok_args* a, const PretokParams& P, cudaStream_t st, bool from_own_lo) {
     int rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
     if (rc) return rc;
     if (a->n_sp == 0) return YABPE_OK;
     int grid = num_sms() * 8;
-    // candidates / resolution need left context for chains that reach into the owned range
-    i64 lo = 0, hi = P.n;
+    // candidates / resolution need left context for chains that reach into the owned range -- unless the caller declares
+    // own_lo a text start (stages bit 4: it is 0 or one of the hard cuts), as the piece-wise upload + count does
+    i64 lo = from_own_lo ? P.own_lo : 0, hi = P.n;
     k_special_candidates<<<grid, 256, 0, st>>>(P, lo, hi); LAUNCHED();
-    k_resolve_specials<<<grid, 256, 0, st>>>(P, lo, hi, 0); LAUNCHED();
+    k_resolve_specials<<<grid, 256, 0, st>>>(P, lo, hi, lo); LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;
 }
@@ -217,7 +218,7 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
     int stages = a->stages;
     if ((stages & 7) == 0) stages |= 7;
     if (stages & 1) {
-        rc = run_specials(a, P, st);
+        rc = run_specials(a, P, st, (stages & 16) != 0);
         if (rc) return rc;
     } else {
         rc = upload_specials(a->sp_blob, a->sp_offs, a->n_sp, st);
@@ -381,6 +382,7 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.partial = (Best*)m->partial; M.bsum = (i64*)m->bsum;
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
     M.num_merges = m->num_merges; M.min_freq = m->min_frequency; M.rebuild_every = m->rebuild_every;
+    M.helper_mode = m->helper_mode;
     M.helper_min_syms = m->helper_min_syms > 0 ? m->helper_min_syms : (m->helper_min_syms < 0 ? 0 : ML_HELPER_MIN_SYMS);
 
     DevInfo& DI = dev_info();

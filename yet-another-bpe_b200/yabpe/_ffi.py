@@ -73,7 +73,7 @@ class MergeArgs(C.Structure):
         ("merge_next", C.c_void_p), ("tok_first", C.c_void_p), ("tok_head", C.c_void_p),
         ("partial", C.c_void_p), ("bsum", C.c_void_p),
         ("merges", C.c_void_p), ("merge_new", C.c_void_p), ("state", C.c_void_p),
-        ("num_merges", C.c_int64), ("min_frequency", C.c_int64), ("rebuild_every", C.c_int64), ("helper_min_syms", C.c_int64),
+        ("num_merges", C.c_int64), ("min_frequency", C.c_int64), ("rebuild_every", C.c_int64), ("helper_min_syms", C.c_int64), ("helper_mode", C.c_int64),
     ]
 
 

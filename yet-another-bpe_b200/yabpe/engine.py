@@ -105,7 +105,8 @@ class PretokResult:
 def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: list[bytes], mode: int,
                  own: tuple[int, int] | None = None, short_cap: int | None = None,
                  long_cap: int | None = None, stage_events: list | None = None,
-                 generic_only: bool = False, mailbox: Mailbox | None = None, sizing: tuple | None = None) -> PretokResult:
+                 generic_only: bool = False, mailbox: Mailbox | None = None, sizing: tuple | None = None,
+                 launch: bool = True, max_cuts: int = 0) -> PretokResult:
     """Launch special resolution + the tile kernel + the long-token kernel (all async).
     `sizing` = PretokResult.sizing() of an earlier, similar text: its layout and hot set are reused and its capacities
     are the default, so no sizing sample is counted.  `mailbox`: statistics reach the host through yabpe_publish."""
@@ -120,7 +121,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
         short_cap = short_cap or est_s
         long_cap = long_cap or est_l
     n_cuts = 0 if cuts is None else int(len(cuts))
-    cuts_t = torch.from_numpy(np.ascontiguousarray(cuts, dtype=np.int64)).to(dev) if n_cuts else None
+    cuts_t = torch.from_numpy(np.ascontiguousarray(cuts, dtype=np.int64)).to(dev) if n_cuts and launch else None
     blob, offs = pack_specials(specials)
     words32 = (n + 63) // 32 + 1
     cand = torch.zeros(words32, dtype=torch.int32, device=dev) if specials else None
@@ -135,7 +136,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     lent = torch.zeros(long_cap * 4, dtype=torch.int64, device=dev)
     ovf_cap = n // 992 + 16         # at most one over-long pre-token per 992-byte chunk of the warp kernel
     ovf = torch.empty(ovf_cap, dtype=torch.int64, device=dev)
-    work_cap = 4 * n_cuts + 64
+    work_cap = 4 * max(n_cuts, max_cuts) + 64
     work = torch.empty(3 * work_cap, dtype=torch.int64, device=dev)
     if mailbox is not None:                      # no host->device copy either: it would queue behind a bulk upload
         stats = torch.zeros(16, dtype=torch.int64, device=dev)
@@ -146,7 +147,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
         stats = torch.from_numpy(stats_np).to(dev)
     a = _ffi.PretokArgs()
     a.text = text_dev.data_ptr(); a.n = n
-    a.cuts = cuts_t.data_ptr() if n_cuts else None; a.n_cuts = n_cuts; a.mode = mode
+    a.cuts = cuts_t.data_ptr() if cuts_t is not None else None; a.n_cuts = n_cuts if cuts_t is not None else 0; a.mode = mode
     a.sp_blob = blob.ctypes.data; a.sp_offs = offs.ctypes.data; a.n_sp = len(specials)
     a.own_lo, a.own_hi = own if own is not None else (0, n)
     a.cand_bits = cand.data_ptr() if specials else None
@@ -159,7 +160,7 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     a.hot_keys = hot.data_ptr() if hot is not None else None
     res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work, hot], stats=stats,
                        short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n, mailbox=mailbox, cold=interleaved, hot=hot)
-    if n > 0:
+    if n > 0 and launch:
         extra = 8 if generic_only else 0        # stages bit 3: generic tile kernel only (A/B parity tests)
         a.stages = extra
         if stage_events is None:
@@ -173,6 +174,46 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
                 ev = torch.cuda.Event(enable_timing=True); ev.record(); stage_events.append(ev)
             a.stages = 0
     return res
+
+
+def pretok_count_pieces(torch, text_dev, n: int, pieces: list[tuple[int, int, int, list[int]]], specials: list[bytes],
+                        ready: list, sample_cuts: np.ndarray | None = None) -> tuple[PretokResult, np.ndarray] | None:
+    """Count a text WHILE it is being uploaded: piece k = (own_lo, own_hi, n_k, cuts_k) is counted as soon as `ready[k]`
+    (a CUDA event: bytes [0, n_k) are on the device) has fired, all pieces into ONE set of tables.  own_lo is 0 or one of
+    cuts_k (a text start), n_k the end of the bytes the piece may look at -- sharding.plan_shards edges with their halo,
+    exactly the per-rank windows of the multi-GPU path, laid out in one buffer.  Nothing here uses a copy engine (the
+    upload owns it): counters travel through the Mailbox, the cut lists are uploaded once, up front.
+    Returns None when the tables overflowed (the caller recounts the resident text in one go)."""
+    L = _ffi.load()
+    mailbox = Mailbox(torch)
+    all_cuts = np.asarray([c for p in pieces for c in p[3]] + [0], dtype=np.int64)
+    cuts_dev = torch.from_numpy(all_cuts).to(text_dev.device)               # before the bulk upload is enqueued
+    torch.cuda.current_stream().wait_event(ready[0])
+    sizing = None
+    if n > 4 * _SAMPLE_BYTES and pieces[0][2] >= _SAMPLE_BYTES + 64:
+        sizing = estimate_table_sizes(torch, text_dev, n, sample_cuts, specials, 0, mailbox)
+    res = pretok_count(torch, text_dev, n, None, specials, 0, mailbox=mailbox, sizing=sizing, launch=False,
+                       max_cuts=max(len(p[3]) for p in pieces))
+    res.keep.append(cuts_dev)
+    a = res.args
+    off = 0
+    stream = _ffi.stream_ptr(torch)
+    for k, (lo, hi, nk, cuts_k) in enumerate(pieces):
+        torch.cuda.current_stream().wait_event(ready[k])
+        a.n, a.own_lo, a.own_hi = nk, lo, hi
+        a.cuts = cuts_dev.data_ptr() + 8 * off if cuts_k else None
+        a.n_cuts = len(cuts_k)
+        off += len(cuts_k)
+        a.stages = 16 | 7
+        if k:
+            res.stats[_ffi.ST_OVF_N:_ffi.ST_OVF_N + 1].zero_()               # per-call lists: over-long pre-tokens, boundary work items
+            res.stats[_ffi.ST_SLOW_N:_ffi.ST_SLOW_N + 1].zero_()
+        _ffi.check(L.yabpe_pretok_count(C.byref(a), stream))
+    a.n, a.own_lo, a.own_hi, a.cuts, a.n_cuts, a.stages = n, 0, n, None, 0, 0
+    st = res.stats_host()
+    if st[_ffi.ST_TABLE_FULL] != 0:
+        return None
+    return res, st
 
 
 _SAMPLE_BYTES = 16 << 20
@@ -383,6 +424,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.merges = merges.data_ptr(); m.merge_new = merge_new.data_ptr(); m.state = state.data_ptr()
         m.num_merges = num_merges; m.min_frequency = min_frequency
         m.rebuild_every = rebuild_period(words.n_syms)
+        m.helper_mode = int(os.environ.get("YABPE_HELPER_MODE", "0"))
         m.helper_min_syms = int(os.environ.get("YABPE_HELPER_MIN_SYMS", "0"))     # tests force the prefetch helpers on small inputs (-1)
         if timing is not None:
             t0 = torch.cuda.Event(enable_timing=True); t0.record()

@@ -123,6 +123,8 @@ class BBPETrainer:
         self.profile = False            # True: record CUDA-event stage durations into self.timing
         self.stream_min_bytes = 64 << 20          # train(files): inputs this large are streamed through pinned staging
         self.stream_piece_bytes = 32 << 20
+        self.pipeline_min_bytes = 256 << 20       # train_from_buffers: inputs this large are counted while they are uploaded
+        self.pipeline_piece_bytes = 256 << 20
         self.timing: dict[str, float] = {}
 
     # -- reference API ---------------------------------------------------------------------
@@ -196,9 +198,62 @@ class BBPETrainer:
             total += int(b.size)
         if total == 0:
             return self._finish(self._init_base_vocab(), [])              # trainer.py:81-85
+        if total >= self.pipeline_min_bytes and not self.profile:
+            return self._train_pipelined(torch, [b for b in blobs], cuts, file_starts, names, total)
         host = blobs[0] if len(blobs) == 1 else np.concatenate([b for b in blobs if b.size])
         text_dev, n = engine.to_device_text(torch, host)
         return self._train_on_device(torch, text_dev, n, cuts, file_starts, names)
+
+    def _train_pipelined(self, torch, blobs: list[np.ndarray], cuts: list[int], file_starts: list[int], names: list[str],
+                         total: int) -> BBPEModel:
+        """Large host buffers: the upload (PCIe, ~55 GB/s) and the pre-tokenise + count kernels (hundreds of GB/s) overlap.
+        The text is cut into pieces at safe edges (sharding.plan_shards: the same edges the multi-GPU path shards at);
+        piece k is copied on a copy stream and counted on the compute stream as soon as piece k + 1 -- its look-ahead
+        halo -- has landed, every piece into the same tables.  Same result as uploading first: tests compare both."""
+        from . import sharding
+        import warnings
+        specials = [s.encode("utf-8") for s in self.config.special_tokens]
+        hard = sorted({c for c in cuts if 0 < c < total})
+        starts = np.asarray(file_starts + [total], dtype=np.int64)
+
+        def read(lo: int, hi: int) -> bytes:
+            out = []
+            for b, s0 in zip(blobs, file_starts):
+                a, e = max(lo, s0), min(hi, s0 + int(b.size))
+                if a < e:
+                    out.append(b[a - s0:e - s0].tobytes())
+            return b"".join(out)
+
+        k_pieces = max(2, -(-total // max(int(self.pipeline_piece_bytes), 1 << 20)))
+        edges = sharding.plan_shards(read, total, k_pieces, specials, hard)
+        edges = sorted(set(edges))
+        text_dev = torch.empty(((total + 15) // 16) * 16 + 64, dtype=torch.uint8, device="cuda")
+        cur, copy = torch.cuda.current_stream(), torch.cuda.Stream()
+        pieces, ready = [], []
+        for lo, hi in zip(edges, edges[1:]):
+            nk = min(total, hi + sharding.HALO)
+            pieces.append((lo, hi, nk, sorted({c for c in hard if c < nk} | ({lo} if lo > 0 else set()))))
+        sample_cuts = np.asarray([c for c in hard if c < (16 << 20)], dtype=np.int64)
+        # cut lists first (a small synchronous copy), then the bulk upload on its own stream
+        text_dev[total:].zero_()
+        copy.wait_stream(cur)
+        uploaded = []
+        with torch.cuda.stream(copy), warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)                  # read-only numpy views are only read
+            for lo, hi in zip(edges, edges[1:]):
+                for b, s0 in zip(blobs, file_starts):
+                    a, e = max(lo, s0), min(hi, s0 + int(b.size))
+                    if a < e:
+                        text_dev[a:e].copy_(torch.from_numpy(b[a - s0:e - s0]), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                uploaded.append(ev)
+        # piece k may look HALO bytes into piece k + 1
+        ready = [uploaded[min(k + 1, len(uploaded) - 1)] for k in range(len(pieces))]
+        counted = engine.pretok_count_pieces(torch, text_dev, total, pieces, specials, ready,
+                                             sample_cuts if len(sample_cuts) else None)
+        cur.wait_stream(copy)
+        return self._train_on_device(torch, text_dev, total, cuts, file_starts, names, counted=counted)
 
     def train_device(self, text_dev, n: int, name: str = "<device buffer>") -> BBPEModel:
         """Train on `n` bytes already resident in HBM (capacity >= round_up(n,16)+16, 16-byte aligned),
@@ -210,7 +265,7 @@ class BBPETrainer:
         return self._train_on_device(torch, text_dev, n, cuts, [0], [name])
 
     def _train_on_device(self, torch, text_dev, n: int, cuts: list[int], file_starts: list[int],
-                         names: list[str]) -> BBPEModel:
+                         names: list[str], counted=None) -> BBPEModel:
         cfg = self.config
         specials = [s.encode("utf-8") for s in cfg.special_tokens]
         base_vocab = self._init_base_vocab()
@@ -218,8 +273,11 @@ class BBPETrainer:
         cuts_np = np.asarray(cuts, dtype=np.int64) if cuts else None
         ev: list = [] if self.profile else None                           # type: ignore[assignment]
         launches0 = _ffi.launch_count()
-        res = engine.pretok_count(torch, text_dev, n, cuts_np, specials, 0, stage_events=ev)
-        st = res.stats_host()
+        if counted is not None:                                           # counted while it was uploaded (_train_pipelined)
+            res, st = counted
+        else:
+            res = engine.pretok_count(torch, text_dev, n, cuts_np, specials, 0, stage_events=ev)
+            st = res.stats_host()
         if st[_ffi.ST_TABLE_FULL] != 0:
             del res
             res, st = engine.pretok_count_checked(torch, text_dev, n, cuts_np, specials, mode=0)
