@@ -262,14 +262,20 @@ class Tokenizer:
             lib().orc_tok_free(self._h)
             self._h = None
 
-    def encode(self, text: str) -> list[int]:
-        if not text:
-            return []
-        a = np.frombuffer(text.encode("utf-8"), dtype=np.uint8)
+    def encode_bytes(self, data) -> np.ndarray:
+        """ids of UTF-8 bytes as an int32 array (large inputs: no Python list of 10^8 ints)."""
+        a = _as_u8(data)
+        if a.size == 0:
+            return np.zeros(0, dtype=np.int32)
         out = np.zeros(a.size, dtype=np.int32)
         n = lib().orc_tok_encode(self._h, _ptr(a), a.size, _ptr(out), out.size)
         assert n <= out.size
-        return out[:n].tolist()
+        return out[:n]
+
+    def encode(self, text: str) -> list[int]:
+        if not text:
+            return []
+        return self.encode_bytes(text.encode("utf-8")).tolist()
 
     def encode_iterable(self, iterable: Iterable[str]) -> Iterator[int]:
         for line in iterable:                                     # adapters.py:30-34

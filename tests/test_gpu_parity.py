@@ -442,9 +442,10 @@ def test_encode_roundtrip_property_large(yabpe):
 
 # ------------------------------------------------------------------------------- full-size properties
 def test_train_properties_at_bench_scale(yabpe):
-    """Size-independent properties at a size no CPU oracle handles in seconds (256 MB of the bench generator,
-    crossing no reference chunk cut, and 1.2 GB crossing one): conservation of pre-token occurrences, run-to-run
-    determinism, dense ids, every merge result present, and agreement of the sharded table with the whole."""
+    """Size-independent properties on 256 MB of the bench generator (no reference chunk cut inside; the 1.2 GB case that
+    crosses a real 2^30 cut is compared with the oracle in tests/test_gpu_baseline_sizes.py): conservation of pre-token
+    occurrences, run-to-run determinism, dense ids, every merge result present, and agreement of the sharded table
+    with the whole."""
     import sys
     import torch
     sys.path.insert(0, str(common.ROOT / "tools"))
