@@ -444,11 +444,13 @@ def run_encode(args) -> None:
     if not args.skip_e2e:
         host = torch.empty(n, dtype=torch.uint8).pin_memory()
         host.copy_(text_dev[:n])
-        ids_h = torch.empty(n_ids, dtype=torch.int32).pin_memory()          # pinned landing buffer for the ids
+        # ids come back as uint16 when the vocabulary allows it (50 257 ids here): the download bounds this path
+        id_dtype = torch.uint16 if (args.id_bits == 16 and args.encode_e2e == "pipelined" and max(vocab) < (1 << 16)) else torch.int32
+        ids_h = torch.empty(n_ids, dtype=id_dtype).pin_memory()             # pinned landing buffer for the ids
 
         def e2e_step():
             if args.encode_e2e == "pipelined":    # the host-buffer API: pieces cut after specials, copies overlap the encode
-                return int(tok.encode_pinned(host, out=ids_h, piece_bytes=args.piece_mb << 20).numel())
+                return int(tok.encode_pinned(host, out=ids_h, piece_bytes=args.piece_mb << 20, id_dtype=id_dtype).numel())
             dev2, n2 = engine.to_device_text(torch, host, non_blocking=True)
             ids2, _ = tok.encode_device(dev2, n2, reuse_output=True)
             ids_h[: ids2.numel()].copy_(ids2, non_blocking=True)
@@ -457,7 +459,7 @@ def run_encode(args) -> None:
         ids_ref = ids.clone()                     # device-resident result of the timed region (the reuse buffer is overwritten below)
         e2e_step()                                # warm-up: allocator blocks for the text copy
         torch.cuda.synchronize()
-        assert torch.equal(ids_h[:n_ids].cuda(), ids_ref), "end-to-end ids differ from the device-resident run"
+        assert torch.equal(ids_h[:n_ids].cuda().to(torch.int32), ids_ref), "end-to-end ids differ from the device-resident run"
         del ids_ref
         reps = max(1, min(args.steps, 3))
         barrier()
@@ -471,13 +473,17 @@ def run_encode(args) -> None:
         text_dev[:n].copy_(host, non_blocking=True); torch.cuda.synchronize()
         h2d_only_ms = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter()
-        ids_h[:n_ids].copy_(ids[:n_ids], non_blocking=True); torch.cuda.synchronize()
+        bare = torch.empty(n_ids, dtype=torch.int32).pin_memory() if id_dtype != torch.int32 else ids_h
+        t0 = time.perf_counter()
+        bare[:n_ids].copy_(ids[:n_ids], non_blocking=True); torch.cuda.synchronize()
         d2h_only_ms = (time.perf_counter() - t0) * 1e3
+        del bare
         if world > 1:
             tm = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(tm, op=dist.ReduceOp.MAX); dt = float(tm.item())
         e2e = {"value": round(total_bytes / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(total_bytes),
-               "d2h_bytes_per_step": int(4 * total_ids), "ms_per_step": round(dt * 1e3, 2),
-               "h2d_only_ms": round(h2d_only_ms, 2), "d2h_only_ms": round(d2h_only_ms, 2),
+               "d2h_bytes_per_step": int((2 if id_dtype == torch.uint16 else 4) * total_ids), "ms_per_step": round(dt * 1e3, 2),
+               "id_dtype": str(id_dtype).replace("torch.", ""),
+               "h2d_only_ms": round(h2d_only_ms, 2), "d2h_only_ms_int32": round(d2h_only_ms, 2),
                "mode": args.encode_e2e + (f" ({args.piece_mb} MiB pieces, H2D / encode / D2H on three streams)" if args.encode_e2e == "pipelined" else "")}
     cpu = same = None
     if not args.skip_cpu and rank == 0:
@@ -525,6 +531,7 @@ def main() -> None:
     ap.add_argument("--encode-mb", type=int, default=256)
     ap.add_argument("--encode-e2e", default="pipelined", choices=["pipelined", "serial"])
     ap.add_argument("--piece-mb", type=int, default=128)
+    ap.add_argument("--id-bits", type=int, default=16, choices=[16, 32], help="encode e2e: ids copied back as uint16 (vocab <= 65536) or int32")
     args = ap.parse_args()
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("YABPE_BENCH_WATCHDOG_S", "900")), exit=True)   # never hang a GPU box

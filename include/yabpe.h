@@ -262,6 +262,20 @@ typedef struct {
 int yabpe_decode_ids(const yabpe_decode_args* d, int32_t pass, void* stream);
 int64_t yabpe_decode_blocks(int64_t n_ids);
 
+/* Short texts (n <= yabpe_encode_small_max_bytes()): the whole of tokenizer.py:152-308 in ONE launch of one CTA -- special
+ * split, pre-tokenisation (the generic start rule), BPE by rank per pre-token, ids in text order.  `text` and `out` may be
+ * device memory or MAPPED pinned host memory (then the call needs no copy at all); scratch: n int32 (device).
+ * out[0] = number of ids, out[1..] = the ids; out[0] = -1 when a pre-token is longer than the kernel handles (64 bytes)
+ * or out_cap (>= n + 1 is always enough) is too small: the caller then uses the batched path.  sp_* as in yabpe_pretok_args,
+ * already sorted longest-first (tokenizer.py:99). */
+int yabpe_encode_small(const yabpe_encode_model* e, const uint8_t* text, int32_t n, const uint8_t* sp_blob,
+                       const int32_t* sp_offs, int32_t n_sp, int32_t* scratch, int32_t* out, int32_t out_cap, void* stream);
+int32_t yabpe_encode_small_max_bytes(void);
+
+/* ids (int32, device) narrowed to uint16 (device) for the copy back to the host: for vocabularies of at most 65 536 entries
+ * the id download that bounds a host-buffer encode halves.  No reference counterpart (tokenizer.py returns list[int]). */
+int yabpe_narrow_ids(const int32_t* ids, uint16_t* out, int64_t n, void* stream);
+
 /* Hot set for the warp kernel's shared-memory cache: from the tables of a counted SAMPLE of the corpus (`sample`, after
  * yabpe_pretok_count on e.g. its first 16 MB) pick, for every cache index, the most frequent key that maps to it.
  * hot_keys: yabpe_hot_cache_entries() * 16 bytes; scratch: yabpe_hot_cache_entries() * 8 bytes.  Result-neutral. */

@@ -427,6 +427,12 @@ def test_encode_pinned_streams_pieces_exactly(yabpe):
     small = torch.empty(1000, dtype=torch.int32).pin_memory()          # too small: a larger buffer is allocated
     assert t.encode_pinned(host, out=small, piece_bytes=250_000).tolist() == want
     assert t.encode_pinned(torch.empty(0, dtype=torch.uint8)).numel() == 0
+    # ids as uint16 (the GPT-2 vocabulary fits): narrowed on the device, half the download
+    got16 = t.encode_pinned(pinned, piece_bytes=300_000, id_dtype=torch.uint16)
+    assert got16.dtype == torch.uint16 and got16.to(torch.int32).tolist() == want
+    big = yabpe.Tokenizer({**v, 70000: b"\xff\xfe"}, m, ["<|endoftext|>"]).inner
+    with pytest.raises(ValueError):
+        big.encode_pinned(pinned, id_dtype=torch.uint16)
     assert t.encode(raw.decode("utf-8")) == want                        # the plain path is untouched by the streams
 
 

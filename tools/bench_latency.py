@@ -1,6 +1,6 @@
 """Python-list API of the tokenizer ("Python-list API timed separately"): `encode(str) -> list[int]` latency
 from 10 bytes to 64 MB, `encode_batch` of short lines, `decode(list[int])`, with the CPU port of the reference next to each figure.
-Not run in round 1 (no GPU minutes left); the first thing to measure for DESIGN.md section 8 item 5.
+Short strings run as ONE launch (yabpe_encode_small, up to 32 KiB); the sweep also has sizes between the decades around 1 KB.
 usage: python tools/bench_latency.py [max_bytes]"""
 import sys, time
 from pathlib import Path
@@ -30,9 +30,11 @@ def timed(f, reps):
 
 
 print(f"{'chars':>10} {'gpu encode ms':>14} {'launches':>9} {'cpu port ms':>12} {'equal':>6}")
-n = 10
-while n <= len(text):
-    s = text[:n]
+sizes = sorted({11} | {10 ** k for k in range(1, 9)} | {30, 300, 500, 2000, 4000, 8000, 16000, 30000, 40000})
+for n in sizes:
+    if n > len(text):
+        break
+    s = text[:n] if n != 11 else "hello world"
     reps = 200 if n <= 10_000 else 20 if n <= 1_000_000 else 2
     l0 = _ffi.launch_count()
     dt, ids = timed(lambda: tok.encode(s), reps)
@@ -41,7 +43,6 @@ while n <= len(text):
     want = otok.encode(s)
     dc = time.perf_counter() - t0
     print(f"{n:>10} {dt * 1e3:>14.3f} {launches:>9} {dc * 1e3:>12.3f} {str(ids == want):>6}", flush=True)
-    n *= 10
 lines = text[:4_000_000].split("\n")
 dt, out = timed(lambda: tok.encode_batch(lines), 3)
 dt1, _ = timed(lambda: [tok.encode(x) for x in lines[:300]], 1)

@@ -786,7 +786,10 @@ __device__ void build_ranges(const MergeParams& M, int32_t slot, int32_t a, int3
     R->n = n; R->total = total;
 }
 __device__ __forceinline__ int32_t range_item(const Ranges& R, i64 it) {
-    for (int r = 0; r < R.n; r++) { if (it < R.len[r]) return R.base[r][it]; it -= R.len[r]; }
+    for (int r = 0; r < R.n; r++) {
+        if (it < R.len[r]) { const int32_t* b = R.base[r]; __builtin_assume(__isGlobal(b)); return b[it]; }    // not a generic load
+        it -= R.len[r];
+    }
     return -1;
 }
 

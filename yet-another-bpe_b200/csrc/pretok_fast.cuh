@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     const int warp = threadIdx.x >> 5;
     WarpSmem* Wp = (WarpSmem*)(pw_smem + PW_NC * 20 + 256 + warp * sizeof(WarpSmem));
     asm volatile("" : "+l"(Wp));
+    __builtin_assume(__isShared(Wp));          // ...but keep the address space: without this every access through W is a GENERIC
+                                               // LD / ST (the token-list reads alone were 19 % of all stall samples)
     WarpSmem& W = *Wp;
 
     // The cache starts from the hot set of the sizing sample when there is one (k_hot_select: for every cache index the

@@ -8,6 +8,7 @@
 #include "pretok_fast.cuh"
 #include "decode.cuh"
 #include "exchange.cuh"
+#include "encode_small.cuh"
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
@@ -95,7 +96,13 @@ static int upload_specials(const uint8_t* blob, const int32_t* offs, int32_t n, 
         }
         h.first_byte_mask[b >> 3] |= (unsigned char)(1u << (b & 7));
     }
+    // the same set on the same device and stream as the last upload is already in place (stream order): short encodes
+    // would otherwise pay this copy on every call
+    static thread_local SpecialSet last; static thread_local int last_dev = -1; static thread_local cudaStream_t last_st = nullptr;
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev == last_dev && st == last_st && memcmp(&last, &h, sizeof h) == 0) return YABPE_OK;
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_sp, &h, sizeof h, 0, cudaMemcpyHostToDevice, st));
+    last = h; last_dev = dev; last_st = st;
     return YABPE_OK;
 }
 
@@ -506,6 +513,23 @@ extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_m
     return YABPE_OK;
 }
 
+// ---- one-launch encode of a short text ----
+extern "C" int32_t yabpe_encode_small_max_bytes(void) { return ES_MAX_BYTES; }
+
+extern "C" int yabpe_encode_small(const yabpe_encode_model* e, const uint8_t* text, int32_t n, const uint8_t* sp_blob,
+                                  const int32_t* sp_offs, int32_t n_sp, int32_t* scratch, int32_t* out, int32_t out_cap, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(e && text && n > 0 && n <= ES_MAX_BYTES && scratch && out && out_cap >= 1);
+    int rc = upload_specials(sp_blob, sp_offs, n_sp, st);
+    if (rc) return rc;
+    EncodeModel E = make_model(e);
+    const int nwords = (n + 31) / 32;
+    const size_t smem = (size_t)(((n + 15) & ~15) + 64) + 3 * (size_t)(nwords + 2) * 4;
+    k_encode_small<<<1, ES_THREADS, smem, st>>>(E, text, n, n_sp, scratch, out, out_cap); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
 // ---- counters to the host without a copy engine ----
 // A few 64-bit words, stored by one warp straight into MAPPED pinned host memory.  A cudaMemcpy of the same words would
 // queue behind whatever bulk transfer occupies the device-to-host copy engine (encode_pinned streams GBs of ids while
@@ -518,6 +542,32 @@ __global__ void k_publish(volatile i64* host_dst, const i64* src, int n_words) {
 extern "C" int yabpe_publish(void* host_mapped_dst, const void* device_src, int32_t n_words, void* stream) {
     ARG_CHECK(host_mapped_dst && device_src && n_words > 0 && n_words <= 4096);
     k_publish<<<1, 32, 0, (cudaStream_t)stream>>>((volatile i64*)host_mapped_dst, (const i64*)device_src, n_words); LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return YABPE_OK;
+}
+
+// ---- ids as uint16 for the way back to the host (vocabularies of at most 65 536 entries) ----
+// The device -> host copy of the ids bounds the host-buffer encode (2 bytes of int32 ids per text byte on English-like text
+// against 1 byte of text going up): half the bytes, half the time.  Ids are stored modulo 2^16; the caller checks the range.
+__global__ void __launch_bounds__(256) k_narrow_ids(const int32_t* __restrict__ ids, uint16_t* __restrict__ out, i64 n) {
+    const i64 stride = (i64)gridDim.x * blockDim.x * 4;
+    for (i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n && (((uintptr_t)(ids + i)) & 15) == 0 && (((uintptr_t)(out + i)) & 7) == 0) {
+            const int4 v = *(const int4*)(ids + i);
+            *(uint2*)(out + i) = make_uint2(((uint32_t)v.x & 0xffffu) | ((uint32_t)v.y << 16), ((uint32_t)v.z & 0xffffu) | ((uint32_t)v.w << 16));
+        } else {
+            for (i64 j = i; j < n && j < i + 4; j++) out[j] = (uint16_t)ids[j];
+        }
+    }
+}
+
+extern "C" int yabpe_narrow_ids(const int32_t* ids, uint16_t* out, int64_t n, void* stream) {
+    ARG_CHECK(n >= 0 && (n == 0 || (ids && out)));
+    if (n == 0) return YABPE_OK;
+    i64 grid = (n / 4 + 255) / 256;
+    if (grid > (i64)num_sms() * 16) grid = (i64)num_sms() * 16;
+    if (grid < 1) grid = 1;
+    k_narrow_ids<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(ids, out, n); LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;
 }

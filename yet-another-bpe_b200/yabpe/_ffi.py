@@ -25,7 +25,7 @@ EXPORTS = [
     "yabpe_last_error", "yabpe_abi_version", "yabpe_device_init", "yabpe_class_of", "yabpe_pretok_count",
     "yabpe_compact_words", "yabpe_merge_loop", "yabpe_encode_words", "yabpe_encode_ids", "yabpe_num_tiles",
     "yabpe_launch_count", "yabpe_insert_words", "yabpe_sizeof", "yabpe_encode_finalize", "yabpe_hot_cache_entries",
-    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks", "yabpe_publish", "yabpe_partition_words",
+    "yabpe_select_hot", "yabpe_token_starts", "yabpe_decode_ids", "yabpe_decode_blocks", "yabpe_publish", "yabpe_partition_words", "yabpe_narrow_ids", "yabpe_encode_small", "yabpe_encode_small_max_bytes",
 ]
 
 
@@ -149,6 +149,12 @@ def load() -> C.CDLL:
     L.yabpe_decode_blocks.argtypes = [C.c_int64]
     L.yabpe_publish.restype = C.c_int
     L.yabpe_publish.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.yabpe_encode_small.restype = C.c_int
+    L.yabpe_encode_small.argtypes = [C.POINTER(EncodeModel), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.yabpe_encode_small_max_bytes.restype = C.c_int32
+    L.yabpe_narrow_ids.restype = C.c_int
+    L.yabpe_narrow_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.yabpe_partition_words.restype = C.c_int
     L.yabpe_partition_words.argtypes = [C.POINTER(PartitionArgs), C.c_int32, C.c_void_p]
     L.yabpe_sizeof.restype = C.c_int64

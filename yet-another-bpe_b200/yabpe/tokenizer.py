@@ -18,6 +18,7 @@ from . import _ffi, engine
 
 _ITER_BATCH_BYTES = 4 << 20
 _ITER_BATCH_ITEMS = 1 << 16
+_SMALL_MAX_BYTES = 1 << 15        # encode(str) up to this many bytes runs as one launch (yabpe_encode_small)
 _DECODE_DEVICE_MIN = 1 << 16       # ids; shorter lists are gathered on the host
 _DECODE_DEVICE_MAX_ID = 1 << 24    # offsets are a dense array over the id range
 
@@ -212,18 +213,26 @@ class BBPETokenizer:
         ends.append(n)
         return ends
 
-    def encode_pinned(self, host, out=None, piece_bytes: int = 128 << 20):
+    def encode_pinned(self, host, out=None, piece_bytes: int = 128 << 20, id_dtype=None):
         """ids of the UTF-8 bytes in `host` (1-D uint8 torch tensor, ideally pinned) as an int32 host tensor.
 
         The text is streamed through the device in pieces cut after special tokens (`_piece_ends`): the
         host->device copy of piece i+1 and the device->host copy of the ids of piece i-1 run on their own
         streams while piece i is encoded, so a large buffer costs about max(copy in, encode, copy out)
         instead of their sum.  `out` (pinned int32, optional) receives the ids when it is large enough; the
-        returned tensor is a view of it.  Same ids as `encode` of the whole text."""
+        returned tensor is a view of it.  Same ids as `encode` of the whole text.
+        id_dtype=torch.uint16: the ids are narrowed on the device (yabpe_narrow_ids) and come back as uint16 -- half the
+        download, which is what bounds this path; only for vocabularies whose ids are all below 65 536 (ValueError otherwise)."""
         torch = _ffi.require_cuda()
         n = int(host.numel())
+        id_dtype = id_dtype or torch.int32
+        if id_dtype not in (torch.int32, torch.uint16):
+            raise ValueError("id_dtype must be torch.int32 or torch.uint16")
+        narrow = id_dtype == torch.uint16
+        if narrow and max(list(self._vocab.values()) + [0]) >= 1 << 16:
+            raise ValueError("uint16 ids need a vocabulary whose ids are all below 65536")
         if n == 0:
-            return torch.empty(0, dtype=torch.int32)
+            return torch.empty(0, dtype=id_dtype)
         assert host.dtype == torch.uint8 and host.dim() == 1 and not host.is_cuda
         ends = self._piece_ends(host.numpy(), n, int(piece_bytes))
         starts = [0] + ends[:-1]
@@ -251,14 +260,14 @@ class BBPETokenizer:
             if out is not None and out.numel() >= need:
                 return
             est = int(need * (n / done) * 1.05) + 4096        # ids per byte so far, scaled to the whole text
-            new = torch.empty(max(est, need), dtype=torch.int32).pin_memory()
+            new = torch.empty(max(est, need), dtype=id_dtype).pin_memory()
             if used:
                 s_out.synchronize()
                 new[:used].copy_(out[:used])
             out = new
 
         if out is not None:
-            assert out.dtype == torch.int32 and out.dim() == 1 and not out.is_cuda
+            assert out.dtype == id_dtype and out.dim() == 1 and not out.is_cuda
         pos = 0
         mailbox = engine.Mailbox(torch)            # counters bypass the copy engines the bulk transfers occupy
         sizing = None                              # table sizes, layout and hot set of the first piece serve the others
@@ -275,6 +284,13 @@ class BBPETokenizer:
             done.record(cur)
             free_ev[i % len(bufs)] = done
             k = int(ids.numel())
+            if narrow and k:
+                ids16 = torch.empty(k, dtype=torch.uint16, device="cuda")
+                _ffi.check(_ffi.load().yabpe_narrow_ids(ids.data_ptr(), ids16.data_ptr(), k, _ffi.stream_ptr(torch)))
+                ids = ids16
+                done = torch.cuda.Event()
+                done.record(cur)
+                free_ev[i % len(bufs)] = done
             ensure_out(pos + k, ends[i], pos)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
@@ -286,11 +302,43 @@ class BBPETokenizer:
         return out[:pos]
 
     # -- reference API --------------------------------------------------------------------------
+    def _encode_small(self, torch, raw: bytes) -> list[int] | None:
+        """Short texts: ONE launch (yabpe_encode_small), text and ids through mapped pinned memory -- no copies, one event
+        wait.  None when the kernel declines (a pre-token longer than 64 bytes): the caller takes the batched path."""
+        L = _ffi.load()
+        dev = torch.cuda.current_device()
+        st = getattr(self, "_small", None)
+        if st is None or st[0] != dev:
+            cap = int(L.yabpe_encode_small_max_bytes())
+            blob, offs = engine.pack_specials(self._sp_bytes)
+            st = (dev, cap, torch.zeros(cap + 64, dtype=torch.uint8).pin_memory(), torch.zeros(cap + 8, dtype=torch.int32).pin_memory(),
+                  torch.empty(cap + 64, dtype=torch.int32, device="cuda"), blob, offs, torch.cuda.Event())
+            self._small = st
+        _, cap, tin, tout, scratch, blob, offs, ev = st
+        n = len(raw)
+        tin.numpy()[:n] = np.frombuffer(raw, dtype=np.uint8)
+        e = self._device_model(torch)
+        _ffi.check(L.yabpe_encode_small(C.byref(e), tin.data_ptr(), n, blob.ctypes.data, offs.ctypes.data, len(self._sp_bytes),
+                                        scratch.data_ptr(), tout.data_ptr(), n + 1, _ffi.stream_ptr(torch)))
+        ev.record()
+        ev.synchronize()
+        out = tout.numpy()
+        cnt = int(out[0])
+        if cnt < 0:
+            return None
+        self.last_launches = 1
+        return out[1:1 + cnt].tolist()
+
     def encode(self, text: str) -> list[int]:
         if not text:
             return []
         torch = _ffi.require_cuda()
-        raw = np.frombuffer(text.encode("utf-8"), dtype=np.uint8)
+        data = text.encode("utf-8")
+        if len(data) <= _SMALL_MAX_BYTES:
+            ids = self._encode_small(torch, data)
+            if ids is not None:
+                return ids
+        raw = np.frombuffer(data, dtype=np.uint8)
         text_dev, n = engine.to_device_text(torch, raw)
         ids, _ = self.encode_device(text_dev, n)
         return ids.cpu().tolist()
