@@ -45,9 +45,24 @@ def test_every_declared_function_is_exported(lib):
 
 def test_struct_layouts_match(lib):
     from yabpe import _ffi
-    for which, st in enumerate((_ffi.PretokArgs, _ffi.WordTable, _ffi.MergeArgs, _ffi.EncodeModel, _ffi.EncodeOut)):
+    for which, st in enumerate((_ffi.PretokArgs, _ffi.WordTable, _ffi.MergeArgs, _ffi.EncodeModel, _ffi.EncodeOut,
+                                _ffi.DecodeArgs, _ffi.PartitionArgs)):
         assert lib.yabpe_sizeof(which) == C.sizeof(st), st.__name__
     assert lib.yabpe_sizeof(99) == -1
+
+
+def test_integration_md_stub_matches_the_library(lib):
+    """INTEGRATION.md shows the ctypes stub a maintainer of the reference would add; its `PretokArgs` must be the struct the
+    library was compiled with ("field for field"), and the ABI version it asserts must be the current one."""
+    text = (ROOT / "INTEGRATION.md").read_text()
+    m = re.search(r"(class PretokArgs\(C\.Structure\):.*?\n)assert lib\.yabpe_sizeof", text, flags=re.S)
+    assert m, "stub not found"
+    ns = {"C": C}
+    exec(m.group(1), ns)
+    assert C.sizeof(ns["PretokArgs"]) == lib.yabpe_sizeof(0)
+    from yabpe import _ffi
+    assert [f[0] for f in ns["PretokArgs"]._fields_] == [f[0] for f in _ffi.PretokArgs._fields_]
+    assert int(re.search(r"yabpe_abi_version\(\) == (\d+)", text).group(1)) == _ffi.ABI_VERSION
 
 
 def test_no_cpu_fallback(lib):

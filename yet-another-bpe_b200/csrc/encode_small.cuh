@@ -6,8 +6,9 @@
 //   text (device or MAPPED pinned host memory) -> shared memory
 //   special-token candidates (thread per byte), leftmost / longest-first resolution (tokenizer.py:97-102,171)
 //   pre-token start bit per byte: the generic rule of common.cuh (is_token_start), the same code k_token_starts uses
-//   thread t owns the pre-tokens that START in bytes [32t, 32t + 32): BPE by rank on each (encode_word_thread, the exact
-//     restatement of the heap loop) in thread-local memory, ids compacted into the scratch range the thread's tokens cover
+//   pre-tokens dealt out evenly over the threads (one each up to 1 024 of them): BPE by rank in thread-local memory
+//     (es_encode_token: the heap loop of tokenizer.py:247-294 with ~3 n table probes), ids compacted into the scratch
+//     range the thread's tokens cover
 //   block scan of the per-thread id counts -> ids in text order -> out[1..], out[0] = count (or -1: fall back)
 // Pre-tokens longer than ES_MAX_TOKEN bytes (the thread-per-token BPE is quadratic) make the kernel report -1; the caller
 // then takes the batched path.  No hash tables, no de-duplication: a short text has few repeats.
@@ -18,9 +19,7 @@
 #define ES_MAX_BYTES 32768
 #define ES_THREADS 1024
 #define ES_MAX_TOKEN 64
-#define ES_WORDS (ES_MAX_BYTES / 32)             // one 32-byte segment per thread
-
-static_assert(ES_WORDS == ES_THREADS, "thread t owns the pre-tokens starting in segment t");
+#define ES_WORDS (ES_MAX_BYTES / 32)
 
 __device__ __forceinline__ int es_next_start(const uint32_t* sbits, int from, int n) {      // first start > from, or n
     int i = from + 1;
@@ -28,6 +27,27 @@ __device__ __forceinline__ int es_next_start(const uint32_t* sbits, int from, in
         const uint32_t w = sbits[i >> 5] >> (i & 31);
         if (w) { const int r = i + __ffs(w) - 1; return r < n ? r : n; }
         i = ((i >> 5) + 1) << 5;
+    }
+    return n;
+}
+
+// tokenizer.py:247-294 on one pre-token in thread-local memory: merge the adjacent pair with the smallest (rank, position),
+// one occurrence at a time.  The rank of every adjacency is looked up once (independent loads) and only the two adjacencies
+// next to a merge are looked up again: about 3 n table probes per pre-token instead of n^2 / 2.
+__device__ int es_encode_token(const EncodeModel& E, int32_t* sym, int n) {
+    uint32_t rk[ES_MAX_TOKEN]; int32_t rs[ES_MAX_TOKEN];
+    for (int j = 0; j < n; j++) sym[j] = E.byte_sym[sym[j]];
+    for (int j = 0; j + 1 < n; j++) { uint32_t r; int32_t res; rk[j] = merge_rank(E, sym[j], sym[j + 1], &r, &res) ? r : 0xffffffffu; rs[j] = res; }
+    while (n > 1) {
+        uint32_t br = 0xffffffffu; int bp = -1;
+        for (int j = 0; j + 1 < n; j++) if (rk[j] < br) { br = rk[j]; bp = j; }
+        if (bp < 0) break;
+        sym[bp] = rs[bp];
+        for (int j = bp + 1; j + 1 < n; j++) { sym[j] = sym[j + 1]; rk[j] = rk[j + 1]; rs[j] = rs[j + 1]; }
+        n--;
+        uint32_t r; int32_t res;
+        if (bp > 0) { rk[bp - 1] = merge_rank(E, sym[bp - 1], sym[bp], &r, &res) ? r : 0xffffffffu; rs[bp - 1] = res; }
+        if (bp + 1 < n) { rk[bp] = merge_rank(E, sym[bp], sym[bp + 1], &r, &res) ? r : 0xffffffffu; rs[bp] = res; }
     }
     return n;
 }
@@ -41,8 +61,9 @@ __global__ void __launch_bounds__(ES_THREADS, 1) k_encode_small(EncodeModel E, c
     uint32_t* cand = (uint32_t*)(es_smem + txt_bytes);                   // nwords + 2 each
     uint32_t* rec = cand + nwords + 2;
     uint32_t* sbits = rec + nwords + 2;
+    int* wpre = (int*)(sbits + nwords + 2);                              // exclusive prefix of the start counts per 32-byte segment
     __shared__ int sh_scan[ES_THREADS / 32];
-    __shared__ int sh_fallback;
+    __shared__ int sh_fallback, sh_ntok;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     for (int i = tid; i < txt_bytes / 4; i += ES_THREADS) {
@@ -93,32 +114,50 @@ __global__ void __launch_bounds__(ES_THREADS, 1) k_encode_small(EncodeModel E, c
     }
     __syncthreads();
 
-    // ---- thread t: the pre-tokens starting in [32t, 32t + 32)
+    // ---- pre-tokens are dealt out evenly: thread t takes tokens [t K, t K + K), K = ceil(T / threads)
+    {
+        const int c = tid < nwords ? __popc(sbits[tid]) : 0;
+        int inc = c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sh_scan[wid] = inc;
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int k = 0; k < ES_THREADS / 32; k++) { const int t = sh_scan[k]; if (k < wid) wbase += t; tot += t; }
+        if (tid < nwords) wpre[tid] = wbase + inc - c;
+        if (tid == 0) { sh_ntok = tot; wpre[nwords] = tot; }
+        __syncthreads();
+    }
+    const int T = sh_ntok, K = (T + ES_THREADS - 1) / ES_THREADS;
     int my_total = 0, my_first = -1;
-    if (tid < nwords) {
-        uint32_t m = sbits[tid];
-        int cursor = -1;
-        while (m) {
-            const int s = (tid << 5) + __ffs(m) - 1; m &= m - 1;
-            if (cursor < 0) { cursor = s; my_first = s; }
+    if (K > 0 && tid * K < T) {
+        const int t0 = tid * K, t1 = t0 + K < T ? t0 + K : T;
+        int lo = 0, hi = nwords;                                         // segment of token t0: last w with wpre[w] <= t0
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (wpre[mid] <= t0) lo = mid; else hi = mid; }
+        uint32_t m = sbits[lo];
+        for (int skip = t0 - wpre[lo]; skip > 0; skip--) m &= m - 1;
+        int s = (lo << 5) + __ffs(m) - 1;
+        int cursor = s; my_first = s;
+        for (int t = t0; t < t1; t++) {
+            const int e = es_next_start(sbits, s, n), len = e - s;
             if (n_sp > 0 && ((rec[s >> 5] >> (s & 31)) & 1u)) {          // a special: its id, or dropped (tokenizer.py:177-181)
                 const int sp = special_match(stxt, s, n);
                 const int32_t id = sp >= 0 ? E.sp_ids[sp] : -1;
                 if (id >= 0) scratch[cursor++] = id;
-                continue;
+            } else if (len > ES_MAX_TOKEN) sh_fallback = 1;
+            else {
+                int32_t sym[ES_MAX_TOKEN];
+                for (int j = 0; j < len; j++) sym[j] = stxt[s + j];
+                const int cnt = es_encode_token(E, sym, len);
+                for (int j = 0; j < cnt; j++) scratch[cursor++] = E.sym_out[sym[j]];
             }
-            const int e = es_next_start(sbits, s, n), len = e - s;
-            if (len > ES_MAX_TOKEN) { sh_fallback = 1; continue; }
-            int32_t sym[ES_MAX_TOKEN];
-            for (int j = 0; j < len; j++) sym[j] = stxt[s + j];
-            const int cnt = encode_word_thread(E, sym, len);
-            for (int j = 0; j < cnt; j++) scratch[cursor++] = E.sym_out[sym[j]];
+            s = e;
         }
-        if (my_first >= 0) my_total = cursor - my_first;
+        my_total = cursor - my_first;
     }
     // ---- ids in text order
     int inc = my_total;
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
     if (lane == 31) sh_scan[wid] = inc;
     __syncthreads();
     int wbase = 0, total = 0;

@@ -32,7 +32,7 @@ static long long g_launches = 0;
 // Per-device state.  Function attributes (dynamic shared-memory opt-in), the SM count and occupancy results belong to
 // ONE device: a process that switches devices (the Python layer supports it) must not reuse what it learnt on the first.
 #define YABPE_MAX_DEVICES 64
-struct DevInfo { int num_sms; bool pretok_attr, merge_attr; int enc_per_sm[2]; };
+struct DevInfo { int num_sms; bool pretok_attr, merge_attr, small_attr; int enc_per_sm[2]; };
 static DevInfo g_dev[YABPE_MAX_DEVICES];
 static DevInfo& dev_info() {
     int dev = 0; cudaGetDevice(&dev);
@@ -524,7 +524,12 @@ extern "C" int yabpe_encode_small(const yabpe_encode_model* e, const uint8_t* te
     if (rc) return rc;
     EncodeModel E = make_model(e);
     const int nwords = (n + 31) / 32;
-    const size_t smem = (size_t)(((n + 15) & ~15) + 64) + 3 * (size_t)(nwords + 2) * 4;
+    const size_t smem = (size_t)(((n + 15) & ~15) + 64) + 4 * (size_t)(nwords + 2) * 4;
+    DevInfo& DI = dev_info();
+    if (!DI.small_attr) {                       // the largest texts need a little more than the default 48 KB
+        CUDA_TRY(cudaFuncSetAttribute(k_encode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
+        DI.small_attr = true;
+    }
     k_encode_small<<<1, ES_THREADS, smem, st>>>(E, text, n, n_sp, scratch, out, out_cap); LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return YABPE_OK;

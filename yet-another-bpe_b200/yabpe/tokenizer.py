@@ -318,12 +318,21 @@ class BBPETokenizer:
         n = len(raw)
         tin.numpy()[:n] = np.frombuffer(raw, dtype=np.uint8)
         e = self._device_model(torch)
+        out = tout.numpy()
+        out[0] = -2                                  # the kernel stores the id count here LAST (after a system-wide fence)
         _ffi.check(L.yabpe_encode_small(C.byref(e), tin.data_ptr(), n, blob.ctypes.data, offs.ctypes.data, len(self._sp_bytes),
                                         scratch.data_ptr(), tout.data_ptr(), n + 1, _ffi.stream_ptr(torch)))
-        ev.record()
-        ev.synchronize()
-        out = tout.numpy()
-        cnt = int(out[0])
+        # the result lands in mapped host memory: polling that word is cheaper than an event round trip; the event is the
+        # fallback when the kernel takes long (or failed: the synchronize then raises)
+        cnt = -2
+        for _ in range(2000):
+            cnt = int(out[0])
+            if cnt != -2:
+                break
+        if cnt == -2:
+            ev.record()
+            ev.synchronize()
+            cnt = int(out[0])
         if cnt < 0:
             return None
         self.last_launches = 1
