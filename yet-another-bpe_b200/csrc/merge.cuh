@@ -74,7 +74,8 @@ __device__ long long* g_trace_row = nullptr;
 #define MS_TIE_CNT 32        // count at which the top list overflowed (more than ML_TOP_N pairs tie for the maximum)
 #define MS_TIE_LEFT 33       // merges left before the next attempt to rebuild the top list in that regime
 #define MS_TOP_N_LIVE 34     // leader mode: current length of the top list (read by the prefetch helpers)
-#define MS_LEADER_SMID 35    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
+#define MS_LEADER_SMID 35
+#define MS_T2_PA 36          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
 #define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
@@ -485,6 +486,7 @@ struct LeaderCtx {
     int32_t newp[ML_NEWP_N];                     // slots of the pairs created by the current merge (spill: M.newp)
     u64 newp_key[ML_NEWP_N];                     // and their keys (tokens known without waiting for the table)
     int top_n, top_ovf, act_n, alog_n, npairs_new, error, nnew;
+    u64 t2pa;                                    // top-list threshold, second component (copy of state[MS_T2_PA])
     int32_t cur_slot;                            // pair-table slot of the pair being merged
 };
 
@@ -520,6 +522,11 @@ __device__ __forceinline__ void pair_sub(const MergeParams& M, int32_t slot, i64
 // per-merge scan to a few hundred entries.  It is rebuilt (grid-wide) when its best entry falls
 // below T2 or when it overflows.  state[MS_T2]: > 0 valid threshold, 0 = rebuild needed,
 // -1 = disabled for this merge (more than ML_TOP_N pairs tie for the maximum).
+// When thousands of pairs tie at one count (small corpora, the tail of any run) a count threshold cannot cut the list to
+// ML_TOP_N entries: the threshold then has a second component, the 8-byte prefix PA of the LEFT token -- the list holds every
+// pair with count > T2, or count == T2 and tok_pre[left] >= PA.  The best pair orders by (count, left bytes, right bytes) and
+// the prefix is monotone in the bytes, so this set is closed upwards in that order: its best entry is the global best as
+// long as it is itself inside the set.  PA = 0 is the plain count threshold.
 // Membership (active set: count >= T, top list: count >= T2) is updated by the add that CROSSES the
 // threshold upwards (before < T <= after): exactly one add sees each crossing, so most adds end with the
 // atomic that returns the new count and never touch the membership bitmaps.
@@ -555,7 +562,18 @@ __device__ __forceinline__ int32_t pair_add(const MergeParams& M, int32_t x, int
             M.act[idx] = (int32_t)s;
         }
     }
-    if (T2 > 0 && now >= T2 && now - f < T2) {
+    bool enters = T2 > 0 && now >= T2 && now - f <= T2;
+    if (enters) {
+        const u64 pa_thr = lc ? lc->t2pa : (u64)__ldcg(&M.state[MS_T2_PA]);
+        if (pa_thr == 0) enters = now - f < T2;
+        else {
+            // grid mode, new product token: its prefix is being written by CTA 0 right now -- count the pair in (a superset is safe)
+            const u64 pre = (!lc && expect_new) ? ~0ULL : M.tok_pre[x];
+            const bool was_in = now - f == T2 && pre >= pa_thr, is_in = now > T2 || pre >= pa_thr;
+            enters = is_in && !was_in;
+        }
+    }
+    if (enters) {
         const uint32_t bit = 1u << (s & 31);
         if (!(atomicOr(&M.intop[s >> 5], bit) & bit)) {
             const i64 idx = lc ? (i64)atomicAdd(&lc->top_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
@@ -585,7 +603,7 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
         const uint32_t bit = 1u << (s & 31);
         atomicOr(&M.inact[s >> 5], bit);
         M.act[atomicAdd(&lc->act_n, 1)] = s;
-        if (cnt >= T2) {
+        if (cnt > T2 || (cnt == T2 && pre_a >= lc->t2pa)) {
             const int idx = atomicAdd(&lc->top_n, 1);
             if (idx < ML_TOP_N) {
                 atomicOr(&M.intop[s >> 5], bit);
@@ -1022,7 +1040,7 @@ __device__ __forceinline__ i64 warp_max_i64(i64 v) {
 //   C  the last warp records the merge / creates the token while every other 8-lane group takes ONE candidate
 //      item, claims its word in a shared-memory set (no global stamp), loads the word and rewrites it
 //   D  thread 0 closes the merge's affected-log segment (plain stores; all counters are in shared memory)
-__device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i64 T, i64 Tmin, const i64 T2) {
+__device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i64 T, i64 Tmin, const i64 T2, const u64 T2pa) {
     __shared__ Ranges R;
     __shared__ int32_t sh_c;
     __shared__ MergedInfo MI;
@@ -1056,7 +1074,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         C.act_n = (int)__ldcg(&M.state[MS_ACT_N]); C.alog_n = (int)__ldcg(&M.state[MS_ALOG_N]);
         C.error = (int)__ldcg(&M.state[MS_ERROR]);
         C.top_n = (int)__ldcg(&M.state[MS_TOP_N]); C.top_ovf = (int)__ldcg(&M.state[MS_TOP_OVF]);
-        C.npairs_new = 0; C.nnew = 0;
+        C.npairs_new = 0; C.nnew = 0; C.t2pa = T2pa;
         sh_ncand = 0; C.cur_slot = -1;
     }
     __syncthreads();
@@ -1173,7 +1191,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
                 if (best.slot >= 0) best.pad = mirror_find(&C.LM, best.slot);      // block_best does not carry the list index
             }
         }
-        if (best.slot < 0 || best.cnt < T2) { reason = LR_TOP; break; }
+        if (best.slot < 0 || best.cnt < T2 || (best.cnt == T2 && best.pad >= 0 && C.tpa[best.pad] < T2pa)) { reason = LR_TOP; break; }
         if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
         ML_CLOCK(c1);
         ML_TR(1);
@@ -1276,19 +1294,66 @@ __device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* s
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh_hist[i] = M.hist[i];
     __syncthreads();
     i64 T2;
+    u64 PA = 0;
     {
         int acc = 0, b = 1023;
         while (b >= 0 && acc + sh_hist[b] <= (ML_TOP_N * 3) / 4) { acc += sh_hist[b]; b--; }
         T2 = b < 0 ? T : (b >= 1023 ? hi : T + ((i64)(b + 1) * span + 1022) / 1023);
         if (T2 < T) T2 = T;
+        // Every bin is ONE count when the span is small (the tie regime).  The bin that did not fit is then cut by the left
+        // token's prefix: radix select (8 bits a level, most significant first) of about the `want` largest prefixes among
+        // the pairs with exactly that count.
+        if (b >= 0 && span <= 1022 && sh_hist[b] > 0) {
+            const i64 cb = span > 0 ? T + ((i64)b * span + 1022) / 1023 : hi;          // the count of bin b
+            const bool exact = span == 0 || (int)(((cb - T) * 1023) / span) == b;
+            int want = (ML_TOP_N * 3) / 4 - acc, room = ML_TOP_N - 32 - acc;
+            if (exact && want > 0) {
+                u64 prefix = 0;
+                bool done = false;
+                for (int level = 0; level < 8 && !done; level++) {
+                    const int shift = 56 - 8 * level;
+                    for (i64 i = gtid; i < 256; i += gstride) M.hist[i] = 0;
+                    grid_barrier(M);
+                    for (i64 i = gtid; i < act_n; i += gstride) {
+                        const int32_t sl = M.act[i];
+                        if (__ldcg(&M.pcnt[sl]) != cb) continue;
+                        const u64 pre = M.tok_pre[(int32_t)((__ldcg(&M.pkey[sl]) >> 32) & 0x7fffffff)];
+                        if (level > 0 && (pre >> (shift + 8)) != (prefix >> (shift + 8))) continue;
+                        atomicAdd(&M.hist[(int)((pre >> shift) & 255)], 1);
+                    }
+                    grid_barrier(M);
+                    if (threadIdx.x < 256) sh_hist[threadIdx.x] = __ldcg(&M.hist[threadIdx.x]);
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        int cum = 0, chosen = -1;
+                        for (int bin = 255; bin >= 0; bin--) {
+                            const int h = sh_hist[bin];
+                            if (cum + h > want) { chosen = bin; break; }
+                            cum += h;
+                        }
+                        sh_hist[256] = chosen; sh_hist[257] = cum; sh_hist[258] = chosen >= 0 ? sh_hist[chosen] : 0;
+                    }
+                    __syncthreads();
+                    const int chosen = sh_hist[256], cum = sh_hist[257], hc = sh_hist[258];
+                    grid_barrier(M);                                  // everybody has read the histogram before it is zeroed again
+                    if (chosen < 0) { done = true; break; }             // everything under this prefix fits
+                    prefix |= (u64)chosen << shift;
+                    want -= cum; room -= cum;
+                    if (hc <= room || level == 7) { done = true; break; }   // take the whole bin (level 7: equal prefixes cannot be split)
+                }
+                T2 = cb; PA = prefix;
+            }
+        }
     }
     for (i64 i = gtid; i < act_n; i += gstride) {
         int32_t sl = M.act[i];
-        if (__ldcg(&M.pcnt[sl]) >= T2) {
-            i64 idx = (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
-            if (idx < ML_TOP_N) { M.top_slot[idx] = sl; M.top_key[idx] = __ldcg(&M.pkey[sl]); atomicOr(&M.intop[sl >> 5], 1u << (sl & 31)); }
-            else M.state[MS_TOP_OVF] = 1;
-        }
+        const i64 c = __ldcg(&M.pcnt[sl]);
+        if (c < T2) continue;
+        const u64 key = __ldcg(&M.pkey[sl]);
+        if (c == T2 && PA != 0 && M.tok_pre[(int32_t)((key >> 32) & 0x7fffffff)] < PA) continue;
+        i64 idx = (i64)atomicAdd((u64*)&M.state[MS_TOP_N], 1ULL);
+        if (idx < ML_TOP_N) { M.top_slot[idx] = sl; M.top_key[idx] = key; atomicOr(&M.intop[sl >> 5], 1u << (sl & 31)); }
+        else M.state[MS_TOP_OVF] = 1;
     }
     grid_barrier(M);
     const bool ovf = M.state[MS_TOP_OVF] != 0;
@@ -1297,8 +1362,8 @@ __device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* s
         i64 n_old = M.state[MS_TOP_N]; if (n_old > ML_TOP_N) n_old = ML_TOP_N;
         for (i64 i = gtid; i < n_old; i += gstride) { int32_t sl = M.top_slot[i]; atomicAnd(&M.intop[sl >> 5], ~(1u << (sl & 31))); }
         grid_barrier(M);
-        if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_T2] = -1; M.state[MS_TIE_CNT] = hi; M.state[MS_TIE_LEFT] = 64; }
-    } else if (gtid == 0) M.state[MS_T2] = T2;
+        if (gtid == 0) { M.state[MS_TOP_N] = 0; M.state[MS_TOP_OVF] = 0; M.state[MS_T2] = -1; M.state[MS_T2_PA] = 0; M.state[MS_TIE_CNT] = hi; M.state[MS_TIE_LEFT] = 64; }
+    } else if (gtid == 0) { M.state[MS_T2] = T2; M.state[MS_T2_PA] = (i64)PA; }
     grid_barrier(M);
     return true;
 }
@@ -1418,6 +1483,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         const i64 act_n = M.state[MS_ACT_N];
         const i64 gen = M.state[MS_LEADER_GEN];
         i64 T2 = M.state[MS_T2];
+        const u64 T2pa = (u64)M.state[MS_T2_PA];
         const i64 tie_cnt = M.state[MS_TIE_CNT], tie_left = M.state[MS_TIE_LEFT];
         const i64 top_n = M.state[MS_TOP_N];
         const bool top_ovf = M.state[MS_TOP_OVF] != 0;
@@ -1437,7 +1503,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             const i64 m0 = m;
             grid_barrier(M);                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
-                leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2);
+                leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2, T2pa);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
             } else if (helper_idx >= 0) {
@@ -1466,7 +1532,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         if (T2 > 0) {
             best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
             grid_barrier(M);
-            if (best.slot < 0 || best.cnt < T2 || best.cnt < T) {
+            if (best.slot < 0 || best.cnt < T2 || best.cnt < T || (best.cnt == T2 && T2pa != 0 && M.tok_pre[best.a] < T2pa)) {
                 if (gtid == 0) M.state[MS_T2] = 0;
                 grid_barrier(M);
                 continue;
