@@ -80,9 +80,38 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The corpus is read exactly once: its lines are marked evict-first in the L2, so that the stream (GBs) does not push the
+// count table's hot sectors (tens of MB, probed over and over) out of the 126 MB L2.  PT_TEXT_EVICT_FIRST=0 restores the default.
+#ifndef PT_TEXT_EVICT_FIRST
+#define PT_TEXT_EVICT_FIRST 1
+#endif
+#ifndef PT_PROBE_EVICT_LAST
+#define PT_PROBE_EVICT_LAST 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+#if PT_TEXT_EVICT_FIRST
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_policy_evict_first()) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#endif
+}
+// 16-byte table probe through the L2 only (ld.global.cg), optionally asking the L2 to keep the sector (evict-last)
+__device__ __forceinline__ ulonglong2 probe_ld16(const void* p) {
+#if PT_PROBE_EVICT_LAST
+    ulonglong2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_policy_evict_last()) : "memory");
+    return v;
+#else
+    return __ldcg((const ulonglong2*)p);
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -250,7 +279,7 @@ __device__ __forceinline__ i64 short_insert_seen(const ShortTab& T, u64 h, u64 k
 #pragma unroll 1
     for (int probe = 0; probe < 8192; probe++) {
         ulonglong2 kv = seen;
-        if (kv.x == ~0ULL) kv = __ldcg((const ulonglong2*)T.key(slot));
+        if (kv.x == ~0ULL) kv = probe_ld16(T.key(slot));
         seen.x = ~0ULL;
         if (kv.x == 0 && kv.y == 0) {
             kv = atom_cas128(T.key(slot), 0ULL, 0ULL, k0, k1);

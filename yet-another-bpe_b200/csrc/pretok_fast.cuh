@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             if (miss) {
                 pend = true; pkx = kx; pky = ky; pkz = kz; pkw = kw;
                 pslot = (uint32_t)(h & smask);
-                pkv = __ldcg((const ulonglong2*)P.st.key(pslot));
+                pkv = probe_ld16(P.st.key(pslot));
             }
             my_miss += __popc(__ballot_sync(0xffffffffu, miss));
             // long (15 bytes .. one chunk) and over-long pre-tokens
