@@ -183,13 +183,13 @@ typedef struct {
     uint64_t* pkey; int64_t* pcnt; int64_t pcap; /* pair table, pow2, zeroed                      */
     uint32_t* ioff;             /* device, pcap + 1                                               */
     uint32_t* icnt;             /* device, pcap                                                   */
-    int32_t* ipost;             /* device, n_syms                                                 */
+    int64_t* ipost;             /* device, n_syms + 8: postings (word | first symbol slot << 32)   */
     uint32_t* inact;            /* device, (pcap + 31) / 32                                       */
     uint32_t* intop;            /* device, (pcap + 31) / 32, zeroed                               */
     int32_t* top_slot; uint64_t* top_key;        /* device, 1024 entries each                     */
     int32_t* hist;              /* device, 1024 ints                                              */
     int32_t* act;               /* device, pcap                                                   */
-    int32_t* alog_word; int64_t alog_cap;        /* affected-word log, >= 2 * n_words + 4096      */
+    int64_t* alog_word; int64_t alog_cap;        /* affected-word log (same entries), >= 2 * n_words + 4096 */
     int32_t* seg_start; int32_t* seg_end;        /* device, num_merges each                       */
     int32_t* merge_next;        /* device, num_merges                                             */
     int32_t* tok_first;         /* device, max_tokens                                             */

@@ -45,6 +45,12 @@ __device__ long long* g_trace_row = nullptr;
 #endif
 #define PAIR_KEY(a, b) (0x8000000000000000ULL | ((u64)(uint32_t)(a) << 32) | (u64)(uint32_t)(b))
 #define TOK_HASH_B 0x100000001b3ULL
+// A posting / log entry carries the word AND its first symbol slot (fixed for the word's life): whoever picks a candidate
+// can ask for the word's symbols in the same round trip as its header instead of after it.
+#define POST_PACK(w, off) ((i64)(((u64)(uint32_t)(off) << 32) | (u64)(uint32_t)(w)))
+#define POST_WORD(e) ((e) < 0 ? -1 : (int32_t)(uint32_t)((u64)(e) & 0xffffffffULL))
+#define POST_OFF(e) ((i64)((u64)(e) >> 32))
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // merge-loop state slots (device int64[32])
 #define MS_NMERGES 0
@@ -75,7 +81,17 @@ __device__ long long* g_trace_row = nullptr;
 #define MS_TIE_LEFT 33       // merges left before the next attempt to rebuild the top list in that regime
 #define MS_TOP_N_LIVE 34     // leader mode: current length of the top list (read by the prefetch helpers)
 #define MS_LEADER_SMID 35
-#define MS_T2_PA 36          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
+#define MS_T2_PA 36
+// phase clocks of CTA 0 (cycles, always on: one thread reads %clock64 at phase boundaries)
+#define MS_CLK_HIST 40       // initial pair histogram
+#define MS_CLK_INDEX0 41     // first index build + active set
+#define MS_CLK_TOPREB 42     // top-list rebuilds (incl. threshold steps)
+#define MS_CLK_IDXREB 43     // later index rebuilds
+#define MS_CLK_LEADER 44     // leader sessions (CTA 0 inside leader_loop)
+#define MS_CLK_GRID 45       // grid-mode merges
+#define MS_CLK_TOTAL 46
+#define MS_N_TOPREB 47
+#define ML_PHASE(slot, t0) do { if (gtid == 0) { const long long _t = clock64(); M.state[slot] += _t - (t0); (t0) = _t; } } while (0)          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
 #define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
@@ -218,10 +234,10 @@ struct MergeParams {
     u64* tset; i64 tset_cap; i64 max_tokens;
     // pairs
     u64* pkey; i64* pcnt; i64 pcap;
-    uint32_t* ioff; uint32_t* icnt; int32_t* ipost; uint32_t* inact; uint32_t* intop; int32_t* act;
+    uint32_t* ioff; uint32_t* icnt; i64* ipost; uint32_t* inact; uint32_t* intop; int32_t* act;      // ipost / alog_word entries: word | first symbol slot << 32
     int32_t* top_slot; u64* top_key; int* hist;
     // affected-word log: alog_word[seg_start[m] .. seg_end[m]) = words rewritten by merge m
-    int32_t* alog_word; i64 alog_cap;
+    i64* alog_word; i64 alog_cap;
     int32_t* seg_start; int32_t* seg_end;      // per merge
     int32_t* merge_next;                        // per merge: previous merge (since rebuild) with the same product token
     int32_t* tok_first;                         // per token: latest merge since the last rebuild producing it, or -1
@@ -463,7 +479,7 @@ __device__ void rebuild_index(const MergeParams& M, i64* sh_scan, i64 m_now) {
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
         int32_t w = M.sym_word[i];
         i64 j = i - M.woff[w];
-        if (j + 1 < M.wlen[w]) { const int32_t s = M.wslot[i]; uint32_t r = atomicSub(&M.icnt[s], 1u) - 1; M.ipost[M.ioff[s] + r] = w; }
+        if (j + 1 < M.wlen[w]) { const int32_t s = M.wslot[i]; uint32_t r = atomicSub(&M.icnt[s], 1u) - 1; M.ipost[M.ioff[s] + r] = POST_PACK(w, i - j); }
     }
     if (gtid == 0) { M.state[MS_ALOG_N] = 0; M.state[MS_LAST_REBUILD_M] = m_now; M.state[MS_REBUILDS]++; }
     grid_barrier(M);
@@ -640,9 +656,9 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
         }
     }
 }
-__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, LeaderCtx* lc) {
+__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, i64 off, LeaderCtx* lc) {
     const i64 d = lc ? (i64)atomicAdd(&lc->alog_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL);
-    if (d < M.alog_cap) M.alog_word[d] = w;
+    if (d < M.alog_cap) M.alog_word[d] = POST_PACK(w, off);
     else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);     // callers reserve space up front
 }
 
@@ -675,7 +691,7 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
             s[o++] = x; prev_new = x; prev_changed = false; j += 1;
         }
     }
-    if (any) { M.wlen[w] = o; alog_append(M, w, lm); }
+    if (any) { M.wlen[w] = o; alog_append(M, w, off, lm); }
 }
 
 // one warp rewrites one word (a != b): every lane owns one old position per 32-symbol chunk, so the
@@ -731,7 +747,7 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
         out += __popc(keepmask);
         __syncwarp();
     }
-    if (any && lane == 0) { M.wlen[w] = out; alog_append(M, w, lm); }
+    if (any && lane == 0) { M.wlen[w] = out; alog_append(M, w, woff_, lm); }
 }
 
 // 32 / G words per warp, one per G-lane group (G = 8: words are ~6 symbols on average; G = 4: twice as many candidates per
@@ -798,12 +814,12 @@ __device__ void rewrite_words_g(const MergeParams& M, int32_t w, i64 off, int n,
         out += __popc(keepmask);
         __syncwarp();
     }
-    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w, lm); }
+    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w, off, lm); }
 }
 
 // candidate ranges for pair (a, b) at slot: CSR postings + affected-log segments of the merges that
 // produced a or b since the last index rebuild.  Returns the number of ranges, or -1 if too many.
-struct Ranges { const int32_t* base[ML_MAX_RANGES]; int len[ML_MAX_RANGES]; int n; i64 total; };
+struct Ranges { const i64* base[ML_MAX_RANGES]; int len[ML_MAX_RANGES]; int n; i64 total; };
 
 __device__ void build_ranges(const MergeParams& M, int32_t slot, int32_t a, int32_t b, Ranges* R, bool have_post = false, uint32_t post0 = 0, uint32_t postlen = 0) {
     int n = 0; i64 total = 0;
@@ -829,9 +845,9 @@ __device__ void build_ranges(const MergeParams& M, int32_t slot, int32_t a, int3
     }
     R->n = n; R->total = total;
 }
-__device__ __forceinline__ int32_t range_item(const Ranges& R, i64 it) {
+__device__ __forceinline__ i64 range_item(const Ranges& R, i64 it) {
     for (int r = 0; r < R.n; r++) {
-        if (it < R.len[r]) { const int32_t* b = R.base[r]; __builtin_assume(__isGlobal(b)); return b[it]; }    // not a generic load
+        if (it < R.len[r]) { const i64* b = R.base[r]; __builtin_assume(__isGlobal(b)); return b[it]; }    // not a generic load
         it -= R.len[r];
     }
     return -1;
@@ -1027,28 +1043,37 @@ __device__ __forceinline__ void leader_rewrite(const MergeParams& M, LeaderCtx& 
     const int ngroups = (nwarps - 1) * GPW, gl = lane & (G - 1), lead = lane & ~(G - 1);
     const int total = (int)R.total;
     const int it0 = warp * GPW + lane / G;
-    int32_t w_cur = it0 < total ? range_item(R, it0) : -1;
-    int32_t w_nx = it0 + ngroups < total ? range_item(R, it0 + ngroups) : -1;
+    const i64 e_cur = it0 < total ? range_item(R, it0) : -1, e_nx = it0 + ngroups < total ? range_item(R, it0 + ngroups) : -1;
+    int32_t w_cur = POST_WORD(e_cur), w_nx = POST_WORD(e_nx);
+    i64 o_nx = POST_OFF(e_nx);
     {
         int take = (w_cur >= 0 && gl == 0) ? (dedupe_claim(&C, w_cur) ? 1 : 0) : 0;
         take = __shfl_sync(0xffffffffu, take, lead);
         if (!take) w_cur = -1;
     }
     uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
-    if (w_cur >= 0) { off_cur = (uint32_t)M.woff[w_cur]; n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur]; }
+    if (w_cur >= 0) {                       // header and symbols in ONE round trip: the entry carries the symbol slot
+        off_cur = (uint32_t)POST_OFF(e_cur);
+        if (gl == 0) { prefetch_l2(&M.wsym[off_cur]); prefetch_l2(&M.wslot[off_cur]); }
+        n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur];
+    }
     for (int base = 0; base + warp * GPW < total; base += ngroups) {     // warps without a candidate go straight to the barrier
         const int it2 = base + it0 + 2 * ngroups;
-        const int32_t w_nx2 = it2 < total ? range_item(R, it2) : -1;
+        const i64 e_nx2 = it2 < total ? range_item(R, it2) : -1;
         {
             int take = (w_nx >= 0 && gl == 0) ? (dedupe_claim(&C, w_nx) ? 1 : 0) : 0;
             take = __shfl_sync(0xffffffffu, take, lead);
             if (!take) w_nx = -1;
         }
         uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
-        if (w_nx >= 0) { off_nx = (uint32_t)M.woff[w_nx]; n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx]; }
+        if (w_nx >= 0) {
+            off_nx = (uint32_t)o_nx;
+            if (gl == 0) { prefetch_l2(&M.wsym[off_nx]); prefetch_l2(&M.wslot[off_nx]); }
+            n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx];
+        }
         if (a != b) rewrite_words_g<G>(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
         else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new, C.cur_slot);
-        w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = w_nx2;
+        w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = POST_WORD(e_nx2); o_nx = POST_OFF(e_nx2);
     }
 }
 
@@ -1409,8 +1434,6 @@ __device__ bool grid_top_rebuild(const MergeParams& M, i64& T, i64 Tmin, Best* s
 #ifndef ML_HELPER_MIN_SYMS
 #define ML_HELPER_MIN_SYMS (8 << 20)      // word arrays below ~100 MB stay in the L2 anyway (126 MB): nothing to prefetch
 #endif
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_keys, Ranges* R) {
     __shared__ int sh_stop;
     for (int round = 0;; round++) {
@@ -1440,7 +1463,7 @@ __device__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_key
             const i64 total = R->total < 2 * ML_LEADER_ITEMS_MAX ? R->total : 2 * ML_LEADER_ITEMS_MAX;
             for (i64 it = threadIdx.x; it < total; it += blockDim.x) {
                 i64 j = it; int32_t w = -1;
-                for (int q = 0; q < R->n; q++) { if (j < R->len[q]) { w = __ldcg(&R->base[q][j]); break; } j -= R->len[q]; }
+                for (int q = 0; q < R->n; q++) { if (j < R->len[q]) { w = POST_WORD(__ldcg(&R->base[q][j])); break; } j -= R->len[q]; }
                 if (w < 0 || w >= M.n_words) continue;
                 prefetch_l2(&M.wcnt[w]);
                 const i64 off = __ldcg(&M.woff[w]);
@@ -1467,6 +1490,8 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     __shared__ Ranges R;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
 
+    long long pclk = clock64();
+    const long long pclk0 = pclk;
     // ---- K4: pair histogram (trainer.py:228-235)
     for (i64 i = gtid; i + 1 < M.n_syms; i += gstride) {
         int32_t w = M.sym_word[i];
@@ -1486,10 +1511,12 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         for (int o = 16; o > 0; o >>= 1) { i64 t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
         if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax((i64*)&M.state[MS_MAXCNT], mx);
     }
+    ML_PHASE(MS_CLK_HIST, pclk);
     rebuild_index(M, sh_scan, 0);      // starts and ends with grid-wide syncs
     const i64 Tmin = M.min_freq > 1 ? M.min_freq : 1;
     i64 T = M.state[MS_MAXCNT] / 2; if (T < Tmin) T = Tmin;
     rebuild_active(M, T);
+    ML_PHASE(MS_CLK_INDEX0, pclk);
 
     // prefetch helpers of the leader mode (result-neutral): which CTAs, if any
     int helper_idx = -1;
@@ -1521,7 +1548,11 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         // ---- (re)build the top list when it cannot prove the maximum any more
         if (T2 == 0 || (T2 > 0 && top_ovf)) {
             grid_barrier(M);                                    // everyone has read the state
-            if (!grid_top_rebuild(M, T, Tmin, sh_best, sh_hist)) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
+            pclk = clock64();
+            const bool more = grid_top_rebuild(M, T, Tmin, sh_best, sh_hist);
+            ML_PHASE(MS_CLK_TOPREB, pclk);
+            if (gtid == 0) M.state[MS_N_TOPREB]++;
+            if (!more) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
             continue;
         }
 
@@ -1531,7 +1562,9 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             const i64 m0 = m;
             grid_barrier(M);                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
+                pclk = clock64();
                 leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2, T2pa);
+                ML_PHASE(MS_CLK_LEADER, pclk);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
             } else if (helper_idx >= 0) {
@@ -1549,13 +1582,14 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             if (m >= M.num_merges || M.state[MS_ERROR]) break;
             grid_barrier(M);                                    // everyone has re-read the state
             if (reason == LR_TOP) continue;                 // top list exhausted: rebuild it first
-            if (reason == LR_REBUILD) { rebuild_index(M, sh_scan, m); continue; }
+            if (reason == LR_REBUILD) { pclk = clock64(); rebuild_index(M, sh_scan, m); ML_PHASE(MS_CLK_IDXREB, pclk); continue; }
         }
 
         // ---- one merge in grid mode.  With a valid top list every CTA finds the best pair on its own
         //      (same data, same answer); the barrier only keeps the rewrite (which changes the counts)
         //      from starting before every CTA has read them.
         Best best;
+        pclk = clock64();
         ML_CLOCK(g0);
         if (T2 > 0) {
             best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
@@ -1602,9 +1636,10 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             i64 off = 0, f = 0; int n = 0;
             int32_t old = stamp;
             if (gg < R.total) {
-                w = range_item(R, gg);
-                if (gl == 0) old = atomicExch(&M.wstamp[w], stamp);
-                off = M.woff[w]; n = M.wlen[w]; f = M.wcnt[w];
+                const i64 e = range_item(R, gg);
+                w = POST_WORD(e); off = POST_OFF(e);
+                if (gl == 0) { old = atomicExch(&M.wstamp[w], stamp); prefetch_l2(&M.wsym[off]); prefetch_l2(&M.wslot[off]); }
+                n = M.wlen[w]; f = M.wcnt[w];
             }
             old = __shfl_sync(0xffffffffu, old, lane & 24);       // all 32 lanes: groups beyond the list carry old == stamp
             if (old == stamp) w = -1;
@@ -1612,7 +1647,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         } else if (a != b && R.total * 32 <= gstride * 4) {
             const i64 gw = gtid >> 5, nw = gstride >> 5;
             for (i64 it = gw; it < R.total; it += nw) {
-                int32_t w = range_item(R, it);
+                const int32_t w = POST_WORD(range_item(R, it));
                 int32_t old = 0;
                 if ((threadIdx.x & 31) == 0) old = atomicExch(&M.wstamp[w], stamp);
                 old = __shfl_sync(0xffffffffu, old, 0);
@@ -1621,7 +1656,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             }
         } else {
             for (i64 it = gtid; it < R.total; it += gstride) {
-                int32_t w = range_item(R, it);
+                const int32_t w = POST_WORD(range_item(R, it));
                 if (atomicExch(&M.wstamp[w], stamp) == stamp) continue;
                 rewrite_word_thread(M, w, a, b, c, T, T2u, nullptr, is_new, best.slot);
             }
@@ -1640,6 +1675,8 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             if (T2 < 0) { if (best.cnt != tie_cnt || tie_left <= 1) M.state[MS_T2] = 0; else M.state[MS_TIE_LEFT] = tie_left - 1; }
         }
         if (gtid == 0) M.state[MS_GRID_MERGES]++;
+        ML_PHASE(MS_CLK_GRID, pclk);
         __syncthreads();
     }
+    if (gtid == 0) M.state[MS_CLK_TOTAL] = clock64() - pclk0;
 }

@@ -380,9 +380,9 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.tok_hash = (u64*)m->tok_hash; M.tok_pow = (u64*)m->tok_pow; M.tok_pre = (u64*)m->tok_pre; M.tset = (u64*)m->tset; M.tset_cap = m->tset_cap;
     M.max_tokens = m->max_tokens;
     M.pkey = (u64*)m->pkey; M.pcnt = (i64*)m->pcnt; M.pcap = m->pcap;
-    M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = m->ipost; M.inact = m->inact; M.intop = m->intop; M.act = m->act;
+    M.ioff = m->ioff; M.icnt = m->icnt; M.ipost = (i64*)m->ipost; M.inact = m->inact; M.intop = m->intop; M.act = m->act;
     M.top_slot = m->top_slot; M.top_key = (u64*)m->top_key; M.hist = m->hist;
-    M.alog_word = m->alog_word; M.alog_cap = m->alog_cap; M.seg_start = m->seg_start; M.seg_end = m->seg_end;
+    M.alog_word = (i64*)m->alog_word; M.alog_cap = m->alog_cap; M.seg_start = m->seg_start; M.seg_end = m->seg_end;
     M.merge_next = m->merge_next; M.tok_first = m->tok_first; M.tok_head = (int4*)m->tok_head;
     ARG_CHECK(((uintptr_t)m->tok_head & 15) == 0);
     ARG_CHECK(m->alog_cap >= 2 * m->n_words + ML_LEADER_ITEMS_MAX);

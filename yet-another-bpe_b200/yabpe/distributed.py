@@ -274,6 +274,8 @@ def _count_exchange_merge(trainer, text_dev, n: int, cuts: list[int], own: tuple
                                     threshold_rebuilds=int(mr.state[_ffi.MS_TREBUILDS]), n_pairs=int(mr.state[_ffi.MS_NPAIRS]),
                                     leader_merges=int(mr.state[_ffi.MS_LEADER_MERGES]), grid_merges=int(mr.state[_ffi.MS_GRID_MERGES]))
     trainer.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13]), int(mr.state[17])]
+    from .trainer import _phase_cycles
+    trainer.timing['merge_phase_cycles'] = _phase_cycles(mr.state)
     vocab = {b: i for i, b in enumerate(mr.tokens)}
     toks = mr.tokens
     merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]

@@ -392,11 +392,11 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         newp = torch.empty(words.n_syms + 8, dtype=torch.int32, device=dev)
         pkey, pcnt = z(pcap, torch.int64), z(pcap, torch.int64)
         ioff, icnt = z(pcap + 1, torch.int32), z(pcap, torch.int32)
-        ipost = z(words.n_syms + 8, torch.int32)
+        ipost = z(words.n_syms + 8, torch.int64)
         inact, act = z((pcap + 31) // 32 + 1, torch.int32), z(pcap, torch.int32)
         intop = z((pcap + 31) // 32 + 1, torch.int32)
         top_slot, top_key, hist = z(1024, torch.int32), z(1024, torch.int64), z(1024, torch.int32)
-        alog_word = z(alog_cap, torch.int32)
+        alog_word = z(alog_cap, torch.int64)
         nm1 = max(num_merges, 1)
         seg_start, seg_end, merge_next = z(nm1, torch.int32), z(nm1, torch.int32), z(nm1, torch.int32)
         tok_first = z(max_tokens, torch.int32)

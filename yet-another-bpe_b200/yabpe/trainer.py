@@ -96,6 +96,12 @@ def device_chunk_cuts(text_dev, n: int, chunk_size: int) -> list[int]:
     return [c for c in cuts if 0 < c < n]
 
 
+def _phase_cycles(state) -> dict:
+    """Phase clocks of the merge kernel (cycles of CTA 0's SM; include/yabpe.h MS_CLK_*)."""
+    names = ["pair_histogram", "first_index_and_active_set", "top_list_rebuilds", "index_rebuilds", "leader_sessions", "grid_merges", "total", "n_top_rebuilds"]
+    return {k: int(state[40 + i]) for i, k in enumerate(names)}
+
+
 @dataclass
 class TrainStats:
     n_bytes: int = 0
@@ -311,6 +317,7 @@ class BBPETrainer:
         stats.leader_merges = int(mr.state[_ffi.MS_LEADER_MERGES])
         stats.grid_merges = int(mr.state[_ffi.MS_GRID_MERGES])
         self.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13]), int(mr.state[17])]
+        self.timing['merge_phase_cycles'] = _phase_cycles(mr.state)
         stats.launches = _ffi.launch_count() - launches0
         self.last_stats = stats
         if self.profile and ev and len(ev) == 4:
