@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YABPE_ABI_VERSION 4
+#define YABPE_ABI_VERSION 5
 
 #define YABPE_OK 0
 #define YABPE_ERR_CUDA (-1)
@@ -106,6 +106,10 @@ typedef struct {
                                 /*   keys the warp kernel pre-loads into its shared-memory cache                 */
     int64_t* work;              /* device scratch, 3 * work_cap int64 (boundary work items), or NULL */
     int64_t work_cap;           /*   >= 4 * n_cuts + 16 enables the warp kernel in trainer mode   */
+    void* hot_table;            /* device, 32-byte aligned, hot_cap * 32 bytes, zeroed once -- or NULL.  A direct-mapped table small   */
+    int64_t hot_cap;            /*   enough to stay in the L2 (power of two, e.g. 2^20 slots = 32 MB), probed before the big short table */
+                                /*   by the warp kernel when the big one is DRAM-sized; its counts are folded into the big table at   */
+                                /*   the end of every call, its claimed keys serve later calls on the same tables.  Result-neutral   */
 } yabpe_pretok_args;
 
 /* Stage 1: special-token candidates + resolution (skipped when n_sp == 0).

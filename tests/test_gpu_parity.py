@@ -263,6 +263,36 @@ def test_short_table_layouts(yabpe, tmp_path, monkeypatch, layout):
     assert t.encode_batch([s[:1000], "", s[1000:5000]]) == [o.encode(s[:1000]), [], o.encode(s[1000:5000])]
 
 
+@pytest.mark.parametrize("slots", [64, 4096])
+def test_hot_table_in_front_of_the_big_table(yabpe, tmp_path, monkeypatch, slots):
+    """DRAM-sized count tables get an L2-resident direct-mapped table in front of them (k_pretok_warp<true>, k_hot_flush).
+    Forced here on small inputs with a tiny hot table (every slot fought over) and a moderate one; counts, training and
+    encode must not move.  Also the piece-wise counting of train_from_buffers, which reuses one hot table across calls."""
+    from yabpe import engine
+    monkeypatch.setenv("YABPE_SHORT_LAYOUT", "interleaved")
+    monkeypatch.setenv("YABPE_HOT_TABLE", "1")
+    monkeypatch.setattr(engine, "_HOT_TABLE_SLOTS", slots)
+    monkeypatch.setattr(engine, "_HOT_TABLE_MIN_FACTOR", 0)
+    rng = random.Random(11)
+    text = "".join(rng.choice(ALPHABET + [" the", " of", "ing", "\n"]) for _ in range(200_000)).encode("utf-8")
+    for sp, mode in (([], "train"), (["<|endoftext|>"], "train"), (["<|endoftext|>"], "encode")):
+        assert _device_counts(text, sp, mode=mode) == _oracle_counts(text, sp, mode=mode), (sp, mode)
+    data = common.synth_owt(6_000_000, seed=31)
+    p = tmp_path / "hot.txt"
+    p.write_bytes(data)
+    want = oracle.train_bpe(p, 1500, ["<|endoftext|>"], fast=True)
+    assert yabpe.train_bpe(p, 1500, ["<|endoftext|>"]) == want
+    tr = yabpe.BBPETrainer(yabpe.BBPETrainerConfig(vocab_size=1500, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
+                                                   special_tokens=["<|endoftext|>"]))
+    tr.pipeline_min_bytes, tr.pipeline_piece_bytes = 0, 1 << 20
+    m = tr.train_from_buffers([np.frombuffer(data, dtype=np.uint8)])
+    assert ({v: k for k, v in m.vocab.items()}, m.merges) == want
+    v, mg = common.gpt2_vocab_and_merges()
+    s = data[:400_000].decode("utf-8", errors="ignore")
+    assert yabpe.Tokenizer(v, mg, ["<|endoftext|>"]).inner.encode_device(*engine.to_device_text(__import__("torch"), np.frombuffer(s.encode(), dtype=np.uint8)))[0].cpu().tolist() \
+        == oracle.Tokenizer(v, mg, ["<|endoftext|>"]).encode(s)
+
+
 def test_train_with_frequent_index_rebuilds(yabpe, tmp_path, monkeypatch):
     """The pair -> words index is rebuilt every `rebuild_every` merges (engine.rebuild_period); force a tiny period so
     that dozens of rebuilds (and leader exits for them) happen, and a zero period (rebuild only when the log is full)."""

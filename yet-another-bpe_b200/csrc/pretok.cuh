@@ -65,6 +65,7 @@ struct PretokParams {
     i64* stats;
     i64 tile_base; i64 n_tiles;
     const uint4* hot_keys;          // PW_NC keys to pre-load into the warp kernel's cache (from the sizing sample), or null
+    ShortTab hot;                   // L2-resident direct-mapped table in front of `st` (interleaved slots; cap 0 = none)
     i64* work; i64 work_cap;        // (tile, own_lo, own_hi) triples: chunks the warp kernel hands to the generic kernel
     int list_mode;                  // generic kernel: iterate over `work` instead of all tiles
 };

@@ -25,6 +25,9 @@
 #define PW_WARPS 28
 #endif
 #define PW_THREADS (PW_WARPS * 32)
+#ifndef PW_WARPS_HOT
+#define PW_WARPS_HOT 24                    // the hot-table variant keeps a second probe in flight per lane: more registers, fewer warps
+#endif
 #ifndef PW_NC
 #define PW_NC 4096                         // cache entries per CTA (power of two)
 #endif
@@ -49,6 +52,8 @@ struct WarpSmem {
 static_assert(sizeof(WarpSmem) % 128 == 0, "warp areas stay 128-byte aligned");
 
 #define PW_SMEM_BYTES (PW_NC * 20 + 256 + PW_WARPS * (int)sizeof(WarpSmem))
+#define PW_SMEM_BYTES_HOT (PW_NC * 20 + 256 + PW_WARPS_HOT * (int)sizeof(WarpSmem))
+#define PW_HOT_SHIFT 5                     // hot-table slot = (hash >> PW_HOT_SHIFT) & (cap - 1)
 
 // first cut >= g (or INT64_MAX)
 __device__ __forceinline__ i64 pw_next_cut(const PretokParams& P, i64 g) {
@@ -84,7 +89,15 @@ __device__ void pw_drain_long(const PretokParams& P, const u64* lqueue, int qn, 
     }
 }
 
-__global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i64 c_lo, i64 c_hi) {
+// HOT = true (tables far larger than the L2: millions of unique pre-tokens).  Random 32-byte DRAM sectors cap the plain kernel
+// (its throughput does not move between 20 and 28 resident warps).  A direct-mapped table of P.hot.cap slots, small enough to
+// stay in the L2, is probed first: a pre-token whose key sits there is counted there (flushed into the big table by
+// k_hot_flush afterwards); only the rest goes on to the DRAM-sized table, through a SECOND probe in flight per lane -- no lane
+// waits for DRAM unless both probes of a lane continue in the same round (rare).
+template <bool HOT>
+__global__ void __launch_bounds__(HOT ? PW_WARPS_HOT * 32 : PW_THREADS, 1) k_pretok_warp(PretokParams P, i64 c_lo, i64 c_hi) {
+    constexpr int NWARPS = HOT ? PW_WARPS_HOT : PW_WARPS;
+    constexpr int NTHREADS = NWARPS * 32;
     extern __shared__ __align__(128) unsigned char pw_smem[];
     uint4* ckeys = (uint4*)pw_smem;                                   // 16-byte keys (k0 = x,y  k1 = z,w)
     uint32_t* ccnt = (uint32_t*)(pw_smem + PW_NC * 16);               // bit 31 = claimed, low bits = occurrences
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
 
     // The cache starts from the hot set of the sizing sample when there is one (k_hot_select: for every cache index the
     // most frequent sample key that maps to it) -- claimed with count 0; the remaining slots are claimed first come.
-    for (int i = threadIdx.x; i < PW_NC; i += PW_THREADS) {
+    for (int i = threadIdx.x; i < PW_NC; i += NTHREADS) {
         const uint4 hk = P.hot_keys ? P.hot_keys[i] : make_uint4(0, 0, 0, 0);
         ckeys[i] = hk; ccnt[i] = hk.w ? 0x80000000u : 0u;
     }
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     uint32_t my_tok = 0, my_miss = 0, n_special = 0;   // warp-uniform
     int lqn = 0;
     uint32_t phase0 = 0, phase1 = 0;
-    const i64 stepA = (i64)gridDim.x * PW_WARPS * PW_CH, endA = c_hi * PW_CH;
+    const i64 stepA = (i64)gridDim.x * NWARPS * PW_CH, endA = c_hi * PW_CH;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const i64 nrec = (P.n + 63) / 32 + 1;
     const u64 smask = (u64)P.scap - 1;
@@ -134,14 +147,44 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
     bool pend = false;
     uint32_t pkx = 0, pky = 0, pkz = 0, pkw = 0, pslot = 0;
     ulonglong2 pkv; pkv.x = 0; pkv.y = 0;
+    // HOT: the probe above goes to the hot table (pslot keeps the HASH); a second one, to the big table, may be in flight too
+    bool pendB = false;
+    uint32_t bkx = 0, bky = 0, bkz = 0, bkw = 0, bslot = 0;
+    ulonglong2 bkv; bkv.x = 0; bkv.y = 0;
+    const u64 hmask = HOT ? (u64)P.hot.cap - 1 : 0;
+    auto main_insert = [&](uint32_t slot, u64 k0, u64 k1, ulonglong2 seen, uint32_t len_tag) {
+        int created;
+        if (short_insert_seen(P.st, slot, k0, k1, 1, &created, seen) < 0) P.stats[ST_TABLE_FULL] = 1;     // `seen`: the probe already read this slot
+        if (created) { my_us++; my_ub += len_tag; }
+    };
     auto consume = [&]() {
+        if (HOT && pendB) {                  // big table: hit, empty slot (insert), or somebody else's key (next slot, next round)
+            const u64 k0 = (u64)bkx | ((u64)bky << 32), k1 = (u64)bkz | ((u64)bkw << 32);
+            if (bkv.x == k0 && bkv.y == k1) { atomicAdd((u64*)P.st.cnt(bslot), 1ULL); pendB = false; }
+            else if ((bkv.x | bkv.y) == 0 || (bkv.x == 0) != (bkv.y == 0)) { main_insert(bslot, k0, k1, bkv, bky >> 24); pendB = false; }
+            else { bslot = (uint32_t)(((u64)bslot + 1) & smask); bkv = probe_ld16(P.st.key(bslot)); }
+        }
         if (pend) {
             const u64 k0 = (u64)pkx | ((u64)pky << 32), k1 = (u64)pkz | ((u64)pkw << 32);
-            if (pkv.x == k0 && pkv.y == k1) atomicAdd((u64*)P.st.cnt(pslot), 1ULL);
-            else {
-                int created;
-                if (short_insert_seen(P.st, pslot, k0, k1, 1, &created, pkv) < 0) P.stats[ST_TABLE_FULL] = 1;     // pkv: the probe already read this slot
-                if (created) { my_us++; my_ub += pky >> 24; }
+            if (!HOT) {
+                if (pkv.x == k0 && pkv.y == k1) atomicAdd((u64*)P.st.cnt(pslot), 1ULL);
+                else main_insert(pslot, k0, k1, pkv, pky >> 24);
+            } else {
+                const u64 hs = ((u64)pslot >> PW_HOT_SHIFT) & hmask;
+                bool in_hot = pkv.x == k0 && pkv.y == k1;
+                if (!in_hot && (pkv.x | pkv.y) == 0) {                  // free hot slot: claim it (one 16-byte CAS, once per slot)
+                    const ulonglong2 old = atom_cas128(P.hot.key(hs), 0ULL, 0ULL, k0, k1);
+                    in_hot = (old.x == 0 && old.y == 0) || (old.x == k0 && old.y == k1);
+                }
+                if (in_hot) atomicAdd((u64*)P.hot.cnt(hs), 1ULL);
+                else if (!pendB) {                                      // on to the big table, consumed next round
+                    pendB = true; bkx = pkx; bky = pky; bkz = pkz; bkw = pkw;
+                    bslot = (uint32_t)((u64)pslot & smask);
+                    bkv = probe_ld16(P.st.key(bslot));
+                } else {                                                // both probes of this lane continue: the rare synchronous case
+                    ulonglong2 none; none.x = ~0ULL; none.y = ~0ULL;
+                    main_insert((uint32_t)((u64)pslot & smask), k0, k1, none, pky >> 24);
+                }
             }
             pend = false;
         }
@@ -159,7 +202,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         return A;
     };
 
-    i64 A = advance((c_lo + (i64)blockIdx.x * PW_WARPS + warp) * PW_CH);
+    i64 A = advance((c_lo + (i64)blockIdx.x * NWARPS + warp) * PW_CH);
     if (A < endA) {
         if (lane == 0) { mbar_expect_tx(&W.bar[0], PW_WIN); tma_load_1d(W.txt[0], P.text + (A - PW_HL), PW_WIN, &W.bar[0]); }
         if (P.n_sp > 0) {
@@ -247,8 +290,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
             consume();                             // the probe issued one round ago has landed by now
             if (miss) {
                 pend = true; pkx = kx; pky = ky; pkz = kz; pkw = kw;
-                pslot = (uint32_t)(h & smask);
-                pkv = probe_ld16(P.st.key(pslot));
+                if (HOT) { pslot = h; pkv = probe_ld16(P.hot.key(((u64)h >> PW_HOT_SHIFT) & hmask)); }
+                else { pslot = (uint32_t)(h & smask); pkv = probe_ld16(P.st.key(pslot)); }
             }
             my_miss += __popc(__ballot_sync(0xffffffffu, miss));
             // long (15 bytes .. one chunk) and over-long pre-tokens
@@ -275,12 +318,14 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         A = An; buf ^= 1;
     }
     consume();
+    if (HOT) consume();                      // a probe moved to the big table by the call above
+    while (HOT && pendB) consume();          // ... or still walking a collision chain
     __syncwarp();
     pw_drain_long(P, W.lqueue, lqn, my_ul, my_ub);
 
     // ---- flush the cache
     __syncthreads();
-    for (int i = threadIdx.x; i < PW_NC; i += PW_THREADS) {
+    for (int i = threadIdx.x; i < PW_NC; i += NTHREADS) {
         const uint32_t cn = ccnt[i] & 0x7fffffffu;
         if (cn == 0) continue;
         const uint4 a = ckeys[i];
@@ -299,6 +344,27 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_pretok_warp(PretokParams P, i
         if (my_ul) atomicAdd((u64*)&P.stats[ST_UNIQ_LONG], my_ul);
         if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
         if (my_tok > my_miss + n_special) atomicAdd((u64*)&P.stats[ST_CACHE_HIT], (u64)(my_tok - my_miss - n_special));
+    }
+}
+
+// ---- hot table -> big table (after every k_pretok_warp<true>): counts move over, the claimed keys stay for the next call ----
+__global__ void __launch_bounds__(256) k_hot_flush(PretokParams P) {
+    u64 my_us = 0, my_ub = 0;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < P.hot.cap; i += stride) {
+        const ulonglong2 kv = *(const ulonglong2*)P.hot.key((u64)i);
+        if (kv.y == 0) continue;
+        const i64 cnt = *P.hot.cnt((u64)i);
+        if (cnt == 0) continue;
+        *P.hot.cnt((u64)i) = 0;
+        int created;
+        if (short_insert(P.st, kv.x, kv.y, cnt, &created) < 0) P.stats[ST_TABLE_FULL] = 1;
+        if (created) { my_us++; my_ub += kv.x >> 56; }
+    }
+    for (int o = 16; o > 0; o >>= 1) { my_us += __shfl_xor_sync(0xffffffffu, my_us, o); my_ub += __shfl_xor_sync(0xffffffffu, my_ub, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_us) atomicAdd((u64*)&P.stats[ST_UNIQ_SHORT], my_us);
+        if (my_ub) atomicAdd((u64*)&P.stats[ST_UNIQ_BYTES], my_ub);
     }
 }
 

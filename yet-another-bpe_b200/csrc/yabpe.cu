@@ -126,6 +126,9 @@ static int make_params(const yabpe_pretok_args* a, PretokParams* P) {
     P->stats = (i64*)a->stats;
     P->work = (i64*)a->work; P->work_cap = a->work ? a->work_cap : 0; P->list_mode = 0;
     P->hot_keys = (const uint4*)a->hot_keys;
+    P->hot.kb = (char*)a->hot_table; P->hot.cb = (char*)a->hot_table + 16; P->hot.ks = 32; P->hot.cs = 32;
+    P->hot.cap = a->hot_table ? a->hot_cap : 0;
+    ARG_CHECK(P->hot.cap == 0 || ((P->hot.cap & (P->hot.cap - 1)) == 0 && ((uintptr_t)a->hot_table & 31) == 0));
     P->tile_base = a->own_lo / PT_TILE;
     P->n_tiles = a->own_hi > a->own_lo ? (a->own_hi - 1) / PT_TILE - P->tile_base + 1 : 0;
     return YABPE_OK;
@@ -235,7 +238,8 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
         DevInfo& DI = dev_info();
         if (!DI.pretok_attr) {
             CUDA_TRY(cudaFuncSetAttribute(k_pretok_count, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_CACHE_BYTES));
-            CUDA_TRY(cudaFuncSetAttribute(k_pretok_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(k_pretok_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(k_pretok_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_BYTES_HOT));
             DI.pretok_attr = true;
         }
         int per_sm = 0;
@@ -248,9 +252,16 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
         const bool warp_path = !(stages & 8) && P.work && P.work_cap >= 4 * (i64)P.n_cuts + 16 &&
                                c_hi - c_lo >= 4 && 8 * (i64)P.n_cuts < c_hi - c_lo;
         if (warp_path) {
-            i64 grid_w = (c_hi - c_lo + PW_WARPS - 1) / PW_WARPS;
-            if (grid_w > num_sms()) grid_w = num_sms();
-            k_pretok_warp<<<(int)grid_w, PW_THREADS, PW_SMEM_BYTES, st>>>(P, c_lo, c_hi); LAUNCHED();
+            if (P.hot.cap > 0) {
+                i64 grid_w = (c_hi - c_lo + PW_WARPS_HOT - 1) / PW_WARPS_HOT;
+                if (grid_w > num_sms()) grid_w = num_sms();
+                k_pretok_warp<true><<<(int)grid_w, PW_WARPS_HOT * 32, PW_SMEM_BYTES_HOT, st>>>(P, c_lo, c_hi); LAUNCHED();
+                k_hot_flush<<<num_sms() * 4, 256, 0, st>>>(P); LAUNCHED();
+            } else {
+                i64 grid_w = (c_hi - c_lo + PW_WARPS - 1) / PW_WARPS;
+                if (grid_w > num_sms()) grid_w = num_sms();
+                k_pretok_warp<false><<<(int)grid_w, PW_THREADS, PW_SMEM_BYTES, st>>>(P, c_lo, c_hi); LAUNCHED();
+            }
             PretokParams PL = P;
             PL.list_mode = 1;
             i64 grid = (i64)num_sms() * per_sm;

@@ -11,7 +11,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libyabpe.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # stats / state slots (include/yabpe.h)
 ST_NTOK, ST_UNIQ_SHORT, ST_UNIQ_LONG, ST_UNIQ_BYTES, ST_ERR_POS, ST_TABLE_FULL, ST_OVF_N = 0, 1, 2, 3, 4, 5, 6
@@ -49,6 +49,7 @@ class PretokArgs(C.Structure):
         ("ovf_pos", C.c_void_p), ("ovf_cap", C.c_int64),
         ("stats", C.c_void_p),
         ("hot_keys", C.c_void_p), ("work", C.c_void_p), ("work_cap", C.c_int64),
+        ("hot_table", C.c_void_p), ("hot_cap", C.c_int64),
     ]
 
 

@@ -158,7 +158,13 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     a.stats = stats.data_ptr()
     a.work = work.data_ptr(); a.work_cap = work_cap
     a.hot_keys = hot.data_ptr() if hot is not None else None
-    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work, hot], stats=stats,
+    # YABPE_HOT_TABLE=1: a DRAM-sized table (interleaved layout) gets an L2-resident table in front of it (2^20 slots of 32
+    # bytes).  Exact (tests force it), but measured SLOWER on the OWT-shaped corpus (264 -> 248 GB/s): off
+    hot_tab = None
+    if interleaved and short_cap > _HOT_TABLE_SLOTS * _HOT_TABLE_MIN_FACTOR and os.environ.get("YABPE_HOT_TABLE", "0") == "1":
+        hot_tab = torch.zeros(_HOT_TABLE_SLOTS * 4, dtype=torch.int64, device=dev)
+        a.hot_table = hot_tab.data_ptr(); a.hot_cap = _HOT_TABLE_SLOTS
+    res = PretokResult(args=a, keep=[text_dev, cuts_t, blob, offs, cand, rec, skeys, scounts, lent, ovf, work, hot, hot_tab], stats=stats,
                        short_cap=short_cap, long_cap=long_cap, text=text_dev, n=n, mailbox=mailbox, cold=interleaved, hot=hot)
     if n > 0 and launch:
         extra = 8 if generic_only else 0        # stages bit 3: generic tile kernel only (A/B parity tests)
@@ -217,6 +223,8 @@ def pretok_count_pieces(torch, text_dev, n: int, pieces: list[tuple[int, int, in
 
 
 _SAMPLE_BYTES = 16 << 20
+_HOT_TABLE_SLOTS = int(os.environ.get("YABPE_HOT_TABLE_SLOTS", str(1 << 20)))
+_HOT_TABLE_MIN_FACTOR = 4          # the big table must be at least this many times the hot one (else it is L2-sized itself)
 
 
 def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode, mailbox: Mailbox | None = None):
