@@ -53,7 +53,7 @@ SPECIALS = ["<|endoftext|>"]
 # (dram__bytes_read + dram__bytes_write) / corpus bytes of the pre-tokenise + count kernel from the committed
 # ncu --set full captures (profiles/): the OWT-shaped corpus has 50x the unique pre-tokens, so its count-table traffic
 # is what the kernel moves besides the text itself
-NCU_TRAFFIC_RATIO = {"tinystories": 1.24, "owt": 7.0}
+NCU_TRAFFIC_RATIO = {"tinystories": 1.21, "owt": 4.70}      # profiles/r2_ncu_pretok_warp_metrics.json (1 GB / 2 GB captures)
 NCU_ENCODE_TRAFFIC_PER_TEXT_BYTE = {"count_pass_ms": 4.42, "write_pass_ms": 11.24}
 METRIC = "train_bpe corpus throughput (pretokenize+count+merge loop)"
 ENCODE_METRIC = "GPT-2 encode throughput (pretokenize + BPE by rank + ids in text order)"
@@ -251,7 +251,7 @@ def run_reference(args) -> None:
     ref = reference_module()
     which = "reference" if ref is not None else "port"
     # every step is a bounded sample: the whole run has to end within a few minutes
-    budget = min(30.0, max(4.0, 200.0 / max(args.steps, 1)))
+    budget = min(30.0, max(4.0, 150.0 / max(args.steps, 1)))
     encode = args.workload.startswith("gpt2-encode")
     if encode:
         gv, gm = common.gpt2_vocab_and_merges()
@@ -644,7 +644,7 @@ def main() -> None:
         achieved = n_local / (tile_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_pretok_warp (+ k_pretok_count on the boundary chunks)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": int(n_local * NCU_TRAFFIC_RATIO[kind]), "peak_source": peak_kind,
-                    "traffic_source": "dram bytes per algorithmic byte from the committed ncu --set full capture (profiles/), scaled to this launch",
+                    "traffic_source": "dram__bytes_read + dram__bytes_write per corpus byte from the committed ncu --set full capture (profiles/r2_ncu_pretok_warp_metrics.json), scaled to this launch",
                     "algorithmic_bytes_per_launch": n_local, "ms_per_launch": round(tile_ms, 3)}
 
     # e2e: pinned host bytes -> H2D -> train -> D2H results (every rank uploads its own shard of the corpus)

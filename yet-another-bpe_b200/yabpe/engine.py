@@ -120,6 +120,8 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
         est_s, est_l, cold_hint, hot = estimate_table_sizes(torch, text_dev, n, cuts, specials, mode, mailbox)
         short_cap = short_cap or est_s
         long_cap = long_cap or est_l
+    if os.environ.get("YABPE_SHORT_CAP_LOG2") and n > 4 * _SAMPLE_BYTES:          # experiments only: force the big table's size
+        short_cap = 1 << int(os.environ["YABPE_SHORT_CAP_LOG2"])
     n_cuts = 0 if cuts is None else int(len(cuts))
     cuts_t = torch.from_numpy(np.ascontiguousarray(cuts, dtype=np.int64)).to(dev) if n_cuts and launch else None
     blob, offs = pack_specials(specials)
@@ -128,7 +130,6 @@ def pretok_count(torch, text_dev, n: int, cuts: np.ndarray | None, specials: lis
     rec = torch.zeros(words32, dtype=torch.int32, device=dev) if specials else None
     # small tables (hot, L2-resident): keys and counts apart, probes never queue behind count atomics;
     # large tables (DRAM-resident): 32-byte slots {key, count, -}, one sector per probe + update
-    import os
     layout = os.environ.get("YABPE_SHORT_LAYOUT")              # tests force either layout on small inputs
     interleaved = layout == "interleaved" if layout else cold_hint
     skeys = torch.zeros(short_cap * (4 if interleaved else 2), dtype=torch.int64, device=dev)
