@@ -720,10 +720,14 @@ def main() -> None:
         def gpu_on(sample_bytes: bytes):
             sd, sn = engine.to_device_text(torch, np.frombuffer(sample_bytes, dtype=np.uint8))
             yabpe.BBPETrainer(cfg).train_device(sd, sn)
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            mdl = yabpe.BBPETrainer(cfg).train_device(sd, sn)
-            torch.cuda.synchronize()
-            return (time.perf_counter() - t0) * 1e3, mdl
+            best = None
+            for _ in range(3):                                # best of three: a sub-second run on a shared host is noisy
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                mdl = yabpe.BBPETrainer(cfg).train_device(sd, sn)
+                torch.cuda.synchronize()
+                dt_ms = (time.perf_counter() - t0) * 1e3
+                best = dt_ms if best is None else min(best, dt_ms)
+            return best, mdl
 
         gms, gm = gpu_on(sample)
         same = {"bytes": len(sample), "vocab": vocab, "gpu_ms": round(gms, 2), "cpu_ms": round(dt * 1e3, 1), "cpu_kind": "port",

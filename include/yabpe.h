@@ -242,7 +242,9 @@ typedef struct {
 } yabpe_encode_out;
 
 /* pass 0: per-tile id counts + exclusive scan (total in tile_count[n_tiles]);
- * pass 1: write ids (out_ids must hold tile_count[n_tiles] entries). */
+ * pass 1: write ids (out_ids must hold tile_count[n_tiles] entries);
+ * pass 2: both in ONE pass (decoupled look-back): tile_count has n_tiles + 2 words, ZEROED; out_ids is sized by a guess,
+ *         ids beyond out_cap are dropped and tile_count[n_tiles] (the total) tells the caller to repeat with that size. */
 int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_model* e, const yabpe_word_table* w,
                      const yabpe_encode_out* o, int32_t pass, void* stream);
 int64_t yabpe_num_tiles(int64_t own_lo, int64_t own_hi);

@@ -245,6 +245,145 @@ __global__ void __launch_bounds__(PT_THREADS) k_encode_tiles(PretokParams P, Enc
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// One pass instead of two: per tile, count the ids (probe per token), obtain the tile's base offset from its
+// predecessors (decoupled look-back over a status word per tile), write the ids.  The tile is scanned and staged once; the
+// second probe of a token re-reads a sector this SM touched microseconds ago.  Tiles are handed out by a ticket counter, so
+// the predecessor of every tile is held by a CTA that is already running (no residency assumption, no deadlock).
+//   state[t]            0 = nothing yet, (1 << 62) | ids of tile t (aggregate), (2 << 62) | ids of tiles 0..t (inclusive prefix)
+//   state[n_tiles]      total number of ids (written by the CTA of the last tile)
+//   state[n_tiles + 1]  ticket counter (zeroed by the caller, like the rest)
+// The caller sizes out_ids by a guess; ids beyond out_cap are dropped and the total tells it to repeat with the exact size.
+// ---------------------------------------------------------------------------------------------------------------------
+#define EF_AGG (1ULL << 62)
+#define EF_PREFIX (2ULL << 62)
+#define EF_VALUE(x) ((x) & ((1ULL << 62) - 1))
+
+__global__ void __launch_bounds__(PT_THREADS, 5) k_encode_tiles_fused(PretokParams P, EncodeModel E, EncodeOut O) {
+    __shared__ TileSmem S;
+    __shared__ i64 sh_min; __shared__ u64 sh_acc; __shared__ i64 sh[4];
+    __shared__ int sh_ovf_k; __shared__ i64 sh_ovf_w;
+    __shared__ i64 sh_base, sh_tile[2];
+    init_tile_smem(S);
+    const int tid = threadIdx.x;
+    uint32_t phase[2] = {0, 0};
+    volatile u64* state = (volatile u64*)O.tile_count;
+    const int buf = 0;
+    for (;;) {
+        // A tile is taken only when its predecessor in THIS CTA is finished: holding a ticket while still working on the
+        // previous tile would make every later tile wait for it (the look-back needs the tiles in ticket order).  The tile's
+        // load (8.5 KB) is therefore not overlapped with the previous tile's work: ~1 us of ~60 per tile.
+        if (tid == 0) {
+            sh_tile[0] = (i64)atomicAdd((u64*)&O.tile_count[P.n_tiles + 1], 1ULL);
+            if (sh_tile[0] < P.n_tiles) tile_issue_load(P, S, sh_tile[0], 0);
+        }
+        __syncthreads();
+        const i64 tile = sh_tile[0];
+        if (tile >= P.n_tiles) break;
+        mbar_wait(&S.bar[buf], phase[buf]); phase[buf] ^= 1;
+        bool has_cut;
+        tile_scan(P, S, tile, buf, &has_cut);
+        const uint8_t* txt = S.txt[buf];
+        const i64 g0 = (P.tile_base + tile) * PT_TILE - PT_HL;
+        const int ntok = S.ntok_own, ntot = S.ntok_total;
+        if (tid == 0) { sh_ovf_k = -1; sh_ovf_w = -1; }
+        __syncthreads();
+        if (ntok > 0 && ntok >= ntot) {                   // the last owned token may end beyond the window
+            int k = ntok - 1;
+            i64 gpos = g0 + S.tokpos[k];
+            const int sk = S.tokpos[k];
+            if (gpos >= P.own_lo && gpos < P.own_hi && !(P.n_sp > 0 && ((S.recw[(sk >> 5) + 4] >> (sk & 31)) & 1))) {
+                i64 e = block_find_token_end(P, gpos, &sh_min);
+                u64 h = block_long_hash(P.text, gpos, e - gpos, &sh_acc);
+                int created;
+                i64 slot = block_long_upsert(P.lent, P.lcap, P.text, h, gpos, e - gpos, 0, true, &created, sh);
+                if (tid == 0) { sh_ovf_k = k; sh_ovf_w = slot >= 0 ? P.lent[slot].count : -1; }
+            }
+            __syncthreads();
+        }
+        i64 running = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {            // 0: count, look back; 1: write
+            running = 0;
+            for (int kbase = 0; kbase < ntok; kbase += PT_THREADS) {
+                int k = kbase + tid;
+                int cnt = 0; i64 info = -1; int32_t spid = -1;
+                int s = 0; i64 gpos = 0; bool live = false;
+                if (k < ntok) { s = S.tokpos[k]; gpos = g0 + s; live = gpos >= P.own_lo && gpos < P.own_hi; }
+                if (live) {
+                    if (P.n_sp > 0 && ((S.recw[(s >> 5) + 4] >> (s & 31)) & 1)) {
+                        int sp = special_match(P.text, gpos, logical_end_after(P, gpos));
+                        spid = sp >= 0 ? E.sp_ids[sp] : -1;
+                        cnt = spid >= 0 ? 1 : 0;
+                    } else if (k == sh_ovf_k) {
+                        info = sh_ovf_w;
+                        cnt = info >= 0 ? (int)(info & 0xffffff) : 0;
+                    } else {
+                        int len = (int)S.tokpos[k + 1] - s;
+                        if (len <= PT_SHORT_MAX) {
+                            u64 k0, k1;
+                            pack_short_key(txt, s, len, &k0, &k1);
+                            info = short_find_info(P.st, k0, k1);
+                        } else {
+                            u64 h = 0;
+                            for (int j = 0; j < len; j++) h += long_hash_term(txt[s + j], j);
+                            i64 slot = long_find(P.lent, P.lcap, P.text, long_hash_fix(h), gpos, len);
+                            info = slot >= 0 ? P.lent[slot].count : -1;
+                        }
+                        cnt = info >= 0 ? (int)(info & 0xffffff) : 0;
+                        if (info < 0) P.stats[ST_TABLE_FULL] = 2;
+                    }
+                }
+                int total;
+                int off = block_exclusive_scan(cnt, S.scan_tmp, &total);
+                if (pass == 1 && live) {
+                    i64 dst = sh_base + running + off;
+                    if (has_cut && O.doc_off) {
+                        int lo = 0, hi = P.n_cuts;
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cuts[mid] < gpos) lo = mid + 1; else hi = mid; }
+                        if (lo < P.n_cuts && P.cuts[lo] == gpos) O.doc_off[lo + 1] = dst;
+                    }
+                    if (spid >= 0) { if (dst < O.out_cap) O.out_ids[dst] = spid; }
+                    else if (info >= 0) {
+                        const int32_t* src = O.wsym + (info >> 24);
+                        for (int j = 0; j < cnt; j++) if (dst + j < O.out_cap) O.out_ids[dst + j] = src[j];
+                    }
+                }
+                running += total;
+            }
+            if (pass == 0) {
+                if (tid < 32) {                           // warp 0 looks back 32 predecessors at a time
+                    i64 base = 0;
+                    if (tile > 0) {
+                        if (tid == 0) { state[tile] = EF_AGG | (u64)running; __threadfence(); }
+                        for (i64 j0 = tile - 1;;) {
+                            const i64 j = j0 - tid;
+                            const u64 v = j >= 0 ? state[j] : EF_PREFIX;            // before the first tile: an empty prefix
+                            const unsigned pm = __ballot_sync(0xffffffffu, (v & EF_PREFIX) != 0);
+                            const unsigned zm = __ballot_sync(0xffffffffu, v == 0);
+                            const int p = pm ? __ffs(pm) - 1 : 32;                     // nearest predecessor with an inclusive prefix
+                            const unsigned need = p >= 32 ? 0xffffffffu : ((2u << p) - 1u);
+                            if (zm & need) continue;                                   // somebody up to there has not published yet
+                            i64 part = (need >> tid) & 1u ? (i64)EF_VALUE(v) : 0;
+                            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                            base += part;
+                            if (p < 32) break;
+                            j0 -= 32;
+                        }
+                    }
+                    if (tid == 0) {
+                        state[tile] = EF_PREFIX | (u64)(base + running);
+                        if (tile == P.n_tiles - 1) state[P.n_tiles] = (u64)(base + running);
+                        sh_base = base;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();     // everyone is done with txt[buf], S and sh_tile before they are reused
+    }
+}
+
 // After the unique words are encoded: (1) symbols -> vocabulary ids in place, (2) every table slot gets the lookup
 // record of its word (first id slot << 24 | id count) where the occurrence count used to be (not needed any more), so
 // that the two tile passes go from a token to its ids with ONE probe instead of slot -> word -> length / offset.

@@ -513,7 +513,10 @@ extern "C" int yabpe_encode_ids(const yabpe_pretok_args* a, const yabpe_encode_m
     }
     int grid = num_sms() * per_sm[pass != 0];
     if ((i64)grid > P.n_tiles) grid = (int)P.n_tiles;
-    if (pass == 0) {
+    if (pass == 2) {                         // one pass: counts, chained scan and ids (tile_count: n_tiles + 2 words, zeroed)
+        ARG_CHECK(o->out_ids || o->out_cap == 0);
+        k_encode_tiles_fused<<<grid, PT_THREADS, 0, st>>>(P, E, O); LAUNCHED();
+    } else if (pass == 0) {
         k_encode_tiles<false><<<grid, PT_THREADS, 0, st>>>(P, E, O); LAUNCHED();
         k_scan_tiles<<<1, 1024, 0, st>>>((i64*)o->tile_count, P.n_tiles); LAUNCHED();
     } else {

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 from collections.abc import Iterable, Iterator, Sequence
 from pathlib import Path
 
@@ -18,6 +19,7 @@ from . import _ffi, engine
 
 _ITER_BATCH_BYTES = 4 << 20
 _ITER_BATCH_ITEMS = 1 << 16
+_FUSED_IDS = os.environ.get("YABPE_ENCODE_FUSED", "1") != "0"      # ids in one pass over the text (chained scan) instead of count + write
 _SMALL_MAX_BYTES = 1 << 15        # encode(str) up to this many bytes runs as one launch (yabpe_encode_small)
 _DECODE_DEVICE_MIN = 1 << 16       # ids; shorter lists are gathered on the host
 _DECODE_DEVICE_MAX_ID = 1 << 24    # offsets are a dense array over the id range
@@ -141,33 +143,60 @@ class BBPETokenizer:
         mark()
         lo, hi = own if own is not None else (0, n)
         n_tiles = int(L.yabpe_num_tiles(lo, hi))
-        tile_count = torch.zeros(n_tiles + 1, dtype=torch.int64, device="cuda")
+        tile_count = torch.zeros(n_tiles + 2, dtype=torch.int64, device="cuda")
         n_cuts = 0 if cuts is None else len(cuts)
         doc_off = torch.full((n_cuts + 2,), -1, dtype=torch.int64, device="cuda") if n_cuts else None
         o = _ffi.EncodeOut()
         o.tile_count = tile_count.data_ptr(); o.out_ids = None; o.out_cap = 0
         o.doc_off = doc_off.data_ptr() if n_cuts else None
-        _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 0, stream))
-        mark()
-        if reuse_output:
-            buf = getattr(self, "_ids_buf", None)
-            want = n // 2 + 4096
+
+        def read_total() -> int:
+            return int(mailbox.read(tile_count[n_tiles:], 1)[0]) if mailbox is not None else int(tile_count[n_tiles].item())
+
+        if _FUSED_IDS:
+            # ONE pass over the text (counts, chained scan, ids): the id buffer is sized by a guess -- ids per byte of the last
+            # call, else 0.6 -- and the pass is repeated with the exact size in the rare case the guess was short
+            mark()                                                # (no separate count pass: its stage time reads 0)
+            buf = getattr(self, "_ids_buf", None) if reuse_output else None
+            want = int(n * getattr(self, "_ids_per_byte", 0.6) * 1.05) + 4096
             if buf is None or buf.numel() < want:
                 buf = torch.empty(want, dtype=torch.int32, device="cuda")
-            while True:                                   # writes beyond out_cap are dropped by the kernel
+            while True:
                 o.out_ids = buf.data_ptr(); o.out_cap = buf.numel()
-                _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
-                total = int(tile_count[n_tiles].item())
+                _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 2, stream))
+                total = read_total()
                 if total <= buf.numel():
                     break
-                buf = torch.empty(total + total // 8, dtype=torch.int32, device="cuda")
-            self._ids_buf = buf
+                buf = torch.empty(total + total // 16 + 4096, dtype=torch.int32, device="cuda")
+                tile_count.zero_()
+                if doc_off is not None:
+                    doc_off.fill_(-1)
+            self._ids_per_byte = max(total / max(n, 1), 0.05)
+            if reuse_output:
+                self._ids_buf = buf
             ids = buf
         else:
-            total = int(mailbox.read(tile_count[n_tiles:], 1)[0]) if mailbox is not None else int(tile_count[n_tiles].item())
-            ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
-            o.out_ids = ids.data_ptr(); o.out_cap = total
-            _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
+            _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 0, stream))
+            mark()
+            if reuse_output:
+                buf = getattr(self, "_ids_buf", None)
+                want = n // 2 + 4096
+                if buf is None or buf.numel() < want:
+                    buf = torch.empty(want, dtype=torch.int32, device="cuda")
+                while True:                                   # writes beyond out_cap are dropped by the kernel
+                    o.out_ids = buf.data_ptr(); o.out_cap = buf.numel()
+                    _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
+                    total = int(tile_count[n_tiles].item())
+                    if total <= buf.numel():
+                        break
+                    buf = torch.empty(total + total // 8, dtype=torch.int32, device="cuda")
+                self._ids_buf = buf
+                ids = buf
+            else:
+                total = read_total()
+                ids = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+                o.out_ids = ids.data_ptr(); o.out_cap = total
+                _ffi.check(L.yabpe_encode_ids(C.byref(res.args), C.byref(e), C.byref(words.table), C.byref(o), 1, stream))
         mark()
         self.last_launches = _ffi.launch_count() - launches0
         if prof:
