@@ -1085,6 +1085,16 @@ __device__ __forceinline__ i64 warp_max_i64(i64 v) {
     return (i64)(((u64)mhi << 32) | mlo);
 }
 
+// block-wide maximum of a 64-bit value, the same result in every thread (two block barriers; sh: one word per warp)
+__device__ __forceinline__ u64 block_max_u64(u64 v, u64* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const u64 wm = warp_max_u64(v);
+    __syncthreads();                       // sh may still be read from the previous use
+    if (lane == 0) sh[warp] = wm;
+    __syncthreads();
+    return warp_max_u64(lane < nwarps ? sh[lane] : 0ULL);
+}
+
 // Leader loop.  Per merge (every stage is bounded by dependent L2 round trips, not by bandwidth):
 //   A  argmax over the top list: counts mirrored in shared memory, warp max -> shared atomicMax -> candidates
 //   B  candidate ranges (thread 0) and merged-token lookup (thread 32), side by side
@@ -1239,9 +1249,29 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
                 best = t;
                 }
             } else {
+                // More than 32 pairs share the maximum (the tie regime: up to the whole list).  Byte-wise comparisons across the
+                // block cost thousands of cycles; the cached prefixes decide almost every time: the greatest LEFT prefix, then --
+                // if every survivor has the same left token -- the greatest RIGHT prefix.  Only what is still tied goes through
+                // the byte-wise reduction.
                 __syncthreads();
-                best = block_best(M, (mine.slot >= 0 && mine.cnt == mx) ? mine : Best{0, -1, 0, 0, 0}, sh_best);
-                if (best.slot >= 0) best.pad = mirror_find(&C.LM, best.slot);      // block_best does not carry the list index
+                bool alive = mine.slot >= 0 && mine.cnt == mx;
+                const u64 mpa = block_max_u64(alive ? C.tpa[threadIdx.x] : 0ULL, (u64*)sh_wmax);
+                alive = alive && C.tpa[threadIdx.x] == mpa;
+                const uint32_t amax = (uint32_t)block_max_u64(alive ? (u64)(uint32_t)mine.a : 0ULL, (u64*)sh_wmax);
+                const uint32_t namin = (uint32_t)block_max_u64(alive ? (u64)(0xffffffffu - (uint32_t)mine.a) : 0ULL, (u64*)sh_wmax);
+                if (amax == 0xffffffffu - namin) {            // one left token: the right one decides
+                    const u64 mpb = block_max_u64(alive ? C.tpb[threadIdx.x] : 0ULL, (u64*)sh_wmax);
+                    alive = alive && C.tpb[threadIdx.x] == mpb;
+                }
+                const int left = __syncthreads_count(alive);
+                if (left == 1) {
+                    if (alive) sh_cand[0] = mine;
+                    __syncthreads();
+                    best = sh_cand[0];
+                } else {
+                    best = block_best(M, alive ? mine : Best{0, -1, 0, 0, 0}, sh_best);
+                    if (best.slot >= 0) best.pad = mirror_find(&C.LM, best.slot);      // block_best does not carry the list index
+                }
             }
         }
         if (best.slot < 0 || best.cnt < T2 || (best.cnt == T2 && best.pad >= 0 && C.tpa[best.pad] < T2pa)) { reason = LR_TOP; break; }
