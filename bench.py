@@ -763,7 +763,8 @@ def main() -> None:
                        "the ceiling of the step's 1 -> N speed-up is step / serial",
                        "max_speedup": round(ms_step / serial_ms, 3) if serial_ms else None},
             "leader_cycles[argmax,ranges,claim+commit,rewrite,close,sum_act,sum_items,sum_words]": timings[-1].get("leader_cycles") if timings else None,
-            "merge_phase_ms": ({k: (round(v / (ph["total"] or 1) * merge_ms, 2) if k not in ("n_top_rebuilds",) else v) for k, v in ph.items()}
+            "merge_phase_ms": ({k: ((round(v / (ph["total"] or 1) * merge_ms, 2) if k != "n_top_rebuilds" else v) if not isinstance(v, list)
+                                    else ([round(x / (ph["total"] or 1) * merge_ms, 2) for x in v] if "cycles" in k else v)) for k, v in ph.items()}
                                if (ph := (timings[-1].get("merge_phase_cycles") if timings else None)) and merge_ms else None),
             "merge_loop": {"index_rebuilds": stats.index_rebuilds, "threshold_rebuilds": stats.threshold_rebuilds,
                            "pairs_created": stats.n_pairs, "leader_mode_merges": stats.leader_merges,

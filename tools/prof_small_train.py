@@ -24,5 +24,5 @@ for nb in sizes:
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     ph = tr.timing["merge_phase_cycles"]; tot = ph["total"] or 1; ms = tr.timing["merge_loop_ms"]
     print(nb, "bytes:", f"{dt * 1e3:.1f} ms wall, merge loop {ms:.1f} ms,", len(m.merges), "merges,",
-          {k: (round(v / tot * ms, 2) if k != "n_top_rebuilds" else v) for k, v in ph.items()},
+          {k: (round(v / tot * ms, 2) if k != "n_top_rebuilds" else v) for k, v in ph.items() if not isinstance(v, list)},
           "leader", tr.last_stats.leader_merges, "grid", tr.last_stats.grid_merges, flush=True)

@@ -91,6 +91,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define MS_CLK_GRID 45       // grid-mode merges
 #define MS_CLK_TOTAL 46
 #define MS_N_TOPREB 47
+#define MS_GRID_CLS 48        // grid merges by candidate-word count: [48..50] merges, [51..53] cycles; classes <= 2 368 (8-lane groups...), <= 18 944, more
 #define ML_PHASE(slot, t0) do { if (gtid == 0) { const long long _t = clock64(); M.state[slot] += _t - (t0); (t0) = _t; } } while (0)          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
 #define MS_STATE_WORDS 64
 
@@ -1704,7 +1705,11 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             close_merge(M, m, c);
             if (T2 < 0) { if (best.cnt != tie_cnt || tie_left <= 1) M.state[MS_T2] = 0; else M.state[MS_TIE_LEFT] = tie_left - 1; }
         }
-        if (gtid == 0) M.state[MS_GRID_MERGES]++;
+        if (gtid == 0) {
+            M.state[MS_GRID_MERGES]++;
+            const int cls = R.total * 64 <= gstride ? 0 : (R.total * 8 <= gstride ? 1 : 2);
+            M.state[MS_GRID_CLS + cls]++; M.state[MS_GRID_CLS + 3 + cls] += clock64() - pclk;
+        }
         ML_PHASE(MS_CLK_GRID, pclk);
         __syncthreads();
     }

@@ -99,7 +99,10 @@ def device_chunk_cuts(text_dev, n: int, chunk_size: int) -> list[int]:
 def _phase_cycles(state) -> dict:
     """Phase clocks of the merge kernel (cycles of CTA 0's SM; include/yabpe.h MS_CLK_*)."""
     names = ["pair_histogram", "first_index_and_active_set", "top_list_rebuilds", "index_rebuilds", "leader_sessions", "grid_merges", "total", "n_top_rebuilds"]
-    return {k: int(state[40 + i]) for i, k in enumerate(names)}
+    out = {k: int(state[40 + i]) for i, k in enumerate(names)}
+    out["grid_merges_by_size[n<=2368,n<=18944,more]"] = [int(x) for x in state[48:51]]
+    out["grid_cycles_by_size"] = [int(x) for x in state[51:54]]
+    return out
 
 
 @dataclass
