@@ -768,6 +768,7 @@ def main() -> None:
                                if (ph := (timings[-1].get("merge_phase_cycles") if timings else None)) and merge_ms else None),
             "merge_loop": {"index_rebuilds": stats.index_rebuilds, "threshold_rebuilds": stats.threshold_rebuilds,
                            "pairs_created": stats.n_pairs, "leader_mode_merges": stats.leader_merges,
+                           "leader_iterations": stats.leader_iterations, "batched_merges": stats.batched_merges,
                            "grid_mode_merges": stats.grid_merges},
             "encode": encode, "sharded_parity": sharded_parity,
             "roofline": roofline, "cpu_baseline": cpu, "same_sample": same, "reference_sample": ref_same, "e2e": e2e,

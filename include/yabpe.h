@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YABPE_ABI_VERSION 5
+#define YABPE_ABI_VERSION 6
 
 #define YABPE_OK 0
 #define YABPE_ERR_CUDA (-1)
@@ -210,6 +210,8 @@ typedef struct {
     int64_t helper_min_syms;    /* leader mode: idle CTAs prefetch the next merges' words into the L2 when n_syms exceeds this
                                  * (0 = default, 8 Mi slots: smaller word arrays stay L2-resident anyway; < 0 = always).  Result-neutral */
     int64_t helper_mode;        /* 0 = no helpers, 1 = CTAs 1..2, 2 = the CTAs on the SMs next to the leader's                      */
+    int64_t batch_max;          /* merges taken per iteration when they provably do not interact (csrc/merge.cuh, "batched merges"):
+                                 * 0 = default (8), 1 = strictly one by one as trainer.py:241-300.  Result-neutral                   */
 } yabpe_merge_args;
 
 int yabpe_merge_loop(const yabpe_merge_args* m, void* stream);

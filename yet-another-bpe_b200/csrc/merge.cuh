@@ -17,8 +17,8 @@
 #ifndef ML_THREADS
 #define ML_THREADS 1024
 #endif
-#ifndef ML_BATCH_STATS
-#define ML_BATCH_STATS 0
+#ifndef ML_BATCH_WHY
+#define ML_BATCH_WHY 0        // 1: state[56..62] count why batches end (no more entries, tie, <= T2, < T, touch; list space, product token)
 #endif
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
@@ -93,6 +93,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define MS_N_TOPREB 47
 #define MS_GRID_CLS 48        // grid merges by candidate-word count: [48..50] merges, [51..53] cycles; classes <= 2 368 (8-lane groups...), <= 18 944, more
 #define ML_PHASE(slot, t0) do { if (gtid == 0) { const long long _t = clock64(); M.state[slot] += _t - (t0); (t0) = _t; } } while (0)          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
+#define MS_LEADER_ITERS 54    // leader iterations (an iteration merges a batch of 1 .. ML_BATCH_MAX pairs)
+#define MS_LEADER_BATCHED 55  // merges done as members of a batch of two or more
 #define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
@@ -250,6 +252,7 @@ struct MergeParams {
     i64 rebuild_every;                           // merges between index rebuilds (0: only when the affected-word log is full)
     i64 helper_min_syms;                         // prefetch helpers run when the word arrays have more symbol slots than this
     i64 helper_mode;                             // 0 off, 1 CTAs 1..ML_HELPERS, 2 the CTAs on the SMs next to the leader's (smid ^ 1, ^ 2)
+    i64 batch_max;                               // merges per leader iteration: 0 = ML_BATCH_MAX, 1 = the reference's one-by-one loop
 };
 
 // Grid-wide barrier on two words of the state array (arrival counter + generation).  The kernel is
@@ -657,8 +660,11 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
         }
     }
 }
-__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, i64 off, LeaderCtx* lc) {
-    const i64 d = lc ? (i64)atomicAdd(&lc->alog_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL);
+// seg_ctr != nullptr: batched merges -- every member of a batch owns a reserved segment [seg_base, seg_base + its candidate count)
+// of the log (the words one merge rewrites must stay contiguous), filled through the member's own counter.
+__device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, i64 off, LeaderCtx* lc, int* seg_ctr = nullptr, i64 seg_base = 0) {
+    const i64 d = seg_ctr ? seg_base + (i64)atomicAdd(seg_ctr, 1)
+                          : (lc ? (i64)atomicAdd(&lc->alog_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL));
     if (d < M.alog_cap) M.alog_word[d] = POST_PACK(w, off);
     else atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_INTERNAL);     // callers reserve space up front
 }
@@ -667,7 +673,8 @@ __device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, i64
 // `cur` = table slot of the pair being merged.  Every site would decrement that ONE counter (thousands of atomics on a single
 // address in a heavy merge: they serialise in the L2); the merge removes every occurrence of the pair (trainer.py:268-285:
 // its count ends at 0 and the key is deleted), so nobody decrements it and its count is stored as 0 once per merge.
-__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew, int32_t cur) {
+__device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew, int32_t cur,
+                                    int* seg_ctr = nullptr, i64 seg_base = 0) {
     const i64 off = M.woff[w];
     int32_t* s = M.wsym + off;
     int32_t* ws = M.wslot + off;
@@ -692,7 +699,7 @@ __device__ void rewrite_word_thread(const MergeParams& M, int32_t w, int32_t a, 
             s[o++] = x; prev_new = x; prev_changed = false; j += 1;
         }
     }
-    if (any) { M.wlen[w] = o; alog_append(M, w, off, lm); }
+    if (any) { M.wlen[w] = o; alog_append(M, w, off, lm, seg_ctr, seg_base); }
 }
 
 // one warp rewrites one word (a != b): every lane owns one old position per 32-symbol chunk, so the
@@ -754,9 +761,11 @@ __device__ void rewrite_word_warp(const MergeParams& M, int32_t w, int32_t a, in
 // 32 / G words per warp, one per G-lane group (G = 8: words are ~6 symbols on average; G = 4: twice as many candidates per
 // pass once the words have shrunk).  Group-local version of rewrite_word_warp; w < 0 marks an idle group.  All 32 lanes
 // must call it together.
+// Returns the word's length after the rewrite (group-uniform; n itself when nothing changed).
 template <int G>
-__device__ void rewrite_words_g(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
-                                 int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew) {
+__device__ int rewrite_words_g(const MergeParams& M, int32_t w, i64 off, int n, i64 f,
+                                int32_t a, int32_t b, int32_t c, i64 T, i64 T2, LeaderCtx* lm, bool xnew,
+                                int* seg_ctr = nullptr, i64 seg_base = 0) {
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), gshift = lane & ~(G - 1);
     constexpr unsigned GM = (1u << G) - 1u;
     int32_t* s = M.wsym + (w >= 0 ? off : 0);
@@ -815,7 +824,8 @@ __device__ void rewrite_words_g(const MergeParams& M, int32_t w, i64 off, int n,
         out += __popc(keepmask);
         __syncwarp();
     }
-    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w, off, lm); }
+    if (any && gl == 0) { M.wlen[w] = out; alog_append(M, w, off, lm, seg_ctr, seg_base); }
+    return any ? out : n;
 }
 
 // candidate ranges for pair (a, b) at slot: CSR postings + affected-log segments of the merges that
@@ -995,42 +1005,49 @@ __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh
 
 
 // ---- batch selection -------------------------------------------------------------------------------
-// The ML_BATCH_MAX + 1 largest entries of the top list in strictly descending (count, then list index) order.
-// key = count << 9 | (511 - index); 0 = none.  Phase 1: every warp extracts the five largest keys of its 32
-// lanes (redux.sync); phase 2 (after ONE block barrier): every warp redundantly extracts the five largest of
-// the per-warp lists, so all warps hold the same result without a second barrier.
-#define ML_BATCH_MAX 4
+// The ML_SEL = ML_BATCH_MAX + 1 largest entries of the top list in strictly descending (count, then list index) order.
+// key = count << 9 | (511 - index); 0 = none.  Phase 1: every warp that holds list entries extracts the ML_SEL largest keys
+// of its 32 lanes (redux.sync); phase 2 (after ONE block barrier): every warp redundantly extracts the ML_SEL largest of the
+// per-warp lists, so all warps hold the same result without a second barrier.  Returned per lane: lane r gets the r-th key.
+#ifndef ML_BATCH_MAX
+#define ML_BATCH_MAX 8
+#endif
 #define ML_SEL (ML_BATCH_MAX + 1)
+#define ML_SEL_WARPS (ML_TOP_N / 32)
 __device__ __forceinline__ u64 warp_max_u64(u64 v) {
     const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
     const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
     const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
     return ((u64)mhi << 32) | mlo;
 }
-__device__ __forceinline__ void select_top(u64 key, u64* sh_keys /* [32][ML_SEL] */, u64* out /* [ML_SEL] */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    u64 k = key;
+__device__ __forceinline__ u64 select_top(u64 key, u64* sh_keys /* [ML_SEL_WARPS][ML_SEL] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < ML_SEL_WARPS) {
+        u64 k = key;
 #pragma unroll
-    for (int r = 0; r < ML_SEL; r++) {
-        const u64 m = warp_max_u64(k);
-        if (k == m) k = 0;                        // keys are unique (the index is part of the key)
-        if (lane == r) sh_keys[warp * ML_SEL + r] = m;
+        for (int r = 0; r < ML_SEL; r++) {
+            const u64 m = warp_max_u64(k);
+            if (k == m) k = 0;                        // keys are unique (the index is part of the key)
+            if (lane == r) sh_keys[warp * ML_SEL + r] = m;
+        }
     }
     __syncthreads();
-    // nwarps * ML_SEL <= 160 keys: five per lane
-    u64 v[ML_SEL];
+    constexpr int NV = (ML_SEL_WARPS * ML_SEL + 31) / 32;
+    u64 v[NV];
 #pragma unroll
-    for (int u = 0; u < ML_SEL; u++) { const int i = lane + 32 * u; v[u] = i < nwarps * ML_SEL ? sh_keys[i] : 0; }
+    for (int u = 0; u < NV; u++) { const int i = lane + 32 * u; v[u] = i < ML_SEL_WARPS * ML_SEL ? sh_keys[i] : 0; }
+    u64 mine = 0;
 #pragma unroll
     for (int r = 0; r < ML_SEL; r++) {
         u64 lm = v[0];
 #pragma unroll
-        for (int u = 1; u < ML_SEL; u++) lm = v[u] > lm ? v[u] : lm;
+        for (int u = 1; u < NV; u++) lm = v[u] > lm ? v[u] : lm;
         const u64 m = warp_max_u64(lm);
-        out[r] = m;
+        if (lane == r) mine = m;
 #pragma unroll
-        for (int u = 0; u < ML_SEL; u++) if (v[u] == m) v[u] = 0;
+        for (int u = 0; u < NV; u++) if (v[u] == m) v[u] = 0;
     }
+    return mine;
 }
 
 // Stage C of the leader: every G-lane group of the first nwarps-1 warps takes candidates it0, it0 + ngroups, ...
@@ -1039,7 +1056,7 @@ __device__ __forceinline__ void select_top(u64 key, u64* sh_keys /* [32][ML_SEL]
 // do not fit the L2: every round trip is a DRAM access).
 template <int G>
 __device__ __forceinline__ void leader_rewrite(const MergeParams& M, LeaderCtx& C, const Ranges& R, int warp, int lane, int nwarps,
-                                               int32_t a, int32_t b, int32_t c, i64 T, i64 T2, bool is_new) {
+                                               int32_t a, int32_t b, int32_t c, i64 T, i64 T2, bool is_new, int32_t cur) {
     constexpr int GPW = 32 / G;                      // groups per warp
     const int ngroups = (nwarps - 1) * GPW, gl = lane & (G - 1), lead = lane & ~(G - 1);
     const int total = (int)R.total;
@@ -1073,7 +1090,7 @@ __device__ __forceinline__ void leader_rewrite(const MergeParams& M, LeaderCtx& 
             n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx];
         }
         if (a != b) rewrite_words_g<G>(M, w_cur, (i64)off_cur, n_cur, f_cur, a, b, c, T, T2, &C, is_new);
-        else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new, C.cur_slot);
+        else if (w_cur >= 0 && gl == 0) rewrite_word_thread(M, w_cur, a, b, c, T, T2, &C, is_new, cur);
         w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; w_nx = POST_WORD(e_nx2); o_nx = POST_OFF(e_nx2);
     }
 }
@@ -1096,22 +1113,257 @@ __device__ __forceinline__ u64 block_max_u64(u64 v, u64* sh) {
     return warp_max_u64(lane < nwarps ? sh[lane] : 0ULL);
 }
 
-// Leader loop.  Per merge (every stage is bounded by dependent L2 round trips, not by bandwidth):
-//   A  argmax over the top list: counts mirrored in shared memory, warp max -> shared atomicMax -> candidates
-//   B  candidate ranges (thread 0) and merged-token lookup (thread 32), side by side
-//   C  the last warp records the merge / creates the token while every other 8-lane group takes ONE candidate
+// ---- stage A of the leader, one merge: best entry of the whole top list --------------------------------------------------
+// `mine` = this thread's entry (pad = list index).  Max count first (redux), ties decided by the cached 8-byte prefixes of the
+// tokens and, where those are equal, by the bytes.  Block-wide: every thread returns the same entry.
+__device__ Best leader_argmax_one(const MergeParams& M, LeaderCtx& C, const Best& mine, i64* sh_wmax, int* sh_ncand, Best* sh_cand, Best* sh_best) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    {
+        const i64 wm = warp_max_i64(mine.cnt);
+        if (lane == 0) sh_wmax[warp] = wm;
+    }
+    __syncthreads();
+    const i64 mx = warp_max_i64(lane < nwarps ? sh_wmax[lane] : 0);
+    if (mine.slot >= 0 && mine.cnt == mx) { const int ci = atomicAdd(sh_ncand, 1); if (ci < 32) sh_cand[ci] = mine; }
+    __syncthreads();
+    Best best{0, -1, 0, 0, 0};
+    const int ncand = *sh_ncand;
+    if (mx <= 0) return best;
+    if (ncand == 1) return sh_cand[0];
+    if (ncand <= 32) {                          // ties: byte-wise comparison, every warp redundantly (no barrier)
+        Best t = lane < ncand ? sh_cand[lane] : Best{0, -1, 0, 0, 0};
+        // fast path: lexicographic maximum of (prefix of a, prefix of b) with four redux.sync rounds.  Different
+        // prefixes order the tokens; equal prefixes decide only when the tokens themselves are equal.
+        {
+            bool alive = lane < ncand;
+            const u64 pa = alive ? C.tpa[t.pad] : 0ULL, pb = alive ? C.tpb[t.pad] : 0ULL;
+            uint32_t wv = (uint32_t)(pa >> 32), mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+            wv = (uint32_t)pa; mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+            const uint32_t amax = __reduce_max_sync(0xffffffffu, alive ? (uint32_t)t.a : 0u);
+            const uint32_t amin = __reduce_min_sync(0xffffffffu, alive ? (uint32_t)t.a : 0xffffffffu);
+            if (amax == amin) {                                  // every survivor has the SAME left token: the right one decides
+                wv = (uint32_t)(pb >> 32); mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+                wv = (uint32_t)pb; mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
+                const uint32_t am = __ballot_sync(0xffffffffu, alive);
+                if (__popc(am) == 1) return shfl_best_from(t, __ffs(am) - 1);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            Best u = shfl_best(t, o);
+            u.pad = __shfl_xor_sync(0xffffffffu, t.pad, o);
+            bool gt = false;                                      // equal counts: (left bytes, right bytes)
+            if (u.slot >= 0 && t.slot < 0) gt = true;
+            else if (u.slot >= 0 && u.slot != t.slot) {
+                int r = tok_cmp_pre(M, u.a, C.tpa[u.pad], t.a, C.tpa[t.pad]);
+                if (r == 0) r = tok_cmp_pre(M, u.b, C.tpb[u.pad], t.b, C.tpb[t.pad]);
+                gt = r > 0;
+            }
+            if (gt) t = u;
+        }
+        return t;
+    }
+    // More than 32 pairs share the maximum (the tie regime: up to the whole list).  Byte-wise comparisons across the
+    // block cost thousands of cycles; the cached prefixes decide almost every time: the greatest LEFT prefix, then --
+    // if every survivor has the same left token -- the greatest RIGHT prefix.  Only what is still tied goes through
+    // the byte-wise reduction.
+    __syncthreads();
+    bool alive = mine.slot >= 0 && mine.cnt == mx;
+    const u64 mpa = block_max_u64(alive ? C.tpa[threadIdx.x] : 0ULL, (u64*)sh_wmax);
+    alive = alive && C.tpa[threadIdx.x] == mpa;
+    const uint32_t amax = (uint32_t)block_max_u64(alive ? (u64)(uint32_t)mine.a : 0ULL, (u64*)sh_wmax);
+    const uint32_t namin = (uint32_t)block_max_u64(alive ? (u64)(0xffffffffu - (uint32_t)mine.a) : 0ULL, (u64*)sh_wmax);
+    if (amax == 0xffffffffu - namin) {            // one left token: the right one decides
+        const u64 mpb = block_max_u64(alive ? C.tpb[threadIdx.x] : 0ULL, (u64*)sh_wmax);
+        alive = alive && C.tpb[threadIdx.x] == mpb;
+    }
+    const int left = __syncthreads_count(alive);
+    if (left == 1) {
+        if (alive) sh_cand[0] = mine;
+        __syncthreads();
+        return sh_cand[0];
+    }
+    best = block_best(M, alive ? mine : Best{0, -1, 0, 0, 0}, sh_best);
+    if (best.slot >= 0) best.pad = mirror_find(&C.LM, best.slot);      // block_best does not carry the list index
+    return best;
+}
+
+// The head of the top list: theta such that between 12 and 32 entries have a count >= theta, found with a 32-bin histogram of
+// the counts in [lo, max] that zooms into the bin that did not fit (counts repeat: a single count can hold more entries than
+// fit, then fewer than 12 -- possibly none -- are taken and *sticky tells the caller not to ask again until the head is empty).
+// Block-wide, every thread returns the same value; ends with a barrier.
+__device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int* hist /* [33] */, bool* sticky) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    {
+        const i64 wm = warp_max_i64(mine.slot >= 0 ? mine.cnt : 0);
+        __syncthreads();
+        if (lane == 0) sh_wmax[warp] = wm;
+    }
+    __syncthreads();
+    i64 hi = warp_max_i64(lane < nwarps ? sh_wmax[lane] : 0) + 1;          // no entry has a count >= hi
+    int above = 0;
+    i64 theta = lo;
+    if (hi <= lo) { *sticky = true; __syncthreads(); return lo; }           // nothing above lo at all
+    for (int round = 0; round < 64; round++) {
+        if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const i64 width = (hi - lo + 31) / 32;
+        if (mine.slot >= 0 && mine.cnt >= lo && mine.cnt < hi) atomicAdd(&hist[(int)((mine.cnt - lo) / width)], 1);
+        __syncthreads();
+        int cum = above, b = 31;
+        for (; b >= 0; b--) { const int h = hist[b]; if (cum + h > 32) break; cum += h; }
+        theta = lo + (i64)(b + 1) * width;
+        __syncthreads();                                                   // everybody has read the histogram
+        if (b < 0) { theta = lo; above = cum; break; }
+        if (cum >= 12 || width == 1) { above = cum; break; }
+        above = cum; hi = theta; lo = lo + (i64)b * width;
+    }
+    *sticky = above < 4;
+    return theta;
+}
+
+// ---- batched leader merges ------------------------------------------------------------------------------------------
+// The reference merges ONE pair per iteration (trainer.py:241-300).  Most consecutive merges do not interact, and the
+// leader's cost per iteration is a chain of dependent round trips that does not depend on how much it rewrites -- so the
+// leader takes the k best pairs p_1 .. p_k of the top list in ONE iteration whenever it can PROVE that the sequential loop
+// would pick exactly these, in this order, with exactly the same state after the k-th:
+//   (1) counts strictly descending, c_1 > c_2 > ... > c_k > (count of every other pair), and c_k > T2: all pairs with a
+//       count >= c_k are on the top list (it is complete above T2), and they are p_1 .. p_k;
+//   (2) no member "touches" an earlier one: merging (a_i, b_i) only decrements pairs (x, a_i) and (b_i, y) and only creates
+//       pairs that contain the new token, so for i < j:  b_j != a_i and a_j != b_i  keep c_j unchanged; every pair created
+//       by the batch is bounded by the count of an OLD pair (x, a_i) or (b_i, y) != p_i, which is not a member (2) and
+//       therefore < c_k (1): nothing new can overtake a member.  (a_i == b_i breaks that bound -- "aaaa" makes (aa, aa)
+//       out of (a, a) itself -- so such a pair is only taken as the LAST member.)
+//   (3) the merged bytes of a member are a NEW token (trainer.py:296-300 gives no new id otherwise, and pairs with an
+//       existing token can GAIN above c_k): a member whose bytes exist already is the last one; two members with the
+//       same merged bytes never share a batch.
+// Old pairs only lose during a batch, so the bounds hold throughout.  Words are rewritten word by word: whoever claims a
+// candidate word applies members 1 .. k to it in order -- the state of a word depends on nothing but the word, and the
+// pair counts are sums over words, so the result is the sequential one bit for bit.  Ties at the top (c_1 == c_2), the
+// tie regime (T2pa != 0) and single heavy merges take the one-merge path below.
+struct BatchCtx {
+    Ranges R[ML_BATCH_MAX];
+    MergedInfo MI[ML_BATCH_MAX];
+    int32_t c[ML_BATCH_MAX];
+    int seg_n[ML_BATCH_MAX];                    // words each member rewrote (its segment of the affected-word log)
+    u64 S[32]; int nS;                          // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
+    int hist[33];
+    struct { int32_t a, b, slot, idx; i64 cnt; } mem[ML_BATCH_MAX];
+    int nb;
+};
+
+// ONE lane records one member of a batch and creates its token (members commit side by side in the lanes of one warp)
+__device__ void commit_member(const MergeParams& M, LeaderCtx& C, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 seg_base,
+                              const MergedInfo& MI, i64 oc, bool publish) {
+    M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c;
+    M.seg_start[m] = (int32_t)seg_base;
+    M.merge_next[m] = is_new ? -1 : M.tok_first[c];
+    if (!is_new) return;
+    if (oc + MI.la + MI.lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
+        atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL); C.error = 1;
+        return;
+    }
+    for (i64 k = 0; k < MI.la; k++) M.tok_bytes[oc + k] = M.tok_bytes[MI.oa + k];
+    for (i64 k = 0; k < MI.lb; k++) M.tok_bytes[oc + MI.la + k] = M.tok_bytes[MI.ob + k];
+    M.tok_off[c + 1] = oc + MI.la + MI.lb;
+    M.tok_hash[c] = MI.H; M.tok_pow[c] = MI.P;
+    M.tok_pre[c] = tok_prefix_concat(M.tok_pre[a], MI.la, M.tok_pre[b]);
+    M.tok_first[c] = -1; M.tok_head[c].x = -1;
+    // two members may have found the same free slot of the token set: claim it, move on when it is taken
+    const u64 mask = (u64)M.tset_cap - 1, val = (MI.H & 0xffffffff00000000ULL) | (u64)(uint32_t)(c + 1);
+    u64 slot = (u64)MI.tslot;
+    while (atomicCAS(&M.tset[slot], 0ULL, val) != 0ULL) slot = (slot + 1) & mask;
+    if (publish) { M.state[MS_NTOK] = c + 1; M.state[MS_POOL_USED] = oc + MI.la + MI.lb; }
+}
+
+// Stage C of a batch.  Lane l of every warp holds member l (pair, product token, candidate count, first item, log segment).
+// The items of all members are laid end to end (every member starts at a multiple of the groups per warp, so the groups of a
+// warp mostly work on the same member); a G-lane group claims its candidate word for the whole batch, finds out which
+// members have a site in it (one pass over its symbols) and applies those, in order.  Software pipeline over the passes of a
+// group as in leader_rewrite: the item of pass p+2 and the word header of pass p+1 are loaded while pass p is rewritten.
+template <int G>
+__device__ __forceinline__ void leader_rewrite_batch(const MergeParams& M, LeaderCtx& C, BatchCtx& BC, int kk, int warp, int lane, int nwarps,
+                                                     int32_t ma, int32_t mb, int32_t mc, int32_t mslot, int mnew, int mtot, int mpst, int mseg,
+                                                     i64 T, i64 T2) {
+    constexpr int GPW = 32 / G;
+    const int ngroups = (nwarps - 1) * GPW, gl = lane & (G - 1), lead = lane & ~(G - 1);
+    const int total_p = __shfl_sync(0xffffffffu, mpst + mtot, kk - 1);
+    const u64 mkey = PAIR_KEY(ma, mb);
+    auto fetch = [&](int it) -> i64 {                    // item `it` of the padded layout (all 32 lanes call this together)
+        int mem = -1, loc = 0;
+        for (int i = 0; i < kk; i++) {
+            const int st = __shfl_sync(0xffffffffu, mpst, i), tt = __shfl_sync(0xffffffffu, mtot, i);
+            if (it >= st && it < st + tt) { mem = i; loc = it - st; }
+        }
+        return mem >= 0 ? range_item(BC.R[mem], loc) : -1;
+    };
+    const int it0 = warp * GPW + lane / G;
+    const i64 e_cur = fetch(it0);
+    i64 e_nx = fetch(it0 + ngroups);
+    int32_t w_cur = POST_WORD(e_cur), w_nx = POST_WORD(e_nx);
+    {
+        int take = (w_cur >= 0 && gl == 0) ? (dedupe_claim(&C, w_cur) ? 1 : 0) : 0;
+        take = __shfl_sync(0xffffffffu, take, lead);
+        if (!take) w_cur = -1;
+    }
+    uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
+    if (w_cur >= 0) {                       // header and symbols in ONE round trip: the entry carries the symbol slot
+        off_cur = (uint32_t)POST_OFF(e_cur);
+        if (gl == 0) { prefetch_l2(&M.wsym[off_cur]); prefetch_l2(&M.wslot[off_cur]); }
+        n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur];
+    }
+    for (int base = 0; base + warp * GPW < total_p; base += ngroups) {      // warps without an item go straight to the barrier
+        const i64 e_nx2 = fetch(base + it0 + 2 * ngroups);
+        {
+            int take = (w_nx >= 0 && gl == 0) ? (dedupe_claim(&C, w_nx) ? 1 : 0) : 0;
+            take = __shfl_sync(0xffffffffu, take, lead);
+            if (!take) w_nx = -1;
+        }
+        uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
+        if (w_nx >= 0) {
+            off_nx = (uint32_t)POST_OFF(e_nx);
+            if (gl == 0) { prefetch_l2(&M.wsym[off_nx]); prefetch_l2(&M.wslot[off_nx]); }
+            n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx];
+        }
+        // ---- the current word: which members have a site in it
+        const int32_t w = w_cur;
+        const i64 off = (i64)off_cur;
+        int n = w >= 0 ? n_cur : 0;
+        uint32_t mask = 0;
+        {
+            const int32_t* s = M.wsym + off;
+            for (int j0 = 0; __any_sync(0xffffffffu, j0 + 1 < n); j0 += G) {
+                const int j = j0 + gl;
+                u64 key = 0;
+                if (j + 1 < n) key = PAIR_KEY(s[j], s[j + 1]);
+                for (int i = 0; i < kk; i++) { const u64 ki = __shfl_sync(0xffffffffu, mkey, i); if (key == ki) mask |= 1u << i; }
+            }
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+        }
+        for (int i = 0; i < kk; i++) {
+            const bool act = w >= 0 && ((mask >> i) & 1u);
+            const int32_t a = __shfl_sync(0xffffffffu, ma, i), b = __shfl_sync(0xffffffffu, mb, i), c = __shfl_sync(0xffffffffu, mc, i);
+            const int32_t sl = __shfl_sync(0xffffffffu, mslot, i);
+            const int isn = __shfl_sync(0xffffffffu, mnew, i), sb = __shfl_sync(0xffffffffu, mseg, i);
+            if (!__any_sync(0xffffffffu, act)) continue;
+            if (a != b) {
+                const int nn = rewrite_words_g<G>(M, act ? w : -1, off, n, f_cur, a, b, c, T, T2, &C, isn != 0, &BC.seg_n[i], (i64)sb);
+                if (act) n = nn;
+            } else if (act && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, &C, isn != 0, sl, &BC.seg_n[i], (i64)sb);
+        }
+        w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; e_nx = e_nx2; w_nx = POST_WORD(e_nx2);
+    }
+}
+
+// Leader loop.  Per iteration (every stage is bounded by dependent L2 / DRAM round trips, not by bandwidth):
+//   A  the ML_SEL best entries of the top list (counts mirrored in shared memory) -> the batch; ties at the top: byte-wise argmax
+//   B  candidate ranges (one thread per member) and merged-token lookups (another thread per member), side by side
+//   C  the last warp records the merges / creates the tokens while every other 8-lane group takes ONE candidate
 //      item, claims its word in a shared-memory set (no global stamp), loads the word and rewrites it
-//   D  thread 0 closes the merge's affected-log segment (plain stores; all counters are in shared memory)
+//   D  the members' affected-log segments are closed (plain stores; all counters are in shared memory), thresholds of the new pairs
 __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i64 T, i64 Tmin, const i64 T2, const u64 T2pa) {
-    __shared__ Ranges R;
-    __shared__ int32_t sh_c;
-    __shared__ MergedInfo MI;
-    __shared__ i64 sh_wmax[ML_THREADS / 32];    // stage A: per-warp maximum count
-#if ML_BATCH_STATS
-    __shared__ u64 sh_selkeys[32 * ML_SEL];
-    __shared__ int sh_skip;
-    if (threadIdx.x == 0) sh_skip = 0;
-#endif
+    __shared__ BatchCtx BC;
+    __shared__ i64 sh_wmax[ML_THREADS / 32];    // block-wide maxima of the tie path
 #if ML_TIMING
     __shared__ long long sh_tacc[8];
     if (threadIdx.x < 8) sh_tacc[threadIdx.x] = 0;
@@ -1124,12 +1376,17 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
     i64 m = M.state[MS_NMERGES];
     int32_t n_tok = (int32_t)M.state[MS_NTOK];
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    #if ML_TIMING
+    int batch_max = M.batch_max > 0 ? (int)M.batch_max : ML_BATCH_MAX;
+    if (batch_max > ML_BATCH_MAX) batch_max = ML_BATCH_MAX;
+    if (T2pa != 0) batch_max = 1;        // tie regime: the list is not complete at the boundary count (and pair_add reads prefixes of tokens being created)
+#if ML_TIMING
     long long t_arg = 0, t_rng = 0, t_rw = 0, t_close = 0;
 #endif
-    int s_act = 0, s_items = 0, n_done = 0;
+    int s_act = 0, s_items = 0, n_done = 0, n_iter = 0, n_batched = 0;
     int reason = LR_OTHER;
     int cached = 0;                      // entries of the top list whose count is mirrored in shared memory
+    i64 theta = 0;                       // head threshold (0: not chosen yet)
+    bool theta_sticky = false;
     const i64 npairs0 = __ldcg(&M.state[MS_NPAIRS]);
     const i64 last_rebuild_m = __ldcg(&M.state[MS_LAST_REBUILD_M]);
     if (threadIdx.x == 0) {
@@ -1137,7 +1394,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         C.error = (int)__ldcg(&M.state[MS_ERROR]);
         C.top_n = (int)__ldcg(&M.state[MS_TOP_N]); C.top_ovf = (int)__ldcg(&M.state[MS_TOP_OVF]);
         C.npairs_new = 0; C.nnew = 0; C.t2pa = T2pa;
-        sh_ncand = 0; C.cur_slot = -1;
+        sh_ncand = 0; C.cur_slot = -1; BC.nS = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;
@@ -1154,7 +1411,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         if (C.top_ovf || C.top_n > ML_TOP_N) { reason = LR_TOP; break; }
         if (M.rebuild_every > 0 && m - last_rebuild_m >= M.rebuild_every) { reason = LR_REBUILD; break; }
         if ((npairs0 + C.npairs_new + C.nnew) * 4 > M.pcap * 3) { if (threadIdx.x == 0) atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_PAIR_TABLE_FULL); break; }
-        // ---- A: best pair of the top list
+        // ---- A: the best pairs of the top list
         const int tn = C.top_n;
         Best mine{0, -1, 0, 0, 0};
         if ((int)threadIdx.x < tn) {
@@ -1173,158 +1430,214 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
         }
         cached = tn;
-#if ML_BATCH_STATS
-        {
-            u64 topk[ML_SEL];
-            select_top(mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL, sh_selkeys, topk);
-            if (threadIdx.x == 0) {
-                int k = 0;
-                int32_t ta[ML_SEL], tb[ML_SEL]; i64 tc[ML_SEL];
-                for (int j = 0; j < ML_SEL; j++) {
-                    tc[j] = (i64)(topk[j] >> 9);
-                    const int idx = 511 - (int)(topk[j] & 511);
-                    const u64 kk = topk[j] ? C.tkey[idx] : 0;
-                    ta[j] = (int32_t)((kk >> 32) & 0x7fffffff); tb[j] = (int32_t)(kk & 0xffffffffu);
+        // member registers: lane l (< ML_BATCH_MAX) of EVERY warp describes member l of the batch
+        int32_t ma = 0, mb = 0, mslot = -1, midx = -1; i64 mcnt = 0;
+        int nb = 0;
+        Best best{0, -1, 0, 0, 0};
+        if (batch_max > 1) {
+            // ---- the HEAD of the list: the (at most 32) entries with count >= theta, collected by the entries themselves
+            const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
+            int nS;
+            for (int pass = 0;; pass++) {
+                if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) { const int p = atomicAdd(&BC.nS, 1); if (p < 32) BC.S[p] = mykey; }
+                __syncthreads();
+                nS = BC.nS;
+                const bool refresh = theta <= 0 || nS > 32 || (nS < 4 && tn > 32 && !theta_sticky && theta > 1);
+                if (!refresh || pass == 2) break;
+                theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BC.hist, &theta_sticky);     // block-wide; ends with a barrier
+                if (tn <= 32) { theta = 1; theta_sticky = false; }
+                if (threadIdx.x == 0) BC.nS = 0;
+                __syncthreads();
+            }
+            if (nS > 32) nS = 0;                        // cannot happen after a refresh; be safe: the one-merge path decides
+            // ---- warp 0: the ML_SEL best of the head in exact order, and how many of them may be merged together
+            if (warp == 0) {
+                u64 k = lane < nS ? BC.S[lane] : 0ULL, sel = 0;
+#pragma unroll
+                for (int r = 0; r < ML_SEL; r++) {
+                    const u64 mxk = warp_max_u64(k);
+                    if (k == mxk) k = 0;                 // keys are unique (the index is part of the key)
+                    if (lane == r) sel = mxk;
                 }
-                for (k = 0; k < ML_BATCH_MAX; k++) {
-                    if (tc[k] < T2 || tc[k] < T || tc[k] <= tc[k + 1]) break;        // strict drop after member k
-                    if (k > 0 && ta[k] == tb[k]) break;
-                    bool clash = false;
-                    for (int i = 0; i < k; i++) clash |= ta[i] == ta[k] || ta[i] == tb[k] || tb[i] == ta[k] || tb[i] == tb[k];
-                    if (clash) break;
+                u64 pa = 0, pb = 0;
+                if (sel != 0) {
+                    midx = 511 - (int)(sel & 511);
+                    const u64 kk2 = C.tkey[midx];
+                    ma = (int32_t)((kk2 >> 32) & 0x7fffffff); mb = (int32_t)(kk2 & 0xffffffffu);
+                    mslot = C.tslot[midx]; mcnt = (i64)(sel >> 9); pa = C.tpa[midx]; pb = C.tpb[midx];
                 }
-                if (k == 0) k = 1;
-                if (ta[0] == tb[0]) k = 1;
-                if (sh_skip > 0) sh_skip--; else { M.state[12] += k; M.state[13] += 1; sh_skip = k - 1; }
+                // entries outside the selection: below theta, or (more than ML_SEL in the head) not above the last selected count
+                const i64 g = nS > ML_SEL ? __shfl_sync(0xffffffffu, mcnt, ML_SEL - 1) : theta - 1;
+                // equal counts among the selected: (left bytes, right bytes) order them (exact: prefixes, then the bytes)
+                const i64 cdown = __shfl_down_sync(0xffffffffu, mcnt, 1);
+                if (__ballot_sync(0xffffffffu, lane < ML_SEL - 1 && sel != 0 && mcnt == cdown && mcnt > g)) {
+                    int rank = 0;
+                    for (int i = 0; i < ML_SEL; i++) {
+                        const i64 ci = __shfl_sync(0xffffffffu, mcnt, i);
+                        const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
+                        const u64 pai = __shfl_sync(0xffffffffu, pa, i), pbi = __shfl_sync(0xffffffffu, pb, i);
+                        if (i == lane || sel == 0 || ci == 0) continue;
+                        bool gt = ci > mcnt;
+                        if (ci == mcnt) {
+                            int r = tok_cmp_pre(M, ai, pai, ma, pa);
+                            if (r == 0) r = tok_cmp_pre(M, bi, pbi, mb, pb);
+                            gt = r > 0;
+                        }
+                        if (gt) rank++;
+                    }
+                    if (sel == 0) rank = lane;                       // empty lanes stay where they are (behind every entry)
+                    int src = lane;
+                    for (int i = 0; i < ML_SEL; i++) { const int ri = __shfl_sync(0xffffffffu, rank, i); if (ri == lane) src = i; }
+                    ma = __shfl_sync(0xffffffffu, ma, src); mb = __shfl_sync(0xffffffffu, mb, src); mslot = __shfl_sync(0xffffffffu, mslot, src);
+                    midx = __shfl_sync(0xffffffffu, midx, src); mcnt = __shfl_sync(0xffffffffu, mcnt, src); sel = __shfl_sync(0xffffffffu, sel, src);
+                }
+                const bool elig = lane < batch_max && sel != 0 && mcnt > g && mcnt > T2 && mcnt >= T && mcnt >= Tmin;
+                int tj = 99;                                           // first earlier entry this one touches (or that has equal tokens)
+#pragma unroll
+                for (int i = ML_SEL - 2; i >= 0; i--) {
+                    const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
+                    if (i < lane && (ma == bi || mb == ai || ai == bi)) tj = i;
+                }
+                int k2 = __ffs(~__ballot_sync(0xffffffffu, elig && tj == 99)) - 1;      // members: eligible and clear of every earlier one
+                // an entry left out with the count of the last member must not touch a member either (its count must stay
+                // what it is, and it bounds the pairs the batch creates): give up members until that holds
+                while (k2 > 1) {
+                    const i64 ck = __shfl_sync(0xffffffffu, mcnt, k2 - 1);
+                    if (!__ballot_sync(0xffffffffu, lane >= k2 && lane < ML_SEL && sel != 0 && mcnt == ck && tj < k2)) break;
+                    k2--;
+                }
+                if (lane < ML_BATCH_MAX) { BC.mem[lane].a = ma; BC.mem[lane].b = mb; BC.mem[lane].slot = mslot; BC.mem[lane].idx = midx; BC.mem[lane].cnt = mcnt; }
+                if (lane == 0) BC.nb = k2;
             }
             __syncthreads();
+            nb = BC.nb;
+            if (lane < ML_BATCH_MAX) { ma = BC.mem[lane].a; mb = BC.mem[lane].b; mslot = BC.mem[lane].slot; midx = BC.mem[lane].idx; mcnt = BC.mem[lane].cnt; }
+            if (nb > 0) best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0),
+                                    __shfl_sync(0xffffffffu, mb, 0), __shfl_sync(0xffffffffu, midx, 0)};
         }
-#endif
-        {
-            const i64 wm = warp_max_i64(mine.cnt);
-            if (lane == 0) sh_wmax[warp] = wm;
-        }
-        __syncthreads();
-        const i64 mx = warp_max_i64(lane < nwarps ? sh_wmax[lane] : 0);
-        if (mine.slot >= 0 && mine.cnt == mx) { const int ci = atomicAdd(&sh_ncand, 1); if (ci < 32) sh_cand[ci] = mine; }
-        __syncthreads();
-        Best best{0, -1, 0, 0, 0};
-        const int ncand = sh_ncand;
-        if (mx > 0) {
-            if (ncand == 1) best = sh_cand[0];
-            else if (ncand <= 32) {                     // ties: byte-wise comparison, every warp redundantly (no barrier)
-                Best t = lane < ncand ? sh_cand[lane] : Best{0, -1, 0, 0, 0};
-                // fast path: lexicographic maximum of (prefix of a, prefix of b) with four redux.sync rounds.  Different
-                // prefixes order the tokens; equal prefixes decide only when the tokens themselves are equal.
-                {
-                    bool alive = lane < ncand;
-                    const u64 pa = alive ? C.tpa[t.pad] : 0ULL, pb = alive ? C.tpb[t.pad] : 0ULL;
-                    uint32_t wv = (uint32_t)(pa >> 32), mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
-                    wv = (uint32_t)pa; mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
-                    const uint32_t amax = __reduce_max_sync(0xffffffffu, alive ? (uint32_t)t.a : 0u);
-                    const uint32_t amin = __reduce_min_sync(0xffffffffu, alive ? (uint32_t)t.a : 0xffffffffu);
-                    if (amax == amin) {                                  // every survivor has the SAME left token: the right one decides
-                        wv = (uint32_t)(pb >> 32); mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
-                        wv = (uint32_t)pb; mw = __reduce_max_sync(0xffffffffu, alive ? wv : 0u); alive = alive && wv == mw;
-                        const uint32_t am = __ballot_sync(0xffffffffu, alive);
-                        if (__popc(am) == 1) {
-                            const int src = __ffs(am) - 1;
-                            t = shfl_best_from(t, src);
-                            best = t;
-                        }
-                    }
-                }
-                if (best.slot < 0) {
-                for (int o = 16; o > 0; o >>= 1) {
-                    Best u = shfl_best(t, o);
-                    u.pad = __shfl_xor_sync(0xffffffffu, t.pad, o);
-                    bool gt = false;                                      // equal counts: (left bytes, right bytes)
-                    if (u.slot >= 0 && t.slot < 0) gt = true;
-                    else if (u.slot >= 0 && u.slot != t.slot) {
-                        int r = tok_cmp_pre(M, u.a, C.tpa[u.pad], t.a, C.tpa[t.pad]);
-                        if (r == 0) r = tok_cmp_pre(M, u.b, C.tpb[u.pad], t.b, C.tpb[t.pad]);
-                        gt = r > 0;
-                    }
-                    if (gt) t = u;
-                }
-                best = t;
-                }
-            } else {
-                // More than 32 pairs share the maximum (the tie regime: up to the whole list).  Byte-wise comparisons across the
-                // block cost thousands of cycles; the cached prefixes decide almost every time: the greatest LEFT prefix, then --
-                // if every survivor has the same left token -- the greatest RIGHT prefix.  Only what is still tied goes through
-                // the byte-wise reduction.
-                __syncthreads();
-                bool alive = mine.slot >= 0 && mine.cnt == mx;
-                const u64 mpa = block_max_u64(alive ? C.tpa[threadIdx.x] : 0ULL, (u64*)sh_wmax);
-                alive = alive && C.tpa[threadIdx.x] == mpa;
-                const uint32_t amax = (uint32_t)block_max_u64(alive ? (u64)(uint32_t)mine.a : 0ULL, (u64*)sh_wmax);
-                const uint32_t namin = (uint32_t)block_max_u64(alive ? (u64)(0xffffffffu - (uint32_t)mine.a) : 0ULL, (u64*)sh_wmax);
-                if (amax == 0xffffffffu - namin) {            // one left token: the right one decides
-                    const u64 mpb = block_max_u64(alive ? C.tpb[threadIdx.x] : 0ULL, (u64*)sh_wmax);
-                    alive = alive && C.tpb[threadIdx.x] == mpb;
-                }
-                const int left = __syncthreads_count(alive);
-                if (left == 1) {
-                    if (alive) sh_cand[0] = mine;
-                    __syncthreads();
-                    best = sh_cand[0];
-                } else {
-                    best = block_best(M, alive ? mine : Best{0, -1, 0, 0, 0}, sh_best);
-                    if (best.slot >= 0) best.pad = mirror_find(&C.LM, best.slot);      // block_best does not carry the list index
-                }
-            }
+        if (nb == 0) {
+            // ---- one merge: the maximum of the whole list, (left bytes, right bytes) among equal counts
+            best = leader_argmax_one(M, C, mine, sh_wmax, &sh_ncand, sh_cand, sh_best);
+            if (best.slot >= 0) { nb = 1; ma = best.a; mb = best.b; mslot = best.slot; midx = best.pad; mcnt = best.cnt; }
         }
         if (best.slot < 0 || best.cnt < T2 || (best.cnt == T2 && best.pad >= 0 && C.tpa[best.pad] < T2pa)) { reason = LR_TOP; break; }
         if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
+        if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
         ML_CLOCK(c1);
         ML_TR(1);
-        // ---- B: candidate ranges + merged token
-        if (threadIdx.x == 0) { build_ranges(M, best.slot, best.a, best.b, &R, best.pad >= 0, best.pad >= 0 ? C.tp0[best.pad] : 0u, best.pad >= 0 ? C.tplen[best.pad] : 0u); C.cur_slot = best.slot; }
-        if (threadIdx.x == 32) sh_c = lookup_merged_leader(M, C, best.pad, best.a, best.b, n_tok, &MI);
+        // ---- B: candidate ranges + merged tokens, one thread each per member (warps 0 .. nb-1 and 8 .. 8+nb-1)
+        if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &BC.R[warp], midx >= 0, midx >= 0 ? C.tp0[midx] : 0u, midx >= 0 ? C.tplen[midx] : 0u);
+        if (warp >= ML_BATCH_MAX && warp < ML_BATCH_MAX + nb && lane == warp - ML_BATCH_MAX)
+            BC.c[lane] = lookup_merged_leader(M, C, midx, ma, mb, n_tok, &BC.MI[lane]);
+        if (threadIdx.x < ML_BATCH_MAX) BC.seg_n[threadIdx.x] = 0;
         for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
-        if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
-        if (R.n < 0 || R.total > ML_LEADER_ITEMS_MAX || alog_n + R.total > M.alog_cap) break;
+        if (threadIdx.x == 0) { sh_ncand = 0; BC.nS = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
+        // how many members fit: candidate lists, log space, distinct NEW product tokens (every warp computes the same)
+        int mtot = 0, mnew = 0, mlen = 0; int32_t mc = -1; u64 mH = 0; bool mbad = true;
+        if (lane < nb) {
+            mtot = (int)(BC.R[lane].total < 0x40000000 ? BC.R[lane].total : 0x40000000);
+            mbad = BC.R[lane].n < 0;
+            mc = BC.c[lane]; mnew = mc == n_tok ? 1 : 0; mH = BC.MI[lane].H; mlen = (int)(BC.MI[lane].la + BC.MI[lane].lb);
+            if (mnew) mc = n_tok + lane;                 // every earlier member makes a new token (or the batch ends there)
+        }
+        int cum = mtot, lcum = mlen;                                 // inclusive scans over the members
+#pragma unroll
+        for (int o = 1; o < ML_BATCH_MAX; o <<= 1) {
+            const int t1 = __shfl_up_sync(0xffffffffu, cum, o), t3 = __shfl_up_sync(0xffffffffu, lcum, o);
+            if (lane >= o) { cum += t1; lcum += t3; }
+        }
+        if (cum > ML_LEADER_ITEMS_MAX || (i64)alog_n + cum > M.alog_cap) mbad = true;
+#pragma unroll
+        for (int i = 0; i < ML_BATCH_MAX - 1; i++) {
+            const u64 Hi = __shfl_sync(0xffffffffu, mH, i);
+            const int newi = __shfl_sync(0xffffffffu, mnew, i);
+            if (i < lane && (Hi == mH || !newi)) mbad = true;      // same merged bytes twice / an earlier member reuses an existing token
+        }
+        const int kk = __ffs(__ballot_sync(0xffffffffu, mbad)) - 1;     // lanes >= nb are bad: kk <= nb
+        if (kk == 0) break;                                              // the best pair alone needs the grid (or an index rebuild)
+#if ML_BATCH_WHY
+        if (warp == 0 && lane == kk && kk < nb) M.state[(cum > ML_LEADER_ITEMS_MAX || (i64)alog_n + cum > M.alog_cap) ? 61 : 62]++;   // 61: candidate lists / log space, 62: product token
+#endif
         ML_CLOCK(c2);
         ML_TR(2);
-        const int32_t a = best.a, b = best.b, c = sh_c;
-        const bool is_new = c == n_tok;
-        // ---- C: commit (last warp) || claim + rewrite (one 8-lane group per candidate item)
-        if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
-        else {
-            // 8-lane groups (124 candidates per pass) while that is one pass, 4-lane groups (248 per pass) beyond
-            if (a != b && R.total > (nwarps - 1) * 8) leader_rewrite<2>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
-            else if (a != b && R.total > (nwarps - 1) * 4) leader_rewrite<4>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
-            else leader_rewrite<8>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new);
-        }
-        if (is_new) { n_tok++; pool_end += MI.la + MI.lb; }
-        ML_T0(qb);
-        ML_TR(7);
-        __syncthreads();
-        ML_TACC(4, qb);
-        ML_CLOCK(c3);
-        ML_TR(8);
-        // ---- D: close the merge; thresholds of the pairs it created
-        if (threadIdx.x == 0) {
-            const int32_t prev = is_new ? -1 : M.tok_first[c];        // == merge_next[m] written by the commit warp
-            M.seg_end[m] = C.alog_n; M.tok_first[c] = (int32_t)m;
-            M.tok_head[c] = make_int4((int32_t)m, alog_n, C.alog_n, prev);
-            *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;        // for the prefetch helpers
-        }
-        if (threadIdx.x == 32) { M.pcnt[best.slot] = 0; const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, 0); }
-        if (is_new) leader_new_pairs(M, &C, T, T2);
-        __syncthreads();
-        ML_CLOCK(c4);
-        ML_TR(9);
-#if ML_TRACE
-        if (threadIdx.x == 0 && m >= ML_TRACE && m < ML_TRACE + 8) { ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + 10] = R.total; ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + 11] = C.alog_n - alog_n; ((long long*)M.bsum)[512 + (m - ML_TRACE) * 24 + 12] = C.nnew; }
-#endif
+        int n_new_batch = 0, len_batch = 0, items_batch = 0;
+        if (kk == 1) {
+            // ---- one merge (the path of every heavy, tied or interacting pair)
+            const Ranges& R = BC.R[0];
+            const MergedInfo& MI = BC.MI[0];
+            const int32_t a = best.a, b = best.b, c = BC.c[0];
+            const bool is_new = c == n_tok;
+            // ---- C: commit (last warp) || claim + rewrite (one 8-lane group per candidate item)
+            if (warp == nwarps - 1) commit_merge_leader(M, m, a, b, c, is_new, alog_n, MI, pool_end);
+            else {
+                // 8-lane groups (124 candidates per pass) while that is one pass, 4-lane groups (248 per pass) beyond
+                if (a != b && R.total > (nwarps - 1) * 8) leader_rewrite<2>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new, best.slot);
+                else if (a != b && R.total > (nwarps - 1) * 4) leader_rewrite<4>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new, best.slot);
+                else leader_rewrite<8>(M, C, R, warp, lane, nwarps, a, b, c, T, T2, is_new, best.slot);
+            }
+            n_new_batch = is_new ? 1 : 0; len_batch = is_new ? (int)(MI.la + MI.lb) : 0; items_batch = (int)R.total;
+            ML_T0(qb);
+            ML_TR(7);
+            __syncthreads();
+            ML_TACC(4, qb);
+            ML_CLOCK(c3);
+            ML_TR(8);
+            // ---- D: close the merge; thresholds of the pairs it created
+            if (threadIdx.x == 0) {
+                const int32_t prev = is_new ? -1 : M.tok_first[c];        // == merge_next[m] written by the commit warp
+                M.seg_end[m] = C.alog_n; M.tok_first[c] = (int32_t)m;
+                M.tok_head[c] = make_int4((int32_t)m, alog_n, C.alog_n, prev);
+                *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;        // for the prefetch helpers
+            }
+            if (threadIdx.x == 32) { M.pcnt[best.slot] = 0; const int bi = mirror_find(&C.LM, best.slot); if (bi >= 0) mirror_set(&C.LM, bi, 0); }
+            if (is_new) leader_new_pairs(M, &C, T, T2);
+            __syncthreads();
 #if ML_TIMING
-        t_arg += c1 - c0; t_rng += c2 - c1; t_rw += c3 - c2; t_close += c4 - c3;
+            { ML_CLOCK(c4); t_arg += c1 - c0; t_rng += c2 - c1; t_rw += c3 - c2; t_close += c4 - c3; }
 #endif
-        s_act += C.alog_n - alog_n; s_items += (int)R.total; n_done++;
-        m++;
+        } else {
+            // ---- a batch of kk merges
+            // lanes per candidate word: 8 while that is one pass (124 items), then 4, then 2 (496 items a pass)
+            const int items_all = __shfl_sync(0xffffffffu, cum, kk - 1);
+            const int G = items_all > (nwarps - 1) * 8 ? 2 : (items_all > (nwarps - 1) * 4 ? 4 : 8), padm = 32 / G - 1;
+            int pcum = lane < kk ? (mtot + padm) & ~padm : 0;                                 // every member starts at a multiple of the groups per warp
+#pragma unroll
+            for (int o = 1; o < ML_BATCH_MAX; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, pcum, o); if (lane >= o) pcum += t2; }
+            const int mpst = pcum - (lane < kk ? (mtot + padm) & ~padm : 0), mseg = alog_n + cum - mtot;     // first item (padded layout), log segment
+            const i64 moc = pool_end + lcum - mlen;                                          // where the member's token bytes go
+            if (threadIdx.x == kk - 1) C.alog_n = alog_n + cum;                              // the members' segments are reserved in full
+            // ---- C: commits (last warp, one lane per member) || claim + rewrite
+            const int last_new = __shfl_sync(0xffffffffu, mnew, kk - 1) ? kk - 1 : kk - 2;   // every member but the last makes a new token
+            if (warp == nwarps - 1) {
+                if (lane < kk) commit_member(M, C, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, BC.MI[lane], moc, lane == last_new);
+            } else if (G == 8) leader_rewrite_batch<8>(M, C, BC, kk, warp, lane, nwarps, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else if (G == 4) leader_rewrite_batch<4>(M, C, BC, kk, warp, lane, nwarps, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else leader_rewrite_batch<2>(M, C, BC, kk, warp, lane, nwarps, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            n_new_batch = __popc(__ballot_sync(0xffffffffu, lane < kk && mnew));
+            len_batch = __shfl_sync(0xffffffffu, lcum, kk - 1) - (__shfl_sync(0xffffffffu, mnew, kk - 1) ? 0 : __shfl_sync(0xffffffffu, mlen, kk - 1));
+            items_batch = __shfl_sync(0xffffffffu, cum, kk - 1);
+            __syncthreads();
+            ML_CLOCK(c3);
+            // ---- D: close the members; thresholds of the pairs the batch created
+            if (warp == 0 && lane < kk) {
+                const int32_t prev = mnew ? -1 : M.tok_first[mc];
+                const int e = mseg + BC.seg_n[lane];
+                M.seg_end[m + lane] = e; M.tok_first[mc] = (int32_t)(m + lane);
+                M.tok_head[mc] = make_int4((int32_t)(m + lane), mseg, e, prev);
+                M.pcnt[mslot] = 0; mirror_set(&C.LM, midx, 0);
+                if (lane == 0) *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;
+            }
+            leader_new_pairs(M, &C, T, T2);
+            __syncthreads();
+#if ML_TIMING
+            { ML_CLOCK(c4); t_arg += c1 - c0; t_rng += c2 - c1; t_rw += c3 - c2; t_close += c4 - c3; }
+#endif
+            n_batched += kk;
+        }
+        ML_TR(9);
+        s_act += C.alog_n - alog_n; s_items += items_batch; n_done += kk; n_iter++;
+        m += kk; n_tok += n_new_batch; pool_end += len_batch;
     }
     __syncthreads();
     // the mirror must agree with the table (cheap self-check, once per leader session)
@@ -1340,6 +1653,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
 #endif
         M.state[25] += s_act; M.state[26] += s_items;
         M.state[MS_LEADER_MERGES] += n_done;
+        M.state[MS_LEADER_ITERS] += n_iter; M.state[MS_LEADER_BATCHED] += n_batched;
         M.state[MS_LEADER_REASON] = reason;
         if (reason == LR_TOP) M.state[MS_T2] = 0;
     }
@@ -1478,12 +1792,12 @@ __device__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_key
             const i64 cnt = __ldcg(&M.pcnt[__ldcg(&M.top_slot[threadIdx.x])]);
             if (cnt > 0) key = ((u64)cnt << 9) | (u64)(511 - (int)threadIdx.x);
         }
-        u64 topk[ML_SEL];
-        select_top(key, sh_keys, topk);                  // one block barrier inside
-        for (int r = hidx; r < ML_SEL; r += ML_HELPERS) {
+        const u64 mykey = select_top(key, sh_keys);      // one block barrier inside; lane r holds the r-th largest key
+        for (int r = hidx; r < ML_SEL && r < 5; r += ML_HELPERS) {
             __syncthreads();
-            if (topk[r] == 0) continue;                  // block-uniform
-            const int idx = 511 - (int)(topk[r] & 511);
+            const u64 kr = __shfl_sync(0xffffffffu, mykey, r);
+            if (kr == 0) continue;                       // block-uniform
+            const int idx = 511 - (int)(kr & 511);
             if (threadIdx.x == 0) {
                 const int32_t slot = __ldcg(&M.top_slot[idx]);
                 const u64 k = __ldcg(&M.top_key[idx]);

@@ -400,7 +400,7 @@ extern "C" int yabpe_merge_loop(const yabpe_merge_args* m, void* stream) {
     M.partial = (Best*)m->partial; M.bsum = (i64*)m->bsum;
     M.merges = m->merges; M.merge_new = m->merge_new; M.state = (i64*)m->state;
     M.num_merges = m->num_merges; M.min_freq = m->min_frequency; M.rebuild_every = m->rebuild_every;
-    M.helper_mode = m->helper_mode;
+    M.helper_mode = m->helper_mode; M.batch_max = m->batch_max;
     M.helper_min_syms = m->helper_min_syms > 0 ? m->helper_min_syms : (m->helper_min_syms < 0 ? 0 : ML_HELPER_MIN_SYMS);
 
     DevInfo& DI = dev_info();

@@ -11,7 +11,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libyabpe.so"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # stats / state slots (include/yabpe.h)
 ST_NTOK, ST_UNIQ_SHORT, ST_UNIQ_LONG, ST_UNIQ_BYTES, ST_ERR_POS, ST_TABLE_FULL, ST_OVF_N = 0, 1, 2, 3, 4, 5, 6
@@ -74,7 +74,7 @@ class MergeArgs(C.Structure):
         ("merge_next", C.c_void_p), ("tok_first", C.c_void_p), ("tok_head", C.c_void_p),
         ("partial", C.c_void_p), ("bsum", C.c_void_p),
         ("merges", C.c_void_p), ("merge_new", C.c_void_p), ("state", C.c_void_p),
-        ("num_merges", C.c_int64), ("min_frequency", C.c_int64), ("rebuild_every", C.c_int64), ("helper_min_syms", C.c_int64), ("helper_mode", C.c_int64),
+        ("num_merges", C.c_int64), ("min_frequency", C.c_int64), ("rebuild_every", C.c_int64), ("helper_min_syms", C.c_int64), ("helper_mode", C.c_int64), ("batch_max", C.c_int64),
     ]
 
 

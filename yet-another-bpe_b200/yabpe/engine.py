@@ -434,6 +434,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         m.num_merges = num_merges; m.min_frequency = min_frequency
         m.rebuild_every = rebuild_period(words.n_syms)
         m.helper_mode = int(os.environ.get("YABPE_HELPER_MODE", "0"))
+        m.batch_max = int(os.environ.get("YABPE_BATCH_MAX", "0"))                  # 1: one merge per iteration (A/B runs, tests)
         m.helper_min_syms = int(os.environ.get("YABPE_HELPER_MIN_SYMS", "0"))     # tests force the prefetch helpers on small inputs (-1)
         if timing is not None:
             t0 = torch.cuda.Event(enable_timing=True); t0.record()
@@ -441,6 +442,8 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         if timing is not None:
             t1 = torch.cuda.Event(enable_timing=True); t1.record()
         st = state.cpu().numpy()
+        if os.environ.get("YABPE_DUMP_STATE"):        # tuning builds (-DML_BATCH_WHY): raw counters
+            print("state[54:64]", st[54:64].tolist(), flush=True)
         import os as _os
         if _os.environ.get('YABPE_TRACE'):           # only meaningful with a -DML_TRACE=<merge> build (tools/trace_merge.sh)
             tr = bsum[512:512 + 8 * 24].cpu().numpy().reshape(8, 24)

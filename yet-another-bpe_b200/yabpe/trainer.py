@@ -118,6 +118,8 @@ class TrainStats:
     n_specials: int = 0
     launches: int = 0
     leader_merges: int = 0
+    leader_iterations: int = 0      # an iteration of the leader merges a batch of 1 .. 8 pairs (csrc/merge.cuh)
+    batched_merges: int = 0         # merges done as members of a batch of two or more
     grid_merges: int = 0
 
 
@@ -319,6 +321,8 @@ class BBPETrainer:
         stats.n_pairs = int(mr.state[_ffi.MS_NPAIRS])
         stats.leader_merges = int(mr.state[_ffi.MS_LEADER_MERGES])
         stats.grid_merges = int(mr.state[_ffi.MS_GRID_MERGES])
+        stats.leader_iterations = int(mr.state[54])
+        stats.batched_merges = int(mr.state[55])
         self.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13]), int(mr.state[17])]
         self.timing['merge_phase_cycles'] = _phase_cycles(mr.state)
         stats.launches = _ffi.launch_count() - launches0
