@@ -769,6 +769,7 @@ def main() -> None:
             "merge_loop": {"index_rebuilds": stats.index_rebuilds, "threshold_rebuilds": stats.threshold_rebuilds,
                            "pairs_created": stats.n_pairs, "leader_mode_merges": stats.leader_merges,
                            "leader_iterations": stats.leader_iterations, "batched_merges": stats.batched_merges,
+                           "grid_batches": stats.grid_batches, "grid_batched_merges": stats.grid_batched_merges,
                            "grid_mode_merges": stats.grid_merges},
             "encode": encode, "sharded_parity": sharded_parity,
             "roofline": roofline, "cpu_baseline": cpu, "same_sample": same, "reference_sample": ref_same, "e2e": e2e,

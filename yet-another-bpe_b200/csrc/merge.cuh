@@ -18,7 +18,10 @@
 #define ML_THREADS 1024
 #endif
 #ifndef ML_BATCH_WHY
-#define ML_BATCH_WHY 0        // 1: state[56..62] count why batches end (no more entries, tie, <= T2, < T, touch; list space, product token)
+#define ML_BATCH_WHY 0        // 1: state[63] counts the leader batches cut short after stage B (candidate lists, log space, product token)
+#endif
+#ifndef ML_DEBUG_SEL
+#define ML_DEBUG_SEL 0
 #endif
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
@@ -95,6 +98,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define ML_PHASE(slot, t0) do { if (gtid == 0) { const long long _t = clock64(); M.state[slot] += _t - (t0); (t0) = _t; } } while (0)          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
 #define MS_LEADER_ITERS 54    // leader iterations (an iteration merges a batch of 1 .. ML_BATCH_MAX pairs)
 #define MS_LEADER_BATCHED 55  // merges done as members of a batch of two or more
+#define MS_GRID_ITERS 56      // grid-mode iterations that merged a batch of two or more
+#define MS_GRID_BATCHED 57    // merges done in those
 #define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
@@ -1240,26 +1245,125 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
 // candidate word applies members 1 .. k to it in order -- the state of a word depends on nothing but the word, and the
 // pair counts are sums over words, so the result is the sequential one bit for bit.  Ties at the top (c_1 == c_2), the
 // tie regime (T2pa != 0) and single heavy merges take the one-merge path below.
-struct BatchCtx {
-    Ranges R[ML_BATCH_MAX];
-    MergedInfo MI[ML_BATCH_MAX];
-    int32_t c[ML_BATCH_MAX];
-    int seg_n[ML_BATCH_MAX];                    // words each member rewrote (its segment of the affected-word log)
+struct BatchSel {
     u64 S[32]; int nS;                          // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
     int hist[33];
     struct { int32_t a, b, slot, idx; i64 cnt; } mem[ML_BATCH_MAX];
     int nb;
 };
+struct BatchCtx {
+    Ranges R[ML_BATCH_MAX];
+    MergedInfo MI[ML_BATCH_MAX];
+    int32_t c[ML_BATCH_MAX];
+    int seg_n[ML_BATCH_MAX];                    // words each member rewrote (its segment of the affected-word log)
+    BatchSel sel;
+};
+
+// ---- stage A, batch: which of the best entries of the top list may be merged together ---------------------------------------
+// `mine` = this thread's entry of the top list (threads >= tn: none; pad = list index), with its current count.  The entries with
+// count >= theta (the HEAD, at most 32) put themselves on a list; warp 0 takes the ML_SEL best of them in exact order (count, then
+// left bytes, right bytes) and decides how many form a batch (rules (1) - (2) above; rule (3) needs the token lookups and is
+// applied by the caller).  theta / sticky persist between calls; theta is re-chosen when the head runs empty or overflows.
+// tpa / tpb: 8-byte prefixes of the entries' tokens by list index (leader: shared memory), or nullptr: M.tok_pre is read.
+// Block-wide; every thread returns the same count nb (0: the caller takes the one-merge path) and finds the members in BS.mem.
+// Deterministic in its inputs: CTAs that see the same list and counts (grid mode) choose the same batch.
+__device__ int select_batch(const MergeParams& M, BatchSel& BS, const Best& mine, int tn, int batch_max, i64 T, i64 Tmin, i64 T2,
+                            const u64* tpa, const u64* tpb, const int32_t* tslot, const u64* tkey, i64* sh_wmax, i64& theta, bool& theta_sticky) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
+    int nS;
+    for (int pass = 0;; pass++) {
+        if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) { const int p = atomicAdd(&BS.nS, 1); if (p < 32) BS.S[p] = mykey; }
+        __syncthreads();
+        nS = BS.nS;
+        const bool refresh = theta <= 0 || nS > 32 || (nS < 4 && tn > 32 && !theta_sticky && theta > 1);
+        if (!refresh || pass == 2) break;
+        theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BS.hist, &theta_sticky);     // block-wide; ends with a barrier
+        if (tn <= 32) { theta = 1; theta_sticky = false; }
+        if (threadIdx.x == 0) BS.nS = 0;
+        __syncthreads();
+    }
+    if (nS > 32) nS = 0;                        // cannot happen after a refresh; be safe: the one-merge path decides
+    if (warp == 0) {
+        int32_t ma = 0, mb = 0, mslot = -1, midx = -1; i64 mcnt = 0;
+        // rank of every head entry by (count, list index): 31 shuffle rounds, no dependent chain
+        const u64 k = lane < nS ? BS.S[lane] : 0ULL;
+        int rank = 0;
+#pragma unroll
+        for (int o = 1; o < 32; o++) {
+            const u64 other = __shfl_sync(0xffffffffu, k, (lane + o) & 31);
+            rank += other > k ? 1 : 0;
+        }
+        if (k != 0 && rank < ML_SEL) BS.S[rank] = k;             // keys are unique: the ML_SEL best land in S[0 .. ML_SEL) in order
+        __syncwarp();
+        u64 sel = (lane < ML_SEL && lane < nS) ? BS.S[lane] : 0ULL;
+        u64 pa = 0, pb = 0;
+        if (sel != 0) {
+            midx = 511 - (int)(sel & 511);
+            const u64 kk2 = tkey[midx];
+            ma = (int32_t)((kk2 >> 32) & 0x7fffffff); mb = (int32_t)(kk2 & 0xffffffffu);
+            mslot = tslot[midx]; mcnt = (i64)(sel >> 9);
+            pa = tpa ? tpa[midx] : __ldcg(&M.tok_pre[ma]); pb = tpb ? tpb[midx] : __ldcg(&M.tok_pre[mb]);
+        }
+        // entries outside the selection: below theta, or (more than ML_SEL in the head) not above the last selected count
+        const i64 g = nS > ML_SEL ? __shfl_sync(0xffffffffu, mcnt, ML_SEL - 1) : theta - 1;
+        // equal counts among the selected: (left bytes, right bytes) order them (exact: prefixes, then the bytes)
+        const i64 cdown = __shfl_down_sync(0xffffffffu, mcnt, 1);
+        if (__ballot_sync(0xffffffffu, lane < ML_SEL - 1 && sel != 0 && mcnt == cdown && mcnt > g)) {
+            int rk = 0;
+            for (int i = 0; i < ML_SEL; i++) {
+                const i64 ci = __shfl_sync(0xffffffffu, mcnt, i);
+                const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
+                const u64 pai = __shfl_sync(0xffffffffu, pa, i), pbi = __shfl_sync(0xffffffffu, pb, i);
+                if (i == lane || sel == 0 || ci == 0) continue;
+                bool gt = ci > mcnt;
+                if (ci == mcnt) {
+                    int r = tok_cmp_pre(M, ai, pai, ma, pa);
+                    if (r == 0) r = tok_cmp_pre(M, bi, pbi, mb, pb);
+                    gt = r > 0;
+                }
+                if (gt) rk++;
+            }
+            if (sel == 0) rk = lane;                         // empty lanes stay where they are (behind every entry)
+            int src = lane;
+            for (int i = 0; i < ML_SEL; i++) { const int ri = __shfl_sync(0xffffffffu, rk, i); if (ri == lane) src = i; }
+            ma = __shfl_sync(0xffffffffu, ma, src); mb = __shfl_sync(0xffffffffu, mb, src); mslot = __shfl_sync(0xffffffffu, mslot, src);
+            midx = __shfl_sync(0xffffffffu, midx, src); mcnt = __shfl_sync(0xffffffffu, mcnt, src); sel = __shfl_sync(0xffffffffu, sel, src);
+        }
+        const bool elig = lane < batch_max && sel != 0 && mcnt > g && mcnt > T2 && mcnt >= T && mcnt >= Tmin;
+        int tj = 99;                                           // first earlier entry this one touches (or that has equal tokens)
+#pragma unroll
+        for (int i = ML_SEL - 2; i >= 0; i--) {
+            const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
+            if (i < lane && (ma == bi || mb == ai || ai == bi)) tj = i;
+        }
+        int k2 = __ffs(~__ballot_sync(0xffffffffu, elig && tj == 99)) - 1;      // members: eligible and clear of every earlier one
+        // an entry left out with the count of the last member must not touch a member either (its count must stay
+        // what it is, and it bounds the pairs the batch creates): give up members until that holds
+        while (k2 > 1) {
+            const i64 ck = __shfl_sync(0xffffffffu, mcnt, k2 - 1);
+            if (!__ballot_sync(0xffffffffu, lane >= k2 && lane < ML_SEL && sel != 0 && mcnt == ck && tj < k2)) break;
+            k2--;
+        }
+        if (lane < ML_BATCH_MAX) { BS.mem[lane].a = ma; BS.mem[lane].b = mb; BS.mem[lane].slot = mslot; BS.mem[lane].idx = midx; BS.mem[lane].cnt = mcnt; }
+        if (lane == 0) BS.nb = k2;
+    }
+    __syncthreads();
+    const int nb = BS.nb;
+    if (threadIdx.x == 0) BS.nS = 0;                           // every thread read it before this barrier; the next call comes after another one
+    return nb;
+}
+
 
 // ONE lane records one member of a batch and creates its token (members commit side by side in the lanes of one warp)
-__device__ void commit_member(const MergeParams& M, LeaderCtx& C, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 seg_base,
+__device__ void commit_member(const MergeParams& M, LeaderCtx* lc, i64 m, int32_t a, int32_t b, int32_t c, bool is_new, i64 seg_base,
                               const MergedInfo& MI, i64 oc, bool publish) {
     M.merges[2 * m] = a; M.merges[2 * m + 1] = b; M.merge_new[m] = c;
     M.seg_start[m] = (int32_t)seg_base;
     M.merge_next[m] = is_new ? -1 : M.tok_first[c];
     if (!is_new) return;
     if (oc + MI.la + MI.lb > M.tok_bytes_cap || c + 1 >= M.max_tokens) {
-        atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL); C.error = 1;
+        atomicOr((u64*)&M.state[MS_ERROR], (u64)ME_TOK_POOL_FULL); if (lc) lc->error = 1;
         return;
     }
     for (i64 k = 0; k < MI.la; k++) M.tok_bytes[oc + k] = M.tok_bytes[MI.oa + k];
@@ -1280,12 +1384,14 @@ __device__ void commit_member(const MergeParams& M, LeaderCtx& C, i64 m, int32_t
 // warp mostly work on the same member); a G-lane group claims its candidate word for the whole batch, finds out which
 // members have a site in it (one pass over its symbols) and applies those, in order.  Software pipeline over the passes of a
 // group as in leader_rewrite: the item of pass p+2 and the word header of pass p+1 are loaded while pass p is rewritten.
+// Leader mode: lc = the leader's context (claims in its shared-memory set, counters in shared memory), group0 / ngroups span
+// the rewriting warps of CTA 0.  Grid mode: lc = nullptr (claims by the per-word stamp, counters in global memory), the
+// groups of ALL CTAs share the items.  seg_n: the members' log counters (shared / global).
 template <int G>
-__device__ __forceinline__ void leader_rewrite_batch(const MergeParams& M, LeaderCtx& C, BatchCtx& BC, int kk, int warp, int lane, int nwarps,
-                                                     int32_t ma, int32_t mb, int32_t mc, int32_t mslot, int mnew, int mtot, int mpst, int mseg,
-                                                     i64 T, i64 T2) {
-    constexpr int GPW = 32 / G;
-    const int ngroups = (nwarps - 1) * GPW, gl = lane & (G - 1), lead = lane & ~(G - 1);
+__device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* lc, const Ranges* RR, int* seg_n, int kk, int lane, int group0, int ngroups, int32_t stamp,
+                                              int32_t ma, int32_t mb, int32_t mc, int32_t mslot, int mnew, int mtot, int mpst, int mseg,
+                                              i64 T, i64 T2) {
+    const int gl = lane & (G - 1), lead = lane & ~(G - 1);
     const int total_p = __shfl_sync(0xffffffffu, mpst + mtot, kk - 1);
     const u64 mkey = PAIR_KEY(ma, mb);
     auto fetch = [&](int it) -> i64 {                    // item `it` of the padded layout (all 32 lanes call this together)
@@ -1294,30 +1400,27 @@ __device__ __forceinline__ void leader_rewrite_batch(const MergeParams& M, Leade
             const int st = __shfl_sync(0xffffffffu, mpst, i), tt = __shfl_sync(0xffffffffu, mtot, i);
             if (it >= st && it < st + tt) { mem = i; loc = it - st; }
         }
-        return mem >= 0 ? range_item(BC.R[mem], loc) : -1;
+        return mem >= 0 ? range_item(RR[mem], loc) : -1;
     };
-    const int it0 = warp * GPW + lane / G;
+    auto claim = [&](int32_t w) -> int32_t {             // first claim of a word in this batch wins
+        int take = 0;
+        if (w >= 0 && gl == 0) take = lc ? (dedupe_claim(lc, w) ? 1 : 0) : (atomicExch(&M.wstamp[w], stamp) != stamp ? 1 : 0);
+        take = __shfl_sync(0xffffffffu, take, lead);
+        return take ? w : -1;
+    };
+    const int it0 = group0 + lane / G;
     const i64 e_cur = fetch(it0);
     i64 e_nx = fetch(it0 + ngroups);
-    int32_t w_cur = POST_WORD(e_cur), w_nx = POST_WORD(e_nx);
-    {
-        int take = (w_cur >= 0 && gl == 0) ? (dedupe_claim(&C, w_cur) ? 1 : 0) : 0;
-        take = __shfl_sync(0xffffffffu, take, lead);
-        if (!take) w_cur = -1;
-    }
+    int32_t w_cur = claim(POST_WORD(e_cur)), w_nx = POST_WORD(e_nx);
     uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
     if (w_cur >= 0) {                       // header and symbols in ONE round trip: the entry carries the symbol slot
         off_cur = (uint32_t)POST_OFF(e_cur);
         if (gl == 0) { prefetch_l2(&M.wsym[off_cur]); prefetch_l2(&M.wslot[off_cur]); }
         n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur];
     }
-    for (int base = 0; base + warp * GPW < total_p; base += ngroups) {      // warps without an item go straight to the barrier
+    for (int base = 0; base + group0 < total_p; base += ngroups) {      // warps without an item go straight to the barrier
         const i64 e_nx2 = fetch(base + it0 + 2 * ngroups);
-        {
-            int take = (w_nx >= 0 && gl == 0) ? (dedupe_claim(&C, w_nx) ? 1 : 0) : 0;
-            take = __shfl_sync(0xffffffffu, take, lead);
-            if (!take) w_nx = -1;
-        }
+        w_nx = claim(w_nx);
         uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
         if (w_nx >= 0) {
             off_nx = (uint32_t)POST_OFF(e_nx);
@@ -1347,9 +1450,9 @@ __device__ __forceinline__ void leader_rewrite_batch(const MergeParams& M, Leade
             const int isn = __shfl_sync(0xffffffffu, mnew, i), sb = __shfl_sync(0xffffffffu, mseg, i);
             if (!__any_sync(0xffffffffu, act)) continue;
             if (a != b) {
-                const int nn = rewrite_words_g<G>(M, act ? w : -1, off, n, f_cur, a, b, c, T, T2, &C, isn != 0, &BC.seg_n[i], (i64)sb);
+                const int nn = rewrite_words_g<G>(M, act ? w : -1, off, n, f_cur, a, b, c, T, T2, lc, isn != 0, &seg_n[i], (i64)sb);
                 if (act) n = nn;
-            } else if (act && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, &C, isn != 0, sl, &BC.seg_n[i], (i64)sb);
+            } else if (act && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, lc, isn != 0, sl, &seg_n[i], (i64)sb);
         }
         w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; e_nx = e_nx2; w_nx = POST_WORD(e_nx2);
     }
@@ -1376,7 +1479,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
     i64 m = M.state[MS_NMERGES];
     int32_t n_tok = (int32_t)M.state[MS_NTOK];
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    int batch_max = M.batch_max > 0 ? (int)M.batch_max : ML_BATCH_MAX;
+    int batch_max = (M.batch_max & 255) > 0 ? (int)(M.batch_max & 255) : ML_BATCH_MAX;
     if (batch_max > ML_BATCH_MAX) batch_max = ML_BATCH_MAX;
     if (T2pa != 0) batch_max = 1;        // tie regime: the list is not complete at the boundary count (and pair_add reads prefixes of tokens being created)
 #if ML_TIMING
@@ -1394,7 +1497,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         C.error = (int)__ldcg(&M.state[MS_ERROR]);
         C.top_n = (int)__ldcg(&M.state[MS_TOP_N]); C.top_ovf = (int)__ldcg(&M.state[MS_TOP_OVF]);
         C.npairs_new = 0; C.nnew = 0; C.t2pa = T2pa;
-        sh_ncand = 0; C.cur_slot = -1; BC.nS = 0;
+        sh_ncand = 0; C.cur_slot = -1; BC.sel.nS = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;
@@ -1435,83 +1538,8 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         int nb = 0;
         Best best{0, -1, 0, 0, 0};
         if (batch_max > 1) {
-            // ---- the HEAD of the list: the (at most 32) entries with count >= theta, collected by the entries themselves
-            const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
-            int nS;
-            for (int pass = 0;; pass++) {
-                if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) { const int p = atomicAdd(&BC.nS, 1); if (p < 32) BC.S[p] = mykey; }
-                __syncthreads();
-                nS = BC.nS;
-                const bool refresh = theta <= 0 || nS > 32 || (nS < 4 && tn > 32 && !theta_sticky && theta > 1);
-                if (!refresh || pass == 2) break;
-                theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BC.hist, &theta_sticky);     // block-wide; ends with a barrier
-                if (tn <= 32) { theta = 1; theta_sticky = false; }
-                if (threadIdx.x == 0) BC.nS = 0;
-                __syncthreads();
-            }
-            if (nS > 32) nS = 0;                        // cannot happen after a refresh; be safe: the one-merge path decides
-            // ---- warp 0: the ML_SEL best of the head in exact order, and how many of them may be merged together
-            if (warp == 0) {
-                u64 k = lane < nS ? BC.S[lane] : 0ULL, sel = 0;
-#pragma unroll
-                for (int r = 0; r < ML_SEL; r++) {
-                    const u64 mxk = warp_max_u64(k);
-                    if (k == mxk) k = 0;                 // keys are unique (the index is part of the key)
-                    if (lane == r) sel = mxk;
-                }
-                u64 pa = 0, pb = 0;
-                if (sel != 0) {
-                    midx = 511 - (int)(sel & 511);
-                    const u64 kk2 = C.tkey[midx];
-                    ma = (int32_t)((kk2 >> 32) & 0x7fffffff); mb = (int32_t)(kk2 & 0xffffffffu);
-                    mslot = C.tslot[midx]; mcnt = (i64)(sel >> 9); pa = C.tpa[midx]; pb = C.tpb[midx];
-                }
-                // entries outside the selection: below theta, or (more than ML_SEL in the head) not above the last selected count
-                const i64 g = nS > ML_SEL ? __shfl_sync(0xffffffffu, mcnt, ML_SEL - 1) : theta - 1;
-                // equal counts among the selected: (left bytes, right bytes) order them (exact: prefixes, then the bytes)
-                const i64 cdown = __shfl_down_sync(0xffffffffu, mcnt, 1);
-                if (__ballot_sync(0xffffffffu, lane < ML_SEL - 1 && sel != 0 && mcnt == cdown && mcnt > g)) {
-                    int rank = 0;
-                    for (int i = 0; i < ML_SEL; i++) {
-                        const i64 ci = __shfl_sync(0xffffffffu, mcnt, i);
-                        const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
-                        const u64 pai = __shfl_sync(0xffffffffu, pa, i), pbi = __shfl_sync(0xffffffffu, pb, i);
-                        if (i == lane || sel == 0 || ci == 0) continue;
-                        bool gt = ci > mcnt;
-                        if (ci == mcnt) {
-                            int r = tok_cmp_pre(M, ai, pai, ma, pa);
-                            if (r == 0) r = tok_cmp_pre(M, bi, pbi, mb, pb);
-                            gt = r > 0;
-                        }
-                        if (gt) rank++;
-                    }
-                    if (sel == 0) rank = lane;                       // empty lanes stay where they are (behind every entry)
-                    int src = lane;
-                    for (int i = 0; i < ML_SEL; i++) { const int ri = __shfl_sync(0xffffffffu, rank, i); if (ri == lane) src = i; }
-                    ma = __shfl_sync(0xffffffffu, ma, src); mb = __shfl_sync(0xffffffffu, mb, src); mslot = __shfl_sync(0xffffffffu, mslot, src);
-                    midx = __shfl_sync(0xffffffffu, midx, src); mcnt = __shfl_sync(0xffffffffu, mcnt, src); sel = __shfl_sync(0xffffffffu, sel, src);
-                }
-                const bool elig = lane < batch_max && sel != 0 && mcnt > g && mcnt > T2 && mcnt >= T && mcnt >= Tmin;
-                int tj = 99;                                           // first earlier entry this one touches (or that has equal tokens)
-#pragma unroll
-                for (int i = ML_SEL - 2; i >= 0; i--) {
-                    const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
-                    if (i < lane && (ma == bi || mb == ai || ai == bi)) tj = i;
-                }
-                int k2 = __ffs(~__ballot_sync(0xffffffffu, elig && tj == 99)) - 1;      // members: eligible and clear of every earlier one
-                // an entry left out with the count of the last member must not touch a member either (its count must stay
-                // what it is, and it bounds the pairs the batch creates): give up members until that holds
-                while (k2 > 1) {
-                    const i64 ck = __shfl_sync(0xffffffffu, mcnt, k2 - 1);
-                    if (!__ballot_sync(0xffffffffu, lane >= k2 && lane < ML_SEL && sel != 0 && mcnt == ck && tj < k2)) break;
-                    k2--;
-                }
-                if (lane < ML_BATCH_MAX) { BC.mem[lane].a = ma; BC.mem[lane].b = mb; BC.mem[lane].slot = mslot; BC.mem[lane].idx = midx; BC.mem[lane].cnt = mcnt; }
-                if (lane == 0) BC.nb = k2;
-            }
-            __syncthreads();
-            nb = BC.nb;
-            if (lane < ML_BATCH_MAX) { ma = BC.mem[lane].a; mb = BC.mem[lane].b; mslot = BC.mem[lane].slot; midx = BC.mem[lane].idx; mcnt = BC.mem[lane].cnt; }
+            nb = select_batch(M, BC.sel, mine, tn, batch_max, T, Tmin, T2, C.tpa, C.tpb, C.tslot, C.tkey, sh_wmax, theta, theta_sticky);
+            if (lane < ML_BATCH_MAX) { ma = BC.sel.mem[lane].a; mb = BC.sel.mem[lane].b; mslot = BC.sel.mem[lane].slot; midx = BC.sel.mem[lane].idx; mcnt = BC.sel.mem[lane].cnt; }
             if (nb > 0) best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0),
                                     __shfl_sync(0xffffffffu, mb, 0), __shfl_sync(0xffffffffu, midx, 0)};
         }
@@ -1532,7 +1560,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         if (threadIdx.x < ML_BATCH_MAX) BC.seg_n[threadIdx.x] = 0;
         for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
-        if (threadIdx.x == 0) { sh_ncand = 0; BC.nS = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
+        if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
         // how many members fit: candidate lists, log space, distinct NEW product tokens (every warp computes the same)
         int mtot = 0, mnew = 0, mlen = 0; int32_t mc = -1; u64 mH = 0; bool mbad = true;
         if (lane < nb) {
@@ -1557,7 +1585,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         const int kk = __ffs(__ballot_sync(0xffffffffu, mbad)) - 1;     // lanes >= nb are bad: kk <= nb
         if (kk == 0) break;                                              // the best pair alone needs the grid (or an index rebuild)
 #if ML_BATCH_WHY
-        if (warp == 0 && lane == kk && kk < nb) M.state[(cum > ML_LEADER_ITEMS_MAX || (i64)alog_n + cum > M.alog_cap) ? 61 : 62]++;   // 61: candidate lists / log space, 62: product token
+        if (warp == 0 && lane == kk && kk < nb) M.state[63]++;          // candidate lists / log space / product token
 #endif
         ML_CLOCK(c2);
         ML_TR(2);
@@ -1610,10 +1638,10 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             // ---- C: commits (last warp, one lane per member) || claim + rewrite
             const int last_new = __shfl_sync(0xffffffffu, mnew, kk - 1) ? kk - 1 : kk - 2;   // every member but the last makes a new token
             if (warp == nwarps - 1) {
-                if (lane < kk) commit_member(M, C, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, BC.MI[lane], moc, lane == last_new);
-            } else if (G == 8) leader_rewrite_batch<8>(M, C, BC, kk, warp, lane, nwarps, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-            else if (G == 4) leader_rewrite_batch<4>(M, C, BC, kk, warp, lane, nwarps, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-            else leader_rewrite_batch<2>(M, C, BC, kk, warp, lane, nwarps, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                if (lane < kk) commit_member(M, &C, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, BC.MI[lane], moc, lane == last_new);
+            } else if (G == 8) rewrite_batch<8>(M, &C, BC.R, BC.seg_n, kk, lane, warp * 4, (nwarps - 1) * 4, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else if (G == 4) rewrite_batch<4>(M, &C, BC.R, BC.seg_n, kk, lane, warp * 8, (nwarps - 1) * 8, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else rewrite_batch<2>(M, &C, BC.R, BC.seg_n, kk, lane, warp * 16, (nwarps - 1) * 16, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
             n_new_batch = __popc(__ballot_sync(0xffffffffu, lane < kk && mnew));
             len_batch = __shfl_sync(0xffffffffu, lcum, kk - 1) - (__shfl_sync(0xffffffffu, mnew, kk - 1) ? 0 : __shfl_sync(0xffffffffu, mlen, kk - 1));
             items_batch = __shfl_sync(0xffffffffu, cum, kk - 1);
@@ -1833,7 +1861,11 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     __shared__ __align__(16) int sh_hist[1024];
     __shared__ int32_t sh_c;
     __shared__ Ranges R;
+    __shared__ BatchCtx GB;                  // grid-mode batches (every CTA builds the same one)
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
+    i64 g_theta = 0; bool g_sticky = false;   // head threshold of the grid-mode batch selection: the same in every CTA
+    int g_parity = 0;
+    if (threadIdx.x == 0) GB.sel.nS = 0;
 
     long long pclk = clock64();
     const long long pclk0 = pclk;
@@ -1895,6 +1927,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             grid_barrier(M);                                    // everyone has read the state
             pclk = clock64();
             const bool more = grid_top_rebuild(M, T, Tmin, sh_best, sh_hist);
+            g_theta = 0; g_sticky = false;
             ML_PHASE(MS_CLK_TOPREB, pclk);
             if (gtid == 0) M.state[MS_N_TOPREB]++;
             if (!more) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
@@ -1934,10 +1967,108 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         //      (same data, same answer); the barrier only keeps the rewrite (which changes the counts)
         //      from starting before every CTA has read them.
         Best best;
+        bool have_best = false;
         pclk = clock64();
         ML_CLOCK(g0);
+        // ---- a BATCH of merges in grid mode (rules: "batched leader merges"): every CTA selects the same members from the
+        //      same list and counts, builds the same candidate ranges, and the groups of all CTAs share the items.
+        //      Barrier 1: every CTA has read the counts.  Barrier 2: every word is rewritten; then every CTA closes the members.
+        if (T2 > 0 && T2pa == 0 && M.state[MS_TOP_OVF] == 0 && ((M.batch_max >> 8) & 255 ? (M.batch_max >> 8) & 255 : M.batch_max & 255) != 1) {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+            const i64 top_now = M.state[MS_TOP_N];              // not the value read above: a leader session may have added entries since
+            const int tn = (int)(top_now < ML_TOP_N ? top_now : ML_TOP_N);
+            int gbmax = (int)((M.batch_max >> 8) & 255 ? (M.batch_max >> 8) & 255 : M.batch_max & 255);      // bits 8..15: grid mode's own limit (tuning)
+            if (gbmax <= 0 || gbmax > ML_BATCH_MAX) gbmax = ML_BATCH_MAX;
+            Best mine{0, -1, 0, 0, 0};
+            if ((int)threadIdx.x < tn) {
+                const int32_t sl = __ldcg(&M.top_slot[threadIdx.x]);
+                const u64 k = __ldcg(&M.top_key[threadIdx.x]);
+                const i64 cnt = __ldcg(&M.pcnt[sl]);
+                if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
+            }
+            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, nullptr, nullptr, M.top_slot, M.top_key, sh_cnt, g_theta, g_sticky);
+            if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
+            int32_t ma = 0, mb = 0, mslot = -1; i64 mcnt = 0;
+            if (lane < ML_BATCH_MAX) { ma = GB.sel.mem[lane].a; mb = GB.sel.mem[lane].b; mslot = GB.sel.mem[lane].slot; mcnt = GB.sel.mem[lane].cnt; }
+            if (nb >= 1) {
+                best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0), __shfl_sync(0xffffffffu, mb, 0), 0};
+                have_best = true;
+            }
+#if ML_DEBUG_SEL
+            {
+                const Best tb = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
+                if (nb >= 1 && tb.slot != best.slot && gtid == 0 && M.state[58] == 0) {
+                    M.state[58] = m + 1; M.state[59] = best.slot; M.state[60] = tb.slot; M.state[61] = best.cnt; M.state[62] = tb.cnt; M.state[63] = g_theta * 1000 + nb;
+                }
+            }
+#endif
+            if (nb >= 2) {
+                grid_barrier(M);                                // 1: every CTA has read the counts
+                if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &GB.R[warp]);
+                if (warp >= ML_BATCH_MAX && warp < ML_BATCH_MAX + nb && lane == warp - ML_BATCH_MAX) GB.c[lane] = lookup_merged(M, ma, mb, n_tok, &GB.MI[lane]);
+                __syncthreads();
+                int mtot = 0, mnew = 0, mlen = 0; int32_t mc = -1; u64 mH = 0; bool mbad = true;
+                if (lane < nb) {
+                    mtot = (int)(GB.R[lane].total < 0x08000000 ? GB.R[lane].total : 0x08000000);
+                    mbad = GB.R[lane].n < 0;
+                    mc = GB.c[lane]; mnew = mc == n_tok ? 1 : 0; mH = GB.MI[lane].H; mlen = (int)(GB.MI[lane].la + GB.MI[lane].lb);
+                    if (mnew) mc = n_tok + lane;
+                }
+                int cum = mtot, lcum = mlen;
+#pragma unroll
+                for (int o = 1; o < ML_BATCH_MAX; o <<= 1) {
+                    const int t1 = __shfl_up_sync(0xffffffffu, cum, o), t3 = __shfl_up_sync(0xffffffffu, lcum, o);
+                    if (lane >= o) { cum += t1; lcum += t3; }
+                }
+                if (alog_n + cum > M.alog_cap) mbad = true;
+#pragma unroll
+                for (int i = 0; i < ML_BATCH_MAX - 1; i++) {
+                    const u64 Hi = __shfl_sync(0xffffffffu, mH, i);
+                    const int newi = __shfl_sync(0xffffffffu, mnew, i);
+                    if (i < lane && (Hi == mH || !newi)) mbad = true;
+                }
+                const int kk = __ffs(__ballot_sync(0xffffffffu, mbad)) - 1;
+                __syncthreads();                                // GB is rewritten by the next selection
+                if (kk >= 2) {
+                    const int items_all = __shfl_sync(0xffffffffu, cum, kk - 1);
+                    const int warps_all = (int)gridDim.x * nwarps;
+                    const int G = items_all > warps_all * 8 ? 2 : (items_all > warps_all * 4 ? 4 : 8), padm = 32 / G - 1;
+                    int pcum = lane < kk ? (mtot + padm) & ~padm : 0;
+#pragma unroll
+                    for (int o = 1; o < ML_BATCH_MAX; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, pcum, o); if (lane >= o) pcum += t2; }
+                    const int mpst = pcum - (lane < kk ? (mtot + padm) & ~padm : 0), mseg = (int)alog_n + cum - mtot;
+                    const i64 pool_end = M.tok_off[n_tok];
+                    const i64 moc = pool_end + lcum - mlen;
+                    const int last_new = __shfl_sync(0xffffffffu, mnew, kk - 1) ? kk - 1 : kk - 2;
+                    int* gseg = (int*)&M.bsum[960] + 16 * g_parity;       // the members' log counters of this batch (zeroed one batch ahead)
+                    if (blockIdx.x == 0) {
+                        if (warp == nwarps - 1 && lane < kk) { commit_member(M, nullptr, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, GB.MI[lane], moc, lane == last_new); M.pcnt[mslot] = 0; }
+                        if (threadIdx.x < ML_BATCH_MAX) ((int*)&M.bsum[960])[16 * (1 - g_parity) + threadIdx.x] = 0;
+                    }
+                    const int32_t stamp = (int32_t)(m + 1);
+                    const int gw = (int)blockIdx.x * nwarps + warp;
+                    if (G == 8) rewrite_batch<8>(M, nullptr, GB.R, gseg, kk, lane, gw * 4, warps_all * 4, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else if (G == 4) rewrite_batch<4>(M, nullptr, GB.R, gseg, kk, lane, gw * 8, warps_all * 8, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else rewrite_batch<2>(M, nullptr, GB.R, gseg, kk, lane, gw * 16, warps_all * 16, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    grid_barrier(M);                            // 2: every word is rewritten, every token created
+                    // every CTA writes the same values: no further barrier before the next iteration
+                    if (warp == 0 && lane < kk) {
+                        const int e = mseg + __ldcg(&gseg[lane]);
+                        M.seg_end[m + lane] = e; M.tok_first[mc] = (int32_t)(m + lane);
+                        M.tok_head[mc] = make_int4((int32_t)(m + lane), mseg, e, M.merge_next[m + lane]);
+                    }
+                    if (threadIdx.x == 0) { M.state[MS_NMERGES] = m + kk; M.state[MS_ALOG_N] = alog_n + items_all; }
+                    if (gtid == 0) { M.state[MS_GRID_MERGES] += kk; M.state[MS_GRID_ITERS]++; M.state[MS_GRID_BATCHED] += kk; }
+                    g_parity ^= 1;
+                    ML_PHASE(MS_CLK_GRID, pclk);
+                    __syncthreads();
+                    continue;
+                }
+                // fewer than two members fit (candidate index / log space, product tokens): the best pair goes alone
+            }
+        }
         if (T2 > 0) {
-            best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
+            if (!have_best) best = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
             grid_barrier(M);
             if (best.slot < 0 || best.cnt < T2 || best.cnt < T || (best.cnt == T2 && T2pa != 0 && M.tok_pre[best.a] < T2pa)) {
                 if (gtid == 0) M.state[MS_T2] = 0;

@@ -120,6 +120,8 @@ class TrainStats:
     leader_merges: int = 0
     leader_iterations: int = 0      # an iteration of the leader merges a batch of 1 .. 8 pairs (csrc/merge.cuh)
     batched_merges: int = 0         # merges done as members of a batch of two or more
+    grid_batches: int = 0           # grid-mode iterations that merged two or more pairs
+    grid_batched_merges: int = 0
     grid_merges: int = 0
 
 
@@ -323,6 +325,8 @@ class BBPETrainer:
         stats.grid_merges = int(mr.state[_ffi.MS_GRID_MERGES])
         stats.leader_iterations = int(mr.state[54])
         stats.batched_merges = int(mr.state[55])
+        stats.grid_batches = int(mr.state[56])
+        stats.grid_batched_merges = int(mr.state[57])
         self.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13]), int(mr.state[17])]
         self.timing['merge_phase_cycles'] = _phase_cycles(mr.state)
         stats.launches = _ffi.launch_count() - launches0
