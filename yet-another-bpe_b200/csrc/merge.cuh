@@ -17,11 +17,14 @@
 #ifndef ML_THREADS
 #define ML_THREADS 1024
 #endif
-#ifndef ML_BATCH_WHY
-#define ML_BATCH_WHY 0        // 1: state[63] counts the leader batches cut short after stage B (candidate lists, log space, product token)
+#ifndef ML_RW_TRACE
+#define ML_RW_TRACE 0         // 1: thread 0 of CTA 0 times the stages of its own rewrite_batch chain (grid mode) into state[48..53]
 #endif
-#ifndef ML_DEBUG_SEL
-#define ML_DEBUG_SEL 0
+#if ML_RW_TRACE
+__device__ unsigned long long g_rw_clk[8];
+#define RWT(k, dep) do { if (!lc && blockIdx.x == 0 && threadIdx.x == 0) { long long _t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(_t) : "r"((int)(dep)) : "memory"); atomicAdd(&g_rw_clk[k], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
+#else
+#define RWT(k, dep)
 #endif
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
@@ -95,11 +98,16 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define MS_CLK_TOTAL 46
 #define MS_N_TOPREB 47
 #define MS_GRID_CLS 48        // grid merges by candidate-word count: [48..50] merges, [51..53] cycles; classes <= 2 368 (8-lane groups...), <= 18 944, more
-#define ML_PHASE(slot, t0) do { if (gtid == 0) { const long long _t = clock64(); M.state[slot] += _t - (t0); (t0) = _t; } } while (0)          // second component of the top-list threshold (see pair_add): left-token prefix, 0 = none    // %smid of CTA 0 (helpers are picked among its neighbours: same TPC / GPC, same die)
+#define ML_PHASE(slot, t0) do { if (gtid == 0) { const long long _t = clock64(); sh_phase[(slot) - 40] += _t - (t0); (t0) = _t; } } while (0)     // accumulated in shared memory, stored once at the end
 #define MS_LEADER_ITERS 54    // leader iterations (an iteration merges a batch of 1 .. ML_BATCH_MAX pairs)
 #define MS_LEADER_BATCHED 55  // merges done as members of a batch of two or more
 #define MS_GRID_ITERS 56      // grid-mode iterations that merged a batch of two or more
 #define MS_GRID_BATCHED 57    // merges done in those
+#define MS_CLK_GB_SELECT 58   // grid-mode batches, cycles of CTA 0: selection | barrier 1 | ranges + lookups | own share of the rewrite | barrier 2
+#define MS_CLK_GB_BAR1 59
+#define MS_CLK_GB_RANGES 60
+#define MS_CLK_GB_REWRITE 61
+#define MS_CLK_GB_BAR2 62
 #define MS_STATE_WORDS 64
 
 #define ME_PAIR_TABLE_FULL 1
@@ -229,6 +237,9 @@ struct Best { i64 cnt; int32_t slot; int32_t a; int32_t b; int32_t pad; };
 #define ML_LEADER_ITEMS_MAX 1024
 #endif
 #define ML_LEADER_BATCH 4096
+#ifndef ML_LEADER_BATCH_ITEMS
+#define ML_LEADER_BATCH_ITEMS 256      // a batch with more candidate words than this goes to the grid
+#endif
 
 struct MergeParams {
     // words
@@ -668,6 +679,7 @@ __device__ __forceinline__ void leader_new_pairs(const MergeParams& M, LeaderCtx
 // seg_ctr != nullptr: batched merges -- every member of a batch owns a reserved segment [seg_base, seg_base + its candidate count)
 // of the log (the words one merge rewrites must stay contiguous), filled through the member's own counter.
 __device__ __forceinline__ void alog_append(const MergeParams& M, int32_t w, i64 off, LeaderCtx* lc, int* seg_ctr = nullptr, i64 seg_base = 0) {
+    if (seg_base < 0) return;                  // batched merges: the member's segment is a copy of its candidate list (rewrite_batch)
     const i64 d = seg_ctr ? seg_base + (i64)atomicAdd(seg_ctr, 1)
                           : (lc ? (i64)atomicAdd(&lc->alog_n, 1) : (i64)atomicAdd((u64*)&M.state[MS_ALOG_N], 1ULL));
     if (d < M.alog_cap) M.alog_word[d] = POST_PACK(w, off);
@@ -1247,6 +1259,7 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
 // tie regime (T2pa != 0) and single heavy merges take the one-merge path below.
 struct BatchSel {
     u64 S[32]; int nS;                          // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
+    u64 Skey[32]; int32_t Sslot[32];            // and their pair keys / table slots (by position in S)
     int hist[33];
     struct { int32_t a, b, slot, idx; i64 cnt; } mem[ML_BATCH_MAX];
     int nb;
@@ -1255,7 +1268,6 @@ struct BatchCtx {
     Ranges R[ML_BATCH_MAX];
     MergedInfo MI[ML_BATCH_MAX];
     int32_t c[ML_BATCH_MAX];
-    int seg_n[ML_BATCH_MAX];                    // words each member rewrote (its segment of the affected-word log)
     BatchSel sel;
 };
 
@@ -1267,13 +1279,16 @@ struct BatchCtx {
 // tpa / tpb: 8-byte prefixes of the entries' tokens by list index (leader: shared memory), or nullptr: M.tok_pre is read.
 // Block-wide; every thread returns the same count nb (0: the caller takes the one-merge path) and finds the members in BS.mem.
 // Deterministic in its inputs: CTAs that see the same list and counts (grid mode) choose the same batch.
-__device__ int select_batch(const MergeParams& M, BatchSel& BS, const Best& mine, int tn, int batch_max, i64 T, i64 Tmin, i64 T2,
+__device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, const Best& mine, int tn, int batch_max, i64 T, i64 Tmin, i64 T2,
                             const u64* tpa, const u64* tpb, const int32_t* tslot, const u64* tkey, i64* sh_wmax, i64& theta, bool& theta_sticky) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
     int nS;
     for (int pass = 0;; pass++) {
-        if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) { const int p = atomicAdd(&BS.nS, 1); if (p < 32) BS.S[p] = mykey; }
+        if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) {
+            const int p = atomicAdd(&BS.nS, 1);
+            if (p < 32) { BS.S[p] = mykey; BS.Skey[p] = PAIR_KEY(mine.a, mine.b); BS.Sslot[p] = mine.slot; }
+        }
         __syncthreads();
         nS = BS.nS;
         const bool refresh = theta <= 0 || nS > 32 || (nS < 4 && tn > 32 && !theta_sticky && theta > 1);
@@ -1288,28 +1303,31 @@ __device__ int select_batch(const MergeParams& M, BatchSel& BS, const Best& mine
         int32_t ma = 0, mb = 0, mslot = -1, midx = -1; i64 mcnt = 0;
         // rank of every head entry by (count, list index): 31 shuffle rounds, no dependent chain
         const u64 k = lane < nS ? BS.S[lane] : 0ULL;
+        const u64 k_pair = lane < nS ? BS.Skey[lane] : 0ULL;
+        const int32_t k_slot = lane < nS ? BS.Sslot[lane] : -1;
         int rank = 0;
 #pragma unroll
         for (int o = 1; o < 32; o++) {
             const u64 other = __shfl_sync(0xffffffffu, k, (lane + o) & 31);
             rank += other > k ? 1 : 0;
         }
-        if (k != 0 && rank < ML_SEL) BS.S[rank] = k;             // keys are unique: the ML_SEL best land in S[0 .. ML_SEL) in order
+        __syncwarp();
+        if (k != 0 && rank < ML_SEL) { BS.S[rank] = k; BS.Skey[rank] = k_pair; BS.Sslot[rank] = k_slot; }   // keys are unique: the ML_SEL best land in [0 .. ML_SEL) in order
         __syncwarp();
         u64 sel = (lane < ML_SEL && lane < nS) ? BS.S[lane] : 0ULL;
         u64 pa = 0, pb = 0;
         if (sel != 0) {
             midx = 511 - (int)(sel & 511);
-            const u64 kk2 = tkey[midx];
+            const u64 kk2 = BS.Skey[lane];
             ma = (int32_t)((kk2 >> 32) & 0x7fffffff); mb = (int32_t)(kk2 & 0xffffffffu);
-            mslot = tslot[midx]; mcnt = (i64)(sel >> 9);
-            pa = tpa ? tpa[midx] : __ldcg(&M.tok_pre[ma]); pb = tpb ? tpb[midx] : __ldcg(&M.tok_pre[mb]);
+            mslot = BS.Sslot[lane]; mcnt = (i64)(sel >> 9);
         }
         // entries outside the selection: below theta, or (more than ML_SEL in the head) not above the last selected count
         const i64 g = nS > ML_SEL ? __shfl_sync(0xffffffffu, mcnt, ML_SEL - 1) : theta - 1;
         // equal counts among the selected: (left bytes, right bytes) order them (exact: prefixes, then the bytes)
         const i64 cdown = __shfl_down_sync(0xffffffffu, mcnt, 1);
         if (__ballot_sync(0xffffffffu, lane < ML_SEL - 1 && sel != 0 && mcnt == cdown && mcnt > g)) {
+            if (sel != 0) { pa = tpa ? tpa[midx] : __ldcg(&M.tok_pre[ma]); pb = tpb ? tpb[midx] : __ldcg(&M.tok_pre[mb]); }
             int rk = 0;
             for (int i = 0; i < ML_SEL; i++) {
                 const i64 ci = __shfl_sync(0xffffffffu, mcnt, i);
@@ -1386,21 +1404,26 @@ __device__ void commit_member(const MergeParams& M, LeaderCtx* lc, i64 m, int32_
 // group as in leader_rewrite: the item of pass p+2 and the word header of pass p+1 are loaded while pass p is rewritten.
 // Leader mode: lc = the leader's context (claims in its shared-memory set, counters in shared memory), group0 / ngroups span
 // the rewriting warps of CTA 0.  Grid mode: lc = nullptr (claims by the per-word stamp, counters in global memory), the
-// groups of ALL CTAs share the items.  seg_n: the members' log counters (shared / global).
+// groups of ALL CTAs share the items.
 template <int G>
-__device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* lc, const Ranges* RR, int* seg_n, int kk, int lane, int group0, int ngroups, int32_t stamp,
+__device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* lc, const Ranges* RR, int kk, int lane, int group0, int ngroups, int32_t stamp,
                                               int32_t ma, int32_t mb, int32_t mc, int32_t mslot, int mnew, int mtot, int mpst, int mseg,
                                               i64 T, i64 T2) {
     const int gl = lane & (G - 1), lead = lane & ~(G - 1);
     const int total_p = __shfl_sync(0xffffffffu, mpst + mtot, kk - 1);
     const u64 mkey = PAIR_KEY(ma, mb);
-    auto fetch = [&](int it) -> i64 {                    // item `it` of the padded layout (all 32 lanes call this together)
-        int mem = -1, loc = 0;
+    // Item `it` of the padded layout (all 32 lanes call this together).  The affected-word segment of a member is simply a
+    // COPY of its candidate list -- a superset of the words it rewrites, which is all the index needs (candidates are ~97 %
+    // hits) -- so the log needs no counter: hundreds of groups appending through one atomic serialised in the L2.
+    auto fetch = [&](int it) -> i64 {
+        int mem = -1, loc = 0, sb = 0;
         for (int i = 0; i < kk; i++) {
-            const int st = __shfl_sync(0xffffffffu, mpst, i), tt = __shfl_sync(0xffffffffu, mtot, i);
-            if (it >= st && it < st + tt) { mem = i; loc = it - st; }
+            const int st = __shfl_sync(0xffffffffu, mpst, i), tt = __shfl_sync(0xffffffffu, mtot, i), sg = __shfl_sync(0xffffffffu, mseg, i);
+            if (it >= st && it < st + tt) { mem = i; loc = it - st; sb = sg; }
         }
-        return mem >= 0 ? range_item(RR[mem], loc) : -1;
+        const i64 e = mem >= 0 ? range_item(RR[mem], loc) : -1;
+        if (mem >= 0 && gl == 0) M.alog_word[sb + loc] = e;
+        return e;
     };
     auto claim = [&](int32_t w) -> int32_t {             // first claim of a word in this batch wins
         int take = 0;
@@ -1409,24 +1432,32 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
         return take ? w : -1;
     };
     const int it0 = group0 + lane / G;
+#if ML_RW_TRACE
+    long long _t0 = clock64();
+#endif
     const i64 e_cur = fetch(it0);
     i64 e_nx = fetch(it0 + ngroups);
-    int32_t w_cur = claim(POST_WORD(e_cur)), w_nx = POST_WORD(e_nx);
+    RWT(0, (int)e_cur + (int)e_nx);
+    // the header (and the symbols: the entry carries their slot) is asked for BEFORE the claim returns: only the claimer
+    // changes a word, so a read that loses the claim is merely dropped, and the two round trips overlap
+    int32_t w_cur = POST_WORD(e_cur), w_nx = POST_WORD(e_nx);
     uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
-    if (w_cur >= 0) {                       // header and symbols in ONE round trip: the entry carries the symbol slot
+    if (w_cur >= 0) {
         off_cur = (uint32_t)POST_OFF(e_cur);
         if (gl == 0) { prefetch_l2(&M.wsym[off_cur]); prefetch_l2(&M.wslot[off_cur]); }
         n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur];
     }
+    w_cur = claim(w_cur);
+    RWT(1, w_cur + n_cur + (int)f_cur);
     for (int base = 0; base + group0 < total_p; base += ngroups) {      // warps without an item go straight to the barrier
         const i64 e_nx2 = fetch(base + it0 + 2 * ngroups);
-        w_nx = claim(w_nx);
         uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
         if (w_nx >= 0) {
             off_nx = (uint32_t)POST_OFF(e_nx);
             if (gl == 0) { prefetch_l2(&M.wsym[off_nx]); prefetch_l2(&M.wslot[off_nx]); }
             n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx];
         }
+        w_nx = claim(w_nx);
         // ---- the current word: which members have a site in it
         const int32_t w = w_cur;
         const i64 off = (i64)off_cur;
@@ -1443,17 +1474,19 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
         }
+        RWT(2, mask + w_nx + n_nx);
         for (int i = 0; i < kk; i++) {
             const bool act = w >= 0 && ((mask >> i) & 1u);
             const int32_t a = __shfl_sync(0xffffffffu, ma, i), b = __shfl_sync(0xffffffffu, mb, i), c = __shfl_sync(0xffffffffu, mc, i);
             const int32_t sl = __shfl_sync(0xffffffffu, mslot, i);
-            const int isn = __shfl_sync(0xffffffffu, mnew, i), sb = __shfl_sync(0xffffffffu, mseg, i);
+            const int isn = __shfl_sync(0xffffffffu, mnew, i);
             if (!__any_sync(0xffffffffu, act)) continue;
             if (a != b) {
-                const int nn = rewrite_words_g<G>(M, act ? w : -1, off, n, f_cur, a, b, c, T, T2, lc, isn != 0, &seg_n[i], (i64)sb);
+                const int nn = rewrite_words_g<G>(M, act ? w : -1, off, n, f_cur, a, b, c, T, T2, lc, isn != 0, nullptr, -1);
                 if (act) n = nn;
-            } else if (act && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, lc, isn != 0, sl, &seg_n[i], (i64)sb);
+            } else if (act && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, lc, isn != 0, sl, nullptr, -1);
         }
+        RWT(3, n);
         w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; e_nx = e_nx2; w_nx = POST_WORD(e_nx2);
     }
 }
@@ -1481,6 +1514,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     int batch_max = (M.batch_max & 255) > 0 ? (int)(M.batch_max & 255) : ML_BATCH_MAX;
     if (batch_max > ML_BATCH_MAX) batch_max = ML_BATCH_MAX;
+    const bool grid_batches_on = ((M.batch_max >> 8) & 255 ? (M.batch_max >> 8) & 255 : M.batch_max & 255) != 1 && !((M.batch_max >> 17) & 1);   // bit 17: keep big batches here (tuning)
     if (T2pa != 0) batch_max = 1;        // tie regime: the list is not complete at the boundary count (and pair_add reads prefixes of tokens being created)
 #if ML_TIMING
     long long t_arg = 0, t_rng = 0, t_rw = 0, t_close = 0;
@@ -1557,7 +1591,6 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &BC.R[warp], midx >= 0, midx >= 0 ? C.tp0[midx] : 0u, midx >= 0 ? C.tplen[midx] : 0u);
         if (warp >= ML_BATCH_MAX && warp < ML_BATCH_MAX + nb && lane == warp - ML_BATCH_MAX)
             BC.c[lane] = lookup_merged_leader(M, C, midx, ma, mb, n_tok, &BC.MI[lane]);
-        if (threadIdx.x < ML_BATCH_MAX) BC.seg_n[threadIdx.x] = 0;
         for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
         if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
@@ -1584,9 +1617,9 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         }
         const int kk = __ffs(__ballot_sync(0xffffffffu, mbad)) - 1;     // lanes >= nb are bad: kk <= nb
         if (kk == 0) break;                                              // the best pair alone needs the grid (or an index rebuild)
-#if ML_BATCH_WHY
-        if (warp == 0 && lane == kk && kk < nb) M.state[63]++;          // candidate lists / log space / product token
-#endif
+        // A batch with many candidate words is better off in grid mode: one pass over 148 SMs instead of several passes here
+        // (the members are the same there; the main loop stays in grid mode with exponential back-off while that goes on).
+        if (nb >= 2 && grid_batches_on && __shfl_sync(0xffffffffu, cum, nb - 1) > ML_LEADER_BATCH_ITEMS) break;
         ML_CLOCK(c2);
         ML_TR(2);
         int n_new_batch = 0, len_batch = 0, items_batch = 0;
@@ -1639,9 +1672,9 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             const int last_new = __shfl_sync(0xffffffffu, mnew, kk - 1) ? kk - 1 : kk - 2;   // every member but the last makes a new token
             if (warp == nwarps - 1) {
                 if (lane < kk) commit_member(M, &C, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, BC.MI[lane], moc, lane == last_new);
-            } else if (G == 8) rewrite_batch<8>(M, &C, BC.R, BC.seg_n, kk, lane, warp * 4, (nwarps - 1) * 4, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-            else if (G == 4) rewrite_batch<4>(M, &C, BC.R, BC.seg_n, kk, lane, warp * 8, (nwarps - 1) * 8, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-            else rewrite_batch<2>(M, &C, BC.R, BC.seg_n, kk, lane, warp * 16, (nwarps - 1) * 16, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            } else if (G == 8) rewrite_batch<8>(M, &C, BC.R, kk, lane, warp * 4, (nwarps - 1) * 4, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else if (G == 4) rewrite_batch<4>(M, &C, BC.R, kk, lane, warp * 8, (nwarps - 1) * 8, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else rewrite_batch<2>(M, &C, BC.R, kk, lane, warp * 16, (nwarps - 1) * 16, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
             n_new_batch = __popc(__ballot_sync(0xffffffffu, lane < kk && mnew));
             len_batch = __shfl_sync(0xffffffffu, lcum, kk - 1) - (__shfl_sync(0xffffffffu, mnew, kk - 1) ? 0 : __shfl_sync(0xffffffffu, mlen, kk - 1));
             items_batch = __shfl_sync(0xffffffffu, cum, kk - 1);
@@ -1650,7 +1683,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             // ---- D: close the members; thresholds of the pairs the batch created
             if (warp == 0 && lane < kk) {
                 const int32_t prev = mnew ? -1 : M.tok_first[mc];
-                const int e = mseg + BC.seg_n[lane];
+                const int e = mseg + mtot;
                 M.seg_end[m + lane] = e; M.tok_first[mc] = (int32_t)(m + lane);
                 M.tok_head[mc] = make_int4((int32_t)(m + lane), mseg, e, prev);
                 M.pcnt[mslot] = 0; mirror_set(&C.LM, midx, 0);
@@ -1862,9 +1895,10 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     __shared__ int32_t sh_c;
     __shared__ Ranges R;
     __shared__ BatchCtx GB;                  // grid-mode batches (every CTA builds the same one)
+    __shared__ long long sh_phase[24];       // phase clocks of CTA 0: state[40 .. 63]
+    if (threadIdx.x < 24) sh_phase[threadIdx.x] = 0;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     i64 g_theta = 0; bool g_sticky = false;   // head threshold of the grid-mode batch selection: the same in every CTA
-    int g_parity = 0;
     if (threadIdx.x == 0) GB.sel.nS = 0;
 
     long long pclk = clock64();
@@ -1929,14 +1963,14 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             const bool more = grid_top_rebuild(M, T, Tmin, sh_best, sh_hist);
             g_theta = 0; g_sticky = false;
             ML_PHASE(MS_CLK_TOPREB, pclk);
-            if (gtid == 0) M.state[MS_N_TOPREB]++;
+            if (gtid == 0) sh_phase[MS_N_TOPREB - 40]++;
             if (!more) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
             continue;
         }
 
         // ---- leader mode while the work per merge is small
         if (skip > 0) skip--;
-        else if (T2 > 0 && alog_n + ML_LEADER_ITEMS_MAX <= M.alog_cap) {
+        else if (T2 > 0 && alog_n + ML_LEADER_ITEMS_MAX <= M.alog_cap && !((M.batch_max >> 16) & 1)) {      // bit 16: no leader mode (tuning)
             const i64 m0 = m;
             grid_barrier(M);                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
@@ -1987,6 +2021,8 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
             }
             int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, nullptr, nullptr, M.top_slot, M.top_key, sh_cnt, g_theta, g_sticky);
+            long long gclk = pclk;
+            ML_PHASE(MS_CLK_GB_SELECT, gclk);
             if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
             int32_t ma = 0, mb = 0, mslot = -1; i64 mcnt = 0;
             if (lane < ML_BATCH_MAX) { ma = GB.sel.mem[lane].a; mb = GB.sel.mem[lane].b; mslot = GB.sel.mem[lane].slot; mcnt = GB.sel.mem[lane].cnt; }
@@ -1994,16 +2030,9 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0), __shfl_sync(0xffffffffu, mb, 0), 0};
                 have_best = true;
             }
-#if ML_DEBUG_SEL
-            {
-                const Best tb = top_best(M, M.state[MS_TOP_N], sh_best, sh_cnt);
-                if (nb >= 1 && tb.slot != best.slot && gtid == 0 && M.state[58] == 0) {
-                    M.state[58] = m + 1; M.state[59] = best.slot; M.state[60] = tb.slot; M.state[61] = best.cnt; M.state[62] = tb.cnt; M.state[63] = g_theta * 1000 + nb;
-                }
-            }
-#endif
             if (nb >= 2) {
                 grid_barrier(M);                                // 1: every CTA has read the counts
+                ML_PHASE(MS_CLK_GB_BAR1, gclk);
                 if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &GB.R[warp]);
                 if (warp >= ML_BATCH_MAX && warp < ML_BATCH_MAX + nb && lane == warp - ML_BATCH_MAX) GB.c[lane] = lookup_merged(M, ma, mb, n_tok, &GB.MI[lane]);
                 __syncthreads();
@@ -2029,10 +2058,11 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 }
                 const int kk = __ffs(__ballot_sync(0xffffffffu, mbad)) - 1;
                 __syncthreads();                                // GB is rewritten by the next selection
+                ML_PHASE(MS_CLK_GB_RANGES, gclk);
                 if (kk >= 2) {
                     const int items_all = __shfl_sync(0xffffffffu, cum, kk - 1);
                     const int warps_all = (int)gridDim.x * nwarps;
-                    const int G = items_all > warps_all * 8 ? 2 : (items_all > warps_all * 4 ? 4 : 8), padm = 32 / G - 1;
+                    const int G = items_all > (warps_all - 1) * 8 ? 2 : (items_all > (warps_all - 1) * 4 ? 4 : 8), padm = 32 / G - 1;
                     int pcum = lane < kk ? (mtot + padm) & ~padm : 0;
 #pragma unroll
                     for (int o = 1; o < ML_BATCH_MAX; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, pcum, o); if (lane >= o) pcum += t2; }
@@ -2040,26 +2070,29 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                     const i64 pool_end = M.tok_off[n_tok];
                     const i64 moc = pool_end + lcum - mlen;
                     const int last_new = __shfl_sync(0xffffffffu, mnew, kk - 1) ? kk - 1 : kk - 2;
-                    int* gseg = (int*)&M.bsum[960] + 16 * g_parity;       // the members' log counters of this batch (zeroed one batch ahead)
                     if (blockIdx.x == 0) {
                         if (warp == nwarps - 1 && lane < kk) { commit_member(M, nullptr, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, GB.MI[lane], moc, lane == last_new); M.pcnt[mslot] = 0; }
-                        if (threadIdx.x < ML_BATCH_MAX) ((int*)&M.bsum[960])[16 * (1 - g_parity) + threadIdx.x] = 0;
                     }
                     const int32_t stamp = (int32_t)(m + 1);
-                    const int gw = (int)blockIdx.x * nwarps + warp;
-                    if (G == 8) rewrite_batch<8>(M, nullptr, GB.R, gseg, kk, lane, gw * 4, warps_all * 4, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-                    else if (G == 4) rewrite_batch<4>(M, nullptr, GB.R, gseg, kk, lane, gw * 8, warps_all * 8, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-                    else rewrite_batch<2>(M, nullptr, GB.R, gseg, kk, lane, gw * 16, warps_all * 16, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    // the committing warp (last of CTA 0) takes no items: its round trips would sit on every batch's critical path
+                    // consecutive items go to warps of DIFFERENT CTAs (a batch of 1 000 items keeps 148 SMs busy, not 8)
+                    const int vw = warp * (int)gridDim.x + (int)blockIdx.x, skipw = (nwarps - 1) * (int)gridDim.x;
+                    const int gw = vw - (vw > skipw ? 1 : 0), rw = warps_all - 1;
+                    if (blockIdx.x == 0 && warp == nwarps - 1) { }
+                    else if (G == 8) rewrite_batch<8>(M, nullptr, GB.R, kk, lane, gw * 4, rw * 4, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else if (G == 4) rewrite_batch<4>(M, nullptr, GB.R, kk, lane, gw * 8, rw * 8, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else rewrite_batch<2>(M, nullptr, GB.R, kk, lane, gw * 16, rw * 16, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    ML_PHASE(MS_CLK_GB_REWRITE, gclk);
                     grid_barrier(M);                            // 2: every word is rewritten, every token created
+                    ML_PHASE(MS_CLK_GB_BAR2, gclk);
                     // every CTA writes the same values: no further barrier before the next iteration
                     if (warp == 0 && lane < kk) {
-                        const int e = mseg + __ldcg(&gseg[lane]);
+                        const int e = mseg + mtot;
                         M.seg_end[m + lane] = e; M.tok_first[mc] = (int32_t)(m + lane);
                         M.tok_head[mc] = make_int4((int32_t)(m + lane), mseg, e, M.merge_next[m + lane]);
                     }
                     if (threadIdx.x == 0) { M.state[MS_NMERGES] = m + kk; M.state[MS_ALOG_N] = alog_n + items_all; }
-                    if (gtid == 0) { M.state[MS_GRID_MERGES] += kk; M.state[MS_GRID_ITERS]++; M.state[MS_GRID_BATCHED] += kk; }
-                    g_parity ^= 1;
+                    if (gtid == 0) { M.state[MS_GRID_MERGES] += kk; sh_phase[MS_GRID_ITERS - 40]++; sh_phase[MS_GRID_BATCHED - 40] += kk; }
                     ML_PHASE(MS_CLK_GRID, pclk);
                     __syncthreads();
                     continue;
@@ -2153,10 +2186,16 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
         if (gtid == 0) {
             M.state[MS_GRID_MERGES]++;
             const int cls = R.total * 64 <= gstride ? 0 : (R.total * 8 <= gstride ? 1 : 2);
-            M.state[MS_GRID_CLS + cls]++; M.state[MS_GRID_CLS + 3 + cls] += clock64() - pclk;
+            sh_phase[MS_GRID_CLS + cls - 40]++; sh_phase[MS_GRID_CLS + 3 + cls - 40] += clock64() - pclk;
         }
         ML_PHASE(MS_CLK_GRID, pclk);
         __syncthreads();
     }
-    if (gtid == 0) M.state[MS_CLK_TOTAL] = clock64() - pclk0;
+    if (gtid == 0) {
+#if ML_RW_TRACE
+        for (int i = 0; i < 6; i++) { sh_phase[8 + i] = (long long)g_rw_clk[i]; g_rw_clk[i] = 0; }
+#endif
+        for (int i = 0; i < 24; i++) if (sh_phase[i]) M.state[40 + i] += sh_phase[i];
+        M.state[MS_CLK_TOTAL] = clock64() - pclk0;
+    }
 }

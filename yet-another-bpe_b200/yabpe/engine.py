@@ -369,7 +369,7 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
         if pcap is None:
             # distinct pairs stay well below the symbol count (0.07-0.2 x on the bench corpora); the kernel reports a
             # table that fills beyond 3/4 and the loop below retries with a four times larger one
-            pcap = _pow2_at_least(min(max(words.n_syms, 1 << 16), 1 << 26))
+            pcap = _pow2_at_least(min(max(words.n_syms >> int(os.environ.get("YABPE_PCAP_SHIFT", "0")), 1 << 16), 1 << 26))
         if pool_cap is None:
             pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
         alog_cap = max(2 * words.n_words, 1 << 16) + 4096

@@ -102,6 +102,7 @@ def _phase_cycles(state) -> dict:
     out = {k: int(state[40 + i]) for i, k in enumerate(names)}
     out["grid_merges_by_size[n<=2368,n<=18944,more]"] = [int(x) for x in state[48:51]]
     out["grid_cycles_by_size"] = [int(x) for x in state[51:54]]
+    out["grid_batch_cycles[select,barrier1,ranges,rewrite,barrier2]"] = [int(x) for x in state[58:63]]
     return out
 
 
