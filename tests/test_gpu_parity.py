@@ -311,6 +311,40 @@ def test_train_with_frequent_index_rebuilds(yabpe, tmp_path, monkeypatch):
             assert tr.last_stats.index_rebuilds >= 30
 
 
+@pytest.mark.parametrize("mode,what", [("1", "one merge per iteration everywhere (trainer.py:241-300 as written)"),
+                                       ("264", "batches in leader mode only"),
+                                       ("2049", "batches in grid mode only"),
+                                       ("65552", "no leader mode: every merge in the grid, batched"),
+                                       ("131088", "big batches stay with the leader"),
+                                       ("2", "pairs"), ("0", "default")])
+def test_train_batched_merges(yabpe, tmp_path, monkeypatch, mode, what):
+    """The merge loop takes up to 16 pairs per iteration when it can prove that the sequential loop would pick exactly these,
+    in this order (csrc/merge.cuh, "batched leader merges").  Every combination of where batching is allowed must give the
+    oracle's merges; the default must actually batch on a corpus of this kind."""
+    monkeypatch.setenv("YABPE_BATCH_MAX", mode)
+    if not hasattr(test_train_batched_merges, "_want"):
+        data = common.synth_owt(24_000_000, seed=78, n_types=200_000)
+        test_train_batched_merges._data = data
+        p0 = tmp_path / "b0.txt"
+        p0.write_bytes(data)
+        test_train_batched_merges._want = oracle.train_bpe(p0, 6000, ["<|endoftext|>"], fast=True)
+    want = test_train_batched_merges._want
+    p = tmp_path / "b.txt"
+    p.write_bytes(test_train_batched_merges._data)
+    tr = yabpe.BBPETrainer(yabpe.BBPETrainerConfig(vocab_size=6000, min_frequency=1, max_workers=1, chunk_size_bytes=1 << 30,
+                                                   special_tokens=["<|endoftext|>"]))
+    model = tr.train([p])
+    assert model.merges == want[1], what
+    assert {v: k for k, v in model.vocab.items()} == want[0], what
+    st = tr.last_stats
+    if mode == "1":
+        assert st.batched_merges == 0 and st.grid_batched_merges == 0
+    if mode == "0":
+        assert st.batched_merges + st.grid_batched_merges > st.n_merges // 4, st
+    if mode == "65552":
+        assert st.leader_merges == 0
+
+
 def test_train_with_prefetch_helpers_and_tie_regime(yabpe, tmp_path, monkeypatch):
     """(1) The leader's prefetch helpers (idle CTAs pulling the next merges' words into the L2) only run on word arrays
     beyond the L2 size; YABPE_HELPER_MIN_SYMS=-1 forces them on a small corpus -- results must not move.

@@ -1027,7 +1027,7 @@ __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh
 // of its 32 lanes (redux.sync); phase 2 (after ONE block barrier): every warp redundantly extracts the ML_SEL largest of the
 // per-warp lists, so all warps hold the same result without a second barrier.  Returned per lane: lane r gets the r-th key.
 #ifndef ML_BATCH_MAX
-#define ML_BATCH_MAX 8
+#define ML_BATCH_MAX 16       // one lane per member; two warps per member in stage B (32 warps)
 #endif
 #define ML_SEL (ML_BATCH_MAX + 1)
 #define ML_SEL_WARPS (ML_TOP_N / 32)
@@ -1441,21 +1441,25 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
     // the header (and the symbols: the entry carries their slot) is asked for BEFORE the claim returns: only the claimer
     // changes a word, so a read that loses the claim is merely dropped, and the two round trips overlap
     int32_t w_cur = POST_WORD(e_cur), w_nx = POST_WORD(e_nx);
-    uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0;
+    // ... and so are the word's first G symbols (almost every word fits): claim, header and symbols are ONE round trip.
+    // (wsym has 8 slots of slack: a read past a short word's end returns its neighbour's symbols, masked by the length)
+    uint32_t off_cur = 0; int n_cur = 0; i64 f_cur = 0; int32_t y0_cur = 0, y1_cur = 0;
     if (w_cur >= 0) {
         off_cur = (uint32_t)POST_OFF(e_cur);
-        if (gl == 0) { prefetch_l2(&M.wsym[off_cur]); prefetch_l2(&M.wslot[off_cur]); }
+        if (gl == 0) prefetch_l2(&M.wslot[off_cur]);
         n_cur = M.wlen[w_cur]; f_cur = M.wcnt[w_cur];
+        y0_cur = M.wsym[off_cur + gl]; y1_cur = M.wsym[off_cur + gl + 1];
     }
     w_cur = claim(w_cur);
     RWT(1, w_cur + n_cur + (int)f_cur);
     for (int base = 0; base + group0 < total_p; base += ngroups) {      // warps without an item go straight to the barrier
         const i64 e_nx2 = fetch(base + it0 + 2 * ngroups);
-        uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0;
+        uint32_t off_nx = 0; int n_nx = 0; i64 f_nx = 0; int32_t y0_nx = 0, y1_nx = 0;
         if (w_nx >= 0) {
             off_nx = (uint32_t)POST_OFF(e_nx);
-            if (gl == 0) { prefetch_l2(&M.wsym[off_nx]); prefetch_l2(&M.wslot[off_nx]); }
+            if (gl == 0) prefetch_l2(&M.wslot[off_nx]);
             n_nx = M.wlen[w_nx]; f_nx = M.wcnt[w_nx];
+            y0_nx = M.wsym[off_nx + gl]; y1_nx = M.wsym[off_nx + gl + 1];
         }
         w_nx = claim(w_nx);
         // ---- the current word: which members have a site in it
@@ -1468,7 +1472,7 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
             for (int j0 = 0; __any_sync(0xffffffffu, j0 + 1 < n); j0 += G) {
                 const int j = j0 + gl;
                 u64 key = 0;
-                if (j + 1 < n) key = PAIR_KEY(s[j], s[j + 1]);
+                if (j + 1 < n) key = j0 == 0 ? PAIR_KEY(y0_cur, y1_cur) : PAIR_KEY(s[j], s[j + 1]);
                 for (int i = 0; i < kk; i++) { const u64 ki = __shfl_sync(0xffffffffu, mkey, i); if (key == ki) mask |= 1u << i; }
             }
 #pragma unroll
@@ -1487,7 +1491,7 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
             } else if (act && gl == 0) rewrite_word_thread(M, w, a, b, c, T, T2, lc, isn != 0, sl, nullptr, -1);
         }
         RWT(3, n);
-        w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; e_nx = e_nx2; w_nx = POST_WORD(e_nx2);
+        w_cur = w_nx; off_cur = off_nx; n_cur = n_nx; f_cur = f_nx; y0_cur = y0_nx; y1_cur = y1_nx; e_nx = e_nx2; w_nx = POST_WORD(e_nx2);
     }
 }
 
@@ -1899,6 +1903,9 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     if (threadIdx.x < 24) sh_phase[threadIdx.x] = 0;
     const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (i64)gridDim.x * blockDim.x;
     i64 g_theta = 0; bool g_sticky = false;   // head threshold of the grid-mode batch selection: the same in every CTA
+    __shared__ int32_t g_tslot[ML_TOP_N];     // this CTA's copy of the top list (grid-mode batches), valid below g_cached
+    __shared__ u64 g_tkey[ML_TOP_N];
+    int g_cached = 0;
     if (threadIdx.x == 0) GB.sel.nS = 0;
 
     long long pclk = clock64();
@@ -1961,7 +1968,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             grid_barrier(M);                                    // everyone has read the state
             pclk = clock64();
             const bool more = grid_top_rebuild(M, T, Tmin, sh_best, sh_hist);
-            g_theta = 0; g_sticky = false;
+            g_theta = 0; g_sticky = false; g_cached = 0;
             ML_PHASE(MS_CLK_TOPREB, pclk);
             if (gtid == 0) sh_phase[MS_N_TOPREB - 40]++;
             if (!more) { if (gtid == 0) M.state[MS_DONE] = 1; break; }
@@ -2015,11 +2022,14 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             if (gbmax <= 0 || gbmax > ML_BATCH_MAX) gbmax = ML_BATCH_MAX;
             Best mine{0, -1, 0, 0, 0};
             if ((int)threadIdx.x < tn) {
-                const int32_t sl = __ldcg(&M.top_slot[threadIdx.x]);
-                const u64 k = __ldcg(&M.top_key[threadIdx.x]);
+                // the list only grows between rebuilds: every CTA keeps a copy, so the count is ONE round trip away
+                if ((int)threadIdx.x >= g_cached) { g_tslot[threadIdx.x] = __ldcg(&M.top_slot[threadIdx.x]); g_tkey[threadIdx.x] = __ldcg(&M.top_key[threadIdx.x]); }
+                const int32_t sl = g_tslot[threadIdx.x];
+                const u64 k = g_tkey[threadIdx.x];
                 const i64 cnt = __ldcg(&M.pcnt[sl]);
                 if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
             }
+            g_cached = tn;
             int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, nullptr, nullptr, M.top_slot, M.top_key, sh_cnt, g_theta, g_sticky);
             long long gclk = pclk;
             ML_PHASE(MS_CLK_GB_SELECT, gclk);
