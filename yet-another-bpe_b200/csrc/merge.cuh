@@ -21,10 +21,12 @@
 #define ML_RW_TRACE 0         // 1: thread 0 of CTA 0 times the stages of its own rewrite_batch chain (grid mode) into state[48..53]
 #endif
 #if ML_RW_TRACE
-__device__ unsigned long long g_rw_clk[8];
+__device__ unsigned long long g_rw_clk[16];
+#define SELT(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_rw_clk[8 + (k)], (unsigned long long)(_t - _s0)); _s0 = _t; } } while (0)
 #define RWT(k, dep) do { if (!lc && blockIdx.x == 0 && threadIdx.x == 0) { long long _t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(_t) : "r"((int)(dep)) : "memory"); atomicAdd(&g_rw_clk[k], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 #else
 #define RWT(k, dep)
+#define SELT(k)
 #endif
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
@@ -1208,28 +1210,41 @@ __device__ Best leader_argmax_one(const MergeParams& M, LeaderCtx& C, const Best
 // the counts in [lo, max] that zooms into the bin that did not fit (counts repeat: a single count can hold more entries than
 // fit, then fewer than 12 -- possibly none -- are taken and *sticky tells the caller not to ask again until the head is empty).
 // Block-wide, every thread returns the same value; ends with a barrier.
-__device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int* hist /* [33] */, bool* sticky) {
+// hi0 > 0: the caller knows that exactly above0 entries have a count >= hi0 (the old head, nearly used up): the search starts
+// below it and the block-wide maximum is not needed.
+__device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int* hist /* [34] */, bool* sticky, i64 hi0 = 0, int above0 = 0) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-    {
+    i64 hi = hi0;
+    int above = above0;
+    if (hi0 <= 0) {
         const i64 wm = warp_max_i64(mine.slot >= 0 ? mine.cnt : 0);
         __syncthreads();
         if (lane == 0) sh_wmax[warp] = wm;
+        __syncthreads();
+        hi = warp_max_i64(lane < nwarps ? sh_wmax[lane] : 0) + 1;          // no entry has a count >= hi
+        above = 0;
     }
-    __syncthreads();
-    i64 hi = warp_max_i64(lane < nwarps ? sh_wmax[lane] : 0) + 1;          // no entry has a count >= hi
-    int above = 0;
     i64 theta = lo;
     if (hi <= lo) { *sticky = true; __syncthreads(); return lo; }           // nothing above lo at all
     for (int round = 0; round < 64; round++) {
-        if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+        if (threadIdx.x < 32) hist[threadIdx.x] = 0;
         __syncthreads();
         const i64 width = (hi - lo + 31) / 32;
         if (mine.slot >= 0 && mine.cnt >= lo && mine.cnt < hi) atomicAdd(&hist[(int)((mine.cnt - lo) / width)], 1);
         __syncthreads();
-        int cum = above, b = 31;
-        for (; b >= 0; b--) { const int h = hist[b]; if (cum + h > 32) break; cum += h; }
+        if (warp == 0) {                               // bins from the top while they fit: suffix sums by shuffles, one warp
+            int suf = hist[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
+            const uint32_t fits = __ballot_sync(0xffffffffu, above + suf <= 32);       // an upper range of bins (suf falls with the bin)
+            const int bl = fits ? __ffs(fits) - 1 : 32;
+            const int cumw = above + (bl < 32 ? __shfl_sync(0xffffffffu, suf, bl & 31) : 0);
+            if (lane == 0) { hist[32] = bl - 1; hist[33] = cumw; }
+        }
+        __syncthreads();
+        const int b = hist[32], cum = hist[33];
         theta = lo + (i64)(b + 1) * width;
-        __syncthreads();                                                   // everybody has read the histogram
+        __syncthreads();                                                   // everybody has read the result
         if (b < 0) { theta = lo; above = cum; break; }
         if (cum >= 12 || width == 1) { above = cum; break; }
         above = cum; hi = theta; lo = lo + (i64)b * width;
@@ -1260,8 +1275,9 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
 struct BatchSel {
     u64 S[32]; int nS;                          // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
     u64 Skey[32]; int32_t Sslot[32];            // and their pair keys / table slots (by position in S)
-    int hist[33];
-    struct { int32_t a, b, slot, idx; i64 cnt; } mem[ML_BATCH_MAX];
+    int hist[34];
+    u64 Spa[ML_SEL], Spb[ML_SEL];               // token prefixes of the selected entries (filled when equal counts need ordering)
+    struct { int32_t a, b, slot, idx; i64 cnt; } mem[ML_SEL];      // the selected entries in exact order; the first nb are the batch
     int nb;
 };
 struct BatchCtx {
@@ -1284,6 +1300,9 @@ __device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
     int nS;
+#if ML_RW_TRACE
+    long long _s0 = clock64();
+#endif
     for (int pass = 0;; pass++) {
         if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) {
             const int p = atomicAdd(&BS.nS, 1);
@@ -1291,82 +1310,92 @@ __device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, 
         }
         __syncthreads();
         nS = BS.nS;
+        if (pass == 0) SELT(0);
         const bool refresh = theta <= 0 || nS > 32 || (nS < 4 && tn > 32 && !theta_sticky && theta > 1);
         if (!refresh || pass == 2) break;
-        theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BS.hist, &theta_sticky);     // block-wide; ends with a barrier
+        const bool below = theta > (T2 > 1 ? T2 : 1) && nS <= 32;                                     // the old head is nearly used up: look below it
+        theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BS.hist, &theta_sticky, below ? theta : 0, below ? nS : 0);     // block-wide; ends with a barrier
         if (tn <= 32) { theta = 1; theta_sticky = false; }
         if (threadIdx.x == 0) BS.nS = 0;
         __syncthreads();
     }
     if (nS > 32) nS = 0;                        // cannot happen after a refresh; be safe: the one-merge path decides
+    SELT(1);
     if (warp == 0) {
+        // One warp, and every step reads what it needs from shared memory with broadcast loads (independent, pipelined): a
+        // first version passed the entries around with ~230 dependent shuffles and spent 3 us per call on their latency.
         int32_t ma = 0, mb = 0, mslot = -1, midx = -1; i64 mcnt = 0;
-        // rank of every head entry by (count, list index): 31 shuffle rounds, no dependent chain
+        // rank of every head entry by (count, list index)
         const u64 k = lane < nS ? BS.S[lane] : 0ULL;
         const u64 k_pair = lane < nS ? BS.Skey[lane] : 0ULL;
         const int32_t k_slot = lane < nS ? BS.Sslot[lane] : -1;
         int rank = 0;
-#pragma unroll
-        for (int o = 1; o < 32; o++) {
-            const u64 other = __shfl_sync(0xffffffffu, k, (lane + o) & 31);
-            rank += other > k ? 1 : 0;
-        }
+#pragma unroll 4
+        for (int j = 0; j < nS; j++) rank += BS.S[j] > k ? 1 : 0;
         __syncwarp();
         if (k != 0 && rank < ML_SEL) { BS.S[rank] = k; BS.Skey[rank] = k_pair; BS.Sslot[rank] = k_slot; }   // keys are unique: the ML_SEL best land in [0 .. ML_SEL) in order
         __syncwarp();
-        u64 sel = (lane < ML_SEL && lane < nS) ? BS.S[lane] : 0ULL;
-        u64 pa = 0, pb = 0;
+        const int nsel = nS < ML_SEL ? nS : ML_SEL;
+        u64 sel = lane < nsel ? BS.S[lane] : 0ULL;
         if (sel != 0) {
             midx = 511 - (int)(sel & 511);
             const u64 kk2 = BS.Skey[lane];
             ma = (int32_t)((kk2 >> 32) & 0x7fffffff); mb = (int32_t)(kk2 & 0xffffffffu);
             mslot = BS.Sslot[lane]; mcnt = (i64)(sel >> 9);
         }
+        SELT(2);
         // entries outside the selection: below theta, or (more than ML_SEL in the head) not above the last selected count
-        const i64 g = nS > ML_SEL ? __shfl_sync(0xffffffffu, mcnt, ML_SEL - 1) : theta - 1;
+        const i64 g = nS > ML_SEL ? (i64)(BS.S[ML_SEL - 1] >> 9) : theta - 1;
         // equal counts among the selected: (left bytes, right bytes) order them (exact: prefixes, then the bytes)
-        const i64 cdown = __shfl_down_sync(0xffffffffu, mcnt, 1);
-        if (__ballot_sync(0xffffffffu, lane < ML_SEL - 1 && sel != 0 && mcnt == cdown && mcnt > g)) {
-            if (sel != 0) { pa = tpa ? tpa[midx] : __ldcg(&M.tok_pre[ma]); pb = tpb ? tpb[midx] : __ldcg(&M.tok_pre[mb]); }
+        int pos = lane;
+        const i64 cdown = lane + 1 < nsel ? (i64)(BS.S[lane + 1] >> 9) : 0;
+        if (__ballot_sync(0xffffffffu, sel != 0 && mcnt == cdown && mcnt > g)) {
+            u64 pa = 0, pb = 0;
+            if (sel != 0) { pa = tpa ? tpa[midx] : __ldcg(&M.tok_pre[ma]); pb = tpb ? tpb[midx] : __ldcg(&M.tok_pre[mb]); BS.Spa[lane] = pa; BS.Spb[lane] = pb; }
+            __syncwarp();
             int rk = 0;
-            for (int i = 0; i < ML_SEL; i++) {
-                const i64 ci = __shfl_sync(0xffffffffu, mcnt, i);
-                const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
-                const u64 pai = __shfl_sync(0xffffffffu, pa, i), pbi = __shfl_sync(0xffffffffu, pb, i);
-                if (i == lane || sel == 0 || ci == 0) continue;
+            for (int i = 0; i < nsel; i++) {
+                const i64 ci = (i64)(BS.S[i] >> 9);
                 bool gt = ci > mcnt;
-                if (ci == mcnt) {
-                    int r = tok_cmp_pre(M, ai, pai, ma, pa);
-                    if (r == 0) r = tok_cmp_pre(M, bi, pbi, mb, pb);
+                if (ci == mcnt && i != lane && sel != 0) {
+                    const u64 ki = BS.Skey[i];
+                    const int32_t ai = (int32_t)((ki >> 32) & 0x7fffffff), bi = (int32_t)(ki & 0xffffffffu);
+                    int r = tok_cmp_pre(M, ai, BS.Spa[i], ma, pa);
+                    if (r == 0) r = tok_cmp_pre(M, bi, BS.Spb[i], mb, pb);
                     gt = r > 0;
                 }
                 if (gt) rk++;
             }
-            if (sel == 0) rk = lane;                         // empty lanes stay where they are (behind every entry)
-            int src = lane;
-            for (int i = 0; i < ML_SEL; i++) { const int ri = __shfl_sync(0xffffffffu, rk, i); if (ri == lane) src = i; }
-            ma = __shfl_sync(0xffffffffu, ma, src); mb = __shfl_sync(0xffffffffu, mb, src); mslot = __shfl_sync(0xffffffffu, mslot, src);
-            midx = __shfl_sync(0xffffffffu, midx, src); mcnt = __shfl_sync(0xffffffffu, mcnt, src); sel = __shfl_sync(0xffffffffu, sel, src);
+            if (sel != 0) pos = rk;
         }
-        const bool elig = lane < batch_max && sel != 0 && mcnt > g && mcnt > T2 && mcnt >= T && mcnt >= Tmin;
+        __syncwarp();
+        if (lane < ML_SEL) {                                   // the selected entries in exact order (empty ones stay behind)
+            BS.mem[pos].a = ma; BS.mem[pos].b = mb; BS.mem[pos].slot = mslot; BS.mem[pos].idx = midx; BS.mem[pos].cnt = sel != 0 ? mcnt : 0;
+        }
+        __syncwarp();
+        if (lane < ML_SEL) { ma = BS.mem[lane].a; mb = BS.mem[lane].b; mslot = BS.mem[lane].slot; midx = BS.mem[lane].idx; mcnt = BS.mem[lane].cnt; }
+        else mcnt = 0;
+        const bool have = lane < nsel;                         // positions [0, nsel) are the entries (ranks are a permutation of them)
+        SELT(3);
+        const bool elig = lane < batch_max && have && mcnt > g && mcnt > T2 && mcnt >= T && mcnt >= Tmin;
         int tj = 99;                                           // first earlier entry this one touches (or that has equal tokens)
-#pragma unroll
-        for (int i = ML_SEL - 2; i >= 0; i--) {
-            const int32_t ai = __shfl_sync(0xffffffffu, ma, i), bi = __shfl_sync(0xffffffffu, mb, i);
+        for (int i = nsel - 2; i >= 0; i--) {
+            const int32_t ai = BS.mem[i].a, bi = BS.mem[i].b;
             if (i < lane && (ma == bi || mb == ai || ai == bi)) tj = i;
         }
         int k2 = __ffs(~__ballot_sync(0xffffffffu, elig && tj == 99)) - 1;      // members: eligible and clear of every earlier one
         // an entry left out with the count of the last member must not touch a member either (its count must stay
         // what it is, and it bounds the pairs the batch creates): give up members until that holds
         while (k2 > 1) {
-            const i64 ck = __shfl_sync(0xffffffffu, mcnt, k2 - 1);
-            if (!__ballot_sync(0xffffffffu, lane >= k2 && lane < ML_SEL && sel != 0 && mcnt == ck && tj < k2)) break;
+            const i64 ck = BS.mem[k2 - 1].cnt;
+            if (!__ballot_sync(0xffffffffu, lane >= k2 && have && mcnt == ck && tj < k2)) break;
             k2--;
         }
-        if (lane < ML_BATCH_MAX) { BS.mem[lane].a = ma; BS.mem[lane].b = mb; BS.mem[lane].slot = mslot; BS.mem[lane].idx = midx; BS.mem[lane].cnt = mcnt; }
         if (lane == 0) BS.nb = k2;
+        SELT(4);
     }
     __syncthreads();
+    SELT(5);
     const int nb = BS.nb;
     if (threadIdx.x == 0) BS.nS = 0;                           // every thread read it before this barrier; the next call comes after another one
     return nb;
@@ -1546,6 +1575,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
     __syncthreads();
     for (int iter = 0; iter < ML_LEADER_BATCH && m < M.num_merges; iter++) {
         ML_CLOCK(c0);
+        ML_T0(qa);
         ML_TR(0);
         const int alog_n = C.alog_n;
         if (C.error) break;
@@ -1571,6 +1601,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
         }
         cached = tn;
+        ML_TACC(0, qa);                       // (timing builds) stage A in three parts: entries | batch selection | one-merge argmax
         // member registers: lane l (< ML_BATCH_MAX) of EVERY warp describes member l of the batch
         int32_t ma = 0, mb = 0, mslot = -1, midx = -1; i64 mcnt = 0;
         int nb = 0;
@@ -1581,11 +1612,13 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             if (nb > 0) best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0),
                                     __shfl_sync(0xffffffffu, mb, 0), __shfl_sync(0xffffffffu, midx, 0)};
         }
+        ML_TACC(1, qa);
         if (nb == 0) {
             // ---- one merge: the maximum of the whole list, (left bytes, right bytes) among equal counts
             best = leader_argmax_one(M, C, mine, sh_wmax, &sh_ncand, sh_cand, sh_best);
             if (best.slot >= 0) { nb = 1; ma = best.a; mb = best.b; mslot = best.slot; midx = best.pad; mcnt = best.cnt; }
         }
+        ML_TACC(2, qa);
         if (best.slot < 0 || best.cnt < T2 || (best.cnt == T2 && best.pad >= 0 && C.tpa[best.pad] < T2pa)) { reason = LR_TOP; break; }
         if (best.cnt < T || best.cnt < Tmin) break;                        // threshold step / termination: grid mode
         if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
@@ -1715,6 +1748,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         if (C.npairs_new + C.nnew) atomicAdd((u64*)&M.state[MS_NPAIRS], (u64)(C.npairs_new + C.nnew));
 #if ML_TIMING
         M.state[20] += t_arg; M.state[21] += t_rng; M.state[23] += t_rw; M.state[24] += t_close;
+        M.state[37] += sh_tacc[0]; M.state[38] += sh_tacc[1]; M.state[39] += sh_tacc[2];
 #endif
         M.state[25] += s_act; M.state[26] += s_items;
         M.state[MS_LEADER_MERGES] += n_done;
@@ -2203,7 +2237,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     }
     if (gtid == 0) {
 #if ML_RW_TRACE
-        for (int i = 0; i < 6; i++) { sh_phase[8 + i] = (long long)g_rw_clk[i]; g_rw_clk[i] = 0; }
+        for (int i = 0; i < 6; i++) { sh_phase[8 + i] = (long long)g_rw_clk[(ML_RW_TRACE == 2 ? 8 : 0) + i]; g_rw_clk[i] = 0; g_rw_clk[8 + i] = 0; }
 #endif
         for (int i = 0; i < 24; i++) if (sh_phase[i]) M.state[40 + i] += sh_phase[i];
         M.state[MS_CLK_TOTAL] = clock64() - pclk0;

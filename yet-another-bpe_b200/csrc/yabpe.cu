@@ -255,32 +255,7 @@ extern "C" int yabpe_pretok_count(const yabpe_pretok_args* a, void* stream) {
             if (P.hot.cap > 0) {
                 i64 grid_w = (c_hi - c_lo + PW_WARPS_HOT - 1) / PW_WARPS_HOT;
                 if (grid_w > num_sms()) grid_w = num_sms();
-                // The hot table is meant to LIVE in the L2 while 11 GB of text stream past it: give it a persisting access-policy
-                // window for the duration of the kernel (YABPE_HOT_PERSIST=0 turns this off for A/B runs).
-                static const bool persist = !(getenv("YABPE_HOT_PERSIST") && getenv("YABPE_HOT_PERSIST")[0] == '0');
-                const size_t hot_bytes = (size_t)P.hot.cap * 32;
-                cudaStreamAttrValue win;
-                memset(&win, 0, sizeof win);
-                if (persist) {
-                    int dev = 0, max_persist = 0, max_win = 0;
-                    CUDA_TRY(cudaGetDevice(&dev));
-                    CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-                    CUDA_TRY(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-                    if ((size_t)max_persist >= hot_bytes && (size_t)max_win >= hot_bytes) {
-                        CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, hot_bytes));
-                        win.accessPolicyWindow.base_ptr = (void*)a->hot_table;
-                        win.accessPolicyWindow.num_bytes = hot_bytes;
-                        win.accessPolicyWindow.hitRatio = 1.0f;
-                        win.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                        win.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                        CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
-                    }
-                }
                 k_pretok_warp<true><<<(int)grid_w, PW_WARPS_HOT * 32, PW_SMEM_BYTES_HOT, st>>>(P, c_lo, c_hi); LAUNCHED();
-                if (win.accessPolicyWindow.num_bytes) {
-                    win.accessPolicyWindow.num_bytes = 0;
-                    CUDA_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
-                }
                 k_hot_flush<<<num_sms() * 4, 256, 0, st>>>(P); LAUNCHED();
             } else {
                 i64 grid_w = (c_hi - c_lo + PW_WARPS - 1) / PW_WARPS;
