@@ -1939,6 +1939,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
     i64 g_theta = 0; bool g_sticky = false;   // head threshold of the grid-mode batch selection: the same in every CTA
     __shared__ int32_t g_tslot[ML_TOP_N];     // this CTA's copy of the top list (grid-mode batches), valid below g_cached
     __shared__ u64 g_tkey[ML_TOP_N];
+    __shared__ u64 g_tpa[ML_TOP_N], g_tpb[ML_TOP_N];      // 8-byte prefixes of the entries' tokens
     int g_cached = 0;
     if (threadIdx.x == 0) GB.sel.nS = 0;
 
@@ -2057,14 +2058,19 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             Best mine{0, -1, 0, 0, 0};
             if ((int)threadIdx.x < tn) {
                 // the list only grows between rebuilds: every CTA keeps a copy, so the count is ONE round trip away
-                if ((int)threadIdx.x >= g_cached) { g_tslot[threadIdx.x] = __ldcg(&M.top_slot[threadIdx.x]); g_tkey[threadIdx.x] = __ldcg(&M.top_key[threadIdx.x]); }
+                if ((int)threadIdx.x >= g_cached) {
+                    const u64 k0 = __ldcg(&M.top_key[threadIdx.x]);
+                    g_tslot[threadIdx.x] = __ldcg(&M.top_slot[threadIdx.x]); g_tkey[threadIdx.x] = k0;
+                    g_tpa[threadIdx.x] = __ldcg(&M.tok_pre[(int32_t)((k0 >> 32) & 0x7fffffff)]);      // tie-breaks without a round trip
+                    g_tpb[threadIdx.x] = __ldcg(&M.tok_pre[(int32_t)(k0 & 0xffffffffu)]);
+                }
                 const int32_t sl = g_tslot[threadIdx.x];
                 const u64 k = g_tkey[threadIdx.x];
                 const i64 cnt = __ldcg(&M.pcnt[sl]);
                 if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
             }
             g_cached = tn;
-            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, nullptr, nullptr, M.top_slot, M.top_key, sh_cnt, g_theta, g_sticky);
+            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, g_tpa, g_tpb, M.top_slot, M.top_key, sh_cnt, g_theta, g_sticky);
             long long gclk = pclk;
             ML_PHASE(MS_CLK_GB_SELECT, gclk);
             if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
