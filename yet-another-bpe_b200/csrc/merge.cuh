@@ -2080,7 +2080,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0), __shfl_sync(0xffffffffu, mb, 0), 0};
                 have_best = true;
             }
-            if (nb >= 2) {
+            if (nb >= 1) {                                      // (a "batch" of one included: the rewrite below has the shorter chain)
                 grid_barrier(M);                                // 1: every CTA has read the counts
                 ML_PHASE(MS_CLK_GB_BAR1, gclk);
                 if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &GB.R[warp]);
@@ -2109,9 +2109,9 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 const int kk = __ffs(__ballot_sync(0xffffffffu, mbad)) - 1;
                 __syncthreads();                                // GB is rewritten by the next selection
                 ML_PHASE(MS_CLK_GB_RANGES, gclk);
-                if (kk >= 2) {
+                const int warps_all = (int)gridDim.x * nwarps;
+                if (kk >= 2 || (kk == 1 && __shfl_sync(0xffffffffu, cum, 0) <= warps_all * 8)) {      // heavy single merges: thread per word, below
                     const int items_all = __shfl_sync(0xffffffffu, cum, kk - 1);
-                    const int warps_all = (int)gridDim.x * nwarps;
                     const int G = items_all > (warps_all - 1) * 8 ? 2 : (items_all > (warps_all - 1) * 4 ? 4 : 8), padm = 32 / G - 1;
                     int pcum = lane < kk ? (mtot + padm) & ~padm : 0;
 #pragma unroll
@@ -2142,7 +2142,11 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                         M.tok_head[mc] = make_int4((int32_t)(m + lane), mseg, e, M.merge_next[m + lane]);
                     }
                     if (threadIdx.x == 0) { M.state[MS_NMERGES] = m + kk; M.state[MS_ALOG_N] = alog_n + items_all; }
-                    if (gtid == 0) { M.state[MS_GRID_MERGES] += kk; sh_phase[MS_GRID_ITERS - 40]++; sh_phase[MS_GRID_BATCHED - 40] += kk; }
+                    if (gtid == 0) {
+                        M.state[MS_GRID_MERGES] += kk;
+                        if (kk >= 2) { sh_phase[MS_GRID_ITERS - 40]++; sh_phase[MS_GRID_BATCHED - 40] += kk; }
+                        else { const int cls = (i64)items_all * 64 <= gstride ? 0 : 1; sh_phase[MS_GRID_CLS + cls - 40]++; sh_phase[MS_GRID_CLS + 3 + cls - 40] += clock64() - pclk; }
+                    }
                     ML_PHASE(MS_CLK_GRID, pclk);
                     __syncthreads();
                     continue;
