@@ -549,7 +549,6 @@ struct LeaderCtx {
     u64 newp_key[ML_NEWP_N];                     // and their keys (tokens known without waiting for the table)
     int top_n, top_ovf, act_n, alog_n, npairs_new, error, nnew;
     u64 t2pa;                                    // top-list threshold, second component (copy of state[MS_T2_PA])
-    int32_t cur_slot;                            // pair-table slot of the pair being merged
 };
 
 __device__ __forceinline__ void mirror_add(LeaderCtx* lc, int32_t slot, i64 d) {
@@ -1258,20 +1257,23 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
 // leader's cost per iteration is a chain of dependent round trips that does not depend on how much it rewrites -- so the
 // leader takes the k best pairs p_1 .. p_k of the top list in ONE iteration whenever it can PROVE that the sequential loop
 // would pick exactly these, in this order, with exactly the same state after the k-th:
-//   (1) counts strictly descending, c_1 > c_2 > ... > c_k > (count of every other pair), and c_k > T2: all pairs with a
-//       count >= c_k are on the top list (it is complete above T2), and they are p_1 .. p_k;
+//   (1) p_1 .. p_k are the first k pairs in the exact order (count, left bytes, right bytes); every pair left out with the
+//       count of p_k comes after it in that order and touches no member (2); c_k > T2: all pairs with a count >= c_k are on
+//       the top list (it is complete above T2), and the selection has seen every one of them;
 //   (2) no member "touches" an earlier one: merging (a_i, b_i) only decrements pairs (x, a_i) and (b_i, y) and only creates
 //       pairs that contain the new token, so for i < j:  b_j != a_i and a_j != b_i  keep c_j unchanged; every pair created
 //       by the batch is bounded by the count of an OLD pair (x, a_i) or (b_i, y) != p_i, which is not a member (2) and
-//       therefore < c_k (1): nothing new can overtake a member.  (a_i == b_i breaks that bound -- "aaaa" makes (aa, aa)
-//       out of (a, a) itself -- so such a pair is only taken as the LAST member.)
+//       therefore < c_k (1: a left-out pair with the count c_k does not touch): nothing new can overtake a member.
+//       (a_i == b_i breaks that bound -- "aaaa" makes (aa, aa) out of (a, a) itself -- so such a pair is only taken as
+//       the LAST member.)
 //   (3) the merged bytes of a member are a NEW token (trainer.py:296-300 gives no new id otherwise, and pairs with an
 //       existing token can GAIN above c_k): a member whose bytes exist already is the last one; two members with the
 //       same merged bytes never share a batch.
 // Old pairs only lose during a batch, so the bounds hold throughout.  Words are rewritten word by word: whoever claims a
 // candidate word applies members 1 .. k to it in order -- the state of a word depends on nothing but the word, and the
-// pair counts are sums over words, so the result is the sequential one bit for bit.  Ties at the top (c_1 == c_2), the
-// tie regime (T2pa != 0) and single heavy merges take the one-merge path below.
+// pair counts are sums over words, so the result is the sequential one bit for bit.  More equal counts at the top than the
+// selection holds, the tie regime (T2pa != 0) and single heavy merges take the one-merge path below.  Grid mode batches by the
+// same rules (k_merge_loop): every CTA selects the same members and the groups of all CTAs share the items.
 struct BatchSel {
     u64 S[32]; int nS;                          // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
     u64 Skey[32]; int32_t Sslot[32];            // and their pair keys / table slots (by position in S)
@@ -1296,7 +1298,7 @@ struct BatchCtx {
 // Block-wide; every thread returns the same count nb (0: the caller takes the one-merge path) and finds the members in BS.mem.
 // Deterministic in its inputs: CTAs that see the same list and counts (grid mode) choose the same batch.
 __device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, const Best& mine, int tn, int batch_max, i64 T, i64 Tmin, i64 T2,
-                            const u64* tpa, const u64* tpb, const int32_t* tslot, const u64* tkey, i64* sh_wmax, i64& theta, bool& theta_sticky) {
+                            const u64* tpa, const u64* tpb, i64* sh_wmax, i64& theta, bool& theta_sticky) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
     int nS;
@@ -1564,7 +1566,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         C.error = (int)__ldcg(&M.state[MS_ERROR]);
         C.top_n = (int)__ldcg(&M.state[MS_TOP_N]); C.top_ovf = (int)__ldcg(&M.state[MS_TOP_OVF]);
         C.npairs_new = 0; C.nnew = 0; C.t2pa = T2pa;
-        sh_ncand = 0; C.cur_slot = -1; BC.sel.nS = 0;
+        sh_ncand = 0; BC.sel.nS = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) *(volatile i64*)&M.state[MS_TOP_N_LIVE] = C.top_n;
@@ -1607,7 +1609,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         int nb = 0;
         Best best{0, -1, 0, 0, 0};
         if (batch_max > 1) {
-            nb = select_batch(M, BC.sel, mine, tn, batch_max, T, Tmin, T2, C.tpa, C.tpb, C.tslot, C.tkey, sh_wmax, theta, theta_sticky);
+            nb = select_batch(M, BC.sel, mine, tn, batch_max, T, Tmin, T2, C.tpa, C.tpb, sh_wmax, theta, theta_sticky);
             if (lane < ML_BATCH_MAX) { ma = BC.sel.mem[lane].a; mb = BC.sel.mem[lane].b; mslot = BC.sel.mem[lane].slot; midx = BC.sel.mem[lane].idx; mcnt = BC.sel.mem[lane].cnt; }
             if (nb > 0) best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0),
                                     __shfl_sync(0xffffffffu, mb, 0), __shfl_sync(0xffffffffu, midx, 0)};
@@ -2070,7 +2072,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
             }
             g_cached = tn;
-            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, g_tpa, g_tpb, M.top_slot, M.top_key, sh_cnt, g_theta, g_sticky);
+            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, g_tpa, g_tpb, sh_cnt, g_theta, g_sticky);
             long long gclk = pclk;
             ML_PHASE(MS_CLK_GB_SELECT, gclk);
             if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
