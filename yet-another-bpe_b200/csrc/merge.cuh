@@ -28,6 +28,9 @@ __device__ unsigned long long g_rw_clk[16];
 #define RWT(k, dep)
 #define SELT(k)
 #endif
+#ifndef ML_SEL_WHY
+#define ML_SEL_WHY 0
+#endif
 #ifndef ML_TIMING
 #define ML_TIMING 0           // 1: per-stage cycle counters of the leader loop in state[20..24] (costs registers)
 #endif
@@ -1258,8 +1261,8 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
 // leader takes the k best pairs p_1 .. p_k of the top list in ONE iteration whenever it can PROVE that the sequential loop
 // would pick exactly these, in this order, with exactly the same state after the k-th:
 //   (1) p_1 .. p_k are the first k pairs in the exact order (count, left bytes, right bytes); every pair left out with the
-//       count of p_k comes after it in that order and touches no member (2); c_k > T2: all pairs with a count >= c_k are on
-//       the top list (it is complete above T2), and the selection has seen every one of them;
+//       count of p_k comes after it in that order and touches no member (2); c_k >= T2: all pairs with a count >= c_k are on
+//       the top list (it is complete from T2 up while the threshold is a plain count), and the selection has seen them all;
 //   (2) no member "touches" an earlier one: merging (a_i, b_i) only decrements pairs (x, a_i) and (b_i, y) and only creates
 //       pairs that contain the new token, so for i < j:  b_j != a_i and a_j != b_i  keep c_j unchanged; every pair created
 //       by the batch is bounded by the count of an OLD pair (x, a_i) or (b_i, y) != p_i, which is not a member (2) and
@@ -1379,7 +1382,14 @@ __device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, 
         else mcnt = 0;
         const bool have = lane < nsel;                         // positions [0, nsel) are the entries (ranks are a permutation of them)
         SELT(3);
-        const bool elig = lane < batch_max && have && mcnt > g && mcnt > T2 && mcnt >= T && mcnt >= Tmin;
+        // (callers batch only under a plain count threshold -- T2pa == 0 --, where the list holds EVERY pair with count >= T2)
+        const bool elig = lane < batch_max && have && mcnt > g && mcnt >= T2 && mcnt >= T && mcnt >= Tmin;
+#if ML_SEL_WHY
+        if (lane == 0 && blockIdx.x == 0 && !elig) {          // why the best entry itself is not eligible: state[37..39] = no entry | tied beyond the selection | below T2, state[63] = below T (tuning build)
+            const int why = !have ? 0 : (!(mcnt > g) ? 1 : (!(mcnt >= T2) ? 2 : (!(mcnt >= T) ? 3 : 4)));
+            atomicAdd((u64*)&M.state[why < 3 ? 37 + why : 63], 1ULL);
+        }
+#endif
         int tj = 99;                                           // first earlier entry this one touches (or that has equal tokens)
         for (int i = nsel - 2; i >= 0; i--) {
             const int32_t ai = BS.mem[i].a, bi = BS.mem[i].b;
