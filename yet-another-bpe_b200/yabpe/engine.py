@@ -263,7 +263,10 @@ def estimate_table_sizes(torch, text_dev, n: int, cuts, specials, mode, mailbox:
     scratch = torch.empty(nc, dtype=torch.int64, device=text_dev.device)
     _ffi.check(L.yabpe_select_hot(C.byref(res.args), hot.data_ptr(), scratch.data_ptr(), _ffi.stream_ptr(torch)))
     hot._yabpe_keep = (res, scratch)              # the sample tables must outlive the (stream-ordered) selection
-    return (_pow2_at_least(int(min(max(4 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))), cold, hot)
+    # Short table: twice the estimate (load factor 25 - 50 %), not four times: probes into a 2 GB table cost more than the
+    # longer probe chains of a 1 GB one (OWT 11 GB: 2^26 slots 41.1 ms, 2^25 38.1 ms, 2^24 36.4 ms); a table that fills up
+    # is detected and the count repeated with a larger one.
+    return (_pow2_at_least(int(min(max(2 * us, 1 << 16), 1 << 26))), _pow2_at_least(int(min(max(4 * ul, 1 << 12), 1 << 24))), cold, hot)
 
 
 def pretok_count_checked(torch, text_dev, n, cuts, specials, mode, own=None,
@@ -367,9 +370,10 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
     max_tokens = n_base + num_merges + 2
     for attempt in range(6):
         if pcap is None:
-            # distinct pairs stay well below the symbol count (0.07-0.2 x on the bench corpora); the kernel reports a
-            # table that fills beyond 3/4 and the loop below retries with a four times larger one
-            pcap = _pow2_at_least(min(max(words.n_syms >> int(os.environ.get("YABPE_PCAP_SHIFT", "0")), 1 << 16), 1 << 26))
+            # distinct pairs stay well below the symbol count (0.07-0.2 x on the bench corpora): half the symbol count keeps
+            # the load factor below 40 % and halves what every rebuild scans; the kernel reports a table that fills beyond
+            # 3/4 and the loop below retries with a four times larger one
+            pcap = _pow2_at_least(min(max(words.n_syms >> int(os.environ.get("YABPE_PCAP_SHIFT", "1")), 1 << 16), 1 << 26))
         if pool_cap is None:
             pool_cap = (4 << 20) + 32 * max_tokens + min(words.n_syms, 1 << 30)
         alog_cap = max(2 * words.n_words, 1 << 16) + 4096
