@@ -352,12 +352,13 @@ class MergeResult:
 def rebuild_period(n_syms: int) -> int:
     """Merges between rebuilds of the pair -> words index.  A rebuild costs O(symbols + table) (0.08 ms on the
     2 GB TinyStories-shaped corpus, 1.8 ms on the 11 GB OWT-shaped one), staleness costs candidates that turn out not to
-    contain the pair; measured optimum ~1 500 merges for the former, ~5 000 for the latter.  (Round 2, batched merges: no
-    period at all -- rebuild on demand only -- is 4 % faster on the 11 GB corpus, 10 % slower on the tie-heavy 1 GB one.)"""
+    contain the pair; measured optimum ~1 500 merges for the former.  With batched merges the big corpora want fewer rebuilds
+    than before (OWT 11 GB: 6 000 -> 165 ms of merge loop, 9 000 -> 162, 12 000 -> 159; the tie-heavy 1 GB corpus 293 -> 289 ms
+    a step at 12 000), but no period at all -- rebuild on demand only -- costs that 1 GB corpus 10 %."""
     env = os.environ.get("YABPE_REBUILD_EVERY")
     if env is not None:
         return int(env)
-    return int(min(max(40.0 * float(max(n_syms, 1)) ** 0.3, 500.0), 6000.0))
+    return int(min(max(40.0 * float(max(n_syms, 1)) ** 0.3, 500.0), 12000.0))
 
 
 def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: int, min_frequency: int,
