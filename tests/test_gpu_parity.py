@@ -311,6 +311,21 @@ def test_train_with_frequent_index_rebuilds(yabpe, tmp_path, monkeypatch):
             assert tr.last_stats.index_rebuilds >= 30
 
 
+def test_tables_grow_when_the_estimate_is_too_small(yabpe, tmp_path, monkeypatch):
+    """The pre-token tables are sized from an extrapolated estimate (engine.estimate_table_sizes: twice the expected number of
+    unique pre-tokens); an estimate that is far too small must be detected (ST_TABLE_FULL) and the count repeated with larger
+    tables -- same result."""
+    from yabpe import engine
+    data = common.synth_owt(3_000_000, seed=21)
+    p = tmp_path / "g.txt"
+    p.write_bytes(data)
+    want = oracle.train_bpe(p, 1500, ["<|endoftext|>"], fast=True)
+    calls = []
+    monkeypatch.setattr(engine, "estimate_table_sizes", lambda *a, **k: (calls.append(1), (1 << 10, 1 << 6, False, None))[1])
+    assert yabpe.train_bpe(p, 1500, ["<|endoftext|>"]) == want
+    assert calls
+
+
 @pytest.mark.parametrize("mode,what", [("1", "one merge per iteration everywhere (trainer.py:241-300 as written)"),
                                        ("264", "batches in leader mode only"),
                                        ("2049", "batches in grid mode only"),
