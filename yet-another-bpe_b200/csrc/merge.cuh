@@ -1031,9 +1031,11 @@ __device__ Best top_best(const MergeParams& M, i64 top_n, Best* sh_best, i64* sh
 // of its 32 lanes (redux.sync); phase 2 (after ONE block barrier): every warp redundantly extracts the ML_SEL largest of the
 // per-warp lists, so all warps hold the same result without a second barrier.  Returned per lane: lane r gets the r-th key.
 #ifndef ML_BATCH_MAX
-#define ML_BATCH_MAX 16       // one lane per member; two warps per member in stage B (32 warps)
+#define ML_BATCH_MAX 31       // one lane per member, and one more lane for the first entry left out
 #endif
-#define ML_SEL (ML_BATCH_MAX + 1)
+#define ML_SEL (ML_BATCH_MAX + 1)          // entries put in exact order by the selection (<= 32: one per lane of a warp)
+#define ML_HEAD 64                         // capacity of the head list the selection starts from
+#define ML_HSEL 5                          // entries the prefetch helpers look at (select_top)
 #define ML_SEL_WARPS (ML_TOP_N / 32)
 __device__ __forceinline__ u64 warp_max_u64(u64 v) {
     const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
@@ -1041,25 +1043,25 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
     const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
     return ((u64)mhi << 32) | mlo;
 }
-__device__ __forceinline__ u64 select_top(u64 key, u64* sh_keys /* [ML_SEL_WARPS][ML_SEL] */) {
+__device__ __forceinline__ u64 select_top(u64 key, u64* sh_keys /* [ML_SEL_WARPS][ML_HSEL] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp < ML_SEL_WARPS) {
         u64 k = key;
 #pragma unroll
-        for (int r = 0; r < ML_SEL; r++) {
+        for (int r = 0; r < ML_HSEL; r++) {
             const u64 m = warp_max_u64(k);
             if (k == m) k = 0;                        // keys are unique (the index is part of the key)
-            if (lane == r) sh_keys[warp * ML_SEL + r] = m;
+            if (lane == r) sh_keys[warp * ML_HSEL + r] = m;
         }
     }
     __syncthreads();
-    constexpr int NV = (ML_SEL_WARPS * ML_SEL + 31) / 32;
+    constexpr int NV = (ML_SEL_WARPS * ML_HSEL + 31) / 32;
     u64 v[NV];
 #pragma unroll
-    for (int u = 0; u < NV; u++) { const int i = lane + 32 * u; v[u] = i < ML_SEL_WARPS * ML_SEL ? sh_keys[i] : 0; }
+    for (int u = 0; u < NV; u++) { const int i = lane + 32 * u; v[u] = i < ML_SEL_WARPS * ML_HSEL ? sh_keys[i] : 0; }
     u64 mine = 0;
 #pragma unroll
-    for (int r = 0; r < ML_SEL; r++) {
+    for (int r = 0; r < ML_HSEL; r++) {
         u64 lm = v[0];
 #pragma unroll
         for (int u = 1; u < NV; u++) lm = v[u] > lm ? v[u] : lm;
@@ -1208,13 +1210,13 @@ __device__ Best leader_argmax_one(const MergeParams& M, LeaderCtx& C, const Best
     return best;
 }
 
-// The head of the top list: theta such that between 12 and 32 entries have a count >= theta, found with a 32-bin histogram of
+// The head of the top list: theta such that between 5/8 head_cap and head_cap entries have a count >= theta, found with a 32-bin histogram of
 // the counts in [lo, max] that zooms into the bin that did not fit (counts repeat: a single count can hold more entries than
-// fit, then fewer than 12 -- possibly none -- are taken and *sticky tells the caller not to ask again until the head is empty).
+// fit, then fewer -- possibly none -- are taken and *sticky tells the caller not to ask again until the head is empty).
 // Block-wide, every thread returns the same value; ends with a barrier.
 // hi0 > 0: the caller knows that exactly above0 entries have a count >= hi0 (the old head, nearly used up): the search starts
 // below it and the block-wide maximum is not needed.
-__device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int* hist /* [34] */, bool* sticky, i64 hi0 = 0, int above0 = 0) {
+__device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int* hist /* [34] */, bool* sticky, int head_cap, i64 hi0 = 0, int above0 = 0) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     i64 hi = hi0;
     int above = above0;
@@ -1238,7 +1240,7 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
             int suf = hist[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
-            const uint32_t fits = __ballot_sync(0xffffffffu, above + suf <= 32);       // an upper range of bins (suf falls with the bin)
+            const uint32_t fits = __ballot_sync(0xffffffffu, above + suf <= head_cap);  // an upper range of bins (suf falls with the bin)
             const int bl = fits ? __ffs(fits) - 1 : 32;
             const int cumw = above + (bl < 32 ? __shfl_sync(0xffffffffu, suf, bl & 31) : 0);
             if (lane == 0) { hist[32] = bl - 1; hist[33] = cumw; }
@@ -1248,10 +1250,10 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
         theta = lo + (i64)(b + 1) * width;
         __syncthreads();                                                   // everybody has read the result
         if (b < 0) { theta = lo; above = cum; break; }
-        if (cum >= 12 || width == 1) { above = cum; break; }
+        if (cum >= head_cap / 2 + head_cap / 8 || width == 1) { above = cum; break; }
         above = cum; hi = theta; lo = lo + (i64)b * width;
     }
-    *sticky = above < 4;
+    *sticky = above < head_cap / 4;
     return theta;
 }
 
@@ -1278,8 +1280,9 @@ __device__ i64 leader_head_threshold(const Best& mine, i64 lo, i64* sh_wmax, int
 // selection holds, the tie regime (T2pa != 0) and single heavy merges take the one-merge path below.  Grid mode batches by the
 // same rules (k_merge_loop): every CTA selects the same members and the groups of all CTAs share the items.
 struct BatchSel {
-    u64 S[32]; int nS;                          // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
-    u64 Skey[32]; int32_t Sslot[32];            // and their pair keys / table slots (by position in S)
+    u64 S[ML_HEAD]; int nS;                     // head of the top list: keys (count << 9 | 511 - index) of the entries with count >= theta
+    u64 Skey[ML_HEAD]; int32_t Sslot[ML_HEAD];  // and their pair keys / table slots (by position in S)
+    u64 Q[ML_SEL], Qkey[ML_SEL]; int32_t Qslot[ML_SEL];      // the ML_SEL best of the head by (count, list index)
     int hist[34];
     u64 Spa[ML_SEL], Spb[ML_SEL];               // token prefixes of the selected entries (filled when equal counts need ordering)
     struct { int32_t a, b, slot, idx; i64 cnt; } mem[ML_SEL];      // the selected entries in exact order; the first nb are the batch
@@ -1296,13 +1299,15 @@ struct BatchCtx {
 // `mine` = this thread's entry of the top list (threads >= tn: none; pad = list index), with its current count.  The entries with
 // count >= theta (the HEAD, at most 32) put themselves on a list; warp 0 takes the ML_SEL best of them in exact order (count, then
 // left bytes, right bytes) and decides how many form a batch (rules (1) - (2) above; rule (3) needs the token lookups and is
-// applied by the caller).  theta / sticky persist between calls; theta is re-chosen when the head runs empty or overflows.
+// applied by the caller).  theta / sticky persist between calls; theta is re-chosen when the head runs empty or overflows;
+// head_cap (<= ML_HEAD) is the size the head is refilled to: 32 for the leader's small batches, 64 for grid mode's.
 // tpa / tpb: 8-byte prefixes of the entries' tokens by list index (leader: shared memory), or nullptr: M.tok_pre is read.
 // Block-wide; every thread returns the same count nb (0: the caller takes the one-merge path) and finds the members in BS.mem.
 // Deterministic in its inputs: CTAs that see the same list and counts (grid mode) choose the same batch.
 __device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, const Best& mine, int tn, int batch_max, i64 T, i64 Tmin, i64 T2,
-                            const u64* tpa, const u64* tpb, i64* sh_wmax, i64& theta, bool& theta_sticky) {
+                            const u64* tpa, const u64* tpb, i64* sh_wmax, i64& theta, bool& theta_sticky, int head_cap) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __builtin_assume(__isShared(&BS));
     const u64 mykey = mine.slot >= 0 ? (((u64)mine.cnt << 9) | (u64)(511 - (int)threadIdx.x)) : 0ULL;
     int nS;
 #if ML_RW_TRACE
@@ -1311,59 +1316,57 @@ __device__ __forceinline__ int select_batch(const MergeParams& M, BatchSel& BS, 
     for (int pass = 0;; pass++) {
         if (theta > 0 && mine.slot >= 0 && mine.cnt >= theta) {
             const int p = atomicAdd(&BS.nS, 1);
-            if (p < 32) { BS.S[p] = mykey; BS.Skey[p] = PAIR_KEY(mine.a, mine.b); BS.Sslot[p] = mine.slot; }
+            if (p < head_cap) { BS.S[p] = mykey; BS.Skey[p] = PAIR_KEY(mine.a, mine.b); BS.Sslot[p] = mine.slot; }
         }
         __syncthreads();
         nS = BS.nS;
         if (pass == 0) SELT(0);
-        const bool refresh = theta <= 0 || nS > 32 || (nS < 4 && tn > 32 && !theta_sticky && theta > 1);
+        const bool refresh = theta <= 0 || nS > head_cap || (nS < head_cap / 4 && tn > head_cap && !theta_sticky && theta > 1);
         if (!refresh || pass == 2) break;
-        const bool below = theta > (T2 > 1 ? T2 : 1) && nS <= 32;                                     // the old head is nearly used up: look below it
-        theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BS.hist, &theta_sticky, below ? theta : 0, below ? nS : 0);     // block-wide; ends with a barrier
-        if (tn <= 32) { theta = 1; theta_sticky = false; }
+        const bool below = theta > (T2 > 1 ? T2 : 1) && nS <= head_cap;                                     // the old head is nearly used up: look below it
+        theta = leader_head_threshold(mine, T2 > 1 ? T2 : 1, sh_wmax, BS.hist, &theta_sticky, head_cap, below ? theta : 0, below ? nS : 0);     // block-wide; ends with a barrier
+        if (tn <= head_cap) { theta = 1; theta_sticky = false; }
         if (threadIdx.x == 0) BS.nS = 0;
         __syncthreads();
     }
-    if (nS > 32) nS = 0;                        // cannot happen after a refresh; be safe: the one-merge path decides
+    if (nS > head_cap) nS = 0;                   // cannot happen after a refresh; be safe: the one-merge path decides
     SELT(1);
     if (warp == 0) {
         // One warp, and every step reads what it needs from shared memory with broadcast loads (independent, pipelined): a
         // first version passed the entries around with ~230 dependent shuffles and spent 3 us per call on their latency.
         int32_t ma = 0, mb = 0, mslot = -1, midx = -1; i64 mcnt = 0;
-        // rank of every head entry by (count, list index)
-        const u64 k = lane < nS ? BS.S[lane] : 0ULL;
-        const u64 k_pair = lane < nS ? BS.Skey[lane] : 0ULL;
-        const int32_t k_slot = lane < nS ? BS.Sslot[lane] : -1;
-        int rank = 0;
+        // rank of every head entry by (count, list index): two entries per lane, every lane walks the whole list
+        const u64 k0 = lane < nS ? BS.S[lane] : 0ULL, k1 = lane + 32 < nS ? BS.S[lane + 32] : 0ULL;
+        int r0 = 0, r1 = 0;
 #pragma unroll 4
-        for (int j = 0; j < nS; j++) rank += BS.S[j] > k ? 1 : 0;
-        __syncwarp();
-        if (k != 0 && rank < ML_SEL) { BS.S[rank] = k; BS.Skey[rank] = k_pair; BS.Sslot[rank] = k_slot; }   // keys are unique: the ML_SEL best land in [0 .. ML_SEL) in order
+        for (int j = 0; j < nS; j++) { const u64 v = BS.S[j]; r0 += v > k0 ? 1 : 0; r1 += v > k1 ? 1 : 0; }
+        if (k0 != 0 && r0 < ML_SEL) { BS.Q[r0] = k0; BS.Qkey[r0] = BS.Skey[lane]; BS.Qslot[r0] = BS.Sslot[lane]; }            // keys are unique:
+        if (k1 != 0 && r1 < ML_SEL) { BS.Q[r1] = k1; BS.Qkey[r1] = BS.Skey[lane + 32]; BS.Qslot[r1] = BS.Sslot[lane + 32]; }  // the ML_SEL best, in order
         __syncwarp();
         const int nsel = nS < ML_SEL ? nS : ML_SEL;
-        u64 sel = lane < nsel ? BS.S[lane] : 0ULL;
+        u64 sel = lane < nsel ? BS.Q[lane] : 0ULL;
         if (sel != 0) {
             midx = 511 - (int)(sel & 511);
-            const u64 kk2 = BS.Skey[lane];
+            const u64 kk2 = BS.Qkey[lane];
             ma = (int32_t)((kk2 >> 32) & 0x7fffffff); mb = (int32_t)(kk2 & 0xffffffffu);
-            mslot = BS.Sslot[lane]; mcnt = (i64)(sel >> 9);
+            mslot = BS.Qslot[lane]; mcnt = (i64)(sel >> 9);
         }
         SELT(2);
         // entries outside the selection: below theta, or (more than ML_SEL in the head) not above the last selected count
-        const i64 g = nS > ML_SEL ? (i64)(BS.S[ML_SEL - 1] >> 9) : theta - 1;
+        const i64 g = nS > ML_SEL ? (i64)(BS.Q[ML_SEL - 1] >> 9) : theta - 1;
         // equal counts among the selected: (left bytes, right bytes) order them (exact: prefixes, then the bytes)
         int pos = lane;
-        const i64 cdown = lane + 1 < nsel ? (i64)(BS.S[lane + 1] >> 9) : 0;
+        const i64 cdown = lane + 1 < nsel ? (i64)(BS.Q[lane + 1] >> 9) : 0;
         if (__ballot_sync(0xffffffffu, sel != 0 && mcnt == cdown && mcnt > g)) {
             u64 pa = 0, pb = 0;
             if (sel != 0) { pa = tpa ? tpa[midx] : __ldcg(&M.tok_pre[ma]); pb = tpb ? tpb[midx] : __ldcg(&M.tok_pre[mb]); BS.Spa[lane] = pa; BS.Spb[lane] = pb; }
             __syncwarp();
             int rk = 0;
             for (int i = 0; i < nsel; i++) {
-                const i64 ci = (i64)(BS.S[i] >> 9);
+                const i64 ci = (i64)(BS.Q[i] >> 9);
                 bool gt = ci > mcnt;
                 if (ci == mcnt && i != lane && sel != 0) {
-                    const u64 ki = BS.Skey[i];
+                    const u64 ki = BS.Qkey[i];
                     const int32_t ai = (int32_t)((ki >> 32) & 0x7fffffff), bi = (int32_t)(ki & 0xffffffffu);
                     int r = tok_cmp_pre(M, ai, BS.Spa[i], ma, pa);
                     if (r == 0) r = tok_cmp_pre(M, bi, BS.Spb[i], mb, pb);
@@ -1457,11 +1460,16 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
     // COPY of its candidate list -- a superset of the words it rewrites, which is all the index needs (candidates are ~97 %
     // hits) -- so the log needs no counter: hundreds of groups appending through one atomic serialised in the L2.
     auto fetch = [&](int it) -> i64 {
-        int mem = -1, loc = 0, sb = 0;
-        for (int i = 0; i < kk; i++) {
-            const int st = __shfl_sync(0xffffffffu, mpst, i), tt = __shfl_sync(0xffffffffu, mtot, i), sg = __shfl_sync(0xffffffffu, mseg, i);
-            if (it >= st && it < st + tt) { mem = i; loc = it - st; sb = sg; }
+        // which member owns item `it`: lane l answers for member l, one ballot per group of the warp (not a loop over members)
+        int mem = -1;
+#pragma unroll
+        for (int q = 0; q < 32 / G; q++) {
+            const int itq = __shfl_sync(0xffffffffu, it, q * G);
+            const uint32_t own = __ballot_sync(0xffffffffu, lane < kk && itq >= mpst && itq < mpst + mtot);
+            if (lane / G == q) mem = own ? __ffs(own) - 1 : -1;
         }
+        const int src = mem >= 0 ? mem : 0;
+        const int loc = it - __shfl_sync(0xffffffffu, mpst, src), sb = __shfl_sync(0xffffffffu, mseg, src);
         const i64 e = mem >= 0 ? range_item(RR[mem], loc) : -1;
         if (mem >= 0 && gl == 0) M.alog_word[sb + loc] = e;
         return e;
@@ -1520,12 +1528,13 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
             for (int o = 1; o < G; o <<= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
         }
         RWT(2, mask + w_nx + n_nx);
-        for (int i = 0; i < kk; i++) {
+        // members with a site in any word of this warp, in order (usually one)
+        for (uint32_t todo = __reduce_or_sync(0xffffffffu, w >= 0 ? mask : 0u); todo; todo &= todo - 1) {
+            const int i = __ffs(todo) - 1;
             const bool act = w >= 0 && ((mask >> i) & 1u);
             const int32_t a = __shfl_sync(0xffffffffu, ma, i), b = __shfl_sync(0xffffffffu, mb, i), c = __shfl_sync(0xffffffffu, mc, i);
             const int32_t sl = __shfl_sync(0xffffffffu, mslot, i);
             const int isn = __shfl_sync(0xffffffffu, mnew, i);
-            if (!__any_sync(0xffffffffu, act)) continue;
             if (a != b) {
                 const int nn = rewrite_words_g<G>(M, act ? w : -1, off, n, f_cur, a, b, c, T, T2, lc, isn != 0, nullptr, -1);
                 if (act) n = nn;
@@ -1542,8 +1551,9 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
 //   C  the last warp records the merges / creates the tokens while every other 8-lane group takes ONE candidate
 //      item, claims its word in a shared-memory set (no global stamp), loads the word and rewrites it
 //   D  the members' affected-log segments are closed (plain stores; all counters are in shared memory), thresholds of the new pairs
-__device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i64 T, i64 Tmin, const i64 T2, const u64 T2pa) {
-    __shared__ BatchCtx BC;
+__device__ void leader_loop(const MergeParams& M, LeaderCtx& C, BatchCtx& BC, Best* sh_best, i64 T, i64 Tmin, const i64 T2, const u64 T2pa) {
+    __builtin_assume(__isShared(&BC));          // a reference parameter hides the address space: without this every access is a generic load
+    __builtin_assume(__isShared(&C));
     __shared__ i64 sh_wmax[ML_THREADS / 32];    // block-wide maxima of the tie path
 #if ML_TIMING
     __shared__ long long sh_tacc[8];
@@ -1558,7 +1568,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
     int32_t n_tok = (int32_t)M.state[MS_NTOK];
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     int batch_max = (M.batch_max & 255) > 0 ? (int)(M.batch_max & 255) : ML_BATCH_MAX;
-    if (batch_max > ML_BATCH_MAX) batch_max = ML_BATCH_MAX;
+    if (batch_max > 16) batch_max = 16;  // its batches are bounded by ML_LEADER_BATCH_ITEMS anyway; a head of 32 keeps the selection short
     const bool grid_batches_on = ((M.batch_max >> 8) & 255 ? (M.batch_max >> 8) & 255 : M.batch_max & 255) != 1 && !((M.batch_max >> 17) & 1);   // bit 17: keep big batches here (tuning)
     if (T2pa != 0) batch_max = 1;        // tie regime: the list is not complete at the boundary count (and pair_add reads prefixes of tokens being created)
 #if ML_TIMING
@@ -1619,7 +1629,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         int nb = 0;
         Best best{0, -1, 0, 0, 0};
         if (batch_max > 1) {
-            nb = select_batch(M, BC.sel, mine, tn, batch_max, T, Tmin, T2, C.tpa, C.tpb, sh_wmax, theta, theta_sticky);
+            nb = select_batch(M, BC.sel, mine, tn, batch_max, T, Tmin, T2, C.tpa, C.tpb, sh_wmax, theta, theta_sticky, 32);
             if (lane < ML_BATCH_MAX) { ma = BC.sel.mem[lane].a; mb = BC.sel.mem[lane].b; mslot = BC.sel.mem[lane].slot; midx = BC.sel.mem[lane].idx; mcnt = BC.sel.mem[lane].cnt; }
             if (nb > 0) best = Best{__shfl_sync(0xffffffffu, mcnt, 0), __shfl_sync(0xffffffffu, mslot, 0), __shfl_sync(0xffffffffu, ma, 0),
                                     __shfl_sync(0xffffffffu, mb, 0), __shfl_sync(0xffffffffu, midx, 0)};
@@ -1636,9 +1646,9 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
         if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
         ML_CLOCK(c1);
         ML_TR(1);
-        // ---- B: candidate ranges + merged tokens, one thread each per member (warps 0 .. nb-1 and 8 .. 8+nb-1)
+        // ---- B: candidate ranges + merged tokens, one thread each per member (ranges: warp i, lookups: warp 31 - i; lane i holds member i)
         if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &BC.R[warp], midx >= 0, midx >= 0 ? C.tp0[midx] : 0u, midx >= 0 ? C.tplen[midx] : 0u);
-        if (warp >= ML_BATCH_MAX && warp < ML_BATCH_MAX + nb && lane == warp - ML_BATCH_MAX)
+        if (nwarps - 1 - warp < nb && lane == nwarps - 1 - warp)
             BC.c[lane] = lookup_merged_leader(M, C, midx, ma, mb, n_tok, &BC.MI[lane]);
         for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
@@ -1658,8 +1668,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, Best* sh_best, i
             if (lane >= o) { cum += t1; lcum += t3; }
         }
         if (cum > ML_LEADER_ITEMS_MAX || (i64)alog_n + cum > M.alog_cap) mbad = true;
-#pragma unroll
-        for (int i = 0; i < ML_BATCH_MAX - 1; i++) {
+        for (int i = 0; i < nb - 1; i++) {                           // (nothing to do for the common single merge)
             const u64 Hi = __shfl_sync(0xffffffffu, mH, i);
             const int newi = __shfl_sync(0xffffffffu, mnew, i);
             if (i < lane && (Hi == mH || !newi)) mbad = true;      // same merged bytes twice / an earlier member reuses an existing token
@@ -1904,7 +1913,7 @@ __device__ void helper_loop(const MergeParams& M, i64 gen, int hidx, u64* sh_key
             if (cnt > 0) key = ((u64)cnt << 9) | (u64)(511 - (int)threadIdx.x);
         }
         const u64 mykey = select_top(key, sh_keys);      // one block barrier inside; lane r holds the r-th largest key
-        for (int r = hidx; r < ML_SEL && r < 5; r += ML_HELPERS) {
+        for (int r = hidx; r < ML_HSEL; r += ML_HELPERS) {
             __syncthreads();
             const u64 kr = __shfl_sync(0xffffffffu, mykey, r);
             if (kr == 0) continue;                       // block-uniform
@@ -2029,7 +2038,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
             grid_barrier(M);                                    // everyone has read the state the leader is about to change
             if (blockIdx.x == 0) {
                 pclk = clock64();
-                leader_loop(M, *(LeaderCtx*)ml_dyn_smem, sh_best, T, Tmin, T2, T2pa);
+                leader_loop(M, *(LeaderCtx*)ml_dyn_smem, GB, sh_best, T, Tmin, T2, T2pa);
                 ML_PHASE(MS_CLK_LEADER, pclk);
                 __syncthreads();
                 if (threadIdx.x == 0) { __threadfence(); atomicAdd((u64*)&M.state[MS_LEADER_GEN], 1ULL); }
@@ -2082,7 +2091,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 if (cnt > 0) mine = Best{cnt, sl, (int32_t)((k >> 32) & 0x7fffffff), (int32_t)(k & 0xffffffffu), (int32_t)threadIdx.x};
             }
             g_cached = tn;
-            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, g_tpa, g_tpb, sh_cnt, g_theta, g_sticky);
+            int nb = select_batch(M, GB.sel, mine, tn, gbmax, T, Tmin, T2, g_tpa, g_tpb, sh_cnt, g_theta, g_sticky, ML_HEAD);
             long long gclk = pclk;
             ML_PHASE(MS_CLK_GB_SELECT, gclk);
             if (m + nb > M.num_merges) nb = (int)(M.num_merges - m);
@@ -2096,7 +2105,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 grid_barrier(M);                                // 1: every CTA has read the counts
                 ML_PHASE(MS_CLK_GB_BAR1, gclk);
                 if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &GB.R[warp]);
-                if (warp >= ML_BATCH_MAX && warp < ML_BATCH_MAX + nb && lane == warp - ML_BATCH_MAX) GB.c[lane] = lookup_merged(M, ma, mb, n_tok, &GB.MI[lane]);
+                if (nwarps - 1 - warp < nb && lane == nwarps - 1 - warp) GB.c[lane] = lookup_merged(M, ma, mb, n_tok, &GB.MI[lane]);
                 __syncthreads();
                 int mtot = 0, mnew = 0, mlen = 0; int32_t mc = -1; u64 mH = 0; bool mbad = true;
                 if (lane < nb) {
@@ -2112,8 +2121,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                     if (lane >= o) { cum += t1; lcum += t3; }
                 }
                 if (alog_n + cum > M.alog_cap) mbad = true;
-#pragma unroll
-                for (int i = 0; i < ML_BATCH_MAX - 1; i++) {
+                for (int i = 0; i < nb - 1; i++) {
                     const u64 Hi = __shfl_sync(0xffffffffu, mH, i);
                     const int newi = __shfl_sync(0xffffffffu, mnew, i);
                     if (i < lane && (Hi == mH || !newi)) mbad = true;
