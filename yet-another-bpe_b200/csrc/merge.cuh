@@ -1292,6 +1292,7 @@ struct BatchCtx {
     Ranges R[ML_BATCH_MAX];
     MergedInfo MI[ML_BATCH_MAX];
     int32_t c[ML_BATCH_MAX];
+    u64 mkey[ML_BATCH_MAX];                     // the members' pair keys (the rewrite tests every adjacency of a word against them)
     BatchSel sel;
 };
 
@@ -1450,12 +1451,11 @@ __device__ void commit_member(const MergeParams& M, LeaderCtx* lc, i64 m, int32_
 // the rewriting warps of CTA 0.  Grid mode: lc = nullptr (claims by the per-word stamp, counters in global memory), the
 // groups of ALL CTAs share the items.
 template <int G>
-__device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* lc, const Ranges* RR, int kk, int lane, int group0, int ngroups, int32_t stamp,
+__device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* lc, const Ranges* RR, const u64* MK, int kk, int lane, int group0, int ngroups, int32_t stamp,
                                               int32_t ma, int32_t mb, int32_t mc, int32_t mslot, int mnew, int mtot, int mpst, int mseg,
                                               i64 T, i64 T2) {
     const int gl = lane & (G - 1), lead = lane & ~(G - 1);
     const int total_p = __shfl_sync(0xffffffffu, mpst + mtot, kk - 1);
-    const u64 mkey = PAIR_KEY(ma, mb);
     // Item `it` of the padded layout (all 32 lanes call this together).  The affected-word segment of a member is simply a
     // COPY of its candidate list -- a superset of the words it rewrites, which is all the index needs (candidates are ~97 %
     // hits) -- so the log needs no counter: hundreds of groups appending through one atomic serialised in the L2.
@@ -1522,7 +1522,8 @@ __device__ __forceinline__ void rewrite_batch(const MergeParams& M, LeaderCtx* l
                 const int j = j0 + gl;
                 u64 key = 0;
                 if (j + 1 < n) key = j0 == 0 ? PAIR_KEY(y0_cur, y1_cur) : PAIR_KEY(s[j], s[j + 1]);
-                for (int i = 0; i < kk; i++) { const u64 ki = __shfl_sync(0xffffffffu, mkey, i); if (key == ki) mask |= 1u << i; }
+#pragma unroll 4
+                for (int i = 0; i < kk; i++) mask |= key == MK[i] ? 1u << i : 0u;        // broadcast loads, independent of each other
             }
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
@@ -1650,6 +1651,7 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, BatchCtx& BC, Be
         if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &BC.R[warp], midx >= 0, midx >= 0 ? C.tp0[midx] : 0u, midx >= 0 ? C.tplen[midx] : 0u);
         if (nwarps - 1 - warp < nb && lane == nwarps - 1 - warp)
             BC.c[lane] = lookup_merged_leader(M, C, midx, ma, mb, n_tok, &BC.MI[lane]);
+        if (warp == nwarps / 2 && lane < nb) BC.mkey[lane] = PAIR_KEY(ma, mb);
         for (int i = threadIdx.x; i < ML_DEDUPE_N; i += blockDim.x) C.dedupe[i] = 0;
         __syncthreads();
         if (threadIdx.x == 0) { sh_ncand = 0; C.npairs_new += C.nnew; C.nnew = 0; }   // everybody has read them; next use is after stage C's barrier
@@ -1730,9 +1732,9 @@ __device__ void leader_loop(const MergeParams& M, LeaderCtx& C, BatchCtx& BC, Be
             const int last_new = __shfl_sync(0xffffffffu, mnew, kk - 1) ? kk - 1 : kk - 2;   // every member but the last makes a new token
             if (warp == nwarps - 1) {
                 if (lane < kk) commit_member(M, &C, m + lane, ma, mb, mc, mnew != 0, (i64)mseg, BC.MI[lane], moc, lane == last_new);
-            } else if (G == 8) rewrite_batch<8>(M, &C, BC.R, kk, lane, warp * 4, (nwarps - 1) * 4, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-            else if (G == 4) rewrite_batch<4>(M, &C, BC.R, kk, lane, warp * 8, (nwarps - 1) * 8, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-            else rewrite_batch<2>(M, &C, BC.R, kk, lane, warp * 16, (nwarps - 1) * 16, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            } else if (G == 8) rewrite_batch<8>(M, &C, BC.R, BC.mkey, kk, lane, warp * 4, (nwarps - 1) * 4, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else if (G == 4) rewrite_batch<4>(M, &C, BC.R, BC.mkey, kk, lane, warp * 8, (nwarps - 1) * 8, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+            else rewrite_batch<2>(M, &C, BC.R, BC.mkey, kk, lane, warp * 16, (nwarps - 1) * 16, 0, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
             n_new_batch = __popc(__ballot_sync(0xffffffffu, lane < kk && mnew));
             len_batch = __shfl_sync(0xffffffffu, lcum, kk - 1) - (__shfl_sync(0xffffffffu, mnew, kk - 1) ? 0 : __shfl_sync(0xffffffffu, mlen, kk - 1));
             items_batch = __shfl_sync(0xffffffffu, cum, kk - 1);
@@ -2106,6 +2108,7 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                 ML_PHASE(MS_CLK_GB_BAR1, gclk);
                 if (warp < nb && lane == warp) build_ranges(M, mslot, ma, mb, &GB.R[warp]);
                 if (nwarps - 1 - warp < nb && lane == nwarps - 1 - warp) GB.c[lane] = lookup_merged(M, ma, mb, n_tok, &GB.MI[lane]);
+                if (warp == nwarps / 2 && lane < nb) GB.mkey[lane] = PAIR_KEY(ma, mb);
                 __syncthreads();
                 int mtot = 0, mnew = 0, mlen = 0; int32_t mc = -1; u64 mH = 0; bool mbad = true;
                 if (lane < nb) {
@@ -2149,9 +2152,9 @@ __global__ void __launch_bounds__(ML_THREADS) k_merge_loop(MergeParams M) {
                     const int vw = warp * (int)gridDim.x + (int)blockIdx.x, skipw = (nwarps - 1) * (int)gridDim.x;
                     const int gw = vw - (vw > skipw ? 1 : 0), rw = warps_all - 1;
                     if (blockIdx.x == 0 && warp == nwarps - 1) { }
-                    else if (G == 8) rewrite_batch<8>(M, nullptr, GB.R, kk, lane, gw * 4, rw * 4, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-                    else if (G == 4) rewrite_batch<4>(M, nullptr, GB.R, kk, lane, gw * 8, rw * 8, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
-                    else rewrite_batch<2>(M, nullptr, GB.R, kk, lane, gw * 16, rw * 16, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else if (G == 8) rewrite_batch<8>(M, nullptr, GB.R, GB.mkey, kk, lane, gw * 4, rw * 4, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else if (G == 4) rewrite_batch<4>(M, nullptr, GB.R, GB.mkey, kk, lane, gw * 8, rw * 8, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
+                    else rewrite_batch<2>(M, nullptr, GB.R, GB.mkey, kk, lane, gw * 16, rw * 16, stamp, ma, mb, mc, mslot, mnew, mtot, mpst, mseg, T, T2);
                     ML_PHASE(MS_CLK_GB_REWRITE, gclk);
                     grid_barrier(M);                            // 2: every word is rewritten, every token created
                     ML_PHASE(MS_CLK_GB_BAR2, gclk);
