@@ -211,7 +211,7 @@ typedef struct {
                                  * (0 = default, 8 Mi slots: smaller word arrays stay L2-resident anyway; < 0 = always).  Result-neutral */
     int64_t helper_mode;        /* 0 = no helpers, 1 = CTAs 1..2, 2 = the CTAs on the SMs next to the leader's                      */
     int64_t batch_max;          /* merges taken per iteration when they provably do not interact (csrc/merge.cuh, "batched merges"):
-                                 * 0 = default (16), 1 = strictly one by one as trainer.py:241-300.  Result-neutral                   */
+                                 * 0 = default (31 in grid mode, 16 in leader mode), 1 = strictly one by one as trainer.py:241-300.  Result-neutral                   */
 } yabpe_merge_args;
 
 int yabpe_merge_loop(const yabpe_merge_args* m, void* stream);

@@ -333,7 +333,7 @@ def test_tables_grow_when_the_estimate_is_too_small(yabpe, tmp_path, monkeypatch
                                        ("131088", "big batches stay with the leader"),
                                        ("2", "pairs"), ("0", "default")])
 def test_train_batched_merges(yabpe, tmp_path, monkeypatch, mode, what):
-    """The merge loop takes up to 16 pairs per iteration when it can prove that the sequential loop would pick exactly these,
+    """The merge loop takes up to 31 pairs per iteration when it can prove that the sequential loop would pick exactly these,
     in this order (csrc/merge.cuh, "batched leader merges").  Every combination of where batching is allowed must give the
     oracle's merges; the default must actually batch on a corpus of this kind."""
     monkeypatch.setenv("YABPE_BATCH_MAX", mode)
