@@ -336,9 +336,10 @@ class BBPETrainer:
             torch.cuda.synchronize()
             self.timing.update(specials_ms=ev[0].elapsed_time(ev[1]), pretok_tiles_ms=ev[1].elapsed_time(ev[2]),
                                long_tokens_ms=ev[2].elapsed_time(ev[3]), compact_ms=e0.elapsed_time(e1))
-        vocab = {b: i for i, b in enumerate(mr.tokens)}
         toks = mr.tokens
-        merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]       # .tolist(): plain ints, not numpy scalars
+        vocab = dict(zip(toks, range(len(toks))))
+        tok_at = toks.__getitem__                       # 32 000 merges: C-level loops (zip / map over plain int lists), a third of the time of a comprehension
+        merges = list(zip(map(tok_at, mr.merges[:, 0].tolist()), map(tok_at, mr.merges[:, 1].tolist())))
         return self._finish(vocab, merges)
 
     def _preprocess_corpus(self, files: Sequence[str | Path]) -> list[list[int]]:
