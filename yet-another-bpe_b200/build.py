@@ -21,7 +21,29 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_SRC = HERE / "csrc" / "hostlist.c"
+HOST_OUT = HERE / "yabpe" / "_hostlist.so"
+
+
+def build_hostlist(force: bool = False) -> Path | None:
+    """gcc -> yabpe/_hostlist.so: the Python objects of a training result built with the C API (host glue, no compute).
+    Optional: without Python.h the package uses its Python construction of the same objects."""
+    import sysconfig
+    if not force and HOST_OUT.exists() and HOST_OUT.stat().st_mtime >= HOST_SRC.stat().st_mtime:
+        return HOST_OUT
+    inc = sysconfig.get_paths()["include"]
+    if not (Path(inc) / "Python.h").exists():
+        return None
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", inc, "-o", str(HOST_OUT), str(HOST_SRC)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        return None
+    return HOST_OUT
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    build_hostlist(force)
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return OUT
     import os

@@ -276,9 +276,7 @@ def _count_exchange_merge(trainer, text_dev, n: int, cuts: list[int], own: tuple
     trainer.timing['leader_cycles'] = [int(x) for x in mr.state[20:29]] + [int(mr.state[12]), int(mr.state[13]), int(mr.state[17])]
     from .trainer import _phase_cycles
     trainer.timing['merge_phase_cycles'] = _phase_cycles(mr.state)
-    vocab = {b: i for i, b in enumerate(mr.tokens)}
-    toks = mr.tokens
-    merges = [(toks[a], toks[b]) for a, b in mr.merges.tolist()]
+    _toks, vocab, merges = mr.materialise()
     return trainer._finish(vocab, merges)
 
 

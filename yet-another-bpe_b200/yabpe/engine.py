@@ -341,12 +341,50 @@ def tok_hash(b: bytes) -> tuple[int, int]:
     return h, p
 
 
+def _load_hostlist():
+    """yabpe/_hostlist.so (csrc/hostlist.c, built by build.py with gcc): result objects built in C; None when it is not there."""
+    try:
+        from . import _hostlist
+        return _hostlist
+    except ImportError:
+        return None
+
+
+_HOSTLIST = _load_hostlist()
+
+
 @dataclass
 class MergeResult:
     merges: np.ndarray          # (n_merges, 2) int32 token ids
     merge_new: np.ndarray       # (n_merges,) int32 resulting id
-    tokens: list[bytes]         # id -> bytes, all tokens
     state: np.ndarray
+    pool: bytes                 # the token bytes, back to back
+    offs: np.ndarray            # int64 [n_tokens + 1]: token i = pool[offs[i]:offs[i + 1]]
+    _tokens: list | None = None
+
+    @property
+    def tokens(self) -> list[bytes]:
+        """id -> bytes, all tokens."""
+        if self._tokens is None:
+            self._tokens = self.materialise()[0]
+        return self._tokens
+
+    def materialise(self) -> tuple[list[bytes], dict[bytes, int], list[tuple[bytes, bytes]]]:
+        """(tokens, vocab, merges) as the Python objects the reference API returns (trainer.py:94-134, 296-300): ~65 000
+        small objects for a 32 000-merge model -- built in C when yabpe/_hostlist.so is there (a tenth of the training
+        step otherwise), else with C-level loops over plain lists."""
+        offs = np.ascontiguousarray(self.offs, dtype=np.int64)
+        mg = np.ascontiguousarray(self.merges, dtype=np.int32).reshape(-1, 2)
+        if _HOSTLIST is not None:
+            toks, vocab, merges = _HOSTLIST.materialise(self.pool, offs, mg)
+        else:
+            o = offs.tolist()
+            toks = list(map(self.pool.__getitem__, map(slice, o[:-1], o[1:])))
+            vocab = dict(zip(toks, range(len(toks))))
+            tok_at = toks.__getitem__
+            merges = list(zip(map(tok_at, mg[:, 0].tolist()), map(tok_at, mg[:, 1].tolist())))
+        self._tokens = toks
+        return toks, vocab, merges
 
 
 def rebuild_period(n_syms: int) -> int:
@@ -465,9 +503,8 @@ def merge_loop(torch, words: WordArrays, base_tokens: list[bytes], num_merges: i
             mn = merge_new[:nm].cpu().numpy()
             used = int(st[_ffi.MS_POOL_USED]) if ntok > n_base else int(tok_off[n_base])
             pool = d_tok_bytes[:max(used, 1)].cpu().numpy().tobytes()
-            offs = d_tok_off[:ntok + 1].cpu().tolist()
-            tokens = [pool[offs[i]:offs[i + 1]] for i in range(ntok)]
-            return MergeResult(merges=mg, merge_new=mn, tokens=tokens, state=st)
+            offs = d_tok_off[:ntok + 1].cpu().numpy()
+            return MergeResult(merges=mg, merge_new=mn, state=st, pool=pool, offs=offs)
         if err & _ffi.ME_INTERNAL:
             raise _ffi.YabpeError(f"merge loop internal error (state={st.tolist()})")
         if restore is None:
