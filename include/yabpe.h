@@ -55,6 +55,15 @@ extern "C" {
 #define YABPE_MS_TREBUILDS 10
 #define YABPE_MS_LEADER_MERGES 15 /* merges run by the single-CTA fast path */
 #define YABPE_MS_GRID_MERGES 16
+/* statistics (informational): [40..47] phase clocks of CTA 0 in cycles (initial histogram, first index + active set, top-list
+ * rebuilds, index rebuilds, leader sessions, grid-mode merges, total, number of top-list rebuilds), [48..53] grid-mode single
+ * merges by candidate count (merges, cycles), [54] leader iterations, [55] merges the leader did in batches of two or more,
+ * [56] grid-mode batches, [57] merges in them, [58..62] cycles of the grid-mode batches (selection, barrier 1, ranges + lookups,
+ * CTA 0's rewrite share, barrier 2) */
+#define YABPE_MS_LEADER_ITERS 54
+#define YABPE_MS_LEADER_BATCHED 55
+#define YABPE_MS_GRID_BATCHES 56
+#define YABPE_MS_GRID_BATCHED 57
 
 const char* yabpe_last_error(void);
 int yabpe_abi_version(void);
